@@ -1,0 +1,284 @@
+/*
+ * mcm_b200.h — C ABI of the B200-native particle-arithmetic engine for
+ * MonteCarloMeasurements.jl (reference: /root/reference, v1.5.1; all file:line
+ * citations below are relative to it).
+ *
+ * The reference has NO FFI: its "operator interface" is Julia method dispatch on
+ * `AbstractParticles{T,N}` (src/types.jl:4-28) whose method bodies are broadcasts
+ * over the `particles::Vector{T}` field.  This header is what a `ccall`-based
+ * device-resident subtype binds instead of those bodies (see INTEGRATION.md for
+ * the Julia stub).  One entry point per reference method family; every function
+ *   - takes plain pointers / sizes / scalars only (no torch, no C++ types),
+ *   - returns an int status (MCM_OK == 0); `mcm_last_error()` gives the text,
+ *   - is asynchronous and ordered on the library stream unless it returns a
+ *     host scalar (reductions, quantiles, downloads synchronise).
+ *
+ * Device pointers are ordinary CUDA device addresses (from `mcm_alloc`, or any
+ * other allocator in the same process, e.g. a torch tensor's data_ptr()).
+ * The N samples of one uncertain scalar are ONE contiguous array of `T`
+ * (SoA; src/types.jl:17-19).  A vector of M uncertain variables is M such
+ * arrays (index-aligned: particle i of every variable is the same draw).
+ */
+#ifndef MCM_B200_H
+#define MCM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCM_B200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+  MCM_OK = 0,
+  MCM_ERR_INVALID = 1,     /* bad argument (ArgumentError in the reference)      */
+  MCM_ERR_CUDA = 2,        /* CUDA runtime error                                  */
+  MCM_ERR_NOMEM = 3,       /* allocation failed                                   */
+  MCM_ERR_UNSUPPORTED = 4, /* op exists in the reference but not on device (MethodError) */
+  MCM_ERR_NCCL = 5,        /* NCCL error / communicator missing                   */
+  MCM_ERR_NOT_INIT = 6     /* mcm_init not called                                 */
+};
+
+/* element types of device-resident particles (src/types.jl:17, T) */
+enum { MCM_F32 = 0, MCM_F64 = 1 };
+
+/* sticky numerical flags (Base scalar functions THROW DomainError; kernels
+ * cannot — they return NaN and raise a flag, surfaced by mcm_check_flags).   */
+enum {
+  MCM_FLAG_DOMAIN = 1u,     /* NaN produced from non-NaN input (sqrt(-1), log(-1), ...) */
+  MCM_FLAG_NAN_QUANTILE = 2u /* NaN met by quantile/sort (Statistics.quantile errors)    */
+};
+
+/* ---- unary primitives -----------------------------------------------------
+ * The first 35 are exactly the list registered at src/particles.jl:185-190
+ * through register_primitive_single (src/register_primitive.jl:89-100); for
+ * Float64/Float32 particles exp/log/sin/cos/asin/acos/atan are the methods of
+ * src/sleefpirates.jl:2-36.  The rest are the per-element bodies of
+ * src/particles.jl:346-348 (round), :388-391 (literal_pow 2,3,-1), floor/ceil/
+ * trunc (Base fallbacks through Real).                                        */
+enum {
+  MCM_U_PLUS = 0, MCM_U_NEG, MCM_U_EXP, MCM_U_EXP2, MCM_U_EXP10, MCM_U_EXPM1,
+  MCM_U_LOG, MCM_U_LOG10, MCM_U_LOG2, MCM_U_LOG1P,
+  MCM_U_SIN, MCM_U_COS, MCM_U_TAN, MCM_U_SIND, MCM_U_COSD, MCM_U_TAND,
+  MCM_U_SINH, MCM_U_COSH, MCM_U_TANH,
+  MCM_U_ASIN, MCM_U_ACOS, MCM_U_ATAN, MCM_U_ASIND, MCM_U_ACOSD, MCM_U_ATAND,
+  MCM_U_ASINH, MCM_U_ACOSH, MCM_U_ATANH,
+  MCM_U_ZERO, MCM_U_SIGN, MCM_U_ABS, MCM_U_SQRT, MCM_U_RAD2DEG, MCM_U_DEG2RAD,
+  MCM_U_FLOAT, /* 34: last registered primitive */
+  MCM_U_ROUND, /* round(x) RoundNearest (ties to even), particles.jl:346 */
+  MCM_U_FLOOR, MCM_U_CEIL, MCM_U_TRUNC,
+  MCM_U_INV,   /* literal_pow(^,x,Val(-1)) == inv(x) */
+  MCM_U_SQR,   /* literal_pow(^,x,Val(2))  == x*x   (particles.jl:388-391) */
+  MCM_U_CUBE,  /* literal_pow(^,x,Val(3))  == x*x*x */
+  MCM_U_COUNT
+};
+
+/* ---- binary primitives ------------------------------------------------------
+ * register_primitive_multi list, src/particles.jl:183:
+ *   + - * / // ^ max min mod mod1 atan atand add_sum hypot clamp
+ * `//` (Rational) has no floating-point method in Base -> MCM_ERR_UNSUPPORTED.
+ * clamp is ternary (mcm_ternary).  rem/div are src/particles.jl:354-358.      */
+enum {
+  MCM_B_ADD = 0, MCM_B_SUB, MCM_B_MUL, MCM_B_DIV, MCM_B_RATDIV, MCM_B_POW,
+  MCM_B_MAX, MCM_B_MIN, MCM_B_MOD, MCM_B_MOD1, MCM_B_ATAN2, MCM_B_ATAND2,
+  MCM_B_ADD_SUM, MCM_B_HYPOT,
+  MCM_B_REM,    /* rem(x,y) == C fmod, exact  (particles.jl:354-355) */
+  MCM_B_FDIV,   /* div(x,y) == round((x-rem(x,y))/y) (particles.jl:356-357) */
+  MCM_B_COUNT
+};
+
+/* ---- ternary primitives */
+enum {
+  MCM_T_CLAMP = 0,  /* clamp(x,lo,hi), particles.jl:183            */
+  MCM_T_MULADD,     /* muladd(x,y,z) — fused (particles.jl:416-422; H8: fusion allowed) */
+  MCM_T_MUL_ADD,    /* x*y+z with two roundings (what `x*y+z` on particles gives) */
+  MCM_T_COUNT
+};
+
+/* ---- reductions (src/particles.jl:302-323) */
+enum {
+  MCM_R_SUM = 0,
+  MCM_R_MEAN,     /* pmean   = mean(p.particles)                 :321 */
+  MCM_R_VAR,      /* pvar    = var(...; corrected=true)          :308-312 */
+  MCM_R_VARP,     /* pvar(...; corrected=false)                        */
+  MCM_R_STD,      /* pstd                                               */
+  MCM_R_STDP,
+  MCM_R_MIN,      /* pminimum */
+  MCM_R_MAX,      /* pmaximum */
+  MCM_R_COUNT
+};
+
+/* comparison kinds for mcm_count (the `@prob` macro, src/bymap.jl:128-136,
+ * and the :montecarlo comparison mode, src/particles.jl:512-515) */
+enum { MCM_CMP_LT = 0, MCM_CMP_LE, MCM_CMP_GT, MCM_CMP_GE, MCM_CMP_EQ, MCM_CMP_NE };
+
+/* ======================= lifecycle / memory ================================ */
+int mcm_version(void);
+/* bind the calling process to CUDA device `device`, create the library stream
+ * and the stream-ordered pool.  Idempotent. */
+int mcm_init(int device);
+int mcm_finalize(void);
+/* run all subsequent work on a caller-owned cudaStream_t (e.g. torch's); NULL restores the library stream */
+int mcm_set_stream(void* cuda_stream);
+void* mcm_get_stream(void);
+int mcm_sync(void);
+const char* mcm_last_error(void);
+/* read (and optionally clear) the sticky numerical flags; synchronises */
+int mcm_check_flags(uint32_t* bits, int reset);
+int mcm_device_info(int* sm_count, size_t* free_bytes, size_t* total_bytes);
+
+/* storage of one `particles` vector (replaces `Vector{T}(undef,N)`; every
+ * reference primitive allocates its result, register_primitive.jl:45,49,53,95) */
+int mcm_alloc(void** dptr, size_t bytes);   /* stream-ordered (cudaMallocAsync pool) */
+int mcm_free(void* dptr);                   /* stream-ordered; safe from a GC finalizer thread */
+int mcm_host_alloc(void** hptr, size_t bytes); /* pinned host staging */
+int mcm_host_free(void* hptr);
+/* Particles(v::Vector) (types.jl:55)  /  Array(p), Vector(p) (particles.jl:458-459) */
+int mcm_upload(void* dst_dev, const void* src_host, size_t bytes);
+int mcm_download(void* dst_host, const void* src_dev, size_t bytes); /* synchronises */
+int mcm_copy(void* dst_dev, const void* src_dev, size_t bytes);
+
+/* ======================= elementwise primitives ============================ */
+/* PT{T,N}(n::Real) = fill(n,N)  (types.jl:57-63) */
+int mcm_fill(int dtype, void* out, size_t n, double value);
+/* convert(PT{T,N}, p::PT{S,N}) (particles.jl:333) */
+int mcm_convert(int src_dtype, const void* src, int dst_dtype, void* dst, size_t n);
+/* f(p)  — register_primitive.jl:94-97 */
+int mcm_unary(int op, int dtype, const void* in, void* out, size_t n);
+/* f(p1,p2) / f(p,a::Real) / f(a::Real,p) — register_primitive.jl:44-58.
+ * A NULL pointer selects the scalar (`sa`/`sb`) for that operand. */
+int mcm_binary(int op, int dtype, const void* a, double sa, const void* b, double sb,
+               void* out, size_t n);
+int mcm_ternary(int op, int dtype, const void* a, double sa, const void* b, double sb,
+                const void* c, double sc, void* out, size_t n);
+/* p^i::Integer (particles.jl:383-386); k in {-2..3} is bit-exact to literal_pow */
+int mcm_powi(int dtype, const void* in, int k, void* out, size_t n);
+
+/* ======================= fused chains ====================================== */
+/* evalpoly(p, c) = c[0] + c[1]x + ... by Horner.  fused=1: muladd (FMA) per step
+ * (what Base.evalpoly emits through particles.jl:416-422); fused=0: separate
+ * rounding of * and + (what `c0 + x*(c1 + ...)` written with * and + gives). */
+int mcm_polyval(int dtype, const void* in, const double* coeffs_host, int ncoef, int fused,
+                void* out, size_t n);
+/* alpha*p + beta with two roundings (bit-exact to the two reference broadcasts) */
+int mcm_affine(int dtype, const void* in, double alpha, double beta, void* out, size_t n);
+/* out = c0*x0 + c1*x1 + ... (left-to-right, unfused): RK4 stage / axpy updates */
+int mcm_lincomb(int dtype, int nterms, const void* const* xs, const double* coeffs_host,
+                void* out, size_t n);
+
+/* Expression tape: a register machine with 8 value slots per particle, executed
+ * entirely in registers; one launch evaluates the whole chain of registered
+ * primitives (no temporaries in HBM — the reference materialises one Vector per
+ * primitive).  Operand byte: 0..7 = slot, 0x40|k = constant k.               */
+typedef struct {
+  uint8_t op;   /* MCM_TAPE_* */
+  uint8_t dst;  /* destination slot 0..7 (or output index for STORE) */
+  uint8_t a, b, c; /* operands (or input index for LOAD; immediate for POWI in b as int8) */
+  uint8_t pad[3];
+} mcm_tape_ins;
+
+enum {
+  MCM_TAPE_UNARY = 0x00,   /* + MCM_U_*  : dst = f(a)            */
+  MCM_TAPE_BINARY = 0x40,  /* + MCM_B_*  : dst = f(a,b)          */
+  MCM_TAPE_TERNARY = 0x60, /* + MCM_T_*  : dst = f(a,b,c)        */
+  MCM_TAPE_LOAD = 0x70,    /* dst = inputs[a][i]                 */
+  MCM_TAPE_STORE = 0x71,   /* outputs[dst][i] = a                */
+  MCM_TAPE_MOV = 0x72,     /* dst = a                            */
+  MCM_TAPE_POWI = 0x73     /* dst = a ^ (int8)b                  */
+};
+#define MCM_TAPE_MAX_INS 96
+#define MCM_TAPE_MAX_CONST 32
+#define MCM_TAPE_MAX_IN 8
+#define MCM_TAPE_MAX_OUT 4
+#define MCM_TAPE_SLOTS 8
+#define MCM_TAPE_CONST 0x40
+
+/* Run `tape[0..loop_begin)` once, `tape[loop_begin..loop_end)` `reps` times and
+ * `tape[loop_end..ntape)` once, per particle (reps>1: in-register time stepping,
+ * e.g. RK4).  If stats_slot >= 0 the final value of that slot is also reduced
+ * on the fly: stats_out_host[0..5] = {n, mean, M2, min, max, sum} (synchronises).
+ * outputs may be NULL entries if only statistics are wanted.                  */
+int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+              int reps, const double* consts, int nconst,
+              const void* const* inputs, int nin, void* const* outputs, int nout,
+              size_t n, int stats_slot, double* stats_out_host);
+
+/* ======================= statistics ======================================== */
+/* one pass: out_host[0..5] = {n, mean, M2 = sum (x-mean)^2, min, max, sum} */
+int mcm_moments(int dtype, const void* in, size_t n, double* out_host);
+/* pmean/pvar/pstd/pminimum/pmaximum/sum (particles.jl:302-323); N==1 -> var/std 0 */
+int mcm_reduce(int kind, int dtype, const void* in, size_t n, double* out_host);
+/* @prob p < a  -> count; (bymap.jl:128-136) */
+int mcm_count(int cmp, int dtype, const void* in, size_t n, double threshold, uint64_t* count_host);
+/* merge two {n,mean,M2,min,max,sum} partials (Chan) — used across GPUs */
+int mcm_moments_merge(const double* a, const double* b, double* out);
+
+/* pcov(v::MvParticles; corrected) = cov(Matrix(v)) (particles.jl:476, 461-465).
+ * vars: M device pointers (host array), each N elements.  cov_out: device, M x M
+ * doubles, column-major == row-major (symmetric).  means_out: device M doubles or NULL.
+ * scale: 1 -> divide by (N-1) [corrected], 0 -> by N, -1 -> raw centred Gram (for
+ * multi-GPU partial Gram blocks). center_host: NULL -> centre on the local column
+ * means; else M doubles to centre on (global means in the sharded case).      */
+int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale,
+             const double* center_host, double* cov_out_dev, double* means_out_dev);
+/* column means of M variables into means_out_host[M] */
+int mcm_colmeans(int dtype, const void* const* vars, int M, size_t n, double* means_out_host);
+
+/* ======================= order statistics ================================== */
+/* sort(p.particles) ; sortperm -> 0-based int64 permutation (stable) */
+int mcm_sort(int dtype, const void* in, void* out, size_t n);
+int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* sorted_out_or_null, size_t n);
+/* pquantile(p, q) = Statistics.quantile(p.particles, q) type-7 (particles.jl:321);
+ * q_host: nq probabilities in [0,1]; out_host: nq values.  pmedian == q=0.5. */
+int mcm_quantile(int dtype, const void* in, size_t n, const double* q_host, int nq, double* out_host);
+
+/* ======================= sampling / resampling ============================= */
+/* quantile(Normal(0,1), p) elementwise on device */
+int mcm_norminvcdf(int dtype, const void* p_in, void* out, size_t n);
+/* systematic_sample(N, Normal(mu,sigma); permute) (sampling.jl:6-13):
+ * out[j] = mu + sigma*Phi^-1((2*i+1)/(2*n_total)) for global index i = i0 + j (or
+ * i = perm[j] when perm != NULL; perm is a 0-based device int64 array of length n). */
+int mcm_systematic_normal(int dtype, void* out, size_t n, double mu, double sigma,
+                          const int64_t* perm_dev, uint64_t i0, uint64_t n_total);
+/* a..b  Uniform systematic sample: out = a + (b-a)*(2i+1)/(2 n_total) */
+int mcm_systematic_uniform(int dtype, void* out, size_t n, double a, double b,
+                           const int64_t* perm_dev, uint64_t i0, uint64_t n_total);
+/* randperm(rng, N) stand-in: device permutation from a counter-based generator
+ * (Philox-4x32-10 keys + stable radix sort).  Stream differs from Julia's RNG (H5). */
+int mcm_randperm(int64_t* perm_out, size_t n, uint64_t seed);
+/* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
+int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
+/* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */
+int mcm_gather(int dtype, const void* src, const int64_t* idx, void* out, size_t n_draw, size_t n_src);
+/* same index vector applied to M variables (resampling.jl:80-84) */
+int mcm_gather_multi(int dtype, const void* const* srcs, void* const* outs, int M,
+                     const int64_t* idx, size_t n_draw, size_t n_src);
+/* systematic resampling by prefix scan (restates the dead reference code at
+ * resampling.jl:45-67): weights w (f64, >=0), offset u in [0,1):
+ * idx_out[i] = smallest b with cumsum(w)[b] > (i+u)*sum(w)/n.  Exact fixed-point scan. */
+int mcm_resample_systematic(const double* w, size_t n, double u, int64_t* idx_out);
+
+/* ======================= multi-GPU (one process per GPU) ==================== */
+/* NCCL is dlopen'ed; the 128-byte unique id is created on rank 0 and distributed
+ * by the host program (torch.distributed / MPI / sockets). */
+int mcm_comm_unique_id(void* id128);
+int mcm_comm_init(const void* id128, int nranks, int rank);
+int mcm_comm_destroy(void);
+int mcm_comm_info(int* nranks, int* rank);
+/* in-place sum all-reduce of `count` doubles on the library stream */
+int mcm_comm_allreduce_sum_f64(double* dptr, size_t count);
+/* sharded statistics: every rank passes its local shard; all ranks get the global
+ * {n, mean, M2, min, max, sum} (all-gather of partials + fixed-order Chan merge) */
+int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_host);
+/* sharded pcov: global means by all-reduce, local centred Gram, all-reduce of the
+ * M x M block, scaled by 1/(N_global - corrected) */
+int mcm_gram_sharded(int dtype, const void* const* vars, int M, size_t n_local, int corrected,
+                     double* cov_out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCM_B200_H */

@@ -1,0 +1,198 @@
+// comm.cu — multi-GPU plumbing: one process per GPU, particles sharded on the
+// particle index (rank r holds the contiguous slice [r*N/g, (r+1)*N/g) of every
+// uncertain variable).  Elementwise work needs no communication; only reduction
+// partials (six moments, M means, one M x M Gram block) cross NVLink, through
+// NCCL.  The reference has no distributed path at all (`bypmap` is a plain map,
+// src/bymap.jl:90-108).
+//
+// NCCL is dlopen'ed at first use so that libmcm_b200.so has no link-time
+// dependency; a host program that already loaded NCCL (torch) shares it.
+#include <dlfcn.h>
+#include <string.h>
+#include <vector>
+#include "mcm_common.cuh"
+
+namespace mcm {
+
+// minimal NCCL ABI (stable since 2.x)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8 };  // ncclDataType_t: ncclDouble
+enum { ncclSum = 0 };      // ncclRedOp_t
+
+struct Nccl {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+  Nccl& n = g_nccl;
+  if (n.h) return MCM_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    n.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.h) break;
+  }
+  if (!n.h) return fail(MCM_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define MCM_SYM(field, name)                                         \
+  *(void**)(&n.field) = dlsym(n.h, name);                            \
+  if (!n.field) return fail(MCM_ERR_NCCL, "libnccl: missing symbol %s", name);
+  MCM_SYM(GetUniqueId, "ncclGetUniqueId")
+  MCM_SYM(CommInitRank, "ncclCommInitRank")
+  MCM_SYM(CommDestroy, "ncclCommDestroy")
+  MCM_SYM(AllReduce, "ncclAllReduce")
+  MCM_SYM(AllGather, "ncclAllGather")
+  MCM_SYM(GetErrorString, "ncclGetErrorString")
+#undef MCM_SYM
+  return MCM_OK;
+}
+
+#define MCM_NCCL(x)                                                                              \
+  do {                                                                                           \
+    ncclResult_t r__ = (x);                                                                      \
+    if (r__ != 0) return fail(MCM_ERR_NCCL, "%s -> %s", #x, g_nccl.GetErrorString(r__));        \
+  } while (0)
+
+struct Mom6 { double v[6]; };
+int moments_device(int dtype, const void* in, size_t n, double* d_out6);
+double* moments_result_slot();
+int read_back(double* host_dst, const double* dev_src, size_t count);
+int gram_dispatch(int dtype, const void* const* vars, int M, size_t n, double scale, const double* center_host,
+                  double* cov_out_dev, double* means_out_dev);
+
+__global__ void k_scale(double* a, size_t n, double s) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] *= s;
+}
+
+}  // namespace mcm
+
+using namespace mcm;
+
+extern "C" int mcm_moments_merge(const double* a, const double* b, double* out);
+extern "C" int mcm_colmeans(int dtype, const void* const* vars, int M, size_t n, double* means_out_host);
+
+extern "C" int mcm_comm_unique_id(void* id128) {
+  if (!id128) return fail(MCM_ERR_INVALID, "mcm_comm_unique_id: null pointer");
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  MCM_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return MCM_OK;
+}
+
+extern "C" int mcm_comm_init(const void* id128, int nranks, int rank) {
+  MCM_NEED_INIT();
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(MCM_ERR_INVALID, "mcm_comm_init: bad arguments");
+  int rc = nccl_load();
+  if (rc) return rc;
+  if (g_nccl.comm) return fail(MCM_ERR_INVALID, "mcm_comm_init: communicator already exists");
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  MCM_NCCL(g_nccl.CommInitRank(&g_nccl.comm, nranks, id, rank));
+  g_nccl.nranks = nranks;
+  g_nccl.rank = rank;
+  return MCM_OK;
+}
+
+extern "C" int mcm_comm_destroy(void) {
+  if (g_nccl.comm) {
+    g_nccl.CommDestroy(g_nccl.comm);
+    g_nccl.comm = nullptr;
+    g_nccl.nranks = 1;
+    g_nccl.rank = 0;
+  }
+  return MCM_OK;
+}
+
+extern "C" int mcm_comm_info(int* nranks, int* rank) {
+  if (nranks) *nranks = g_nccl.nranks;
+  if (rank) *rank = g_nccl.rank;
+  return MCM_OK;
+}
+
+extern "C" int mcm_comm_allreduce_sum_f64(double* dptr, size_t count) {
+  MCM_NEED_INIT();
+  if (!g_nccl.comm) {
+    if (g_nccl.nranks == 1) return MCM_OK;  // single rank: identity
+    return fail(MCM_ERR_NCCL, "mcm_comm_allreduce_sum_f64: no communicator");
+  }
+  MCM_NCCL(g_nccl.AllReduce(dptr, dptr, count, ncclFloat64, ncclSum, g_nccl.comm, ctx().stream));
+  return MCM_OK;
+}
+
+// All ranks: local six moments -> all-gather (6 doubles per rank) -> every rank merges the
+// partials in rank order with the Chan update, so all ranks return bit-identical results.
+extern "C" int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_host) {
+  MCM_NEED_INIT();
+  if (!out_host) return fail(MCM_ERR_INVALID, "mcm_moments_sharded: null output");
+  Ctx& c = ctx();
+  const int g = g_nccl.comm ? g_nccl.nranks : 1;
+  double* slot = moments_result_slot();      // 6 doubles (local)
+  double* gathered = c.d_scratch + (c.scratch_doubles - 16 - 6 * 64);  // up to 64 ranks
+  if (g > 64) return fail(MCM_ERR_UNSUPPORTED, "mcm_moments_sharded: at most 64 ranks");
+  if (n_local) {
+    int rc = moments_device(dtype, in, n_local, slot);
+    if (rc) return rc;
+  } else {
+    const double e[6] = {0.0, 0.0, 0.0, __builtin_huge_val(), -__builtin_huge_val(), 0.0};
+    MCM_CUDA(cudaMemcpyAsync(slot, e, sizeof(e), cudaMemcpyHostToDevice, c.stream));
+  }
+  if (g == 1) return read_back(out_host, slot, 6);
+  MCM_NCCL(g_nccl.AllGather(slot, gathered, 6, ncclFloat64, g_nccl.comm, c.stream));
+  std::vector<double> h(6 * (size_t)g);
+  int rc = read_back(h.data(), gathered, 6 * (size_t)g);
+  if (rc) return rc;
+  double acc[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
+  for (int r = 1; r < g; ++r) {
+    double t[6];
+    mcm_moments_merge(acc, &h[6 * r], t);
+    memcpy(acc, t, sizeof(t));
+  }
+  memcpy(out_host, acc, sizeof(acc));
+  return MCM_OK;
+}
+
+// Sharded pcov: (1) global column means = allreduce(local sums)/N; (2) local centred Gram on
+// the global means (raw, unscaled); (3) allreduce(sum) of the M x M block; (4) scale.
+extern "C" int mcm_gram_sharded(int dtype, const void* const* vars, int M, size_t n_local, int corrected,
+                                double* cov_out_dev) {
+  MCM_NEED_INIT();
+  if (!vars || !cov_out_dev || M < 1) return fail(MCM_ERR_INVALID, "mcm_gram_sharded: bad arguments");
+  Ctx& c = ctx();
+  const int g = g_nccl.comm ? g_nccl.nranks : 1;
+  std::vector<double> means((size_t)M + 1);
+  int rc = MCM_OK;
+  if (n_local) rc = mcm_colmeans(dtype, vars, M, n_local, means.data());
+  if (rc) return rc;
+  // local sums + local count -> allreduce
+  for (int j = 0; j < M; ++j) means[j] *= (double)n_local;
+  means[M] = (double)n_local;
+  double* d_tmp = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_tmp, ((size_t)M + 1) * sizeof(double), c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_tmp, means.data(), ((size_t)M + 1) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  if (g > 1) MCM_NCCL(g_nccl.AllReduce(d_tmp, d_tmp, (size_t)M + 1, ncclFloat64, ncclSum, g_nccl.comm, c.stream));
+  MCM_CUDA(cudaMemcpyAsync(means.data(), d_tmp, ((size_t)M + 1) * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_tmp, c.stream));
+  const double n_glob = means[M];
+  for (int j = 0; j < M; ++j) means[j] /= n_glob;
+  rc = gram_dispatch(dtype, vars, M, n_local, 1.0, means.data(), cov_out_dev, nullptr);
+  if (rc) return rc;
+  if (g > 1)
+    MCM_NCCL(g_nccl.AllReduce(cov_out_dev, cov_out_dev, (size_t)M * M, ncclFloat64, ncclSum, g_nccl.comm, c.stream));
+  const double scale = 1.0 / (n_glob - (corrected ? 1.0 : 0.0));
+  k_scale<<<c.sm_count * 4, 256, 0, c.stream>>>(cov_out_dev, (size_t)M * M, scale);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}

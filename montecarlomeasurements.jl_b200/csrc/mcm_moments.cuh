@@ -1,0 +1,144 @@
+// mcm_moments.cuh — single-pass, numerically robust moments {n, mean, M2, min, max, sum}.
+//
+// pmean / pvar / pstd / pextrema in the reference are Statistics.mean (pairwise
+// sum / N) and a two-pass corrected variance over p.particles
+// (src/particles.jl:302-323).  Here ONE pass over HBM produces all of them:
+// each thread folds the 16-byte packs it loads into chunk statistics
+// (chunk mean, chunk sum of squared deviations) and merges chunks with the
+// Chan/Golub/LeVeque update, so there is no catastrophic cancellation for any
+// data offset (unlike sum-of-squares) at one division per chunk.  Lanes, warps
+// and CTAs are then merged in a fixed order (shuffle tree -> shared memory ->
+// last-CTA-done ticket), which makes results reproducible launch to launch.
+#pragma once
+#include "mcm_common.cuh"
+
+namespace mcm {
+
+struct Mom {
+  double n, mean, m2, mn, mx, sum;
+};
+
+__host__ __device__ __forceinline__ Mom mom_empty() {
+  Mom m;
+  m.n = 0.0; m.mean = 0.0; m.m2 = 0.0;
+  m.mn = __builtin_huge_val(); m.mx = -__builtin_huge_val();
+  m.sum = 0.0;
+  return m;
+}
+
+// NaN-propagating min/max (Base.minimum/maximum propagate NaN)
+__host__ __device__ __forceinline__ double nmin(double a, double b) {
+  return (a != a) ? a : ((b != b) ? b : (b < a ? b : a));
+}
+__host__ __device__ __forceinline__ double nmax(double a, double b) {
+  return (a != a) ? a : ((b != b) ? b : (b > a ? b : a));
+}
+
+__host__ __device__ __forceinline__ Mom mom_merge(const Mom& a, const Mom& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Mom r;
+  r.n = a.n + b.n;
+  const double d = b.mean - a.mean;
+  const double fb = b.n / r.n;
+  r.mean = a.mean + d * fb;
+  r.m2 = (a.m2 + b.m2) + (d * d) * (a.n * fb);
+  r.mn = nmin(a.mn, b.mn);
+  r.mx = nmax(a.mx, b.mx);
+  r.sum = a.sum + b.sum;
+  return r;
+}
+
+#ifdef __CUDACC__
+
+// Fold a chunk of C values (already in registers) into the thread's running moments.
+template <int C>
+__device__ __forceinline__ void mom_push_chunk(Mom& m, const double (&v)[C]) {
+  double s = 0.0, lo = v[0], hi = v[0];
+  bool nan = false;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    s += v[i];
+    lo = fmin(lo, v[i]);
+    hi = fmax(hi, v[i]);
+    nan |= (v[i] != v[i]);
+  }
+  const double cm = s * (1.0 / C);
+  double q = 0.0;
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const double d = v[i] - cm;
+    q = fma(d, d, q);
+  }
+  if (nan) lo = hi = s;  // s is NaN
+  const double nn = m.n + (double)C;
+  const double fb = (double)C / nn;
+  const double d = cm - m.mean;
+  m.mean = (m.n == 0.0) ? cm : m.mean + d * fb;
+  m.m2 = (m.m2 + q) + (d * d) * (m.n * fb);
+  m.n = nn;
+  m.sum += s;
+  m.mn = nmin(m.mn, lo);
+  m.mx = nmax(m.mx, hi);
+}
+
+__device__ __forceinline__ void mom_push_one(Mom& m, double x) {
+  const double v[1] = {x};
+  mom_push_chunk<1>(m, v);
+}
+
+__device__ __forceinline__ Mom mom_shfl_down(const Mom& a, int d) {
+  Mom b;
+  b.n = shfl_down_d(a.n, d); b.mean = shfl_down_d(a.mean, d); b.m2 = shfl_down_d(a.m2, d);
+  b.mn = shfl_down_d(a.mn, d); b.mx = shfl_down_d(a.mx, d); b.sum = shfl_down_d(a.sum, d);
+  return b;
+}
+
+// Fixed-order CTA reduction; result valid in thread 0.
+__device__ __forceinline__ Mom mom_block_reduce(Mom m) {
+  __shared__ Mom s_w[kThreads / 32];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = mom_merge(m, mom_shfl_down(m, d));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_w[warp] = m;
+  __syncthreads();
+  if (warp == 0) {
+    m = (lane < kThreads / 32) ? s_w[lane] : mom_empty();
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) m = mom_merge(m, mom_shfl_down(m, d));
+  }
+  __syncthreads();
+  return m;
+}
+
+// Grid-level finish: every CTA deposits its partial; the last CTA to arrive
+// merges all partials in index order and writes out[0..5].  `ticket` must be 0
+// on entry and is reset to 0 on exit (so launches can be queued back to back).
+__device__ __forceinline__ void mom_grid_finish(Mom block_m, Mom* partials, unsigned int* ticket,
+                                                double* out) {
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = block_m;
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  Mom m = mom_empty();
+  for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
+    const volatile Mom* p = partials + i;
+    Mom b;
+    b.n = p->n; b.mean = p->mean; b.m2 = p->m2; b.mn = p->mn; b.mx = p->mx; b.sum = p->sum;
+    m = mom_merge(m, b);
+  }
+  m = mom_block_reduce(m);
+  if (threadIdx.x == 0) {
+    out[0] = m.n; out[1] = m.mean; out[2] = m.m2; out[3] = m.mn; out[4] = m.mx; out[5] = m.sum;
+    *ticket = 0u;
+  }
+}
+
+#endif  // __CUDACC__
+}  // namespace mcm

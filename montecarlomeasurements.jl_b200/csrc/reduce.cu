@@ -1,0 +1,199 @@
+// reduce.cu — pmean / pvar / pstd / pminimum / pmaximum / sum / @prob counts.
+// Reference: src/particles.jl:302-313 (pvar, pstd; N==1 -> zero(T)),
+// :316-323 (pmean, pextrema, pminimum, pmaximum forwarded to Statistics/Base),
+// src/bymap.jl:128-136 (@prob == mean(p.particles .< a)).
+#include <math.h>
+#include "mcm_moments.cuh"
+
+namespace mcm {
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out) {
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  constexpr int UNROLL = 4;
+  constexpr int C = V * UNROLL;
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const size_t nvec = vec ? n / V : 0;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  const size_t rows_full = nvec / (stride * UNROLL);
+  const P* pin = reinterpret_cast<const P*>(in);
+
+  Mom m = mom_empty();
+  for (size_t r = 0; r < rows_full; ++r) {
+    const size_t base = r * stride * UNROLL + tid;
+    P x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) x[u] = ld_stream(pin + base + (size_t)u * stride);
+    double v[C];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[u * V + e] = (double)x[u].v[e];
+    mom_push_chunk<C>(m, v);
+  }
+  for (size_t j = rows_full * stride * UNROLL + tid; j < nvec; j += stride) {
+    const P x = ld_stream(pin + j);
+    double v[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) v[e] = (double)x.v[e];
+    mom_push_chunk<V>(m, v);
+  }
+  for (size_t i = nvec * V + tid; i < n; i += stride) mom_push_one(m, (double)in[i]);
+
+  m = mom_block_reduce(m);
+  mom_grid_finish(m, partials, ticket, out);
+}
+
+template <typename T, int CMP>
+__global__ void __launch_bounds__(kThreads)
+k_count(const T* __restrict__ in, size_t n, T thr, unsigned long long* out) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  unsigned long long c = 0;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const T x = in[i];
+    bool b;
+    if constexpr (CMP == MCM_CMP_LT) b = x < thr;
+    else if constexpr (CMP == MCM_CMP_LE) b = x <= thr;
+    else if constexpr (CMP == MCM_CMP_GT) b = x > thr;
+    else if constexpr (CMP == MCM_CMP_GE) b = x >= thr;
+    else if constexpr (CMP == MCM_CMP_EQ) b = x == thr;
+    else b = x != thr;
+    c += b ? 1ull : 0ull;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
+  Ctx& c = ctx();
+  static int occ64 = 0, occ32 = 0;
+  if (occ64 == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_moments<double>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ32, k_moments<float>, kThreads, 0);
+    if (occ64 < 1) occ64 = 1;
+    if (occ32 < 1) occ32 = 1;
+  }
+  Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
+  const size_t max_grid = c.scratch_doubles / 8;  // 6 doubles per partial, keep headroom
+  if (dtype == MCM_F64) {
+    int grid = stream_grid((n + 1) / 2, 4, occ64 > 4 ? 4 : occ64);
+    if ((size_t)grid > max_grid) grid = (int)max_grid;
+    k_moments<double><<<grid, kThreads, 0, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6);
+  } else if (dtype == MCM_F32) {
+    int grid = stream_grid((n + 3) / 4, 4, occ32 > 4 ? 4 : occ32);
+    if ((size_t)grid > max_grid) grid = (int)max_grid;
+    k_moments<float><<<grid, kThreads, 0, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6);
+  } else {
+    return fail(MCM_ERR_INVALID, "moments: bad dtype %d", dtype);
+  }
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+// device result slot (6 doubles) lives at the end of the scratch buffer
+double* moments_result_slot() { return ctx().d_scratch + (ctx().scratch_doubles - 16); }
+
+int read_back(double* host_dst, const double* dev_src, size_t count) {
+  Ctx& c = ctx();
+  if (count * sizeof(double) > c.pinned_bytes) return fail(MCM_ERR_INVALID, "read_back: too large");
+  MCM_CUDA(cudaMemcpyAsync(c.h_pinned, dev_src, count * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  for (size_t i = 0; i < count; ++i) host_dst[i] = static_cast<double*>(c.h_pinned)[i];
+  return MCM_OK;
+}
+
+}  // namespace mcm
+
+using namespace mcm;
+
+extern "C" int mcm_moments(int dtype, const void* in, size_t n, double* out_host) {
+  MCM_NEED_INIT();
+  if (!out_host || (n && !in)) return fail(MCM_ERR_INVALID, "mcm_moments: null pointer");
+  if (n == 0) {
+    Mom e = mom_empty();
+    out_host[0] = 0; out_host[1] = NAN; out_host[2] = 0; out_host[3] = e.mn; out_host[4] = e.mx; out_host[5] = 0;
+    return MCM_OK;
+  }
+  double* slot = moments_result_slot();
+  int rc = moments_device(dtype, in, n, slot);
+  if (rc) return rc;
+  return read_back(out_host, slot, 6);
+}
+
+extern "C" int mcm_moments_merge(const double* a, const double* b, double* out) {
+  if (!a || !b || !out) return fail(MCM_ERR_INVALID, "mcm_moments_merge: null pointer");
+  Mom ma{a[0], a[1], a[2], a[3], a[4], a[5]}, mb{b[0], b[1], b[2], b[3], b[4], b[5]};
+  Mom r = mom_merge(ma, mb);
+  out[0] = r.n; out[1] = r.mean; out[2] = r.m2; out[3] = r.mn; out[4] = r.mx; out[5] = r.sum;
+  return MCM_OK;
+}
+
+// kind -> scalar from the six moments; shared with the sharded path
+extern "C" int mcm_reduce_from_moments(int kind, const double* m, double* out) {
+  const double n = m[0];
+  switch (kind) {
+    case MCM_R_SUM: *out = m[5]; break;
+    case MCM_R_MEAN: *out = m[1]; break;
+    // particles.jl:308-312: N == 1 -> zero(T)
+    case MCM_R_VAR: *out = (n == 1.0) ? 0.0 : m[2] / (n - 1.0); break;
+    case MCM_R_VARP: *out = (n == 1.0) ? 0.0 : m[2] / n; break;
+    case MCM_R_STD: *out = (n == 1.0) ? 0.0 : sqrt(m[2] / (n - 1.0)); break;
+    case MCM_R_STDP: *out = (n == 1.0) ? 0.0 : sqrt(m[2] / n); break;
+    case MCM_R_MIN: *out = m[3]; break;
+    case MCM_R_MAX: *out = m[4]; break;
+    default: return fail(MCM_ERR_INVALID, "mcm_reduce: unknown kind %d", kind);
+  }
+  return MCM_OK;
+}
+
+extern "C" int mcm_reduce(int kind, int dtype, const void* in, size_t n, double* out_host) {
+  MCM_NEED_INIT();
+  if (!out_host) return fail(MCM_ERR_INVALID, "mcm_reduce: null output");
+  if (n == 0) return fail(MCM_ERR_INVALID, "mcm_reduce: empty particles (ArgumentError in Base for mean/extrema of empty)");
+  double m[6];
+  int rc = mcm_moments(dtype, in, n, m);
+  if (rc) return rc;
+  return mcm_reduce_from_moments(kind, m, out_host);
+}
+
+template <typename T>
+static int run_count(int cmp, const T* in, size_t n, T thr, unsigned long long* d_out) {
+  Ctx& c = ctx();
+  const int grid = stream_grid(n, 8, 8);
+  switch (cmp) {
+#define MCM_CASE(K) \
+  case K: k_count<T, K><<<grid, kThreads, 0, c.stream>>>(in, n, thr, d_out); break;
+    MCM_CASE(MCM_CMP_LT) MCM_CASE(MCM_CMP_LE) MCM_CASE(MCM_CMP_GT) MCM_CASE(MCM_CMP_GE)
+    MCM_CASE(MCM_CMP_EQ) MCM_CASE(MCM_CMP_NE)
+#undef MCM_CASE
+    default: return fail(MCM_ERR_INVALID, "mcm_count: unknown comparison %d", cmp);
+  }
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+extern "C" int mcm_count(int cmp, int dtype, const void* in, size_t n, double threshold, uint64_t* count_host) {
+  MCM_NEED_INIT();
+  if (!count_host || (n && !in)) return fail(MCM_ERR_INVALID, "mcm_count: null pointer");
+  Ctx& c = ctx();
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(moments_result_slot() + 8);
+  MCM_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), c.stream));
+  int rc = MCM_OK;
+  if (n) {
+    if (dtype == MCM_F64) rc = run_count<double>(cmp, (const double*)in, n, threshold, d_out);
+    else if (dtype == MCM_F32) rc = run_count<float>(cmp, (const float*)in, n, (float)threshold, d_out);
+    else return fail(MCM_ERR_INVALID, "mcm_count: bad dtype %d", dtype);
+  }
+  if (rc) return rc;
+  double tmp;
+  rc = read_back(&tmp, reinterpret_cast<const double*>(d_out), 1);
+  if (rc) return rc;
+  uint64_t bits;
+  memcpy(&bits, &tmp, 8);
+  *count_host = bits;
+  return MCM_OK;
+}

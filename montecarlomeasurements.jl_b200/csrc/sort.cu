@@ -1,0 +1,400 @@
+// sort.cu — hand-written stable LSD radix sort (8-bit digits) for particle
+// vectors, sortperm, and pquantile/pmedian on top of it.
+//
+// Reference: pquantile(p,q) = Statistics.quantile(p.particles, q), pmedian
+// (src/particles.jl:316-323); sort is also what wasserstein (src/distances.jl:7-13)
+// needs.  Order is Julia's `isless` on floats: -0.0 < +0.0, NaN last.
+//
+// Per pass: k_hist (per-CTA digit histogram, warp-aggregated shared atomics),
+// an exclusive scan over the [digit][CTA] table, and k_scatter, which ranks keys
+// stably with __match_any_sync inside each warp segment and places warp segments
+// by a per-digit prefix over the 8 warps of the CTA.
+#include <math.h>
+#include <string.h>
+#include "mcm_common.cuh"
+
+namespace mcm {
+
+constexpr int RB = 8;
+constexpr int NBINS = 1 << RB;
+constexpr int ST = 256;          // threads per CTA (== NBINS, one thread per digit in the prefix step)
+constexpr int IPT = 16;          // keys per thread
+constexpr int TILE = ST * IPT;   // keys per CTA
+constexpr int SEG = 32 * IPT;    // keys per warp segment
+
+// ---- order-preserving key transforms ----------------------------------------
+__device__ __forceinline__ uint64_t to_key(double x, bool& nan) {
+  if (x != x) { nan = true; return ~0ull; }
+  const uint64_t u = (uint64_t)__double_as_longlong(x);
+  return u ^ ((u >> 63) ? ~0ull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ uint32_t to_key(float x, bool& nan) {
+  if (x != x) { nan = true; return ~0u; }
+  const uint32_t u = __float_as_uint(x);
+  return u ^ ((u >> 31) ? ~0u : 0x80000000u);
+}
+__device__ __forceinline__ double from_key(uint64_t k) {
+  if (k == ~0ull) return __longlong_as_double(0x7ff8000000000000ll);
+  const uint64_t u = k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull);
+  return __longlong_as_double((long long)u);
+}
+__device__ __forceinline__ float from_key(uint32_t k) {
+  if (k == ~0u) return __uint_as_float(0x7fc00000u);
+  const uint32_t u = k ^ ((k >> 31) ? 0x80000000u : ~0u);
+  return __uint_as_float(u);
+}
+
+template <typename T, typename K>
+__global__ void __launch_bounds__(256) k_to_keys(const T* __restrict__ in, K* __restrict__ keys, size_t n, uint32_t* flags) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  bool nan = false;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) keys[i] = to_key(in[i], nan);
+  if (nan) atomicOr(flags, (uint32_t)MCM_FLAG_NAN_QUANTILE);
+}
+template <typename T, typename K>
+__global__ void __launch_bounds__(256) k_from_keys(const K* __restrict__ keys, T* __restrict__ out, size_t n) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) out[i] = from_key(keys[i]);
+}
+__global__ void __launch_bounds__(256) k_iota(uint32_t* v, size_t n) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) v[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) k_u32_to_i64(const uint32_t* __restrict__ v, int64_t* __restrict__ o, size_t n) {
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) o[i] = (int64_t)v[i];
+}
+
+// ---- per-CTA digit histogram ---------------------------------------------------
+template <typename K>
+__global__ void __launch_bounds__(ST)
+k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks) {
+  __shared__ uint32_t h[NBINS];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * TILE;
+  const int lane = threadIdx.x & 31;
+#pragma unroll 4
+  for (int i = 0; i < IPT; ++i) {
+    const uint32_t idx = base + i * ST + threadIdx.x;
+    const bool valid = idx < n;
+    const uint32_t d = valid ? (uint32_t)((keys[idx] >> shift) & (NBINS - 1)) : (uint32_t)(NBINS + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// ---- exclusive scan (3 kernels; chunk = 2048 per CTA) ---------------------------
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_CHUNK = 256 * SCAN_IPT;
+
+template <typename U>
+__device__ __forceinline__ U block_exclusive_scan(U v, U* total) {
+  // v: this thread's value; returns exclusive prefix within the CTA of 256 threads
+  __shared__ U wsum[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  U inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const U t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  U woff = 0, tot = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (i < w) woff += wsum[i];
+    tot += wsum[i];
+  }
+  __syncthreads();
+  *total = tot;
+  return woff + inc - v;
+}
+
+template <typename U>
+__global__ void __launch_bounds__(256) k_scan_reduce(const U* __restrict__ a, size_t n, U* __restrict__ sums) {
+  const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_IPT;
+  U s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_IPT; ++i)
+    if (base + i < n) s += a[base + i];
+  U tot;
+  block_exclusive_scan<U>(s, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+template <typename U>
+__global__ void __launch_bounds__(256) k_scan_sums(U* sums, size_t nb, U* grand_total) {
+  __shared__ U carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (size_t b0 = 0; b0 < nb; b0 += 256) {
+    const size_t i = b0 + threadIdx.x;
+    const U v = i < nb ? sums[i] : (U)0;
+    U tot;
+    const U ex = block_exclusive_scan<U>(v, &tot);
+    const U carry = carry_s;
+    if (i < nb) sums[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && grand_total) *grand_total = carry_s;
+}
+// INCLUSIVE=false: exclusive scan in place; true: inclusive
+template <typename U, bool INCLUSIVE>
+__global__ void __launch_bounds__(256) k_scan_final(U* a, size_t n, const U* __restrict__ sums) {
+  const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_IPT;
+  U v[SCAN_IPT];
+  U s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_IPT; ++i) {
+    v[i] = (base + i < n) ? a[base + i] : (U)0;
+    s += v[i];
+  }
+  U tot;
+  U run = block_exclusive_scan<U>(s, &tot) + sums[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_IPT; ++i) {
+    if (INCLUSIVE) run += v[i];
+    if (base + i < n) a[base + i] = run;
+    if (!INCLUSIVE) run += v[i];
+  }
+}
+
+template <typename U, bool INCLUSIVE>
+int device_scan(U* a, size_t n, U* grand_total_dev) {
+  Ctx& c = ctx();
+  const size_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  U* sums = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&sums, nb * sizeof(U), c.stream));
+  k_scan_reduce<U><<<(unsigned)nb, 256, 0, c.stream>>>(a, n, sums);
+  MCM_CHECK_LAUNCH();
+  k_scan_sums<U><<<1, 256, 0, c.stream>>>(sums, nb, grand_total_dev);
+  MCM_CHECK_LAUNCH();
+  k_scan_final<U, INCLUSIVE><<<(unsigned)nb, 256, 0, c.stream>>>(a, n, sums);
+  MCM_CHECK_LAUNCH();
+  MCM_CUDA(cudaFreeAsync(sums, c.stream));
+  return MCM_OK;
+}
+template int device_scan<uint32_t, false>(uint32_t*, size_t, uint32_t*);
+template int device_scan<unsigned long long, true>(unsigned long long*, size_t, unsigned long long*);
+
+// ---- stable scatter ---------------------------------------------------------------
+template <typename K, bool HAS_VAL>
+__global__ void __launch_bounds__(ST)
+k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin,
+          uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ hist_scanned,
+          uint32_t nblocks) {
+  __shared__ uint32_t wh[ST / 32][NBINS];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < (ST / 32) * NBINS; i += ST) (&wh[0][0])[i] = 0;
+  __syncthreads();
+  const uint32_t seg = blockIdx.x * TILE + w * SEG;
+  K key[IPT];
+  uint32_t rank[IPT];
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    const uint32_t idx = seg + r * 32 + lane;
+    const bool valid = idx < n;
+    key[r] = valid ? kin[idx] : (K)0;
+    const uint32_t d = valid ? (uint32_t)((key[r] >> shift) & (NBINS - 1)) : (uint32_t)(NBINS + lane);
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t old = valid ? wh[w][d] : 0u;
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) wh[w][d] = old + (uint32_t)__popc(peers);
+    __syncwarp();
+    rank[r] = old + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+  }
+  __syncthreads();
+  {
+    const int d = threadIdx.x;
+    uint32_t run = hist_scanned[(size_t)d * nblocks + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < ST / 32; ++ww) {
+      const uint32_t cnt = wh[ww][d];
+      wh[ww][d] = run;
+      run += cnt;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < IPT; ++r) {
+    const uint32_t idx = seg + r * 32 + lane;
+    if (idx < n) {
+      const uint32_t d = (uint32_t)((key[r] >> shift) & (NBINS - 1));
+      const uint32_t pos = wh[w][d] + rank[r];
+      kout[pos] = key[r];
+      if constexpr (HAS_VAL) vout[pos] = vin[idx];
+    }
+  }
+}
+
+// Sort n keys held in bufA (ping-pong with bufB); after an even number of passes the
+// result is back in bufA.  vals likewise.
+template <typename K, bool HAS_VAL>
+int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) {
+  Ctx& c = ctx();
+  if (n >= 0xFFFF0000ull) return fail(MCM_ERR_UNSUPPORTED, "sort: n must be < 2^32");
+  const uint32_t nblocks = (uint32_t)((n + TILE - 1) / TILE);
+  uint32_t* hist = nullptr;
+  const size_t hlen = (size_t)NBINS * nblocks;
+  MCM_CUDA(cudaMallocAsync((void**)&hist, hlen * sizeof(uint32_t), c.stream));
+  K* src = bufA; K* dst = bufB;
+  uint32_t* vs = valA; uint32_t* vd = valB;
+  constexpr int passes = (int)sizeof(K);
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * RB;
+    k_hist<K><<<nblocks, ST, 0, c.stream>>>(src, (uint32_t)n, shift, hist, nblocks);
+    MCM_CHECK_LAUNCH();
+    int rc = device_scan<uint32_t, false>(hist, hlen, nullptr);
+    if (rc) return rc;
+    k_scatter<K, HAS_VAL><<<nblocks, ST, 0, c.stream>>>(src, dst, vs, vd, (uint32_t)n, shift, hist, nblocks);
+    MCM_CHECK_LAUNCH();
+    K* t = src; src = dst; dst = t;
+    uint32_t* tv = vs; vs = vd; vd = tv;
+  }
+  MCM_CUDA(cudaFreeAsync(hist, c.stream));
+  return MCM_OK;
+}
+template int radix_sort_keys<uint64_t, true>(uint64_t*, uint64_t*, uint32_t*, uint32_t*, size_t);
+
+template <typename T, typename K>
+static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
+  Ctx& c = ctx();
+  if (n == 0) return MCM_OK;
+  K* A = nullptr; K* B = nullptr;
+  uint32_t* vA = nullptr; uint32_t* vB = nullptr;
+  const bool own_A = (out == nullptr);
+  if (own_A) MCM_CUDA(cudaMallocAsync((void**)&A, n * sizeof(K), c.stream));
+  else A = reinterpret_cast<K*>(out);
+  MCM_CUDA(cudaMallocAsync((void**)&B, n * sizeof(K), c.stream));
+  const int grid = stream_grid(n, 4, 8);
+  k_to_keys<T, K><<<grid, 256, 0, c.stream>>>(in, A, n, c.d_flags);
+  MCM_CHECK_LAUNCH();
+  int rc;
+  if (perm_out) {
+    MCM_CUDA(cudaMallocAsync((void**)&vA, n * sizeof(uint32_t), c.stream));
+    MCM_CUDA(cudaMallocAsync((void**)&vB, n * sizeof(uint32_t), c.stream));
+    k_iota<<<grid, 256, 0, c.stream>>>(vA, n);
+    MCM_CHECK_LAUNCH();
+    rc = radix_sort_keys<K, true>(A, B, vA, vB, n);
+    if (rc) return rc;
+    k_u32_to_i64<<<grid, 256, 0, c.stream>>>(vA, perm_out, n);
+    MCM_CHECK_LAUNCH();
+    MCM_CUDA(cudaFreeAsync(vA, c.stream));
+    MCM_CUDA(cudaFreeAsync(vB, c.stream));
+  } else {
+    rc = radix_sort_keys<K, false>(A, B, nullptr, nullptr, n);
+    if (rc) return rc;
+  }
+  if (!own_A) {
+    k_from_keys<T, K><<<grid, 256, 0, c.stream>>>(A, out, n);  // in place: same element size
+    MCM_CHECK_LAUNCH();
+  } else {
+    MCM_CUDA(cudaFreeAsync(A, c.stream));
+  }
+  MCM_CUDA(cudaFreeAsync(B, c.stream));
+  return MCM_OK;
+}
+
+template <typename T>
+__global__ void k_pick(const T* __restrict__ sorted, const uint64_t* __restrict__ idx, int cnt, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) out[i] = (double)sorted[idx[i]];
+}
+
+int read_back(double* host_dst, const double* dev_src, size_t count);
+
+}  // namespace mcm
+
+using namespace mcm;
+
+extern "C" int mcm_sort(int dtype, const void* in, void* out, size_t n) {
+  MCM_NEED_INIT();
+  if (n && (!in || !out)) return fail(MCM_ERR_INVALID, "mcm_sort: null pointer");
+  if (dtype == MCM_F64) return sort_impl<double, uint64_t>((const double*)in, (double*)out, nullptr, n);
+  if (dtype == MCM_F32) return sort_impl<float, uint32_t>((const float*)in, (float*)out, nullptr, n);
+  return fail(MCM_ERR_INVALID, "mcm_sort: bad dtype %d", dtype);
+}
+
+extern "C" int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* sorted_out_or_null, size_t n) {
+  MCM_NEED_INIT();
+  if (n && (!in || !perm_out)) return fail(MCM_ERR_INVALID, "mcm_sortperm: null pointer");
+  if (dtype == MCM_F64) return sort_impl<double, uint64_t>((const double*)in, (double*)sorted_out_or_null, perm_out, n);
+  if (dtype == MCM_F32) return sort_impl<float, uint32_t>((const float*)in, (float*)sorted_out_or_null, perm_out, n);
+  return fail(MCM_ERR_INVALID, "mcm_sortperm: bad dtype %d", dtype);
+}
+
+// Statistics.quantile(v, p) with the default alpha = beta = 1 (type 7):
+//   aleph = n*p + (1-p); j = clamp(trunc(aleph), 1, n-1); g = clamp(aleph-j, 0, 1)
+//   a = v[j], b = v[j+1] (1-based, sorted);  a + g*(b-a)  (or (1-g)a + g b if not finite)
+extern "C" int mcm_quantile(int dtype, const void* in, size_t n, const double* q_host, int nq, double* out_host) {
+  MCM_NEED_INIT();
+  if (!in || !q_host || !out_host || nq < 1) return fail(MCM_ERR_INVALID, "mcm_quantile: null pointer");
+  if (n == 0) return fail(MCM_ERR_INVALID, "mcm_quantile: empty particles");
+  if (nq > 4096) return fail(MCM_ERR_INVALID, "mcm_quantile: at most 4096 probabilities per call");
+  for (int i = 0; i < nq; ++i)
+    if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
+      return fail(MCM_ERR_INVALID, "mcm_quantile: input probability out of [0,1] range");
+  Ctx& c = ctx();
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile: bad dtype %d", dtype);
+  void* sorted = nullptr;
+  MCM_CUDA(cudaMallocAsync(&sorted, n * esz, c.stream));
+  int rc = mcm_sort(dtype, in, sorted, n);
+  if (rc) return rc;
+  // indices (0-based) of a and b for every q, plus the last element (NaN check)
+  const int cnt = 2 * nq + 1;
+  uint64_t* h_idx = static_cast<uint64_t*>(c.h_pinned);
+  double* gam = new double[nq];
+  for (int i = 0; i < nq; ++i) {
+    const double p = q_host[i];
+    const double aleph = (double)n * p + (1.0 - p);
+    long long j = (long long)trunc(aleph);
+    if (j > (long long)n - 1) j = (long long)n - 1;
+    if (j < 1) j = 1;
+    double g = aleph - (double)j;
+    g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
+    gam[i] = g;
+    if (n == 1) { h_idx[2 * i] = 0; h_idx[2 * i + 1] = 0; }
+    else { h_idx[2 * i] = (uint64_t)(j - 1); h_idx[2 * i + 1] = (uint64_t)j; }
+  }
+  h_idx[2 * nq] = n - 1;
+  uint64_t* d_idx = nullptr;
+  double* d_val = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_idx, cnt * sizeof(uint64_t), c.stream));
+  MCM_CUDA(cudaMallocAsync((void**)&d_val, cnt * sizeof(double), c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_idx, h_idx, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+  if (dtype == MCM_F64) k_pick<double><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const double*)sorted, d_idx, cnt, d_val);
+  else k_pick<float><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const float*)sorted, d_idx, cnt, d_val);
+  MCM_CHECK_LAUNCH();
+  double* vals = new double[cnt];
+  rc = read_back(vals, d_val, cnt);
+  MCM_CUDA(cudaFreeAsync(d_idx, c.stream));
+  MCM_CUDA(cudaFreeAsync(d_val, c.stream));
+  MCM_CUDA(cudaFreeAsync(sorted, c.stream));
+  if (rc == MCM_OK) {
+    if (vals[2 * nq] != vals[2 * nq]) {
+      rc = fail(MCM_ERR_INVALID, "mcm_quantile: quantiles are undefined in presence of NaNs");
+    } else {
+      for (int i = 0; i < nq; ++i) {
+        const double g = gam[i];
+        if (dtype == MCM_F64) {
+          const double a = vals[2 * i], b = vals[2 * i + 1];
+          out_host[i] = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
+        } else {
+          const float a = (float)vals[2 * i], b = (float)vals[2 * i + 1];
+          // Float32 data, Float64 probability: (b-a) rounds in Float32, the rest promotes
+          out_host[i] = (isfinite(a) && isfinite(b)) ? (double)a + g * (double)(b - a)
+                                                     : (1.0 - g) * (double)a + g * (double)b;
+        }
+      }
+    }
+  }
+  delete[] gam;
+  delete[] vals;
+  return rc;
+}
