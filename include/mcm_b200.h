@@ -169,13 +169,12 @@ int mcm_affine(int dtype, const void* in, double alpha, double beta, void* out, 
 int mcm_lincomb(int dtype, int nterms, const void* const* xs, const double* coeffs_host,
                 void* out, size_t n);
 
-/* Expression tape: a register machine with 8 value slots per particle, executed
- * entirely in registers; one launch evaluates the whole chain of registered
+/* Expression tape: a register machine with 16 value slots per particle; one launch evaluates the whole chain of registered
  * primitives (no temporaries in HBM — the reference materialises one Vector per
- * primitive).  Operand byte: 0..7 = slot, 0x40|k = constant k.               */
+ * primitive).  Operand byte: 0..15 = slot, 0x40|k = constant k.               */
 typedef struct {
   uint8_t op;   /* MCM_TAPE_* */
-  uint8_t dst;  /* destination slot 0..7 (or output index for STORE) */
+  uint8_t dst;  /* destination slot 0..15 (or output index for STORE) */
   uint8_t a, b, c; /* operands (or input index for LOAD; immediate for POWI in b as int8) */
   uint8_t pad[3];
 } mcm_tape_ins;
@@ -193,7 +192,7 @@ enum {
 #define MCM_TAPE_MAX_CONST 32
 #define MCM_TAPE_MAX_IN 8
 #define MCM_TAPE_MAX_OUT 4
-#define MCM_TAPE_SLOTS 8
+#define MCM_TAPE_SLOTS 16
 #define MCM_TAPE_CONST 0x40
 
 /* Run `tape[0..loop_begin)` once, `tape[loop_begin..loop_end)` `reps` times and
@@ -205,6 +204,14 @@ int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, in
               int reps, const double* consts, int nconst,
               const void* const* inputs, int nin, void* const* outputs, int nout,
               size_t n, int stats_slot, double* stats_out_host);
+
+/* Engine introspection: chains listed in csrc/chain_registry.def are compiled ahead of
+ * time into straight-line kernels (the analogue of register_primitive's `eval`,
+ * register_primitive.jl:19-82); every other tape runs on the interpreter kernel.
+ * last_engine: 1 = registered kernel, 2 = interpreter.  force_interpreter(1) makes
+ * registered tapes run on the interpreter too (parity tests compare the two). */
+int mcm_chain_last_engine(void);
+int mcm_chain_force_interpreter(int on);
 
 /* ======================= statistics ======================================== */
 /* one pass: out_host[0..5] = {n, mean, M2 = sum (x-mean)^2, min, max, sum} */
@@ -273,6 +280,8 @@ int mcm_comm_allreduce_sum_f64(double* dptr, size_t count);
 /* sharded statistics: every rank passes its local shard; all ranks get the global
  * {n, mean, M2, min, max, sum} (all-gather of partials + fixed-order Chan merge) */
 int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_host);
+/* merge host-resident per-rank moments (e.g. mcm_chain's fused statistics) across ranks, in place */
+int mcm_moments_allmerge(double* inout_host6);
 /* sharded pcov: global means by all-reduce, local centred Gram, all-reduce of the
  * M x M block, scaled by 1/(N_global - corrected) */
 int mcm_gram_sharded(int dtype, const void* const* vars, int M, size_t n_local, int corrected,

@@ -1,0 +1,37 @@
+"""montecarlomeasurements.jl_b200 — B200-native particle arithmetic behind the
+MonteCarloMeasurements.jl API (hot path only).
+
+Import name: the directory name contains a dot, so import it through the shim
+`mcm_b200` at the repository root (`import mcm_b200 as mcm`).
+
+Everything device-side goes through libmcm_b200.so (include/mcm_b200.h); there
+is no CPU implementation of any primitive in this package.
+"""
+from . import _lib
+from ._lib import MCMError, ArgumentError, MethodError, init, is_initialised
+from .particles import (
+    Particles, Moments, DeviceIndex, ComparisonError, DomainError,
+    DEFAULT_NUM_PARTICLES, DEFAULT_STATIC_NUM_PARTICLES,
+    fill, fused, evalpoly, affine, lincomb,
+    exp, exp2, exp10, expm1, log, log10, log2, log1p,
+    sin, cos, tan, sind, cosd, tand, sinh, cosh, tanh,
+    asin, acos, atan, asind, acosd, atand, asinh, acosh, atanh,
+    zero, sign, sqrt, rad2deg, deg2rad, floor, ceil, trunc, inv, abs2, float_, round_,
+    maximum, minimum, mod, mod1, rem, div, hypot, add_sum, clamp, muladd, minmax, sincos, ratdiv,
+    moments, pmean, psum, pvar, pstd, pminimum, pmaximum, pextrema, pmiddle, meanstd, meanvar,
+    pquantile, pmedian, psort, psortperm, pcov, pcor, to_matrix,
+    unsafe_comparisons, set_comparison_function, approx, lesssim, gtrsim,
+    check_domain, nparticles, particleeltype,
+)
+from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
+                       mvnormal_particles)
+from .resampling import bootstrap, resample, resample_indices, rand_indices
+from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
+from . import sharded, tape
+
+StaticParticles = Particles  # storage is identical on device; N defaults differ (types.jl:26-30)
+
+
+def sync():
+    """Block until all queued device work is done."""
+    _lib.check(_lib.lib().mcm_sync())

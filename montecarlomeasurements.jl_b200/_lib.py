@@ -100,6 +100,8 @@ SIGNATURES = {
     "mcm_affine": (_i, [_i, _vp, _d, _d, _vp, _sz]),
     "mcm_lincomb": (_i, [_i, _i, _vpp, _dp, _vp, _sz]),
     "mcm_chain": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
+    "mcm_chain_last_engine": (_i, []),
+    "mcm_chain_force_interpreter": (_i, [_i]),
     "mcm_moments": (_i, [_i, _vp, _sz, _dp]),
     "mcm_reduce": (_i, [_i, _i, _vp, _sz, _dp]),
     "mcm_count": (_i, [_i, _i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
@@ -123,6 +125,7 @@ SIGNATURES = {
     "mcm_comm_info": (_i, [C.POINTER(_i), C.POINTER(_i)]),
     "mcm_comm_allreduce_sum_f64": (_i, [_vp, _sz]),
     "mcm_moments_sharded": (_i, [_i, _vp, _sz, _dp]),
+    "mcm_moments_allmerge": (_i, [_dp]),
     "mcm_gram_sharded": (_i, [_i, _vpp, _i, _sz, _i, _vp]),
 }
 

@@ -3,13 +3,21 @@
 // The reference evaluates `sin(a)*a^2 + exp(-a)` as five separate broadcasts,
 // each allocating a Vector{T}(N) (src/register_primitive.jl:44-58,94-97).  At
 // N = 1e8 that is 10 x 16-24 B/particle of HBM traffic for the canonical chain.
-// Here the chain is a tape for a tiny register machine (8 value slots per
-// particle, all in registers): one launch reads each input once, writes each
-// requested output once, and optionally folds the result into the one-pass
-// moments of mcm_moments.cuh (pmean/pstd, src/particles.jl:302-323) so that
-// y never has to exist in HBM when only statistics are wanted.
-// A loop section [loop_begin, loop_end) x reps allows in-register time
-// stepping (RK4 on the pendulum of examples/ode_sim.jl:20-25).
+// Here the chain is a tape for a tiny register machine with 16 value slots per
+// particle: one launch reads each input once, writes each requested output once
+// and optionally folds the result into the one-pass moments of mcm_moments.cuh
+// (pmean/pstd, src/particles.jl:302-323), so y never has to exist in HBM when
+// only statistics are wanted.  A loop section [loop_begin, loop_end) x reps
+// allows in-register time stepping (RK4 on the pendulum, examples/ode_sim.jl:20-25).
+//
+// Two execution engines behind the same mcm_chain entry point:
+//  * REGISTERED chains (chain_registry.def): the analogue of `register_primitive`,
+//    which `eval`s new methods at load time (src/register_primitive.jl:19-82) —
+//    here a tape listed in the registry is compiled ahead of time into a
+//    straight-line kernel by template recursion over the constexpr tape (slots
+//    live in registers, no dispatch cost).
+//  * any other tape: an interpreter whose slot file lives in shared memory
+//    (one 128-bit LDS/STS per operand, one jump-table dispatch per instruction).
 #include <string.h>
 #include "mcm_math.cuh"
 #include "mcm_moments.cuh"
@@ -28,105 +36,284 @@ struct ChainParams {
 
 constexpr int S = MCM_TAPE_SLOTS;
 
+// ---------------------------------------------------------------------------
+// shared pieces
+// ---------------------------------------------------------------------------
 template <typename T, int V>
-__device__ __forceinline__ void slot_get(const T (&r)[S][V], const ChainParams& p, int idx, T (&x)[V]) {
+__device__ __forceinline__ void load_input(const void* base, size_t j, int nvalid, T (&x)[V]) {
+  using P = Pack<T>;
+  const T* src = static_cast<const T*>(base);
+  if (nvalid == V) {
+    const P t = ld_stream(reinterpret_cast<const P*>(src) + j);
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = t.v[v];
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? src[j * V + v] : T(1);
+  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_output(void* base, size_t j, int nvalid, const T (&x)[V]) {
+  using P = Pack<T>;
+  T* dst = static_cast<T*>(base);
+  if (dst == nullptr) return;
+  if (nvalid == V) {
+    P t;
+#pragma unroll
+    for (int v = 0; v < V; ++v) t.v[v] = x[v];
+    st_stream(reinterpret_cast<P*>(dst) + j, t);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (v < nvalid) dst[j * V + v] = x[v];
+  }
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void stats_push(Mom& m, const T (&x)[V], int nvalid) {
+  if (nvalid == V) {
+    double d[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) d[v] = (double)x[v];
+    mom_push_chunk<V>(m, d);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (v < nvalid) mom_push_one(m, (double)x[v]);
+  }
+}
+
+// apply opcode OP (compile-time) to V lanes; result in x
+template <int OP, typename T, int V>
+__device__ __forceinline__ void apply_op(T (&x)[V], const T (&y)[V], const T (&z)[V], int imm, int nvalid, bool& bad) {
+  if constexpr (OP < MCM_TAPE_BINARY) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const T t = math::unary_apply<OP - MCM_TAPE_UNARY, T>(x[v]);
+      if constexpr (math::UnaryCanDomainError<OP - MCM_TAPE_UNARY>::value) bad |= (t != t) && (x[v] == x[v]) && (v < nvalid);
+      x[v] = t;
+    }
+  } else if constexpr (OP < MCM_TAPE_TERNARY) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const T t = math::binary_apply<OP - MCM_TAPE_BINARY, T>(x[v], y[v]);
+      if constexpr (math::BinaryCanDomainError<OP - MCM_TAPE_BINARY>::value)
+        bad |= (t != t) && (x[v] == x[v]) && (y[v] == y[v]) && (v < nvalid);
+      x[v] = t;
+    }
+  } else if constexpr (OP < MCM_TAPE_LOAD) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = math::ternary_apply<OP - MCM_TAPE_TERNARY, T>(x[v], y[v], z[v]);
+  } else if constexpr (OP == MCM_TAPE_POWI) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = math::m_powi(x[v], imm);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// engine 1: registered (ahead-of-time specialised) chains
+// ---------------------------------------------------------------------------
+struct SIns { int op, dst, a, b, c; };
+
+template <int IDX, typename T, int V>
+__device__ __forceinline__ void sget(const T (&r)[S][V], const ChainParams& p, T (&x)[V]) {
+  if constexpr ((IDX & MCM_TAPE_CONST) != 0) {
+    const T c = (T)p.consts[IDX & (MCM_TAPE_MAX_CONST - 1)];
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = c;
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = r[IDX][v];
+  }
+}
+
+template <class TP, int PC, int END, typename T, int V>
+__device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, size_t j, int nvalid, bool& bad) {
+  if constexpr (PC < END) {
+    constexpr SIns I = TP::ins[PC];
+    T x[V], y[V], z[V];
+    if constexpr (I.op == MCM_TAPE_LOAD) {
+      load_input<T, V>(p.in[I.a], j, nvalid, x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
+    } else if constexpr (I.op == MCM_TAPE_STORE) {
+      sget<I.a, T, V>(r, p, x);
+      store_output<T, V>(p.out[I.dst], j, nvalid, x);
+    } else if constexpr (I.op == MCM_TAPE_MOV) {
+      sget<I.a, T, V>(r, p, x);
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
+    } else {
+      sget<I.a, T, V>(r, p, x);
+      if constexpr (I.op >= MCM_TAPE_BINARY && I.op < MCM_TAPE_LOAD) sget<I.b, T, V>(r, p, y);
+      if constexpr (I.op >= MCM_TAPE_TERNARY && I.op < MCM_TAPE_LOAD) sget<I.c, T, V>(r, p, z);
+      apply_op<I.op, T, V>(x, y, z, (int)(signed char)I.b, nvalid, bad);
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
+    }
+    exec_static<TP, PC + 1, END, T, V>(r, p, j, nvalid, bad);
+  }
+}
+
+template <class TP, typename T, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
+               uint32_t* flags) {
+  constexpr int V = Pack<T>::N;
+  const size_t n = p.n;
+  const size_t nvec = (n + V - 1) / V;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  bool bad = false;
+  Mom m = mom_empty();
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) {
+    const int nvalid = (j + 1) * V <= n ? V : (int)(n - j * V);
+    T r[S][V];
+#pragma unroll
+    for (int k = 0; k < S; ++k)
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[k][v] = T(0);
+    exec_static<TP, 0, TP::loop_begin, T, V>(r, p, j, nvalid, bad);
+    if constexpr (TP::loop_end > TP::loop_begin) {
+      for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V>(r, p, j, nvalid, bad);
+    }
+    exec_static<TP, TP::loop_end, TP::n, T, V>(r, p, j, nvalid, bad);
+    if constexpr (STATS) {
+      T x[V];
+      // stats slot is a runtime choice among 8 registers: resolved by a uniform switch once per vector
+      switch (p.stats_slot) {
+#define MCM_SS(K) case K: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = r[K][v]; break;
+        MCM_SS(0) MCM_SS(1) MCM_SS(2) MCM_SS(3) MCM_SS(4) MCM_SS(5) MCM_SS(6) MCM_SS(7) MCM_SS(8) MCM_SS(9)
+        MCM_SS(10) MCM_SS(11) MCM_SS(12) MCM_SS(13) MCM_SS(14) default: MCM_SS(15)
+#undef MCM_SS
+      }
+      stats_push<T, V>(m, x, nvalid);
+    }
+  }
+  if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
+  if constexpr (STATS) {
+    m = mom_block_reduce(m);
+    mom_grid_finish(m, partials, ticket, stats_out);
+  }
+}
+
+// ---- the registry ------------------------------------------------------------
+#define TU(op) (MCM_TAPE_UNARY + (op))
+#define TB(op) (MCM_TAPE_BINARY + (op))
+#define TT(op) (MCM_TAPE_TERNARY + (op))
+#define KC(k) (MCM_TAPE_CONST | (k))
+#define MCM_CHAIN_BEGIN(NAME, LB, LE) \
+  struct NAME {                       \
+    static constexpr int loop_begin_decl = (LB), loop_end_decl = (LE); \
+    static constexpr SIns ins[] = {
+#define MCM_CHAIN_END(NAME)                                                      \
+    };                                                                           \
+    static constexpr int n = (int)(sizeof(ins) / sizeof(ins[0]));                \
+    static constexpr int loop_begin = loop_begin_decl < 0 ? n : loop_begin_decl; \
+    static constexpr int loop_end = loop_end_decl < 0 ? n : loop_end_decl;       \
+  };
+#include "chain_registry.def"
+#undef MCM_CHAIN_BEGIN
+#undef MCM_CHAIN_END
+
+template <class TP>
+static bool tape_matches(const ChainParams& p) {
+  if (p.ntape != TP::n || p.loop_begin != TP::loop_begin || p.loop_end != TP::loop_end) return false;
+  for (int i = 0; i < TP::n; ++i) {
+    const SIns& s = TP::ins[i];
+    const mcm_tape_ins& t = p.tape[i];
+    if (t.op != s.op || t.dst != s.dst || t.a != s.a) return false;
+    const bool uses_b = (s.op >= MCM_TAPE_BINARY && s.op < MCM_TAPE_LOAD) || s.op == MCM_TAPE_POWI;
+    const bool uses_c = (s.op >= MCM_TAPE_TERNARY && s.op < MCM_TAPE_LOAD);
+    if (uses_b && t.b != (uint8_t)s.b) return false;
+    if (uses_c && t.c != s.c) return false;
+  }
+  return true;
+}
+
+template <class TP, typename T>
+static int launch_static(const ChainParams& p, bool stats, double* stats_dev) {
+  Ctx& c = ctx();
+  constexpr int V = Pack<T>::N;
+  static int occ[2] = {0, 0};
+  if (occ[0] == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_chain_static<TP, T, false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_chain_static<TP, T, true>, kThreads, 0);
+    if (occ[0] < 1) occ[0] = 1;
+    if (occ[1] < 1) occ[1] = 1;
+  }
+  const size_t nvec = (p.n + V - 1) / V;
+  int grid = stream_grid(nvec, 1, occ[stats ? 1 : 0]);
+  const size_t max_grid = c.scratch_doubles / 8;
+  if ((size_t)grid > max_grid) grid = (int)max_grid;
+  Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
+  if (stats)
+    k_chain_static<TP, T, true><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+  else
+    k_chain_static<TP, T, false><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+// returns -1 if no registered chain matches
+template <typename T>
+static int try_registered(const ChainParams& p, bool stats, double* stats_dev) {
+#define MCM_CHAIN_USE(NAME) \
+  if (tape_matches<NAME>(p)) return launch_static<NAME, T>(p, stats, stats_dev);
+  MCM_REGISTERED_CHAINS(MCM_CHAIN_USE)
+#undef MCM_CHAIN_USE
+  return -1;
+}
+
+// ---------------------------------------------------------------------------
+// engine 2: interpreter, slot file in shared memory
+// ---------------------------------------------------------------------------
+// smem layout: slot s of thread t is the Pack at sm[s * kThreads + t] -> every
+// quarter-warp touches 128 contiguous bytes: conflict-free 128-bit LDS/STS.
+template <typename T, int V>
+__device__ __forceinline__ void iget(const Pack<T>* sm, const ChainParams& p, int idx, T (&x)[V]) {
   if (idx & MCM_TAPE_CONST) {
     const T c = (T)p.consts[idx & (MCM_TAPE_MAX_CONST - 1)];
 #pragma unroll
     for (int v = 0; v < V; ++v) x[v] = c;
-    return;
+  } else {
+    const Pack<T> t = sm[(idx & (S - 1)) * kThreads + threadIdx.x];
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = t.v[v];
   }
-  switch (idx & (S - 1)) {
-#define MCM_G(K) \
-  case K: _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = r[K][v]; break;
-    MCM_G(0) MCM_G(1) MCM_G(2) MCM_G(3) MCM_G(4) MCM_G(5) MCM_G(6) MCM_G(7)
-#undef MCM_G
-  }
+}
+template <typename T, int V>
+__device__ __forceinline__ void iput(Pack<T>* sm, int idx, const T (&x)[V]) {
+  Pack<T> t;
+#pragma unroll
+  for (int v = 0; v < V; ++v) t.v[v] = x[v];
+  sm[(idx & (S - 1)) * kThreads + threadIdx.x] = t;
 }
 
 template <typename T, int V>
-__device__ __forceinline__ void slot_put(T (&r)[S][V], int idx, const T (&x)[V]) {
-  switch (idx & (S - 1)) {
-#define MCM_P(K) \
-  case K: _Pragma("unroll") for (int v = 0; v < V; ++v) r[K][v] = x[v]; break;
-    MCM_P(0) MCM_P(1) MCM_P(2) MCM_P(3) MCM_P(4) MCM_P(5) MCM_P(6) MCM_P(7)
-#undef MCM_P
-  }
-}
-
-template <typename T, int V>
-__device__ __forceinline__ void exec_range(T (&r)[S][V], const ChainParams& p, int pc0, int pc1, size_t j,
+__device__ __forceinline__ void exec_range(Pack<T>* sm, const ChainParams& p, int pc0, int pc1, size_t j,
                                            int nvalid, bool& bad) {
-  using P = Pack<T>;
   for (int pc = pc0; pc < pc1; ++pc) {
     const mcm_tape_ins ins = p.tape[pc];
     const int op = ins.op;
     T x[V], y[V], z[V];
     if (op == MCM_TAPE_LOAD) {
-      const T* src = static_cast<const T*>(p.in[ins.a & (MCM_TAPE_MAX_IN - 1)]);
-      if (nvalid == V) {
-        const P t = ld_stream(reinterpret_cast<const P*>(src) + j);
-#pragma unroll
-        for (int v = 0; v < V; ++v) x[v] = t.v[v];
-      } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v) x[v] = (v < nvalid) ? src[j * V + v] : T(1);
-      }
-      slot_put<T, V>(r, ins.dst, x);
+      load_input<T, V>(p.in[ins.a & (MCM_TAPE_MAX_IN - 1)], j, nvalid, x);
+      iput<T, V>(sm, ins.dst, x);
       continue;
     }
-    slot_get<T, V>(r, p, ins.a, x);
+    iget<T, V>(sm, p, ins.a, x);
     if (op == MCM_TAPE_STORE) {
-      T* dst = static_cast<T*>(p.out[ins.dst & (MCM_TAPE_MAX_OUT - 1)]);
-      if (dst != nullptr) {
-        if (nvalid == V) {
-          P t;
-#pragma unroll
-          for (int v = 0; v < V; ++v) t.v[v] = x[v];
-          st_stream(reinterpret_cast<P*>(dst) + j, t);
-        } else {
-#pragma unroll
-          for (int v = 0; v < V; ++v)
-            if (v < nvalid) dst[j * V + v] = x[v];
-        }
-      }
+      store_output<T, V>(p.out[ins.dst & (MCM_TAPE_MAX_OUT - 1)], j, nvalid, x);
       continue;
     }
-    if (op == MCM_TAPE_MOV) {
-      slot_put<T, V>(r, ins.dst, x);
-      continue;
-    }
-    if (op == MCM_TAPE_POWI) {
-      const int k = (int)(signed char)ins.b;
-#pragma unroll
-      for (int v = 0; v < V; ++v) x[v] = math::m_powi(x[v], k);
-      slot_put<T, V>(r, ins.dst, x);
-      continue;
-    }
-    if (op >= MCM_TAPE_BINARY) slot_get<T, V>(r, p, ins.b, y);
-    if (op >= MCM_TAPE_TERNARY) slot_get<T, V>(r, p, ins.c, z);
-
-#define MCM_U(OP)                                                                        \
-  case MCM_TAPE_UNARY + OP:                                                              \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) {                                      \
-      const T t = math::unary_apply<OP, T>(x[v]);                                        \
-      if (math::UnaryCanDomainError<OP>::value) bad |= (t != t) && (x[v] == x[v]) && (v < nvalid); \
-      x[v] = t;                                                                          \
-    }                                                                                    \
-    break;
-#define MCM_B(OP)                                                                        \
-  case MCM_TAPE_BINARY + OP:                                                             \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) {                                      \
-      const T t = math::binary_apply<OP, T>(x[v], y[v]);                                 \
-      if (math::BinaryCanDomainError<OP>::value)                                         \
-        bad |= (t != t) && (x[v] == x[v]) && (y[v] == y[v]) && (v < nvalid);             \
-      x[v] = t;                                                                          \
-    }                                                                                    \
-    break;
-#define MCM_T(OP)                                                                        \
-  case MCM_TAPE_TERNARY + OP:                                                            \
-    _Pragma("unroll") for (int v = 0; v < V; ++v) x[v] = math::ternary_apply<OP, T>(x[v], y[v], z[v]); \
-    break;
+    if (op >= MCM_TAPE_BINARY && op < MCM_TAPE_LOAD) iget<T, V>(sm, p, ins.b, y);
+    if (op >= MCM_TAPE_TERNARY && op < MCM_TAPE_LOAD) iget<T, V>(sm, p, ins.c, z);
+    const int imm = (int)(signed char)ins.b;
+#define MCM_OPC(OPC) \
+  case OPC: apply_op<OPC, T, V>(x, y, z, imm, nvalid, bad); break;
+#define MCM_U(OP) MCM_OPC(MCM_TAPE_UNARY + OP)
+#define MCM_B(OP) MCM_OPC(MCM_TAPE_BINARY + OP)
+#define MCM_T(OP) MCM_OPC(MCM_TAPE_TERNARY + OP)
     switch (op) {
       MCM_U(MCM_U_PLUS) MCM_U(MCM_U_NEG) MCM_U(MCM_U_EXP) MCM_U(MCM_U_EXP2) MCM_U(MCM_U_EXP10)
       MCM_U(MCM_U_EXPM1) MCM_U(MCM_U_LOG) MCM_U(MCM_U_LOG10) MCM_U(MCM_U_LOG2) MCM_U(MCM_U_LOG1P)
@@ -141,12 +328,14 @@ __device__ __forceinline__ void exec_range(T (&r)[S][V], const ChainParams& p, i
       MCM_B(MCM_B_MAX) MCM_B(MCM_B_MIN) MCM_B(MCM_B_MOD) MCM_B(MCM_B_MOD1) MCM_B(MCM_B_ATAN2)
       MCM_B(MCM_B_ATAND2) MCM_B(MCM_B_ADD_SUM) MCM_B(MCM_B_HYPOT) MCM_B(MCM_B_REM) MCM_B(MCM_B_FDIV)
       MCM_T(MCM_T_CLAMP) MCM_T(MCM_T_MULADD) MCM_T(MCM_T_MUL_ADD)
-      default: break;
+      MCM_OPC(MCM_TAPE_POWI)
+      default: break;  // MOV
     }
 #undef MCM_U
 #undef MCM_B
 #undef MCM_T
-    slot_put<T, V>(r, ins.dst, x);
+#undef MCM_OPC
+    iput<T, V>(sm, ins.dst, x);
   }
 }
 
@@ -155,35 +344,29 @@ __global__ void __launch_bounds__(kThreads)
 k_chain(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
         uint32_t* flags) {
   constexpr int V = Pack<T>::N;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Pack<T>* sm = reinterpret_cast<Pack<T>*>(smem_raw);
   const size_t n = p.n;
   const size_t nvec = (n + V - 1) / V;
   const size_t stride = (size_t)gridDim.x * kThreads;
   bool bad = false;
   Mom m = mom_empty();
-
+  {
+    T zero[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) zero[v] = T(0);
+#pragma unroll
+    for (int k = 0; k < S; ++k) iput<T, V>(sm, k, zero);
+  }
   for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) {
     const int nvalid = (j + 1) * V <= n ? V : (int)(n - j * V);
-    T r[S][V];
-#pragma unroll
-    for (int k = 0; k < S; ++k)
-#pragma unroll
-      for (int v = 0; v < V; ++v) r[k][v] = T(0);
-    exec_range<T, V>(r, p, 0, p.loop_begin, j, nvalid, bad);
-    for (int rep = 0; rep < p.reps; ++rep) exec_range<T, V>(r, p, p.loop_begin, p.loop_end, j, nvalid, bad);
-    exec_range<T, V>(r, p, p.loop_end, p.ntape, j, nvalid, bad);
+    exec_range<T, V>(sm, p, 0, p.loop_begin, j, nvalid, bad);
+    for (int rep = 0; rep < p.reps; ++rep) exec_range<T, V>(sm, p, p.loop_begin, p.loop_end, j, nvalid, bad);
+    exec_range<T, V>(sm, p, p.loop_end, p.ntape, j, nvalid, bad);
     if constexpr (STATS) {
       T x[V];
-      slot_get<T, V>(r, p, p.stats_slot, x);
-      if (nvalid == V) {
-        double d[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) d[v] = (double)x[v];
-        mom_push_chunk<V>(m, d);
-      } else {
-#pragma unroll
-        for (int v = 0; v < V; ++v)
-          if (v < nvalid) mom_push_one(m, (double)x[v]);
-      }
+      iget<T, V>(sm, p, p.stats_slot, x);
+      stats_push<T, V>(m, x, nvalid);
     }
   }
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
@@ -221,14 +404,22 @@ static int validate(const ChainParams& p, int nconst, int nin, int nout) {
   return MCM_OK;
 }
 
+static int g_last_engine = 0;  // 1 = registered/static, 2 = interpreter (introspection for tests)
+
 template <typename T>
-static int run_chain(const ChainParams& p, bool stats, double* stats_dev) {
+static int run_chain(const ChainParams& p, bool stats, double* stats_dev, bool allow_registered) {
+  int rc = allow_registered ? try_registered<T>(p, stats, stats_dev) : -1;
+  if (rc >= 0) { g_last_engine = 1; return rc; }
+  g_last_engine = 2;
   Ctx& c = ctx();
   constexpr int V = Pack<T>::N;
+  constexpr size_t kSmem = (size_t)S * kThreads * sizeof(Pack<T>);  // 64 KiB: 16 slots x 256 threads x 16 B
   static int occ[2] = {0, 0};
   if (occ[0] == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_chain<T, false>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_chain<T, true>, kThreads, 0);
+    MCM_CUDA(cudaFuncSetAttribute(k_chain<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_chain<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_chain<T, false>, kThreads, kSmem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_chain<T, true>, kThreads, kSmem);
     if (occ[0] < 1) occ[0] = 1;
     if (occ[1] < 1) occ[1] = 1;
   }
@@ -238,9 +429,9 @@ static int run_chain(const ChainParams& p, bool stats, double* stats_dev) {
   if ((size_t)grid > max_grid) grid = (int)max_grid;
   Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
   if (stats)
-    k_chain<T, true><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain<T, true><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
   else
-    k_chain<T, false><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain<T, false><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
@@ -248,6 +439,12 @@ static int run_chain(const ChainParams& p, bool stats, double* stats_dev) {
 }  // namespace mcm
 
 using namespace mcm;
+
+// 1 if the last mcm_chain call ran a registered (ahead-of-time specialised) kernel, 2 if interpreted
+extern "C" int mcm_chain_last_engine(void) { return g_last_engine; }
+
+static int g_force_interpreter = 0;
+extern "C" int mcm_chain_force_interpreter(int on) { g_force_interpreter = on; return MCM_OK; }
 
 extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
                          int reps, const double* consts, int nconst, const void* const* inputs, int nin,
@@ -260,9 +457,9 @@ extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loo
   if (stats_slot >= S) return fail(MCM_ERR_INVALID, "mcm_chain: stats_slot out of range");
   if (stats_slot >= 0 && !stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain: stats requested without output");
   if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_chain: bad dtype %d", dtype);
+  if (ntape > MCM_TAPE_MAX_INS || ntape < 0) return fail(MCM_ERR_INVALID, "mcm_chain: ntape out of range");
   ChainParams p;
   memset(&p, 0, sizeof(p));
-  if (ntape > MCM_TAPE_MAX_INS || ntape < 0) return fail(MCM_ERR_INVALID, "mcm_chain: ntape out of range");
   for (int i = 0; i < ntape; ++i) p.tape[i] = tape[i];
   for (int i = 0; i < nconst; ++i) p.consts[i] = consts[i];
   for (int i = 0; i < nin; ++i) {
@@ -285,7 +482,8 @@ extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loo
     return MCM_OK;
   }
   double* slot = moments_result_slot();
-  rc = (dtype == MCM_F64) ? run_chain<double>(p, stats, slot) : run_chain<float>(p, stats, slot);
+  const bool allow = !g_force_interpreter;
+  rc = (dtype == MCM_F64) ? run_chain<double>(p, stats, slot, allow) : run_chain<float>(p, stats, slot, allow);
   if (rc) return rc;
   if (stats) return read_back(stats_out_host, slot, 6);
   return MCM_OK;

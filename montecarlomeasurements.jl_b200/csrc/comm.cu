@@ -163,6 +163,32 @@ extern "C" int mcm_moments_sharded(int dtype, const void* in, size_t n_local, do
   return MCM_OK;
 }
 
+// Merge per-rank moments that already sit on the host (e.g. the fused statistics of mcm_chain):
+// upload 6 doubles, all-gather, Chan-merge in rank order.  In place.
+extern "C" int mcm_moments_allmerge(double* inout_host6) {
+  MCM_NEED_INIT();
+  if (!inout_host6) return fail(MCM_ERR_INVALID, "mcm_moments_allmerge: null pointer");
+  const int g = g_nccl.comm ? g_nccl.nranks : 1;
+  if (g == 1) return MCM_OK;
+  if (g > 64) return fail(MCM_ERR_UNSUPPORTED, "mcm_moments_allmerge: at most 64 ranks");
+  Ctx& c = ctx();
+  double* slot = moments_result_slot();
+  double* gathered = c.d_scratch + (c.scratch_doubles - 16 - 6 * 64);
+  MCM_CUDA(cudaMemcpyAsync(slot, inout_host6, 6 * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  MCM_NCCL(g_nccl.AllGather(slot, gathered, 6, ncclFloat64, g_nccl.comm, c.stream));
+  std::vector<double> h(6 * (size_t)g);
+  int rc = read_back(h.data(), gathered, 6 * (size_t)g);
+  if (rc) return rc;
+  double acc[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
+  for (int r = 1; r < g; ++r) {
+    double t[6];
+    mcm_moments_merge(acc, &h[6 * r], t);
+    memcpy(acc, t, sizeof(t));
+  }
+  memcpy(inout_host6, acc, sizeof(acc));
+  return MCM_OK;
+}
+
 // Sharded pcov: (1) global column means = allreduce(local sums)/N; (2) local centred Gram on
 // the global means (raw, unscaled); (3) allreduce(sum) of the M x M block; (4) scale.
 extern "C" int mcm_gram_sharded(int dtype, const void* const* vars, int M, size_t n_local, int corrected,
