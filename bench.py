@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of BASELINE.json on 1..8 B200.
+
+Workload: one uncertain scalar with N = 1e8 Float64 particles PER GPU,
+a = pi + 0.1 * Phi^-1((2i+1)/(2N)) (the systematic sample of `pi ± 0.1`); a step is ONE pass of the hot
+path: the canonical 10-primitive chain (sin, ^2, *, neg, exp, +, abs, sqrt, ^1.5, /) evaluated as one
+fused launch that materialises y and reduces pmean(y)/pstd(y) in the same pass, then the six moments
+are read back to the host (and, for N > 1 ranks, merged across ranks through NCCL).
+metric = Gparticle-ops/s = 10 * particles / time, whole job.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU execution model (stand-in)
+
+One JSON line on stdout (rank 0).  See DESIGN.md §measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 100_000_000
+OPS_PER_PARTICLE = 10
+ALGO_BYTES_PER_PARTICLE = 16          # read a (8 B) + write y (8 B); statistics are fused
+CPU_SAMPLE_N = 10_000_000             # bounded CPU sample: 1/10 of the per-GPU workload
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Sample SM clocks and throttle reasons DURING the timed region (NVML, 20 ms period)."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                bits = get(self.h)
+                for b, nm in names.items():
+                    if bits & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_arm(steps: int, warmup: int, threads: int | None = None):
+    """The reference's CPU execution model, timed on this box's host cores (oracle/ref_cpu.cpp: one SIMD
+    pass per primitive with SLEEF kernels, temporaries materialised, mean 1 pass + std 2 passes)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    # compile for THIS host (the .so shipped from the build container may target another CPU)
+    orc.build(force=True)
+    r = orc.refcpu()
+    threads = threads or r.ref_max_threads()
+    a = orc.systematic_normal(CPU_SAMPLE_N, np.pi, 0.1)
+    times = []
+    res = None
+    for i in range(warmup + steps):
+        y, m, s, dt = orc.ref_chain10(a, threads=threads)
+        res = (m, s)
+        if i >= warmup:
+            times.append(dt)
+    n_eff = (CPU_SAMPLE_N // r.ref_vector_width()) * r.ref_vector_width()
+    total = sum(times)
+    value = OPS_PER_PARTICLE * n_eff * len(times) / total / 1e9
+    return {"value": value, "ms_per_step": 1e3 * total / len(times), "threads": threads, "n": n_eff,
+            "mean": res[0], "std": res[1], "simd_width": r.ref_vector_width()}
+
+
+def print_reference_line(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 runs the CPU arm
+    r = cpu_reference_arm(args.steps, args.warmup)
+    sample = (f"chain10 + pmean/pstd on N={r['n']} Float64 particles per step (1/10 of the per-GPU workload), "
+              f"SLEEF 3.8 AVX{'-512' if r['simd_width'] == 8 else '2'} loop-per-primitive port of the reference's execution model, "
+              f"{r['threads']} host threads; the Julia reference itself cannot run here (no julia binary)")
+    line = {
+        "impl": "reference", "metric": "Gparticle-ops/s", "value": r["value"], "unit": "Gparticle-ops/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: chain10 + pmean/pstd, Float64 (CPU arm: bounded sample N=1e7 per step)"},
+        "cpu_baseline": {"value": r["value"], "unit": "Gparticle-ops/s", "cores": r["threads"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["value"], "unit": "Gparticle-ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "check": {"pmean": r["mean"], "pstd": r["std"]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-families", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return print_reference_line(args)
+
+    import torch
+    import torch.distributed as dist
+    import mcm_b200 as mcm
+    from mcm_b200 import chains, tape as tp
+    L = mcm._lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    mcm.sharded.init_distributed(rank, world, local_rank)
+    lib = L.lib()
+    stream = torch.cuda.Stream()
+    L.check(lib.mcm_set_stream(C.c_void_p(stream.cuda_stream)))
+
+    N = args.n
+    t10 = tp.trace(chains.chain10, 1)
+    # this rank's slice of the GLOBAL systematic grid of world*N points (weak scaling: N per GPU)
+    lo = rank * N
+    a = mcm.systematic_sample(world * N, mcm.Normal(np.pi, 0.1), permute=False, i0=lo, n_total=world * N,
+                              n_local=N, as_particles=True)
+    y = mcm.particles._empty(N, L.F64)
+
+    def step():
+        st = tp.run_tape(t10, [a.ptr], N, L.F64, [y.ptr], stats_output=0)
+        m = mcm.Moments(*st)
+        if world > 1:
+            m = mcm.sharded.allmerge(m)
+        return m
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            m = step()
+        assert lib.mcm_chain_last_engine() == 1, "chain10 must run on the registered straight-line kernel"
+        barrier()
+        sampler = ClockSampler(local_rank); sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(args.steps):
+            m = step()
+        ev1.record(stream)
+        barrier()
+        clocks = sampler.result()
+        elapsed_ms = ev0.elapsed_time(ev1)
+        # kernel-only duration for the roofline: the same launches queued back to back, statistics left on device
+        kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kreps = max(20, min(args.steps, 100))
+        tp_args = (t10, [a.ptr], N, L.F64, [y.ptr])
+        ins = (C.c_void_p * 1)(a.ptr); outs = (C.c_void_p * 1)(y.ptr)
+        consts = np.asarray(t10.consts); tape_c = t10.as_ctypes(); lb, le = t10.bounds
+        kev0.record(stream)
+        for _ in range(kreps):
+            L.check(lib.mcm_chain(L.F64, tape_c, len(t10.ins), lb, le, 0, consts.ctypes.data_as(L._dp), len(t10.consts),
+                                  ins, 1, outs, 1, N, t10.out_slots[0], None))
+        kev1.record(stream)
+        torch.cuda.synchronize()
+        kernel_ms = kev0.elapsed_time(kev1) / kreps
+
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = OPS_PER_PARTICLE * N * world * args.steps / (elapsed_ms * 1e-3) / 1e9
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned input, H2D inside the timed region) ----
+    e2e = None
+    hp = C.c_void_p()
+    L.check(lib.mcm_host_alloc(C.byref(hp), N * 8))
+    L.check(lib.mcm_download(hp, C.c_void_p(a.ptr), N * 8))
+    hin = (C.c_void_p * 1)(hp.value)
+    e2e_steps = max(3, min(10, args.steps))
+    st = np.zeros(6)
+
+    def e2e_step():
+        L.check(lib.mcm_chain_host(L.F64, tape_c, len(t10.ins), lb, le, 0, consts.ctypes.data_as(L._dp), len(t10.consts),
+                                   hin, 1, None, 1, N, t10.out_slots[0], st.ctypes.data_as(L._dp)))
+        mm = mcm.Moments(*st)
+        return mcm.sharded.allmerge(mm) if world > 1 else mm
+    for _ in range(2):
+        me = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        me = e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = OPS_PER_PARTICLE * N * world * e2e_steps / float(te.item()) / 1e9
+    e2e = {"value": e2e_val, "unit": "Gparticle-ops/s", "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 48,
+           "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+           "how": "mcm_chain_host: pinned host input -> chunked H2D overlapped with the fused kernel -> 6 moments D2H; y not returned",
+           "check": {"pmean": me.mean, "pstd": me.std()}}
+    L.check(lib.mcm_host_free(hp))
+
+    peak, peak_src = measured_peaks()
+    achieved = ALGO_BYTES_PER_PARTICLE * N / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("chain10_static_f64_bytes_per_launch_1e8")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_chain_static<Chain10,double,stats>",
+                "kernel_ms": kernel_ms,
+                "note": "algorithmic 16 B/particle; this chain is FP64-pipe-bound (see DESIGN.md), the HBM-bound family is in hbm_family"}
+
+    line = {
+        "metric": "Gparticle-ops/s", "value": value, "unit": "Gparticle-ops/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: single uncertain scalar, N=1e8 Float64 particles per GPU, fused 10-primitive chain "
+                               "(sin,^2,*,neg,exp,+,abs,sqrt,^1.5,/) + pmean/pstd in one launch",
+                   "particles_per_gpu": N, "l2": "inputs (800 MB) and outputs (800 MB) far exceed the 126 MB L2",
+                   "parallelism": f"particle index sharded over {world} GPU(s); 6 moments per rank all-gathered (NCCL)"},
+        "roofline": roofline, "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * world,
+        "check": {"pmean": m.mean, "pstd": m.std(), "n": m.n},
+    }
+
+    if rank == 0 and world == 1 and not args.no_families:
+        line["hbm_family"] = hbm_family(mcm, L, lib, stream, a, y, N, peak)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_arm(steps=5, warmup=1)
+        line["cpu_baseline"] = {
+            "value": r["value"], "unit": "Gparticle-ops/s", "cores": r["threads"], "kind": "port",
+            "sample": f"chain10 + pmean/pstd on N={r['n']} Float64 (1/10 of the workload), best-effort mean of 5 passes, "
+                      f"SLEEF 3.8 SIMD loop-per-primitive port (oracle/ref_cpu.cpp), {r['threads']} host threads",
+            "check": {"pmean": r["mean"], "pstd": r["std"]}}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def hbm_family(mcm, L, lib, stream, a, y, N, peak):
+    """The low-intensity chains the >= 80 % HBM target is about: CUDA-event timing, inputs > L2."""
+    import torch
+    out = {}
+    b = mcm.particles._empty(N, L.F64); c = mcm.particles._empty(N, L.F64)
+    L.check(lib.mcm_affine(L.F64, C.c_void_p(a.ptr), 0.5, 1.0, C.c_void_p(b.ptr), N))
+    L.check(lib.mcm_affine(L.F64, C.c_void_p(a.ptr), -0.25, 2.0, C.c_void_p(c.ptr), N))
+    coeffs = np.array([0.5, -1.0, 0.25, 2.0, -0.125, 0.3, 0.01, -0.02, 0.003])
+    ptrs = (C.c_void_p * 3)(a.ptr, b.ptr, c.ptr)
+    cs = np.array([1.0, 0.01 / 6, 0.02 / 6])
+    mom = np.zeros(6)
+    cases = {
+        "affine (alpha*a+beta)": (16, lambda: lib.mcm_affine(L.F64, C.c_void_p(a.ptr), 1.5, 0.5, C.c_void_p(y.ptr), N)),
+        "poly8 (Horner, 8 FMA)": (16, lambda: lib.mcm_polyval(L.F64, C.c_void_p(a.ptr), coeffs.ctypes.data_as(L._dp), 9, 1, C.c_void_p(y.ptr), N)),
+        "axpy3 (u + h*k1 + h*k2, RK4 stage)": (32, lambda: lib.mcm_lincomb(L.F64, 3, ptrs, cs.ctypes.data_as(L._dp), C.c_void_p(y.ptr), N)),
+        "add (p1 + p2)": (24, lambda: lib.mcm_binary(L.ENUMS["MCM_B_ADD"], L.F64, C.c_void_p(a.ptr), 0.0, C.c_void_p(b.ptr), 0.0, C.c_void_p(y.ptr), N)),
+        "sqrt": (16, lambda: lib.mcm_unary(L.ENUMS["MCM_U_SQRT"], L.F64, C.c_void_p(a.ptr), C.c_void_p(y.ptr), N)),
+        "exp": (16, lambda: lib.mcm_unary(L.ENUMS["MCM_U_EXP"], L.F64, C.c_void_p(a.ptr), C.c_void_p(y.ptr), N)),
+        "sin": (16, lambda: lib.mcm_unary(L.ENUMS["MCM_U_SIN"], L.F64, C.c_void_p(a.ptr), C.c_void_p(y.ptr), N)),
+        "pmean+pstd (one pass)": (8, lambda: lib.mcm_moments(L.F64, C.c_void_p(a.ptr), N, mom.ctypes.data_as(L._dp))),
+    }
+    with torch.cuda.stream(stream):
+        for name, (bpp, fn) in cases.items():
+            for _ in range(3):
+                L.check(fn())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record(stream)
+            for _ in range(reps):
+                L.check(fn())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = bpp * N / (ms * 1e-3) / 1e9
+            out[name] = {"ms": ms, "GB/s": gbs, "frac_of_measured_hbm": gbs / peak, "bytes_per_particle": bpp}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -205,6 +205,19 @@ int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, in
               const void* const* inputs, int nin, void* const* outputs, int nout,
               size_t n, int stats_slot, double* stats_out_host);
 
+/* Statistics of the most recent mcm_chain call made with stats_slot >= 0 and
+ * stats_out_host == NULL (the launch is then fully asynchronous); synchronises. */
+int mcm_chain_stats_fetch(double* stats_out_host);
+
+/* Same as mcm_chain but inputs/outputs are HOST arrays (the `particles::Vector{T}` of an
+ * ordinary reference Particles, types.jl:18): chunks are copied host->device, computed and
+ * copied back on three overlapping streams.  Use mcm_host_alloc'ed (pinned) buffers for
+ * full PCIe bandwidth.  Synchronises before returning. */
+int mcm_chain_host(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                   int reps, const double* consts, int nconst,
+                   const void* const* host_inputs, int nin, void* const* host_outputs, int nout,
+                   size_t n, int stats_slot, double* stats_out_host);
+
 /* Engine introspection: chains listed in csrc/chain_registry.def are compiled ahead of
  * time into straight-line kernels (the analogue of register_primitive's `eval`,
  * register_primitive.jl:19-82); every other tape runs on the interpreter kernel.

@@ -21,7 +21,7 @@ from .particles import (
     moments, pmean, psum, pvar, pstd, pminimum, pmaximum, pextrema, pmiddle, meanstd, meanvar,
     pquantile, pmedian, psort, psortperm, pcov, pcor, to_matrix,
     unsafe_comparisons, set_comparison_function, approx, lesssim, gtrsim,
-    check_domain, nparticles, particleeltype,
+    check_domain, nparticles, particleeltype, flat_particles, is_particle_array,
 )
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
                        mvnormal_particles)

@@ -100,6 +100,8 @@ SIGNATURES = {
     "mcm_affine": (_i, [_i, _vp, _d, _d, _vp, _sz]),
     "mcm_lincomb": (_i, [_i, _i, _vpp, _dp, _vp, _sz]),
     "mcm_chain": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
+    "mcm_chain_stats_fetch": (_i, [_dp]),
+    "mcm_chain_host": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
     "mcm_chain_last_engine": (_i, []),
     "mcm_chain_force_interpreter": (_i, [_i]),
     "mcm_moments": (_i, [_i, _vp, _sz, _dp]),

@@ -19,8 +19,7 @@ from . import tape as _tape
 
 
 def _is_parray(a):
-    return isinstance(a, (list, tuple, np.ndarray)) and len(a) > 0 and \
-        isinstance(np.asarray(a, dtype=object).flat[0], P.Particles)
+    return P.is_particle_array(a)
 
 
 def bymap(f, *args):
@@ -40,8 +39,9 @@ def bymap(f, *args):
         if isinstance(a, P.Particles):
             host.append(("p", a.to_numpy()))
         elif _is_parray(a):
-            arr = np.asarray(a, dtype=object)
-            host.append(("a", np.stack([q.to_numpy() for q in arr.flat], axis=-1).reshape((N,) + arr.shape)))
+            shape = a.shape if isinstance(a, np.ndarray) else (len(a),)
+            flat = P.flat_particles(a)
+            host.append(("a", np.stack([q.to_numpy() for q in flat], axis=-1).reshape((N,) + tuple(shape))))
         else:
             host.append(("c", a))
     individuals = []

@@ -446,16 +446,15 @@ extern "C" int mcm_chain_last_engine(void) { return g_last_engine; }
 static int g_force_interpreter = 0;
 extern "C" int mcm_chain_force_interpreter(int on) { g_force_interpreter = on; return MCM_OK; }
 
-extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
-                         int reps, const double* consts, int nconst, const void* const* inputs, int nin,
-                         void* const* outputs, int nout, size_t n, int stats_slot, double* stats_out_host) {
-  MCM_NEED_INIT();
+// Validate + launch; statistics (if stats_slot >= 0) land in the 6 doubles at stats_dev.  No sync.
+static int chain_launch(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                        int reps, const double* consts, int nconst, const void* const* inputs, int nin,
+                        void* const* outputs, int nout, size_t n, int stats_slot, double* stats_dev) {
   if (!tape && ntape) return fail(MCM_ERR_INVALID, "mcm_chain: null tape");
   if (nconst < 0 || nconst > MCM_TAPE_MAX_CONST || nin < 0 || nin > MCM_TAPE_MAX_IN || nout < 0 ||
       nout > MCM_TAPE_MAX_OUT)
     return fail(MCM_ERR_INVALID, "mcm_chain: nconst/nin/nout out of range");
   if (stats_slot >= S) return fail(MCM_ERR_INVALID, "mcm_chain: stats_slot out of range");
-  if (stats_slot >= 0 && !stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain: stats requested without output");
   if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_chain: bad dtype %d", dtype);
   if (ntape > MCM_TAPE_MAX_INS || ntape < 0) return fail(MCM_ERR_INVALID, "mcm_chain: ntape out of range");
   ChainParams p;
@@ -475,16 +474,139 @@ extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loo
   p.stats_slot = stats_slot < 0 ? 0 : stats_slot;
   int rc = validate(p, nconst, nin, nout);
   if (rc) return rc;
-  const bool stats = stats_slot >= 0;
-  if (n == 0) {
-    if (stats) { stats_out_host[0] = 0; stats_out_host[1] = NAN; stats_out_host[2] = 0;
-                 stats_out_host[3] = INFINITY; stats_out_host[4] = -INFINITY; stats_out_host[5] = 0; }
-    return MCM_OK;
-  }
-  double* slot = moments_result_slot();
+  if (n == 0) return MCM_OK;
   const bool allow = !g_force_interpreter;
-  rc = (dtype == MCM_F64) ? run_chain<double>(p, stats, slot, allow) : run_chain<float>(p, stats, slot, allow);
+  const bool stats = stats_slot >= 0;
+  return (dtype == MCM_F64) ? run_chain<double>(p, stats, stats_dev, allow) : run_chain<float>(p, stats, stats_dev, allow);
+}
+
+static void empty_stats(double* s) {
+  s[0] = 0; s[1] = NAN; s[2] = 0; s[3] = INFINITY; s[4] = -INFINITY; s[5] = 0;
+}
+
+extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                         int reps, const double* consts, int nconst, const void* const* inputs, int nin,
+                         void* const* outputs, int nout, size_t n, int stats_slot, double* stats_out_host) {
+  MCM_NEED_INIT();
+  double* slot = moments_result_slot();
+  int rc = chain_launch(dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
+                        stats_slot, slot);
   if (rc) return rc;
-  if (stats) return read_back(stats_out_host, slot, 6);
-  return MCM_OK;
+  if (stats_slot >= 0 && stats_out_host) {
+    if (n == 0) { empty_stats(stats_out_host); return MCM_OK; }
+    return read_back(stats_out_host, slot, 6);
+  }
+  return MCM_OK;  // stats_out_host == NULL: statistics stay on device until mcm_chain_stats_fetch
+}
+
+// Fetch the statistics of the most recent mcm_chain launched with stats_out_host == NULL (synchronises).
+extern "C" int mcm_chain_stats_fetch(double* stats_out_host) {
+  MCM_NEED_INIT();
+  if (!stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain_stats_fetch: null pointer");
+  return read_back(stats_out_host, moments_result_slot(), 6);
+}
+
+// Host-buffer entry point: the whole chain with inputs/outputs in HOST memory (what a Julia caller holding
+// ordinary Vector{T}s would pass).  The particle range is cut into chunks; chunk c+1 is copied host->device on
+// a copy stream while chunk c computes, results stream back on a third stream; per-chunk moments are merged
+// on the host in chunk order.  Pinned host memory (mcm_host_alloc) makes the copies truly asynchronous.
+extern "C" int mcm_moments_merge(const double* a, const double* b, double* out);
+
+extern "C" int mcm_chain_host(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                              int reps, const double* consts, int nconst, const void* const* host_inputs, int nin,
+                              void* const* host_outputs, int nout, size_t n, int stats_slot,
+                              double* stats_out_host) {
+  MCM_NEED_INIT();
+  if (nin < 1 || nin > MCM_TAPE_MAX_IN || nout < 0 || nout > MCM_TAPE_MAX_OUT)
+    return fail(MCM_ERR_INVALID, "mcm_chain_host: nin/nout out of range");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_chain_host: bad dtype %d", dtype);
+  if (stats_slot >= 0 && !stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain_host: stats requested without output");
+  for (int i = 0; i < nin; ++i)
+    if (!host_inputs || (!host_inputs[i] && n)) return fail(MCM_ERR_INVALID, "mcm_chain_host: null input %d", i);
+  if (n == 0) { if (stats_slot >= 0) empty_stats(stats_out_host); return MCM_OK; }
+  Ctx& c = ctx();
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  const size_t chunk = (size_t)1 << 23;  // 8 Mi particles per chunk (64 MiB of Float64 per stream buffer)
+  const size_t nchunks = (n + chunk - 1) / chunk;
+  static cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  if (!s_h2d) {
+    MCM_CUDA(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+    MCM_CUDA(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+  }
+  const size_t cbytes = (n < chunk ? n : chunk) * esz;
+  void* dbuf_in[2][MCM_TAPE_MAX_IN];
+  void* dbuf_out[2][MCM_TAPE_MAX_OUT];
+  for (int b = 0; b < 2; ++b) {
+    for (int i = 0; i < nin; ++i) MCM_CUDA(cudaMallocAsync(&dbuf_in[b][i], cbytes, c.stream));
+    for (int i = 0; i < nout; ++i) {
+      dbuf_out[b][i] = nullptr;
+      if (host_outputs && host_outputs[i]) MCM_CUDA(cudaMallocAsync(&dbuf_out[b][i], cbytes, c.stream));
+    }
+  }
+  double* d_stats = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_stats, nchunks * 6 * sizeof(double), c.stream));
+  cudaEvent_t ev_in[2], ev_comp[2], ev_out[2], ev_alloc;
+  for (int b = 0; b < 2; ++b) {
+    MCM_CUDA(cudaEventCreateWithFlags(&ev_in[b], cudaEventDisableTiming));
+    MCM_CUDA(cudaEventCreateWithFlags(&ev_comp[b], cudaEventDisableTiming));
+    MCM_CUDA(cudaEventCreateWithFlags(&ev_out[b], cudaEventDisableTiming));
+  }
+  MCM_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+  MCM_CUDA(cudaEventRecord(ev_alloc, c.stream));
+  MCM_CUDA(cudaStreamWaitEvent(s_h2d, ev_alloc, 0));
+  MCM_CUDA(cudaStreamWaitEvent(s_d2h, ev_alloc, 0));
+  int rc = MCM_OK;
+  for (size_t k = 0; k < nchunks && rc == MCM_OK; ++k) {
+    const int b = (int)(k & 1);
+    const size_t off = k * chunk;
+    const size_t len = (n - off < chunk) ? n - off : chunk;
+    // the input buffer b is free once chunk k-2 has computed; the output buffer once its D2H finished
+    if (k >= 2) {
+      MCM_CUDA(cudaStreamWaitEvent(s_h2d, ev_comp[b], 0));
+      MCM_CUDA(cudaStreamWaitEvent(c.stream, ev_out[b], 0));
+    }
+    for (int i = 0; i < nin; ++i)
+      MCM_CUDA(cudaMemcpyAsync(dbuf_in[b][i], static_cast<const char*>(host_inputs[i]) + off * esz, len * esz,
+                               cudaMemcpyHostToDevice, s_h2d));
+    MCM_CUDA(cudaEventRecord(ev_in[b], s_h2d));
+    MCM_CUDA(cudaStreamWaitEvent(c.stream, ev_in[b], 0));
+    rc = chain_launch(dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, dbuf_in[b], nin, dbuf_out[b],
+                      nout, len, stats_slot, d_stats + 6 * k);
+    if (rc) break;
+    MCM_CUDA(cudaEventRecord(ev_comp[b], c.stream));
+    bool any_out = false;
+    for (int i = 0; i < nout; ++i)
+      if (dbuf_out[b][i]) {
+        if (!any_out) { MCM_CUDA(cudaStreamWaitEvent(s_d2h, ev_comp[b], 0)); any_out = true; }
+        MCM_CUDA(cudaMemcpyAsync(static_cast<char*>(host_outputs[i]) + off * esz, dbuf_out[b][i], len * esz,
+                                 cudaMemcpyDeviceToHost, s_d2h));
+      }
+    MCM_CUDA(cudaEventRecord(ev_out[b], s_d2h));
+  }
+  if (rc == MCM_OK && stats_slot >= 0) {
+    double* h = new double[nchunks * 6];
+    MCM_CUDA(cudaMemcpyAsync(h, d_stats, nchunks * 6 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    MCM_CUDA(cudaStreamSynchronize(c.stream));
+    double acc[6];
+    memcpy(acc, h, sizeof(acc));
+    for (size_t k = 1; k < nchunks; ++k) {
+      double t[6];
+      mcm_moments_merge(acc, h + 6 * k, t);
+      memcpy(acc, t, sizeof(t));
+    }
+    memcpy(stats_out_host, acc, sizeof(acc));
+    delete[] h;
+  }
+  MCM_CUDA(cudaStreamSynchronize(s_d2h));
+  MCM_CUDA(cudaStreamSynchronize(s_h2d));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  for (int b = 0; b < 2; ++b) {
+    for (int i = 0; i < nin; ++i) MCM_CUDA(cudaFreeAsync(dbuf_in[b][i], c.stream));
+    for (int i = 0; i < nout; ++i)
+      if (dbuf_out[b][i]) MCM_CUDA(cudaFreeAsync(dbuf_out[b][i], c.stream));
+    cudaEventDestroy(ev_in[b]); cudaEventDestroy(ev_comp[b]); cudaEventDestroy(ev_out[b]);
+  }
+  cudaEventDestroy(ev_alloc);
+  MCM_CUDA(cudaFreeAsync(d_stats, c.stream));
+  return rc;
 }

@@ -14,13 +14,16 @@
 
 namespace mcm {
 
+// The mean is carried as the unevaluated sum K + dm: K is a fixed shift taken from the data (so that
+// deviations v - K are formed exactly for data with a large common offset, e.g. 1e9 +- 1), dm the mean of
+// the shifted values.  All second-moment arithmetic happens on O(sigma)-sized numbers.
 struct Mom {
-  double n, mean, m2, mn, mx, sum;
+  double n, K, dm, m2, mn, mx, sum;
 };
 
 __host__ __device__ __forceinline__ Mom mom_empty() {
   Mom m;
-  m.n = 0.0; m.mean = 0.0; m.m2 = 0.0;
+  m.n = 0.0; m.K = 0.0; m.dm = 0.0; m.m2 = 0.0;
   m.mn = __builtin_huge_val(); m.mx = -__builtin_huge_val();
   m.sum = 0.0;
   return m;
@@ -39,9 +42,10 @@ __host__ __device__ __forceinline__ Mom mom_merge(const Mom& a, const Mom& b) {
   if (a.n == 0.0) return b;
   Mom r;
   r.n = a.n + b.n;
-  const double d = b.mean - a.mean;
+  const double d = (b.K - a.K) + (b.dm - a.dm);  // difference of the two means, shifts subtracted first
   const double fb = b.n / r.n;
-  r.mean = a.mean + d * fb;
+  r.K = a.K;
+  r.dm = a.dm + d * fb;
   r.m2 = (a.m2 + b.m2) + (d * d) * (a.n * fb);
   r.mn = nmin(a.mn, b.mn);
   r.mx = nmax(a.mx, b.mx);
@@ -52,29 +56,42 @@ __host__ __device__ __forceinline__ Mom mom_merge(const Mom& a, const Mom& b) {
 #ifdef __CUDACC__
 
 // Fold a chunk of C values (already in registers) into the thread's running moments.
+__device__ __forceinline__ double median3(double a, double b, double c) {
+  return fmax(fmin(a, b), fmin(fmax(a, b), c));
+}
+
 template <int C>
 __device__ __forceinline__ void mom_push_chunk(Mom& m, const double (&v)[C]) {
-  double s = 0.0, lo = v[0], hi = v[0];
+  if (m.n == 0.0) {
+    // the thread's shift: a value from the data; median of three guards against a lone outlier
+    if constexpr (C >= 3) m.K = median3(v[0], v[1], v[2]);
+    else m.K = v[0];
+    if (!(fabs(m.K) <= 1.7976931348623157e308)) m.K = 0.0;  // Inf/NaN shift would poison everything
+  }
+  double s = 0.0, sd = 0.0, lo = v[0], hi = v[0];
   bool nan = false;
+  double dv[C];
 #pragma unroll
   for (int i = 0; i < C; ++i) {
     s += v[i];
+    dv[i] = v[i] - m.K;
+    sd += dv[i];
     lo = fmin(lo, v[i]);
     hi = fmax(hi, v[i]);
     nan |= (v[i] != v[i]);
   }
-  const double cm = s * (1.0 / C);
+  const double cm = sd * (1.0 / C);  // chunk mean in shifted coordinates
   double q = 0.0;
 #pragma unroll
   for (int i = 0; i < C; ++i) {
-    const double d = v[i] - cm;
+    const double d = dv[i] - cm;
     q = fma(d, d, q);
   }
   if (nan) lo = hi = s;  // s is NaN
   const double nn = m.n + (double)C;
   const double fb = (double)C / nn;
-  const double d = cm - m.mean;
-  m.mean = (m.n == 0.0) ? cm : m.mean + d * fb;
+  const double d = cm - m.dm;
+  m.dm = (m.n == 0.0) ? cm : m.dm + d * fb;
   m.m2 = (m.m2 + q) + (d * d) * (m.n * fb);
   m.n = nn;
   m.sum += s;
@@ -89,7 +106,7 @@ __device__ __forceinline__ void mom_push_one(Mom& m, double x) {
 
 __device__ __forceinline__ Mom mom_shfl_down(const Mom& a, int d) {
   Mom b;
-  b.n = shfl_down_d(a.n, d); b.mean = shfl_down_d(a.mean, d); b.m2 = shfl_down_d(a.m2, d);
+  b.n = shfl_down_d(a.n, d); b.K = shfl_down_d(a.K, d); b.dm = shfl_down_d(a.dm, d); b.m2 = shfl_down_d(a.m2, d);
   b.mn = shfl_down_d(a.mn, d); b.mx = shfl_down_d(a.mx, d); b.sum = shfl_down_d(a.sum, d);
   return b;
 }
@@ -130,12 +147,12 @@ __device__ __forceinline__ void mom_grid_finish(Mom block_m, Mom* partials, unsi
   for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
     const volatile Mom* p = partials + i;
     Mom b;
-    b.n = p->n; b.mean = p->mean; b.m2 = p->m2; b.mn = p->mn; b.mx = p->mx; b.sum = p->sum;
+    b.n = p->n; b.K = p->K; b.dm = p->dm; b.m2 = p->m2; b.mn = p->mn; b.mx = p->mx; b.sum = p->sum;
     m = mom_merge(m, b);
   }
   m = mom_block_reduce(m);
   if (threadIdx.x == 0) {
-    out[0] = m.n; out[1] = m.mean; out[2] = m.m2; out[3] = m.mn; out[4] = m.mx; out[5] = m.sum;
+    out[0] = m.n; out[1] = m.K + m.dm; out[2] = m.m2; out[3] = m.mn; out[4] = m.mx; out[5] = m.sum;
     *ticket = 0u;
   }
 }

@@ -126,9 +126,9 @@ extern "C" int mcm_moments(int dtype, const void* in, size_t n, double* out_host
 
 extern "C" int mcm_moments_merge(const double* a, const double* b, double* out) {
   if (!a || !b || !out) return fail(MCM_ERR_INVALID, "mcm_moments_merge: null pointer");
-  Mom ma{a[0], a[1], a[2], a[3], a[4], a[5]}, mb{b[0], b[1], b[2], b[3], b[4], b[5]};
+  Mom ma{a[0], a[1], 0.0, a[2], a[3], a[4], a[5]}, mb{b[0], b[1], 0.0, b[2], b[3], b[4], b[5]};
   Mom r = mom_merge(ma, mb);
-  out[0] = r.n; out[1] = r.mean; out[2] = r.m2; out[3] = r.mn; out[4] = r.mx; out[5] = r.sum;
+  out[0] = r.n; out[1] = r.K + r.dm; out[2] = r.m2; out[3] = r.mn; out[4] = r.mx; out[5] = r.sum;
   return MCM_OK;
 }
 

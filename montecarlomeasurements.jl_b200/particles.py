@@ -55,6 +55,8 @@ class Particles:
 
     def __new__(cls, *args, **kw):
         from . import sampling as _s
+        if "_ptr" in kw:
+            return object.__new__(cls)
         if cls is Particles and len(args) >= 1 and isinstance(args[0], np.ndarray) and args[0].ndim >= 2:
             m = args[0]
             return _from_matrix(m)
@@ -712,15 +714,33 @@ def check_domain(reset: bool = True):
     return bits.value
 
 
+def flat_particles(p):
+    """Elements of a Particles / list / tuple / object ndarray of Particles, in storage order.
+    (np.asarray on a list of Particles would call __array__ and download them — never do that.)"""
+    if isinstance(p, Particles):
+        return [p]
+    if isinstance(p, np.ndarray):
+        return list(p.flat)
+    out = []
+    for q in p:
+        out.extend(flat_particles(q) if isinstance(q, (list, tuple, np.ndarray)) else [q])
+    return out
+
+
+def is_particle_array(a) -> bool:
+    if isinstance(a, np.ndarray):
+        return a.dtype == object and a.size > 0 and isinstance(a.flat[0], Particles)
+    return isinstance(a, (list, tuple)) and len(a) > 0 and all(isinstance(q, Particles) for q in flat_particles(a))
+
+
 def nparticles(p) -> int:
     """nparticles (bymap.jl:3-8)."""
     if isinstance(p, Particles): return p.N
-    if isinstance(p, (list, tuple, np.ndarray)) and len(p) and isinstance(np.asarray(p, dtype=object).flat[0], Particles):
-        return np.asarray(p, dtype=object).flat[0].N
+    if is_particle_array(p): return flat_particles(p)[0].N
     return 1
 
 
 def particleeltype(p):
     """particleeltype (bymap.jl:14-15)."""
     if isinstance(p, Particles): return p.np_dtype
-    return np.asarray(p, dtype=object).flat[0].np_dtype
+    return flat_particles(p)[0].np_dtype

@@ -30,7 +30,7 @@ def bootstrap(p, n: int | None = None, *, seed: int = 0, inds=None):
     element (resampling.jl:80-84).  `inds` (0-based) supplies the indices explicitly (e.g. from Julia's rng).
     """
     single = isinstance(p, P.Particles)
-    ps = [p] if single else P._check_mv(list(np.asarray(p, dtype=object).flat))
+    ps = [p] if single else P._check_mv(P.flat_particles(p))
     N, dt = ps[0].N, ps[0].dtype
     n = N if n is None else int(n)
     idx = _as_index(inds) if inds is not None else rand_indices(n, N, seed)

@@ -44,7 +44,7 @@ def merge_moments(a, b):
     fb = b[0] / n
     mn = a[3] if np.isnan(a[3]) else (b[3] if np.isnan(b[3]) else min(a[3], b[3]))
     mx = a[4] if np.isnan(a[4]) else (b[4] if np.isnan(b[4]) else max(a[4], b[4]))
-    return np.array([n, a[1] + d * fb, (a[2] + b[2]) + (d * d) * (a[0] * fb), mn, mx, a[5] + b[5]])
+    return np.array([n, a[1] + (0.0 + d * fb), (a[2] + b[2]) + (d * d) * (a[0] * fb), mn, mx, a[5] + b[5]])
 
 
 _comm = {"rank": 0, "world": 1, "ready": False}

@@ -291,24 +291,31 @@ ORC_API int orc_powi(int dtype, const void* in, int k, void* out, size_t n) {
 /* out = {n, mean, M2, min, max, sum}; long double two-pass (the arbiter for the
  * 1e-12 tolerance tier).  Statistics.mean is pairwise-sum/N, var is two-pass. */
 ORC_API int orc_moments(int dtype, const void* in, size_t n, double* out) {
-  long double s = 0.0L;
-  double mn = INFINITY, mx = -INFINITY;
+  /* shift by the first finite element so that the long double sums stay exact-ish even for
+   * data like 1e15 +- 1e3 (a plain long double sum of 4e4 such values already exceeds 2^64) */
+  long double s = 0.0L, sd = 0.0L;
+  double mn = INFINITY, mx = -INFINITY, K = 0.0;
   int has_nan = 0;
   for (size_t i = 0; i < n; ++i) {
     double x = dtype == MCM_F64 ? ((const double*)in)[i] : (double)((const float*)in)[i];
+    if (isfinite(x)) { K = x; break; }
+  }
+  for (size_t i = 0; i < n; ++i) {
+    double x = dtype == MCM_F64 ? ((const double*)in)[i] : (double)((const float*)in)[i];
     s += x;
+    sd += (long double)x - (long double)K;
     if (isnan(x)) has_nan = 1;
     if (x < mn) mn = x;
     if (x > mx) mx = x;
   }
-  long double mean = n ? s / (long double)n : NAN;
+  long double dm = n ? sd / (long double)n : NAN;
   long double m2 = 0.0L;
   for (size_t i = 0; i < n; ++i) {
     double x = dtype == MCM_F64 ? ((const double*)in)[i] : (double)((const float*)in)[i];
-    long double d = (long double)x - mean;
+    long double d = ((long double)x - (long double)K) - dm;
     m2 += d * d;
   }
-  out[0] = (double)n; out[1] = (double)mean; out[2] = (double)m2;
+  out[0] = (double)n; out[1] = (double)((long double)K + dm); out[2] = (double)m2;
   out[3] = has_nan ? NAN : mn; out[4] = has_nan ? NAN : mx; out[5] = (double)s;
   return MCM_OK;
 }

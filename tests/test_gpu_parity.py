@@ -201,7 +201,7 @@ def test_chain10_fused_vs_oracle_and_engines_agree(mcm, orc, dt):
 
 def test_unregistered_chain_runs_on_interpreter(mcm, orc):
     rng = np.random.default_rng(7)
-    a = rng.normal(size=N); b = rng.normal(size=N) + 3
+    a = rng.normal(size=N); b = np.abs(rng.normal(size=N)) + 0.5
     f = mcm.fused(lambda p, q: (mcm.log(q) * p - mcm.cos(p / q) ** 3, mcm.clamp(p, -1.0, 1.0) + 2.0 * q))
     y0, y1 = f(mcm.Particles(a), mcm.Particles(b))
     assert mcm._lib.lib().mcm_chain_last_engine() == 2
@@ -217,7 +217,8 @@ def test_register_primitive(mcm, orc):
     p = mcm.Particles(np.random.default_rng(8).normal(size=2000))
     assert bits_equal(testf(p, p).to_numpy(), (p + p).to_numpy())
     g = mcm.register_primitive(lambda x, s: mcm.exp(x * s) - 1.0, "g")
-    assert ulp_err(g(p, 0.5).to_numpy(), orc.binary("SUB", orc.unary("EXP", orc.binary("MUL", p.to_numpy(), 0.5)), 1.0)).max() <= 2
+    e = orc.unary("EXP", orc.binary("MUL", p.to_numpy(), 0.5))
+    assert np.all(np.abs(g(p, 0.5).to_numpy() - orc.binary("SUB", e, 1.0)) <= 2 * np.finfo(np.float64).eps * e)
     assert testf(2.0, 3.0) == 5.0                                      # plain numbers pass through
 
 
@@ -346,8 +347,9 @@ def test_systematic_sample_and_constructors(mcm, orc, golden, dt):
     s = mcm.systematic_sample(2000, mcm.Normal(dt(np.pi), dt(0.1)), permute=False)
     ref = orc.systematic_normal(2000, np.pi, 0.1, dtype=dt)
     assert np.all(np.diff(s) > 0)                                        # permute=false -> sorted (sampling.jl:4)
-    zerr = np.abs(s.astype(np.float64) - ref.astype(np.float64)) / 0.1
-    assert zerr.max() <= (8 if dt == np.float64 else 4) * np.finfo(dt).eps * 4
+    # device z is within 8 ulp(Float64) of the oracle's z; the final μ + σz rounds once more in T
+    err = np.abs(s.astype(np.float64) - ref.astype(np.float64))
+    assert err.max() <= 0.1 * 8 * 4 * np.finfo(np.float64).eps + np.spacing(dt(np.pi + 0.5))
     # an explicit permutation (e.g. a Julia randperm) is honoured exactly
     perm = orc.randperm(2000, seed=5)
     sp = mcm.systematic_sample(2000, mcm.Normal(dt(np.pi), dt(0.1)), perm=perm)
