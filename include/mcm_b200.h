@@ -229,6 +229,9 @@ int mcm_chain_force_interpreter(int on);
 /* ======================= statistics ======================================== */
 /* one pass: out_host[0..5] = {n, mean, M2 = sum (x-mean)^2, min, max, sum} */
 int mcm_moments(int dtype, const void* in, size_t n, double* out_host);
+/* A/B switch for the moments kernel on large inputs: 1 (default) = bulk-async (TMA) shared-memory
+ * pipeline, 0 = direct 128-bit global loads.  Results are identical up to merge order. */
+int mcm_moments_use_bulk(int on);
 /* pmean/pvar/pstd/pminimum/pmaximum/sum (particles.jl:302-323); N==1 -> var/std 0 */
 int mcm_reduce(int kind, int dtype, const void* in, size_t n, double* out_host);
 /* @prob p < a  -> count; (bymap.jl:128-136) */

@@ -105,6 +105,7 @@ SIGNATURES = {
     "mcm_chain_last_engine": (_i, []),
     "mcm_chain_force_interpreter": (_i, [_i]),
     "mcm_moments": (_i, [_i, _vp, _sz, _dp]),
+    "mcm_moments_use_bulk": (_i, [_i]),
     "mcm_reduce": (_i, [_i, _i, _vp, _sz, _dp]),
     "mcm_count": (_i, [_i, _i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
     "mcm_moments_merge": (_i, [_dp, _dp, _dp]),

@@ -35,6 +35,9 @@ struct ChainParams {
 };
 
 constexpr int S = MCM_TAPE_SLOTS;
+#ifndef MCM_CHAIN_MIN_CTAS
+#define MCM_CHAIN_MIN_CTAS 4  // 64 registers/thread -> 32 resident warps per SM (latency-bound FP64 chains)
+#endif
 
 // ---------------------------------------------------------------------------
 // shared pieces
@@ -156,7 +159,7 @@ __device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, 
 }
 
 template <class TP, typename T, bool STATS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, MCM_CHAIN_MIN_CTAS)
 k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
                uint32_t* flags) {
   constexpr int V = Pack<T>::N;

@@ -1,21 +1,243 @@
-// mcm_fastmath.cuh — Float64 kernels for the hot transcendental primitives of
-// the headline chain (exp, sin, cos, log, pow).  These are the device
-// counterparts of SLEEFPirates.exp / sin_fast / cos_fast / log_fast
-// (src/sleefpirates.jl:2-36) and Base `^` (src/particles.jl:183).
+// mcm_fastmath.cuh — hand-written Float64 kernels for the hot transcendental
+// primitives of the headline chain: sin, cos, exp, and `^` with a half-integer
+// exponent.  They stand where the reference calls SLEEFPirates.sin_fast /
+// cos_fast / exp (src/sleefpirates.jl:2-36) and Base `^` (src/particles.jl:183).
 //
-// Round-1 baseline: CUDA's libdevice double-precision routines (documented
-// maximum errors: exp 1 ulp, log 1 ulp, sin/cos 2 ulp, pow 2 ulp).
+// Design target: <= 1 ulp from the correctly rounded result on the fast path
+// (measured on the host twin against mpmath / long double, tests/test_fastmath_twin.py),
+// with as few FP64-pipe instructions as possible — on B200 the fused Float64
+// chain is bound by the FP64 pipe and issue slots, not by HBM.
+// Anything outside a fast path's domain falls through to the CUDA math library.
+//
+// The file also compiles as plain C++ (MCM_HOST_TWIN) so that every routine can be
+// checked bit-for-bit on the CPU: all arithmetic is IEEE double with explicit
+// fma(), the library is built with -fmad=false, so host and device agree exactly.
 #pragma once
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+// Polynomial coefficients live in __constant__ memory so that they are read as constant-bank
+// operands of DFMA (no instruction); as literals every 64-bit constant costs two UMOV issue slots.
+#ifdef MCM_HOST_TWIN
+#define MCM_FM_CONST static const
+#define MCM_FM_HD inline
+namespace mcm { namespace fast {
+inline int64_t d2bits(double x) { int64_t b; memcpy(&b, &x, 8); return b; }
+inline double bits2d(int64_t b) { double x; memcpy(&x, &b, 8); return x; }
+inline double lib_sin(double x) { return ::sin(x); }
+inline double lib_cos(double x) { return ::cos(x); }
+inline double lib_exp(double x) { return ::exp(x); }
+inline double lib_pow(double x, double y) { return ::pow(x, y); }
+}}
+#else
+#define MCM_FM_CONST static __constant__
+#define MCM_FM_HD __device__ __forceinline__
+namespace mcm { namespace fast {
+__device__ __forceinline__ int64_t d2bits(double x) { return __double_as_longlong(x); }
+__device__ __forceinline__ double bits2d(int64_t b) { return __longlong_as_double(b); }
+// out-of-range arguments take the CUDA math library; kept out of line so the rare paths cost the hot
+// loop neither registers nor instruction-cache footprint
+static __device__ __noinline__ double lib_sin(double x) { return ::sin(x); }
+static __device__ __noinline__ double lib_cos(double x) { return ::cos(x); }
+static __device__ __noinline__ double lib_exp(double x) { return ::exp(x); }
+static __device__ __noinline__ double lib_pow(double x, double y) { return ::pow(x, y); }
+}}
+#endif
 
 namespace mcm {
 namespace fast {
 
-__device__ __forceinline__ double exp_f64(double x) { return ::exp(x); }
-__device__ __forceinline__ double sin_f64(double x) { return ::sin(x); }
-__device__ __forceinline__ double cos_f64(double x) { return ::cos(x); }
-__device__ __forceinline__ double log_f64(double x) { return ::log(x); }
-__device__ __forceinline__ double pow_f64(double x, double y) { return ::pow(x, y); }
+// ---------------------------------------------------------------------------------
+// sin / cos
+// ---------------------------------------------------------------------------------
+// Argument reduction x = n*(pi/2) + (r + rl), |r| <= pi/4 (+ rounding), valid for |x| <= 2^17*pi/2:
+// pi/2 = P1 + P2 + P3 with P1 holding 33 bits, so n*P1 (n < 2^18) and r0 = x - n*P1 are exact.
+// n*P2 is formed exactly as th + tl (one FMA); r1 = r0 - th is exact whenever the cancellation is
+// heavy (Sterbenz), i.e. exactly in the cases where x sits next to a multiple of pi/2, and the
+// Fast2Sum remainder picks up its rounding error otherwise; P3 supplies the tail.  Worst-case
+// doubles near multiples of pi/2 therefore keep full relative accuracy — no slow path is needed.
+MCM_FM_CONST double kTrig[20] = {
+    6.36619772367581382433e-01,   // [0] 2/pi
+    1.57079632673412561417e+00,   // [1] P1: first 33 bits of pi/2
+    6.07710050650619224932e-11,   // [2] P2: pi/2 - P1, rounded to 53 bits
+    3.52155986518320018165e-27,   // [3] P3: pi/2 - P1 - P2 (scripts/fit_fastmath.py)
+    // sin kernel S6..S1 (fdlibm __kernel_sin)
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, 1.66666666666666324348e-01,
+    // cos kernel C6..C1 (fdlibm __kernel_cos)
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    205887.0,                      // [16] fast-path limit 2^17 * pi/2
+    0.0, 0.0, 0.0};
+#define kTwoOverPi kTrig[0]
+#define kPio2_1 kTrig[1]
+#define kPio2_2 kTrig[2]
+#define kPio2_3 kTrig[3]
+#define kTrigFastMax kTrig[16]
+
+struct Reduced { double r, rl; int q; };
+
+MCM_FM_HD Reduced trig_reduce(double x) {
+  Reduced o;
+  const double n = rint(x * kTwoOverPi);
+  const double r0 = fma(-n, kPio2_1, x);          // exact
+  const double th = n * kPio2_2;
+  const double tl = fma(n, kPio2_2, -th);         // n*P2 == th + tl exactly
+  const double r1 = r0 - th;
+  const double d = (r0 - r1) - th;                // rounding error of r1 (Fast2Sum)
+  o.r = r1;
+  o.rl = fma(-n, kPio2_3, d - tl);
+  o.q = (int)n;
+  return o;
+}
+
+// minimax kernels on |r| <= pi/4 (coefficients of the classic fdlibm __kernel_sin/__kernel_cos)
+MCM_FM_HD double sin_kernel(double r, double rl) {
+  const double z = r * r;
+  const double v = z * r;
+  double p = kTrig[4];
+  p = fma(p, z, kTrig[5]);
+  p = fma(p, z, kTrig[6]);
+  p = fma(p, z, kTrig[7]);
+  p = fma(p, z, kTrig[8]);
+  // r - ((z*(rl/2 - v*p) - rl) - v*S1)
+  const double t = fma(z, fma(-v, p, 0.5 * rl), -rl);
+  return r - fma(v, kTrig[9], t);
+}
+MCM_FM_HD double cos_kernel(double r, double rl) {
+  const double z = r * r;
+  double p = kTrig[10];
+  p = fma(p, z, kTrig[11]);
+  p = fma(p, z, kTrig[12]);
+  p = fma(p, z, kTrig[13]);
+  p = fma(p, z, kTrig[14]);
+  p = fma(p, z, kTrig[15]);
+  // 1 - (z/2 - (z*z*p - r*rl)), arranged so that the two large terms cancel exactly
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  return w + (((1.0 - w) - hz) + fma(z * z, p, -r * rl));
+}
+
+MCM_FM_HD double sin_f64(double x) {
+  if (!(fabs(x) <= kTrigFastMax)) return lib_sin(x);  // huge, Inf, NaN: library (Payne-Hanek)
+  const Reduced a = trig_reduce(x);
+  const double s = (a.q & 1) ? cos_kernel(a.r, a.rl) : sin_kernel(a.r, a.rl);
+  const double y = (a.q & 2) ? -s : s;
+  return (x == 0.0) ? x : y;                           // keep -0.0
+}
+MCM_FM_HD double cos_f64(double x) {
+  if (!(fabs(x) <= kTrigFastMax)) return lib_cos(x);
+  const Reduced a = trig_reduce(x);
+  const double c = (a.q & 1) ? sin_kernel(a.r, a.rl) : cos_kernel(a.r, a.rl);
+  return ((a.q + 1) & 2) ? -c : c;
+}
+
+// ---------------------------------------------------------------------------------
+// exp
+// ---------------------------------------------------------------------------------
+// x = n*ln2 + r, |r| <= ln2/2 (two-constant Cody-Waite, ln2_hi has 32 trailing zero bits);
+// exp(r) = 1 + (r + r^2 * Q(r)) with Q a degree-10 minimax polynomial (scripts/fit_fastmath.py);
+// 2^n by exponent arithmetic.  |x| > 708: library (overflow / gradual underflow).
+#include "mcm_fastmath_coeffs.inc"  // MCM_EXPQ_LIST: kExpQ0 .. kExpQ10
+MCM_FM_CONST double kExp[16] = {
+    1.44269504088896338700e+00,   // [0] log2(e)
+    6.93147180369123816490e-01,   // [1] ln2_hi
+    1.90821492927058770002e-10,   // [2] ln2_lo
+    708.0,                        // [3] fast-path limit
+    MCM_EXPQ_LIST,                // [4..14] Q0..Q10
+    0.0};
+#define kLog2e kExp[0]
+#define kLn2Hi kExp[1]
+#define kLn2Lo kExp[2]
+
+MCM_FM_HD double exp_f64(double x) {
+  if (!(fabs(x) <= kExp[3])) return lib_exp(x);
+  const double n = rint(x * kLog2e);
+  const double rh = fma(-n, kLn2Hi, x);            // exact (n*ln2_hi has <= 53 bits)
+  const double r = fma(-n, kLn2Lo, rh);
+  const double rl = fma(-n, kLn2Lo, rh - r);       // rounding error of the line above
+  double q = kExp[14];
+  q = fma(q, r, kExp[13]); q = fma(q, r, kExp[12]); q = fma(q, r, kExp[11]); q = fma(q, r, kExp[10]);
+  q = fma(q, r, kExp[9]); q = fma(q, r, kExp[8]); q = fma(q, r, kExp[7]); q = fma(q, r, kExp[6]);
+  q = fma(q, r, kExp[5]); q = fma(q, r, kExp[4]);
+  // exp(r + rl) = 1 + r + r^2 q + rl (to first order in rl)
+  const double t = fma(r * r, q, rl);
+  const double p = 1.0 + (r + t);
+  return bits2d(d2bits(p) + ((int64_t)n << 52));   // p in [0.70, 1.42], |n| <= 1022: stays normal
+}
+
+// ---------------------------------------------------------------------------------
+// x^y for half-integer y  (a^1.5 of the headline chain, a^0.5, a^2.5, a^-0.5 ...)
+// ---------------------------------------------------------------------------------
+// x^(m + 1/2) = x^m * sqrt(x).  sqrt is correctly rounded and its residual x - s*s is exactly
+// representable, so sqrt(x) = s + rs with rs = (x - s^2)/(2s) known to ~2^-106; x^m is carried as an
+// unevaluated pair by compensated power-by-squaring; one double-double product, one final rounding.
+// Error < 1 ulp (typically 0.5).  General exponents use the CUDA library pow.
+MCM_FM_HD void two_prod(double a, double b, double& hi, double& lo) { hi = a * b; lo = fma(a, b, -hi); }
+
+MCM_FM_HD void powi_dd(double x, int m, double& hi, double& lo) {  // m >= 0
+  double yh = 1.0, yl = 0.0, xh = x, xl = 0.0;
+  while (m > 0) {
+    if (m & 1) {
+      double ph, pl;
+      two_prod(yh, xh, ph, pl);
+      yl = fma(yh, xl, fma(yl, xh, pl));
+      yh = ph;
+    }
+    m >>= 1;
+    if (m) {
+      double sh, sl;
+      two_prod(xh, xh, sh, sl);
+      xl = fma(2.0 * xh, xl, sl);
+      xh = sh;
+    }
+  }
+  hi = yh; lo = yl;
+}
+
+MCM_FM_HD double pow_half_int(double x, int k) {  // k odd, exponent k/2; 1e-280 < x < 1e280
+  const double s = sqrt(x);
+  const double res = fma(-s, s, x);                 // exact
+  const double rs = res * (0.5 / s);                // sqrt(x) = s + rs
+  int m = (k - 1) / 2;                              // floor for k > 0
+  if (k < 0) m = (-k + 1) / 2;                      // x^(k/2) = 1 / (x^m' / sqrt(x)) handled below
+  double ph, pl;
+  powi_dd(x, m, ph, pl);
+  if (k > 0) {
+    double hi, lo;
+    two_prod(ph, s, hi, lo);
+    lo = fma(ph, rs, fma(pl, s, lo));
+    return hi + lo;
+  }
+  // negative: x^(-m' + 1/2) = sqrt(x) / x^m'
+  const double q = s / ph;
+  // one Newton correction in double-double: q += ((s + rs) - q*(ph + pl)) / ph
+  const double rem = fma(-q, ph, s) + fma(-q, pl, rs);
+  return q + rem / ph;
+}
+
+// x^1.5 = x*sqrt(x): p = x*s with its exact rounding error, plus x*rs ~= s*res/2 (x/s = s to 2^-53).
+MCM_FM_HD double pow_three_halves(double x) {
+  const double s = sqrt(x);
+  const double res = fma(-s, s, x);
+  const double p = x * s;
+  const double pe = fma(x, s, -p);
+  return p + fma(0.5 * res, s, pe);
+}
+
+MCM_FM_HD double pow_f64(double x, double y) {
+  const double t = y + y;
+  if (fabs(t) <= 17.0 && t == rint(t) && x > 1e-280 && x < 1e280) {
+    if (t == 3.0) return pow_three_halves(x);
+    if (t == 1.0) return sqrt(x);
+    const int k = (int)t;
+    if (k & 1) return pow_half_int(x, k);
+  }
+  return lib_pow(x, y);
+}
+
+MCM_FM_HD double log_f64(double x) { return ::log(x); }
 
 }  // namespace fast
 }  // namespace mcm

@@ -47,6 +47,93 @@ k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticke
   mom_grid_finish(m, partials, ticket, out);
 }
 
+// ---- TMA (bulk async copy) variant for large inputs ---------------------------------------
+// One elected thread streams 16 KiB tiles global -> shared with cp.async.bulk, completion tracked by
+// an mbarrier per stage (SASS: UBLKCP + SYNCS); all 256 threads then read the tile from shared
+// memory with conflict-free 128-bit LDS.  Bytes in flight per SM no longer depend on registers or
+// occupancy: 3 resident CTAs x 4 stages x 16 KiB.  Same per-thread chunk statistics as k_moments.
+constexpr int MB_STAGES = 4;
+constexpr int MB_TILE_BYTES = 16384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE_%=;\n"
+      "bra MBAR_WAIT_%=;\n"
+      "MBAR_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_moments_bulk(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out) {
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  constexpr int EPT = MB_TILE_BYTES / (int)sizeof(T);           // elements per tile
+  constexpr int PPT = MB_TILE_BYTES / 16 / kThreads;            // packs per thread per tile (4)
+  constexpr int C = PPT * V;                                    // chunk size (8 doubles / 16 floats)
+  extern __shared__ __align__(128) unsigned char smem_tiles[];
+  __shared__ __align__(8) unsigned long long full_bar[MB_STAGES];
+  const int tid = threadIdx.x;
+  const size_t ntiles = n / EPT;
+  const size_t my_tiles = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < MB_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < MB_STAGES && (size_t)s < my_tiles; ++s) {
+      const size_t tile = blockIdx.x + (size_t)s * gridDim.x;
+      mbar_expect_tx(&full_bar[s], MB_TILE_BYTES);
+      bulk_g2s(smem_tiles + (size_t)s * MB_TILE_BYTES, in + tile * EPT, MB_TILE_BYTES, &full_bar[s]);
+    }
+  }
+  Mom m = mom_empty();
+  for (size_t i = 0; i < my_tiles; ++i) {
+    const int s = (int)(i % MB_STAGES);
+    const unsigned parity = (unsigned)((i / MB_STAGES) & 1);
+    mbar_wait(&full_bar[s], parity);
+    const P* tile = reinterpret_cast<const P*>(smem_tiles + (size_t)s * MB_TILE_BYTES);
+    double v[C];
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const P x = tile[k * kThreads + tid];
+#pragma unroll
+      for (int e = 0; e < V; ++e) v[k * V + e] = (double)x.v[e];
+    }
+    mom_push_chunk<C>(m, v);
+    __syncthreads();  // every thread has read stage s: it may be refilled
+    if (tid == 0 && i + MB_STAGES < my_tiles) {
+      const size_t tile_next = blockIdx.x + (i + MB_STAGES) * gridDim.x;
+      mbar_expect_tx(&full_bar[s], MB_TILE_BYTES);
+      bulk_g2s(smem_tiles + (size_t)s * MB_TILE_BYTES, in + tile_next * EPT, MB_TILE_BYTES, &full_bar[s]);
+    }
+  }
+  // remainder (< one tile) through the generic path
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t j = ntiles * EPT + (size_t)blockIdx.x * kThreads + tid; j < n; j += stride) mom_push_one(m, (double)in[j]);
+  m = mom_block_reduce(m);
+  mom_grid_finish(m, partials, ticket, out);
+}
+
 template <typename T, int CMP>
 __global__ void __launch_bounds__(kThreads)
 k_count(const T* __restrict__ in, size_t n, T thr, unsigned long long* out) {
@@ -68,6 +155,8 @@ k_count(const T* __restrict__ in, size_t n, T thr, unsigned long long* out) {
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+static int g_use_bulk = 1;  // mcm_moments_use_bulk(0) forces the LDG kernel (A/B measurements, tests)
+
 int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
   Ctx& c = ctx();
   static int occ64 = 0, occ32 = 0;
@@ -78,7 +167,30 @@ int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
     if (occ32 < 1) occ32 = 1;
   }
   Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
-  const size_t max_grid = c.scratch_doubles / 8;  // 6 doubles per partial, keep headroom
+  const size_t max_grid = c.scratch_doubles / 8;  // 7 doubles per partial, keep headroom
+  // large aligned inputs: bulk-async (TMA) pipeline
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  if (g_use_bulk && (dtype == MCM_F64 || dtype == MCM_F32) && n * esz >= ((size_t)8 << 20) &&
+      (reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+    constexpr size_t kSmem = (size_t)MB_STAGES * MB_TILE_BYTES;
+    static int occb = 0;
+    if (occb == 0) {
+      MCM_CUDA(cudaFuncSetAttribute(k_moments_bulk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      MCM_CUDA(cudaFuncSetAttribute(k_moments_bulk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, k_moments_bulk<double>, kThreads, kSmem);
+      if (occb < 1) occb = 1;
+      if (occb > 3) occb = 3;
+    }
+    int grid = c.sm_count * occb;
+    const size_t ntiles = n * esz / MB_TILE_BYTES;
+    if ((size_t)grid > ntiles) grid = (int)(ntiles ? ntiles : 1);
+    if (dtype == MCM_F64)
+      k_moments_bulk<double><<<grid, kThreads, kSmem, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6);
+    else
+      k_moments_bulk<float><<<grid, kThreads, kSmem, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6);
+    MCM_CHECK_LAUNCH();
+    return MCM_OK;
+  }
   if (dtype == MCM_F64) {
     int grid = stream_grid((n + 1) / 2, 4, occ64 > 4 ? 4 : occ64);
     if ((size_t)grid > max_grid) grid = (int)max_grid;
@@ -109,6 +221,8 @@ int read_back(double* host_dst, const double* dev_src, size_t count) {
 }  // namespace mcm
 
 using namespace mcm;
+
+extern "C" int mcm_moments_use_bulk(int on) { g_use_bulk = on; return MCM_OK; }
 
 extern "C" int mcm_moments(int dtype, const void* in, size_t n, double* out_host) {
   MCM_NEED_INIT();

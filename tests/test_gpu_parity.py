@@ -495,3 +495,32 @@ def test_domain_errors_raise_sticky_flag(mcm):
     mcm.fused(lambda a: mcm.log(a) + 1.0)(mcm.Particles(np.array([-2.0, 1.0])))
     with pytest.raises(mcm.DomainError):
         mcm.check_domain()
+
+
+def test_device_math_is_bit_identical_to_host_twin(mcm, golden):
+    """The hand-written Float64 kernels (mcm_fastmath.cuh, mcm_norminv.cuh) compiled for sm_100a with
+    -fmad=false must reproduce the host twin bit for bit — which carries the twin's measured ulp bounds
+    (tests/test_fastmath_twin.py, millions of points) over to the GPU."""
+    from test_fastmath_twin import build_twin, call1
+    twin = build_twin()
+    rng = np.random.default_rng(21)
+    n = 200_000
+    k = rng.integers(1, 130000, n).astype(np.float64)
+    near = k * (np.pi / 2); near = near + np.spacing(near) * rng.integers(-3, 4, n)
+    # fast-path range only: beyond 2^17*pi/2 both sides call their own math library (CUDA vs glibc)
+    xs = np.concatenate([rng.uniform(-8, 8, n), np.pi + rng.normal(0, 0.1, n), rng.uniform(-2e5, 2e5, n), near,
+                         [0.0, -0.0, np.inf, -np.inf, np.nan, 205886.9, -205886.9]])
+    for dev, name in ((mcm.sin, "twin_sin"), (mcm.cos, "twin_cos")):
+        assert bits_equal(dev(mcm.Particles(xs)).to_numpy(), call1(twin, name, xs)), name
+    xe = np.concatenate([rng.uniform(-708, 708, n), rng.uniform(-5, 5, n), [0.0, 708.0, -708.0, 710.0, -760.0, np.inf, -np.inf, np.nan]])
+    assert bits_equal(mcm.exp(mcm.Particles(xe)).to_numpy(), call1(twin, "twin_exp", xe))
+    xp = np.concatenate([np.abs(np.pi + rng.normal(0, 0.3, n)), np.exp(rng.uniform(-60, 60, n))])
+    for y in (1.5, 0.5, 2.5, -0.5, -1.5, 7.5):
+        e = np.full(xp.size, y); out = np.empty_like(xp)
+        twin.twin_pow(xp.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_long(xp.size))
+        assert bits_equal((mcm.Particles(xp) ** y).to_numpy(), out), y
+    p = golden["norminv_p"]
+    got = mcm.particles._empty(len(p), mcm._lib.F64)
+    mcm._lib.check(mcm._lib.lib().mcm_norminvcdf(mcm._lib.F64, C.c_void_p(mcm.Particles(p).ptr), C.c_void_p(got.ptr), len(p)))
+    assert bits_equal(got.to_numpy(), call1(twin, "twin_norminv", p))
+    mcm._lib.lib().mcm_check_flags(C.byref(C.c_uint32()), 1)
