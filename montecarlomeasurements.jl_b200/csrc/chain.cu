@@ -93,7 +93,7 @@ __device__ __forceinline__ void apply_op(T (&x)[V], const T (&y)[V], const T (&z
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const T t = math::unary_apply<OP - MCM_TAPE_UNARY, T>(x[v]);
-      if constexpr (math::UnaryCanDomainError<OP - MCM_TAPE_UNARY>::value) bad |= (t != t) && (x[v] == x[v]) && (v < nvalid);
+      if constexpr (math::UnaryCanDomainError<OP - MCM_TAPE_UNARY>::value) bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && (v < nvalid);
       x[v] = t;
     }
   } else if constexpr (OP < MCM_TAPE_TERNARY) {
@@ -101,7 +101,7 @@ __device__ __forceinline__ void apply_op(T (&x)[V], const T (&y)[V], const T (&z
     for (int v = 0; v < V; ++v) {
       const T t = math::binary_apply<OP - MCM_TAPE_BINARY, T>(x[v], y[v]);
       if constexpr (math::BinaryCanDomainError<OP - MCM_TAPE_BINARY>::value)
-        bad |= (t != t) && (x[v] == x[v]) && (y[v] == y[v]) && (v < nvalid);
+        bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && !is_nan_fast(y[v]) && (v < nvalid);
       x[v] = t;
     }
   } else if constexpr (OP < MCM_TAPE_LOAD) {

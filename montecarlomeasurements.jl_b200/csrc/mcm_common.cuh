@@ -81,6 +81,11 @@ __device__ __forceinline__ void st_stream(Pack<T>* p, const Pack<T>& v) {
   __stcs(reinterpret_cast<int4*>(p), *reinterpret_cast<const int4*>(&v));
 }
 
+// NaN test on the integer pipe (the FP64 pipe is the scarce resource of Float64 chains): exponent all
+// ones and a non-zero HIGH mantissa word — exact for every NaN arithmetic can produce (quiet NaNs).
+__device__ __forceinline__ bool is_nan_fast(double v) { return ((unsigned)__double2hiint(v) << 1) > 0xffe00000u; }
+__device__ __forceinline__ bool is_nan_fast(float v) { return (__float_as_uint(v) << 1) > 0xff000000u; }
+
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 __device__ __forceinline__ double shfl_down_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 

@@ -27,7 +27,7 @@ template <typename T, int NIN>
 __device__ __forceinline__ bool any_nan(const T (&a)[NIN]) {
   bool r = false;
 #pragma unroll
-  for (int k = 0; k < NIN; ++k) r |= (a[k] != a[k]);
+  for (int k = 0; k < NIN; ++k) r |= is_nan_fast(a[k]);
   return r;
 }
 
@@ -66,7 +66,7 @@ k_map(Operands<T, NIN> ops, T* __restrict__ out, size_t n, F f, uint32_t* __rest
 #pragma unroll
             for (int k = 0; k < NIN; ++k) a[k] = (ops.p[k] != nullptr) ? x[k][u].v[e] : ops.s[k];
             const T y = call_f(f, a);
-            if constexpr (FLAG) bad |= (y != y) && !any_nan(a);
+            if constexpr (FLAG) bad |= is_nan_fast(y) && !any_nan(a);
             r.v[e] = y;
           }
           st_stream(reinterpret_cast<P*>(out) + j, r);
@@ -80,7 +80,7 @@ k_map(Operands<T, NIN> ops, T* __restrict__ out, size_t n, F f, uint32_t* __rest
 #pragma unroll
     for (int k = 0; k < NIN; ++k) a[k] = (ops.p[k] != nullptr) ? ops.p[k][i] : ops.s[k];
     const T y = call_f(f, a);
-    if constexpr (FLAG) bad |= (y != y) && !any_nan(a);
+    if constexpr (FLAG) bad |= is_nan_fast(y) && !any_nan(a);
     out[i] = y;
   }
   if constexpr (FLAG) {

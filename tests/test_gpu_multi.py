@@ -1,0 +1,75 @@
+"""Multi-GPU path (needs >= 2 GPUs; skipped otherwise): one process per GPU, particle index sharded, only
+reduction partials cross NVLink (NCCL inside libmcm_b200.so).  Results must equal the single-process oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, N, M, ret):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import mcm_b200 as mcm
+    from mcm_b200 import chains
+    mcm.sharded.init_distributed(rank, world, rank)
+    # elementwise + fused chain are rank-local; statistics are merged across ranks
+    a = mcm.sharded.systematic_normal_shard(N, np.pi, 0.1)
+    y, st = mcm.fused(chains.chain10)(a, stats=True)
+    g = mcm.sharded.allmerge(st)
+    gm = mcm.sharded.pmoments(y)
+    # sharded pcov of M variables
+    rng = np.random.default_rng(5)
+    X = rng.normal(1.0, 2.0, size=(M, N)); X[2] = X[0] - 3 * X[1]
+    lo, hi = mcm.sharded.shard_range(N, rank, world)
+    v = [mcm.Particles(np.ascontiguousarray(X[j, lo:hi])) for j in range(M)]
+    Cg = mcm.sharded.pcov(v)
+    ret[rank] = {"fused": [g.n, g.mean, g.m2, g.min, g.max], "pm": [gm.n, gm.mean, gm.m2, gm.min, gm.max], "cov": Cg,
+                 "local_n": a.N}
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_statistics_and_pcov_match_oracle(orc):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    N, M = 2_000_001, 6
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, N, M, ret)) for r in range(world)]
+    for p in procs: p.start()
+    for p in procs: p.join(500)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    a = orc.systematic_normal(N, np.pi, 0.1)
+    want = orc.moments(orc.chain10(a))
+    assert sum(ret[r]["local_n"] for r in range(world)) == N
+    for r in range(world):
+        for key in ("fused", "pm"):
+            got = ret[r][key]
+            assert got[0] == N
+            assert abs(got[1] - want[1]) <= 1e-12 * abs(want[1]) and abs(got[2] - want[2]) <= 1e-11 * want[2], (r, key)
+        assert ret[r]["fused"] == ret[0]["fused"]                  # identical on every rank
+    rng = np.random.default_rng(5)
+    X = rng.normal(1.0, 2.0, size=(M, N)); X[2] = X[0] - 3 * X[1]
+    Cr = orc.cov(X)
+    for r in range(world):
+        assert np.max(np.abs(ret[r]["cov"] - Cr)) <= 1e-12 * np.max(np.abs(Cr))
+        assert np.array_equal(ret[r]["cov"], ret[0]["cov"])
