@@ -9,7 +9,7 @@
 // copy, no centred copy: the reference makes two).
 //
 // Float64 path: tcgen05 has no f64 kind, so the contraction runs on the FP64
-// tensor pipe through mma.sync.m8n8k4.f64 (DMMA), 128x128x16 CTA tiles,
+// tensor pipe through mma.sync.m16n8k16.f64 (DMMA), 128x128x16 CTA tiles,
 // upper-triangular tile set (symmetry), split-K with a fixed-order second pass
 // when there are too few tiles to fill 148 SMs.
 #include "mcm_common.cuh"
@@ -21,10 +21,16 @@ constexpr int BK = 16;       // k-slab
 constexpr int LDS = BK + 4;  // padded smem row (conflict-free 64-bit fragment loads)
 constexpr int GT = 256;      // threads: 8 warps as 4 (rows) x 2 (cols), warp tile 32 x 64
 
-__device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c[0]), "+d"(c[1])
-               : "d"(a), "d"(b));
+// FP64 tensor-pipe MMA, 16x8x16 (sm_90+ shape; one instruction = 2048 FMA).  Fragment layout
+// (lane = 4*g + t): A[v]: row g + 8*(v&1), k = t + 4*(v>>1);  B[v]: k = t + 4*v, col g;
+// C[v]: row g + 8*(v>>1), col 2*t + (v&1).
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]),
+        "d"(b[2]), "d"(b[3]));
 }
 
 // column means (Statistics.mean per column): grid (M, nsplit); CTA (j, s) sums a
@@ -88,13 +94,37 @@ __device__ __forceinline__ void tri_decode(int t, int nb, int& bi, int& bj) {
 // C_partial[tile] (+)= sum_k (x_i[k]-mu_i)(x_j[k]-mu_j) over k in this CTA's K range.
 // out: if ksplit == 1 -> scaled result straight into C (both triangles);
 //      else raw partial tile into ws[(split*ntiles + tile) * BM*BM].
+//
+// Operand staging: RAW particle values stream global -> shared with cp.async (16 B per request, no
+// registers), GSTAGES-deep ring, one __syncthreads per 16-particle slab; the column means are
+// subtracted when fragments are read from shared memory (4 + 8 means live in registers), so the
+// centred matrix never exists anywhere.  A slab that crosses the end of the K range is written
+// synchronously with the tail padded by the row mean (centred value 0).
+constexpr int GSTAGES = 4;
+
+template <typename T> struct GramSmem {
+  static constexpr int LD = BK + 4;                       // elements per padded row (conflict-free for 4- and 8-byte T)
+  static constexpr int STAGE_ELEMS = 2 * BM * LD;         // A rows then B rows
+  static constexpr size_t BYTES = (size_t)GSTAGES * STAGE_ELEMS * sizeof(T);
+};
+
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename T>
 __global__ void __launch_bounds__(GT)
 k_gram(const T* const* __restrict__ vars, const double* __restrict__ means, int M, size_t n, int nb,
        int ksplit, size_t kchunk, double scale, double* __restrict__ C, double* __restrict__ ws) {
-  extern __shared__ __align__(16) double smem_dyn[];
-  double(*sA)[BM][LDS] = reinterpret_cast<double(*)[BM][LDS]>(smem_dyn);
-  double(*sB)[BM][LDS] = reinterpret_cast<double(*)[BM][LDS]>(smem_dyn + 2 * BM * LDS);
+  using SM = GramSmem<T>;
+  constexpr int LD = SM::LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* smem = reinterpret_cast<T*>(smem_raw);
   const int tile = blockIdx.x, split = blockIdx.y;
   int bi, bj;
   tri_decode(tile, nb, bi, bj);
@@ -107,114 +137,114 @@ k_gram(const T* const* __restrict__ vars, const double* __restrict__ means, int 
   const int wr = warp >> 1, wc = warp & 1;  // warp tile origin: rows wr*32, cols wc*64
   const int g = lane >> 2, t4 = lane & 3;
 
-  // staging assignment: 128 rows x 16 k per operand = 1024 pairs; 4 pairs/thread/operand
-  // pair p = tid + 256*q : row = p / 8, kk = (p % 8) * 2
-  double accum[4][8][2];
+  // ---- loader assignment: 128 rows x 16 k per operand = 1024 pairs of elements; 4 pairs/thread/operand.
+  // pair p = tid + 256*q : row = p / 8, kk = (p % 8) * 2.  Row pointers are loop invariant.
+  const T* rowA[4];
+  const T* rowB[4];
+  double fillA[4], fillB[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int q = 0; q < 4; ++q) {
+    const int row = (tid + GT * q) >> 3;
+    const int ga = bi * BM + row, gb = bj * BM + row;
+    rowA[q] = ga < M ? vars[ga] : nullptr;
+    rowB[q] = gb < M ? vars[gb] : nullptr;
+    fillA[q] = ga < M ? means[ga] : 0.0;
+    fillB[q] = gb < M ? means[gb] : 0.0;
+  }
+  // ---- means of the rows this thread's fragments touch (rows beyond M: mean 0, data 0)
+  double muA[2][2], muB[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) accum[i][j][0] = accum[i][j][1] = 0.0;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = bi * BM + wr * 32 + i * 16 + g + 8 * h;
+      muA[i][h] = r < M ? means[r] : 0.0;
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int r = bj * BM + wc * 64 + j * 8 + g;
+    muB[j] = r < M ? means[r] : 0.0;
+  }
 
-  double ra[4][2], rb[4][2];
-  auto load_regs = [&](size_t k0) {
+  double accum[2][8][4];  // [m16 block][n8 block][fragment]
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int p = tid + GT * q;
-      const int row = p >> 3, kk = (p & 7) * 2;
-      const size_t k = k0 + kk;
-      {
-        const int gr = bi * BM + row;
-        double v0 = 0.0, v1 = 0.0;
-        if (gr < M) {
-          const T* x = vars[gr];
-          const double mu = means[gr];
-          if (k + 1 < k_end) {
-            if constexpr (sizeof(T) == 8) {
-              const double2 t = __ldg(reinterpret_cast<const double2*>(x + k));
-              v0 = t.x - mu; v1 = t.y - mu;
-            } else {
-              const float2 t = __ldg(reinterpret_cast<const float2*>(x + k));
-              v0 = (double)t.x - mu; v1 = (double)t.y - mu;
-            }
-          } else if (k < k_end) {
-            v0 = (double)x[k] - mu;
-          }
-        }
-        ra[q][0] = v0; ra[q][1] = v1;
-      }
-      if (!diag) {
-        const int gr = bj * BM + row;
-        double v0 = 0.0, v1 = 0.0;
-        if (gr < M) {
-          const T* x = vars[gr];
-          const double mu = means[gr];
-          if (k + 1 < k_end) {
-            if constexpr (sizeof(T) == 8) {
-              const double2 t = __ldg(reinterpret_cast<const double2*>(x + k));
-              v0 = t.x - mu; v1 = t.y - mu;
-            } else {
-              const float2 t = __ldg(reinterpret_cast<const float2*>(x + k));
-              v0 = (double)t.x - mu; v1 = (double)t.y - mu;
-            }
-          } else if (k < k_end) {
-            v0 = (double)x[k] - mu;
-          }
-        }
-        rb[q][0] = v0; rb[q][1] = v1;
-      }
-    }
-  };
-  auto store_smem = [&](int buf) {
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int p = tid + GT * q;
-      const int row = p >> 3, kk = (p & 7) * 2;
-      sA[buf][row][kk] = ra[q][0];
-      sA[buf][row][kk + 1] = ra[q][1];
-      if (!diag) {
-        sB[buf][row][kk] = rb[q][0];
-        sB[buf][row][kk + 1] = rb[q][1];
-      }
-    }
-  };
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) accum[i][j][e] = 0.0;
 
   const size_t nk = (k_end > k_begin) ? (k_end - k_begin + BK - 1) / BK : 0;
-  if (nk > 0) {
-    load_regs(k_begin);
-    store_smem(0);
-  }
-  __syncthreads();
-  for (size_t s = 0; s < nk; ++s) {
-    const int buf = (int)(s & 1);
-    if (s + 1 < nk) load_regs(k_begin + (s + 1) * BK);
-    const double(*A)[LDS] = sA[buf];
-    const double(*B)[LDS] = diag ? sA[buf] : sB[buf];
-#pragma unroll
-    for (int k4 = 0; k4 < BK; k4 += 4) {
-      double af[4], bf[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) af[i] = A[wr * 32 + i * 8 + g][k4 + t4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bf[j] = B[wc * 64 + j * 8 + g][k4 + t4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dmma884(accum[i][j], af[i], bf[j]);
-    }
-    if (s + 1 < nk) store_smem(buf ^ 1);
-    __syncthreads();
-  }
 
-  // epilogue: accumulator (i,j): row = wr*32 + i*8 + g, cols = wc*64 + j*8 + t4*2 + {0,1}
+  auto issue = [&](size_t slab) {
+    T* st = smem + (size_t)(slab % GSTAGES) * SM::STAGE_ELEMS;
+    const size_t k0 = k_begin + slab * BK;
+    const bool full = (k0 + BK <= k_end);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = tid + GT * q;
+      const int row = p >> 3, kk = (p & 7) * 2;
+      T* dA = st + row * LD + kk;
+      T* dB = st + (BM + row) * LD + kk;
+      if (full) {
+        if (rowA[q]) { if constexpr (sizeof(T) == 8) cp_async16(dA, rowA[q] + k0 + kk); else cp_async8(dA, rowA[q] + k0 + kk); }
+        else { dA[0] = T(0); dA[1] = T(0); }
+        if (!diag) {
+          if (rowB[q]) { if constexpr (sizeof(T) == 8) cp_async16(dB, rowB[q] + k0 + kk); else cp_async8(dB, rowB[q] + k0 + kk); }
+          else { dB[0] = T(0); dB[1] = T(0); }
+        }
+      } else {  // tail slab: synchronous, padded with the row mean so the centred value is exactly 0
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const size_t k = k0 + kk + e;
+          dA[e] = (rowA[q] && k < k_end) ? rowA[q][k] : (T)fillA[q];
+          if (!diag) dB[e] = (rowB[q] && k < k_end) ? rowB[q][k] : (T)fillB[q];
+        }
+      }
+    }
+  };
+  // NOTE (Float32 tail): (T)fill rounds the mean to Float32, so a padded element contributes
+  // (fl32(mu) - mu)^2 ~ 1e-15 * mu^2 — far below the Float32 tolerance.
+
+#pragma unroll 1
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if ((size_t)s < nk) issue(s);
+    cp_async_commit();
+  }
+  for (size_t s = 0; s < nk; ++s) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();  // slab s landed for everyone; everyone finished reading slab s-1
+    if (s + GSTAGES - 1 < nk) issue(s + GSTAGES - 1);
+    cp_async_commit();
+    const T* A = smem + (size_t)(s % GSTAGES) * SM::STAGE_ELEMS;
+    const T* B = diag ? A : A + BM * LD;
+    double af[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int v = 0; v < 8; ++v)
+        af[i][v] = (double)A[(wr * 32 + i * 16 + g + 8 * (v & 1)) * LD + t4 + 4 * (v >> 1)] - muA[i][v & 1];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      double bf[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bf[v] = (double)B[(wc * 64 + j * 8 + g) * LD + t4 + 4 * v] - muB[j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) dmma16816(accum[i][j], af[i], bf);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: fragment e of block (i,j): row = wr*32 + i*16 + g + 8*(e>>1), col = wc*64 + j*8 + 2*t4 + (e&1)
   if (ksplit == 1) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int r = bi * BM + wr * 32 + i * 8 + g;
-          const int c = bj * BM + wc * 64 + j * 8 + t4 * 2 + e;
+        for (int e = 0; e < 4; ++e) {
+          const int r = bi * BM + wr * 32 + i * 16 + g + 8 * (e >> 1);
+          const int c = bj * BM + wc * 64 + j * 8 + t4 * 2 + (e & 1);
           if (r < M && c < M) {
             const double v = accum[i][j][e] * scale;
             C[(size_t)r * M + c] = v;
@@ -224,13 +254,15 @@ k_gram(const T* const* __restrict__ vars, const double* __restrict__ means, int 
   } else {
     double* w = ws + ((size_t)split * gridDim.x + tile) * (size_t)(BM * BM);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = wr * 32 + i * 8 + g;
-        const int c = wc * 64 + j * 8 + t4 * 2;
-        *reinterpret_cast<double2*>(w + r * BM + c) = make_double2(accum[i][j][0], accum[i][j][1]);
-      }
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int r = wr * 32 + i * 16 + g + 8 * h;
+          const int c = wc * 64 + j * 8 + t4 * 2;
+          *reinterpret_cast<double2*>(w + r * BM + c) = make_double2(accum[i][j][2 * h], accum[i][j][2 * h + 1]);
+        }
   }
 }
 
@@ -291,7 +323,7 @@ static int gram_impl(const void* const* vars_host, int M, size_t n, double scale
   if (ksplit > 1)
     MCM_CUDA(cudaMallocAsync((void**)&ws, (size_t)ksplit * ntiles * BM * BM * sizeof(double), c.stream));
   dim3 grid(ntiles, ksplit);
-  constexpr size_t kSmem = 4 * BM * LDS * sizeof(double);  // 80 KiB: A and B, double buffered
+  constexpr size_t kSmem = GramSmem<T>::BYTES;  // 4 stages x (A + B) x 128 rows x 20 elements
   static bool attr_set = false;
   if (!attr_set) {
     MCM_CUDA(cudaFuncSetAttribute(k_gram<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
