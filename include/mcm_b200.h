@@ -257,6 +257,9 @@ int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* sorted_out_
 /* pquantile(p, q) = Statistics.quantile(p.particles, q) type-7 (particles.jl:321);
  * q_host: nq probabilities in [0,1]; out_host: nq values.  pmedian == q=0.5. */
 int mcm_quantile(int dtype, const void* in, size_t n, const double* q_host, int nq, double* out_host);
+/* A/B switch: 1 (default) = MSD radix select (one 8 B/key read per pass), 0 = full sort + index.
+ * Both return the exact order statistics. */
+int mcm_quantile_use_select(int on);
 
 /* ======================= sampling / resampling ============================= */
 /* quantile(Normal(0,1), p) elementwise on device */

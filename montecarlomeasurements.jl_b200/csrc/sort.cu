@@ -11,7 +11,9 @@
 // by a per-digit prefix over the 8 warps of the CTA.
 #include <math.h>
 #include <string.h>
+#include <vector>
 #include "mcm_common.cuh"
+#include "mcm_keys.cuh"
 
 namespace mcm {
 
@@ -21,28 +23,6 @@ constexpr int ST = 256;          // threads per CTA (== NBINS, one thread per di
 constexpr int IPT = 16;          // keys per thread
 constexpr int TILE = ST * IPT;   // keys per CTA
 constexpr int SEG = 32 * IPT;    // keys per warp segment
-
-// ---- order-preserving key transforms ----------------------------------------
-__device__ __forceinline__ uint64_t to_key(double x, bool& nan) {
-  if (x != x) { nan = true; return ~0ull; }
-  const uint64_t u = (uint64_t)__double_as_longlong(x);
-  return u ^ ((u >> 63) ? ~0ull : 0x8000000000000000ull);
-}
-__device__ __forceinline__ uint32_t to_key(float x, bool& nan) {
-  if (x != x) { nan = true; return ~0u; }
-  const uint32_t u = __float_as_uint(x);
-  return u ^ ((u >> 31) ? ~0u : 0x80000000u);
-}
-__device__ __forceinline__ double from_key(uint64_t k) {
-  if (k == ~0ull) return __longlong_as_double(0x7ff8000000000000ll);
-  const uint64_t u = k ^ ((k >> 63) ? 0x8000000000000000ull : ~0ull);
-  return __longlong_as_double((long long)u);
-}
-__device__ __forceinline__ float from_key(uint32_t k) {
-  if (k == ~0u) return __uint_as_float(0x7fc00000u);
-  const uint32_t u = k ^ ((k >> 31) ? 0x80000000u : ~0u);
-  return __uint_as_float(u);
-}
 
 template <typename T, typename K>
 __global__ void __launch_bounds__(256) k_to_keys(const T* __restrict__ in, K* __restrict__ keys, size_t n, uint32_t* flags) {
@@ -328,6 +308,46 @@ extern "C" int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* 
   return fail(MCM_ERR_INVALID, "mcm_sortperm: bad dtype %d", dtype);
 }
 
+static int g_use_select = 1;
+extern "C" int mcm_quantile_use_select(int on) { g_use_select = on; return MCM_OK; }
+
+namespace mcm {
+template <typename T>
+int order_statistics(const T* in, size_t n, const unsigned long long* ranks, int nr, double* vals_host, int* has_nan);
+}
+
+// order statistics through a full sort (A/B reference for the select path)
+static int order_statistics_sort(int dtype, const void* in, size_t n, const unsigned long long* ranks, int nr,
+                                 double* vals, int* has_nan) {
+  Ctx& c = ctx();
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  void* sorted = nullptr;
+  MCM_CUDA(cudaMallocAsync(&sorted, n * esz, c.stream));
+  int rc = mcm_sort(dtype, in, sorted, n);
+  if (rc) return rc;
+  const int cnt = nr + 1;
+  uint64_t* h_idx = static_cast<uint64_t*>(c.h_pinned);
+  for (int i = 0; i < nr; ++i) h_idx[i] = ranks[i];
+  h_idx[nr] = n - 1;
+  uint64_t* d_idx = nullptr;
+  double* d_val = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_idx, cnt * sizeof(uint64_t), c.stream));
+  MCM_CUDA(cudaMallocAsync((void**)&d_val, cnt * sizeof(double), c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_idx, h_idx, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+  if (dtype == MCM_F64) k_pick<double><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const double*)sorted, d_idx, cnt, d_val);
+  else k_pick<float><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const float*)sorted, d_idx, cnt, d_val);
+  MCM_CHECK_LAUNCH();
+  std::vector<double> v(cnt);
+  rc = read_back(v.data(), d_val, cnt);
+  MCM_CUDA(cudaFreeAsync(d_idx, c.stream));
+  MCM_CUDA(cudaFreeAsync(d_val, c.stream));
+  MCM_CUDA(cudaFreeAsync(sorted, c.stream));
+  if (rc) return rc;
+  for (int i = 0; i < nr; ++i) vals[i] = v[i];
+  *has_nan = v[nr] != v[nr];
+  return MCM_OK;
+}
+
 // Statistics.quantile(v, p) with the default alpha = beta = 1 (type 7):
 //   aleph = n*p + (1-p); j = clamp(trunc(aleph), 1, n-1); g = clamp(aleph-j, 0, 1)
 //   a = v[j], b = v[j+1] (1-based, sorted);  a + g*(b-a)  (or (1-g)a + g b if not finite)
@@ -339,17 +359,9 @@ extern "C" int mcm_quantile(int dtype, const void* in, size_t n, const double* q
   for (int i = 0; i < nq; ++i)
     if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
       return fail(MCM_ERR_INVALID, "mcm_quantile: input probability out of [0,1] range");
-  Ctx& c = ctx();
-  const size_t esz = dtype == MCM_F64 ? 8 : 4;
   if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile: bad dtype %d", dtype);
-  void* sorted = nullptr;
-  MCM_CUDA(cudaMallocAsync(&sorted, n * esz, c.stream));
-  int rc = mcm_sort(dtype, in, sorted, n);
-  if (rc) return rc;
-  // indices (0-based) of a and b for every q, plus the last element (NaN check)
-  const int cnt = 2 * nq + 1;
-  uint64_t* h_idx = static_cast<uint64_t*>(c.h_pinned);
-  double* gam = new double[nq];
+  std::vector<double> gam(nq), vals(2 * (size_t)nq);
+  std::vector<unsigned long long> ranks(2 * (size_t)nq);
   for (int i = 0; i < nq; ++i) {
     const double p = q_host[i];
     const double aleph = (double)n * p + (1.0 - p);
@@ -359,42 +371,41 @@ extern "C" int mcm_quantile(int dtype, const void* in, size_t n, const double* q
     double g = aleph - (double)j;
     g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
     gam[i] = g;
-    if (n == 1) { h_idx[2 * i] = 0; h_idx[2 * i + 1] = 0; }
-    else { h_idx[2 * i] = (uint64_t)(j - 1); h_idx[2 * i + 1] = (uint64_t)j; }
+    if (n == 1) { ranks[2 * i] = 0; ranks[2 * i + 1] = 0; }
+    else { ranks[2 * i] = (unsigned long long)(j - 1); ranks[2 * i + 1] = (unsigned long long)j; }
   }
-  h_idx[2 * nq] = n - 1;
-  uint64_t* d_idx = nullptr;
-  double* d_val = nullptr;
-  MCM_CUDA(cudaMallocAsync((void**)&d_idx, cnt * sizeof(uint64_t), c.stream));
-  MCM_CUDA(cudaMallocAsync((void**)&d_val, cnt * sizeof(double), c.stream));
-  MCM_CUDA(cudaMemcpyAsync(d_idx, h_idx, cnt * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
-  if (dtype == MCM_F64) k_pick<double><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const double*)sorted, d_idx, cnt, d_val);
-  else k_pick<float><<<(cnt + 127) / 128, 128, 0, c.stream>>>((const float*)sorted, d_idx, cnt, d_val);
-  MCM_CHECK_LAUNCH();
-  double* vals = new double[cnt];
-  rc = read_back(vals, d_val, cnt);
-  MCM_CUDA(cudaFreeAsync(d_idx, c.stream));
-  MCM_CUDA(cudaFreeAsync(d_val, c.stream));
-  MCM_CUDA(cudaFreeAsync(sorted, c.stream));
-  if (rc == MCM_OK) {
-    if (vals[2 * nq] != vals[2 * nq]) {
-      rc = fail(MCM_ERR_INVALID, "mcm_quantile: quantiles are undefined in presence of NaNs");
-    } else {
-      for (int i = 0; i < nq; ++i) {
-        const double g = gam[i];
-        if (dtype == MCM_F64) {
-          const double a = vals[2 * i], b = vals[2 * i + 1];
-          out_host[i] = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
-        } else {
-          const float a = (float)vals[2 * i], b = (float)vals[2 * i + 1];
-          // Float32 data, Float64 probability: (b-a) rounds in Float32, the rest promotes
-          out_host[i] = (isfinite(a) && isfinite(b)) ? (double)a + g * (double)(b - a)
-                                                     : (1.0 - g) * (double)a + g * (double)b;
-        }
-      }
+  int has_nan = 0, rc = MCM_OK;
+  const int nr = 2 * nq;
+  if (g_use_select && (reinterpret_cast<uintptr_t>(in) % (dtype == MCM_F64 ? 8 : 4)) == 0) {
+    for (int r0 = 0; r0 < nr && rc == MCM_OK; r0 += 64) {
+      const int cnt = nr - r0 < 64 ? nr - r0 : 64;
+      int hn = 0;
+      rc = (dtype == MCM_F64)
+               ? order_statistics<double>((const double*)in, n, ranks.data() + r0, cnt, vals.data() + r0, &hn)
+               : order_statistics<float>((const float*)in, n, ranks.data() + r0, cnt, vals.data() + r0, &hn);
+      has_nan |= hn;
+    }
+  } else {
+    for (int r0 = 0; r0 < nr && rc == MCM_OK; r0 += 1024) {
+      const int cnt = nr - r0 < 1024 ? nr - r0 : 1024;
+      int hn = 0;
+      rc = order_statistics_sort(dtype, in, n, ranks.data() + r0, cnt, vals.data() + r0, &hn);
+      has_nan |= hn;
     }
   }
-  delete[] gam;
-  delete[] vals;
-  return rc;
+  if (rc) return rc;
+  if (has_nan) return fail(MCM_ERR_INVALID, "mcm_quantile: quantiles are undefined in presence of NaNs");
+  for (int i = 0; i < nq; ++i) {
+    const double g = gam[i];
+    if (dtype == MCM_F64) {
+      const double a = vals[2 * i], b = vals[2 * i + 1];
+      out_host[i] = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
+    } else {
+      const float a = (float)vals[2 * i], b = (float)vals[2 * i + 1];
+      // Float32 data, Float64 probability: (b-a) rounds in Float32, the rest promotes
+      out_host[i] = (isfinite(a) && isfinite(b)) ? (double)a + g * (double)(b - a)
+                                                 : (1.0 - g) * (double)a + g * (double)b;
+    }
+  }
+  return MCM_OK;
 }

@@ -293,6 +293,27 @@ def test_ragged_sizes(mcm, orc, n):
     assert mcm.pquantile(p, 0.5) == orc.quantile(x, 0.5)[0]
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_radix_select_edge_cases(mcm, orc, dt):
+    """MSD radix select must return exact order statistics for degenerate key distributions."""
+    rng = np.random.default_rng(31)
+    q = np.array([0.0, 0.01, 0.25, 0.5, 0.75, 0.99, 1.0, 1 / 3])
+    cases = {
+        "constant": np.full(100_001, 2.5), "two values": np.repeat([1.0, -3.0], 60_000),
+        "small ints": rng.integers(0, 50, 300_000).astype(np.float64),
+        "wide range": np.exp(rng.uniform(-80, 80, 200_000)) * rng.choice([-1.0, 1.0], 200_000),
+        "with inf": np.concatenate([rng.normal(size=5000), [np.inf, -np.inf, np.inf]]),
+        "signed zeros": np.concatenate([np.zeros(3000), -np.zeros(3001)]),
+        "n=1": np.array([4.0]), "n=2": np.array([4.0, -1.0]), "n=4097": rng.normal(size=4097),
+        "heavy ties": np.round(rng.normal(size=500_000), 1),
+    }
+    for name, x in cases.items():
+        x = x.astype(dt)
+        got = mcm.pquantile(mcm.Particles(x), q)
+        want = orc.quantile(x, q)
+        assert np.array_equal(got, want) or (np.isnan(got) == np.isnan(want)).all() and np.array_equal(np.nan_to_num(got), np.nan_to_num(want)), name
+
+
 def test_empty_and_unaligned_views(mcm):
     L = mcm._lib
     e = mcm.Particles(np.zeros(0))
@@ -322,6 +343,11 @@ def test_sort_sortperm_quantile_bit_exact(mcm, orc, dt):
     assert np.array_equal(mcm.psortperm(p).to_numpy(), orc.sortperm(x))    # stable, 0-based
     q = np.array([0.0, 0.025, 0.25, 0.5, 0.975, 1.0, 1 / 3, 0.9999])
     assert np.array_equal(mcm.pquantile(p, q), orc.quantile(x, q))         # bit-exact given exact order statistics
+    mcm._lib.lib().mcm_quantile_use_select(0)                              # full-sort path gives the same bits
+    try:
+        assert np.array_equal(mcm.pquantile(p, q), orc.quantile(x, q))
+    finally:
+        mcm._lib.lib().mcm_quantile_use_select(1)
     assert mcm.pquantile(p, 0.5) == orc.quantile(x, 0.5)[0]
     even = mcm.Particles(x[:-1])
     s = orc.sort(x[:-1]).astype(np.float64)
