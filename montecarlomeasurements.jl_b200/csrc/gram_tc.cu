@@ -1,0 +1,393 @@
+// gram_tc.cu — pcov on the 5th-generation tensor cores (tcgen05 + TMEM) for Float64 particles.
+//
+// tcgen05 has no f64 kind, so the Float64 Gram is computed by an Ozaki-style error-free
+// splitting onto the int8 tensor path, which accumulates EXACTLY in int32:
+//   1. every centred row (variable) x_i - mu_i is scaled by a power of two 2^-(e_i+1) to |y| <= 1/2
+//      and split into S = 7 signed 7-bit digits  y = sum_s d_s 2^(-7(s+1)),  |d_s| <= 64
+//      (k_rowmax, k_slice; all steps exact in Float64; 49 bits are kept);
+//   2. sum_k y_i y_j = sum_{s,t} 2^(-7(s+t+2)) D_s^i . D_t^j  with exact integer dot products.
+//      Pairs with s+t = d share the weight, so they accumulate into ONE int32 TMEM accumulator
+//      per diagonal d = 0..6 (tcgen05.mma kind::i8, M = 128, N = 64, K = 32 per instruction);
+//      pairs with s + t > 6 fall below 2^-56 relative to |y_i||y_j| and are dropped;
+//   3. every 65536 particles (int32 headroom: 7 pairs x 64 x 64 x 65536 < 2^31) the accumulators are
+//      read back with tcgen05.ld, weighted in Float64 and added to Float64 registers.
+// Centring happens before the split, so the result is the same centred Gram the DMMA kernel
+// (gram.cu) computes, to ~1e-14 relative to sigma_i sigma_j N (tests compare the two).
+//
+// Kernel organisation (one CTA per 128 x 64 output tile, 256 threads, 1 CTA/SM):
+//   all threads : cp.async the 7+7 digit tiles of the next k-block into a 4-stage shared-memory ring
+//                 (canonical K-major no-swizzle UMMA layout: 8-row x 16-byte core matrices)
+//   thread 0    : issues the 28 tcgen05.mma of a k-block, tcgen05.commit -> mbarrier frees the stage
+//   all threads : flush / epilogue through tcgen05.ld (warp w owns TMEM lanes 32*(w%4)..+31)
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "mcm_common.cuh"
+
+namespace mcm {
+
+constexpr int OZ_S = 7;              // digits per value
+constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 32;   // tile rows, tile cols, k per block (== UMMA K for i8)
+constexpr int OZ_STAGES = 4;
+constexpr int OZ_THREADS = 256;
+constexpr int OZ_A_SLICE = OZ_TM * OZ_KB;            // 4096 B
+constexpr int OZ_B_SLICE = OZ_TN * OZ_KB;            // 2048 B
+constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);  // 43008 B
+constexpr int OZ_CHUNK_KB = 65536 / OZ_KB;           // k-blocks between flushes
+constexpr int OZ_TMEM_COLS = 512;
+
+// ---- operand preparation ------------------------------------------------------------------
+// e[i] = exponent with max_k |x_i[k] - mu_i| < 2^e[i]  (e = INT_MIN/2 marks an all-zero row)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_rowmax(const T* const* __restrict__ vars, const double* __restrict__ means, size_t n, int* __restrict__ ex) {
+  const T* x = vars[blockIdx.x];
+  const double mu = means[blockIdx.x];
+  double m = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += 256) m = fmax(m, fabs((double)x[i] - mu));
+  __shared__ double sh[8];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmax(m, sh[w]);
+    int e = 0;
+    if (m > 0.0 && m < 1.7e308) { frexp(m, &e); } else e = (m > 0.0) ? 2000 : -2000;  // Inf/NaN rows: huge e -> zeros
+    ex[blockIdx.x] = e;
+  }
+}
+
+// digits in TILE-READY order: slices[s][kb][rg][c][r8][16] (kb = k / 32, rg = row / 8, c = (k % 32) / 16,
+// r8 = row % 8): the 8-row x 16-byte core matrices of the canonical K-major no-swizzle UMMA layout are
+// contiguous, so the 128 (or 64) rows of one k-block of one digit plane are ONE contiguous 4096 (2048) byte
+// run that a single cp.async.bulk drops into shared memory already in MMA layout.
+// One thread = 16 consecutive k of one row (reads 128 contiguous bytes of Float64, writes 16 bytes per digit).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, const int* __restrict__ ex, int M,
+        size_t n, size_t kpad, size_t mpad, int8_t* __restrict__ slices) {
+  const size_t chunks_per_row = kpad / 16;
+  const size_t total = (size_t)M * chunks_per_row;
+  const size_t stride = (size_t)gridDim.x * 256;
+  const size_t nkb = kpad / OZ_KB, nrg = mpad / 8;
+  for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < total; w += stride) {
+    const size_t row = w / chunks_per_row, ch = w % chunks_per_row;
+    const T* x = vars[row];
+    const double mu = means[row];
+    const int e = ex[row];
+    const double sc = (e > -1500 && e < 1500) ? scalbn(1.0, -(e + 1) + 7) : 0.0;  // y * 2^7
+    alignas(16) int8_t dg[OZ_S][16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const size_t k = ch * 16 + j;
+      double v = (k < n) ? ((double)x[k] - mu) * sc : 0.0;   // |v| <= 64, exact
+#pragma unroll
+      for (int s = 0; s < OZ_S; ++s) {
+        const double d = rint(v);
+        dg[s][j] = (int8_t)(int)d;
+        v = (v - d) * 128.0;                                    // exact
+      }
+    }
+    const size_t kb = ch >> 1, c = ch & 1;
+    const size_t off = ((kb * nrg + (row >> 3)) * 2 + c) * 128 + (row & 7) * 16;
+#pragma unroll
+    for (int s = 0; s < OZ_S; ++s)
+      *reinterpret_cast<int4*>(slices + (size_t)s * (mpad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
+  }
+}
+
+// ---- tcgen05 helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices; LBO = byte distance between the two
+// core matrices along K, SBO = byte distance between consecutive 8-row groups.  version = 1 (sm_100).
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// instruction descriptor, kind::i8: D = s32, A = B = signed int8, both K-major, M x N
+__device__ __forceinline__ uint32_t umma_idesc_i8(int Mt, int Nt) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nt >> 3) << 17) | ((uint32_t)(Mt >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_init_tc(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait_tc(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE_%=;\n"
+      "bra TC_WAIT_%=;\n"
+      "TC_DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void cp_async16_tc(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// tile t -> (bi over 128-row blocks, bj over 64-col blocks) with bj >= 2*bi (upper part incl. the diagonal)
+__device__ __forceinline__ void oz_tile_decode(int t, int mb, int nbk, int& bi, int& bj) {
+  int i = 0, rem = t;
+  while (rem >= nbk - 2 * i) { rem -= nbk - 2 * i; ++i; }
+  bi = i; bj = 2 * i + rem;
+}
+
+__device__ __forceinline__ void mbar_expect_tx_tc(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_tc(uint32_t dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// Warp-specialised: warp 0 lane 0 = TMA producer (14 bulk copies per k-block), warp 1 lane 0 = MMA issuer
+// (28 tcgen05.mma per k-block), all 8 warps = TMEM flush + epilogue.  K range [kb_begin, kb_end) of this CTA
+// (split-K when there are fewer tiles than SMs); `out` is C (ksplit == 1) or the split workspace.
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, size_t mpad, size_t kpad,
+          int ksplit, int kb_per_split, double scale, double* __restrict__ C, double* __restrict__ ws) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar_full[OZ_STAGES];
+  __shared__ __align__(8) unsigned long long bar_free[OZ_STAGES];
+  __shared__ __align__(8) unsigned long long bar_acc;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int mb = (int)(mpad / OZ_TM), nbk = (int)(mpad / OZ_TN);
+  int bi, bj;
+  oz_tile_decode(blockIdx.x, mb, nbk, bi, bj);
+  const size_t plane = mpad * kpad;                 // bytes per digit plane
+  const size_t nrg = mpad / 8;
+  const int nkb_total = (int)(kpad / OZ_KB);
+  const int kb_begin = blockIdx.y * kb_per_split;
+  const int kb_end = min(nkb_total, kb_begin + kb_per_split);
+  const int nkb = max(0, kb_end - kb_begin);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_sh)), "r"(OZ_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < OZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 1); }
+    mbar_init_tc(&bar_acc, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+  const uint32_t idesc = umma_idesc_i8(OZ_TM, OZ_TN);
+  const uint32_t smem0 = smem_addr(smem);
+
+  double facc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) facc[j] = 0.0;
+
+  int chunk = 0;
+  for (int c0 = 0; c0 < nkb; c0 += OZ_CHUNK_KB, ++chunk) {
+    const int c1 = min(nkb, c0 + OZ_CHUNK_KB);
+    if (warp == 0 && lane == 0) {
+      // ---- producer: digit planes of k-block kb -> stage (it % STAGES); `it` counts k-blocks of this CTA
+      for (int it = c0; it < c1; ++it) {
+        const int st = it % OZ_STAGES;
+        if (it >= OZ_STAGES) mbar_wait_tc(&bar_free[st], (unsigned)((it / OZ_STAGES - 1) & 1));
+        mbar_expect_tx_tc(&bar_full[st], OZ_STAGE_BYTES);
+        const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
+        const size_t kb = (size_t)(kb_begin + it);
+        const int8_t* srcA = slices + (kb * nrg + (size_t)bi * (OZ_TM / 8)) * 256;
+        const int8_t* srcB = slices + (kb * nrg + (size_t)bj * (OZ_TN / 8)) * 256;
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) {
+          bulk_g2s_tc(sbase + s * OZ_A_SLICE, srcA + (size_t)s * plane, OZ_A_SLICE, &bar_full[st]);
+          bulk_g2s_tc(sbase + OZ_S * OZ_A_SLICE + s * OZ_B_SLICE, srcB + (size_t)s * plane, OZ_B_SLICE, &bar_full[st]);
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer
+      for (int it = c0; it < c1; ++it) {
+        const int st = it % OZ_STAGES;
+        mbar_wait_tc(&bar_full[st], (unsigned)((it / OZ_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
+        const uint64_t dA0 = umma_desc_kmajor(sbase, 128, 256);
+        const uint64_t dB0 = umma_desc_kmajor(sbase + OZ_S * OZ_A_SLICE, 128, 256);
+        uint32_t started = (it == c0) ? 0u : 0x7fu;
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) {
+#pragma unroll
+          for (int t = 0; t < OZ_S; ++t) {
+            if (s + t < OZ_S) {
+              const int d = s + t;
+              umma_i8(tmem_base + (uint32_t)d * OZ_TN, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4),
+                      dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc, (started >> d) & 1u);
+              started |= 1u << d;
+            }
+          }
+        }
+        umma_commit(&bar_free[st]);                 // stage reusable once these MMAs have read it
+        if (it == c1 - 1) umma_commit(&bar_acc);    // chunk accumulated
+      }
+    }
+    __syncwarp();
+    // ---- flush: int32 accumulators -> Float64 registers (all warps)
+    mbar_wait_tc(&bar_acc, (unsigned)(chunk & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int d = 0; d < OZ_S; ++d) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(d * OZ_TN + (warp >> 2) * 32);
+      tmem_ld32(taddr, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const double w = scalbn(1.0, -7 * (d + 2));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) facc[j] = fma((double)(int)v[j], w, facc[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();  // TMEM drained before the next chunk overwrites it
+  }
+
+  // ---- epilogue: TMEM lane = tile row, 32 columns per thread
+  {
+    const int r = bi * OZ_TM + (warp & 3) * 32 + lane;
+    const int cbase = bj * OZ_TN + (warp >> 2) * 32;
+    if (ksplit == 1) {
+      if (r < M) {
+        const int er = ex[r];
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const int c = cbase + j;
+          if (c < M) {
+            const int ec = ex[c];
+            double v = 0.0;
+            if (er > -1500 && er < 1500 && ec > -1500 && ec < 1500) v = scalbn(facc[j], er + ec + 2) * scale;
+            C[(size_t)r * M + c] = v;
+            C[(size_t)c * M + r] = v;
+          }
+        }
+      }
+    } else {
+      // raw partial sums (still in scaled units) for the fixed-order split-K reduction
+      double* w = ws + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (size_t)(OZ_TM * OZ_TN) +
+                  (size_t)((warp & 3) * 32 + lane) * OZ_TN + (warp >> 2) * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(w + j) = make_double2(facc[j], facc[j + 1]);
+    }
+  }
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(OZ_TMEM_COLS));
+}
+
+__global__ void __launch_bounds__(256)
+k_gram_i8_reduce(const double* __restrict__ ws, const int* __restrict__ ex, int M, int mb, int nbk, int ntiles,
+                 int ksplit, double scale, double* __restrict__ C) {
+  int bi, bj;
+  oz_tile_decode(blockIdx.x, mb, nbk, bi, bj);
+  for (int e = threadIdx.x; e < OZ_TM * OZ_TN; e += 256) {
+    double sum = 0.0;
+    for (int sp = 0; sp < ksplit; ++sp) sum += ws[((size_t)sp * ntiles + blockIdx.x) * (size_t)(OZ_TM * OZ_TN) + e];
+    const int r = bi * OZ_TM + e / OZ_TN, c = bj * OZ_TN + e % OZ_TN;
+    if (r < M && c < M) {
+      const int er = ex[r], ec = ex[c];
+      double v = 0.0;
+      if (er > -1500 && er < 1500 && ec > -1500 && ec < 1500) v = scalbn(sum, er + ec + 2) * scale;
+      C[(size_t)r * M + c] = v;
+      C[(size_t)c * M + r] = v;
+    }
+  }
+}
+
+template <typename T>
+int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C) {
+  Ctx& c = ctx();
+  const size_t mpad = ((size_t)M + OZ_TM - 1) / OZ_TM * OZ_TM;
+  const size_t kpad = (n + OZ_KB - 1) / OZ_KB * OZ_KB;
+  int8_t* slices = nullptr;
+  int* ex = nullptr;
+  const size_t sbytes = (size_t)OZ_S * mpad * kpad;
+  MCM_CUDA(cudaMallocAsync((void**)&slices, sbytes, c.stream));
+  MCM_CUDA(cudaMallocAsync((void**)&ex, mpad * sizeof(int), c.stream));
+  if (mpad > (size_t)M) {
+    // padded rows interleave with real rows in the tile-ready layout: clear everything first
+    MCM_CUDA(cudaMemsetAsync(slices, 0, sbytes, c.stream));
+    MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
+  }
+  k_rowmax<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex);
+  MCM_CHECK_LAUNCH();
+  {
+    const size_t total = (size_t)M * (kpad / 16);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)c.sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_slice<T><<<(unsigned)blocks, 256, 0, c.stream>>>(d_vars, d_means, ex, M, n, kpad, mpad, slices);
+    MCM_CHECK_LAUNCH();
+  }
+  const int mb = (int)(mpad / OZ_TM), nbk = (int)(mpad / OZ_TN);
+  int ntiles = 0;
+  for (int i = 0; i < mb; ++i) ntiles += nbk - 2 * i;
+  constexpr size_t kSmem = (size_t)OZ_STAGES * OZ_STAGE_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    MCM_CUDA(cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    attr = true;
+  }
+  // split-K when the tiles alone cannot fill the GPU
+  const int nkb_total = (int)(kpad / OZ_KB);
+  int ksplit = 1;
+  if (ntiles < c.sm_count) {
+    ksplit = (2 * c.sm_count + ntiles - 1) / ntiles;
+    const int max_split = std::max(1, nkb_total / 256);   // keep >= 8192 particles per split
+    if (ksplit > max_split) ksplit = max_split;
+  }
+  int kb_per_split = (nkb_total + ksplit - 1) / ksplit;
+  ksplit = (nkb_total + kb_per_split - 1) / kb_per_split;
+  double* ws = nullptr;
+  if (ksplit > 1) MCM_CUDA(cudaMallocAsync((void**)&ws, (size_t)ksplit * ntiles * OZ_TM * OZ_TN * sizeof(double), c.stream));
+  k_gram_i8<<<dim3(ntiles, ksplit), OZ_THREADS, kSmem, c.stream>>>(slices, ex, M, mpad, kpad, ksplit, kb_per_split, scale, C, ws);
+  MCM_CHECK_LAUNCH();
+  if (ksplit > 1) {
+    k_gram_i8_reduce<<<ntiles, 256, 0, c.stream>>>(ws, ex, M, mb, nbk, ntiles, ksplit, scale, C);
+    MCM_CHECK_LAUNCH();
+    MCM_CUDA(cudaFreeAsync(ws, c.stream));
+  }
+  MCM_CUDA(cudaFreeAsync(slices, c.stream));
+  MCM_CUDA(cudaFreeAsync(ex, c.stream));
+  return MCM_OK;
+}
+
+template int gram_tensor_impl<double>(const double* const*, const double*, int, size_t, double, double*);
+template int gram_tensor_impl<float>(const float* const*, const double*, int, size_t, double, double*);
+
+}  // namespace mcm
