@@ -247,10 +247,13 @@ int mcm_moments_merge(const double* a, const double* b, double* out);
  * means; else M doubles to centre on (global means in the sharded case).      */
 int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale,
              const double* center_host, double* cov_out_dev, double* means_out_dev);
-/* Gram engine for large problems (M >= 256, N >= 4096): 0 = FP64 tensor pipe (DMMA), 1 = tcgen05/TMEM
- * int8 tensor cores with an Ozaki error-free split of the centred Float64 data (exact int32
- * accumulation, 49 bits kept).  Both meet the 1e-12 tolerance; small problems always use DMMA. */
+/* Gram engine for large problems (M >= 256, N >= 4096): 1 (default) = tcgen05/TMEM int8 tensor cores
+ * with an Ozaki error-free split of the centred Float64 data (exact int32 accumulation, 48 bits kept;
+ * rows with max/sigma > 10 make it decline and the FP64 kernel runs instead), 0 = always the FP64
+ * tensor pipe (DMMA).  Both meet the 1e-12 tolerance; small problems always use DMMA.
+ * mcm_gram_last_engine: 0 = DMMA, 1 = tcgen05 for the most recent mcm_gram call. */
 int mcm_gram_use_tensor(int on);
+int mcm_gram_last_engine(void);
 /* column means of M variables into means_out_host[M] */
 int mcm_colmeans(int dtype, const void* const* vars, int M, size_t n, double* means_out_host);
 

@@ -290,7 +290,8 @@ int read_back(double* host_dst, const double* dev_src, size_t count);
 // tcgen05 / TMEM path (gram_tc.cu)
 template <typename T>
 int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C);
-static int g_use_tensor = 0;  // mcm_gram_use_tensor: 0 = FP64 DMMA kernel, 1 = Ozaki int8 on tcgen05 for large problems
+static int g_use_tensor = 1;  // mcm_gram_use_tensor: 0 = FP64 DMMA kernel only, 1 = Ozaki int8 on tcgen05 for large problems
+static int g_last_engine = 0; // 0 = DMMA, 1 = tcgen05
 
 template <typename T>
 static int gram_impl(const void* const* vars_host, int M, size_t n, double scale, const double* center_host,
@@ -311,11 +312,15 @@ static int gram_impl(const void* const* vars_host, int M, size_t n, double scale
   if (means_out_dev)
     MCM_CUDA(cudaMemcpyAsync(means_out_dev, d_means, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 
+  g_last_engine = 0;
   if (g_use_tensor && M >= 256 && n >= 4096) {
     int rc = gram_tensor_impl<T>(d_vars, d_means, M, n, scale, cov_out_dev);
-    MCM_CUDA(cudaFreeAsync(d_vars, c.stream));
-    MCM_CUDA(cudaFreeAsync(d_means, c.stream));
-    return rc;
+    if (rc >= 0) {  // -1: declined by the accuracy guard (heavy-tailed rows) -> DMMA below
+      g_last_engine = 1;
+      MCM_CUDA(cudaFreeAsync(d_vars, c.stream));
+      MCM_CUDA(cudaFreeAsync(d_means, c.stream));
+      return rc;
+    }
   }
   const int nb = (M + BM - 1) / BM;
   const int ntiles = nb * (nb + 1) / 2;
@@ -364,6 +369,7 @@ int gram_dispatch(int dtype, const void* const* vars, int M, size_t n, double sc
 using namespace mcm;
 
 extern "C" int mcm_gram_use_tensor(int on) { g_use_tensor = on; return MCM_OK; }
+extern "C" int mcm_gram_last_engine(void) { return g_last_engine; }
 
 extern "C" int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale_mode,
                         const double* center_host, double* cov_out_dev, double* means_out_dev) {

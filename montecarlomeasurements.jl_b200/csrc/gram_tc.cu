@@ -2,15 +2,21 @@
 //
 // tcgen05 has no f64 kind, so the Float64 Gram is computed by an Ozaki-style error-free
 // splitting onto the int8 tensor path, which accumulates EXACTLY in int32:
-//   1. every centred row (variable) x_i - mu_i is scaled by a power of two 2^-(e_i+1) to |y| <= 1/2
-//      and split into S = 7 signed 7-bit digits  y = sum_s d_s 2^(-7(s+1)),  |d_s| <= 64
-//      (k_rowmax, k_slice; all steps exact in Float64; 49 bits are kept);
-//   2. sum_k y_i y_j = sum_{s,t} 2^(-7(s+t+2)) D_s^i . D_t^j  with exact integer dot products.
+//   1. every centred row (variable) x_i - mu_i is scaled by a power of two 2^-(e_i+1) to |y| < 1/2
+//      and split into S = 6 signed 8-bit digits  y = sum_s d_s 2^(-8(s+1)),  d_s in [-128, 127]
+//      (k_rowstats, k_slice; all steps exact in Float64; 48 bits are kept);
+//   2. sum_k y_i y_j = sum_{s,t} 2^(-8(s+t+2)) D_s^i . D_t^j  with exact integer dot products.
 //      Pairs with s+t = d share the weight, so they accumulate into ONE int32 TMEM accumulator
-//      per diagonal d = 0..6 (tcgen05.mma kind::i8, M = 128, N = 64, K = 32 per instruction);
-//      pairs with s + t > 6 fall below 2^-56 relative to |y_i||y_j| and are dropped;
-//   3. every 65536 particles (int32 headroom: 7 pairs x 64 x 64 x 65536 < 2^31) the accumulators are
+//      per diagonal d = 0..5 (tcgen05.mma kind::i8, M = 128, N = 64, K = 32 per instruction): 21 MMAs
+//      per k-block; pairs with s + t > 5 fall below 2^-56 relative to |y_i||y_j| and are dropped;
+//   3. every 16384 particles (int32 headroom: 6 pairs x 128 x 128 x 16384 < 2^31) the accumulators are
 //      read back with tcgen05.ld, weighted in Float64 and added to Float64 registers.
+// Error: the only inexact step is dropping digits beyond 48 bits / pairs beyond the 6th diagonal, a
+// zero-mean perturbation of at most 2^-47 max_i max_j per product (max_i = max_k |x_i - mu_i|).  Relative
+// to the sigma_i sigma_j N scale of the result the worst case is (max/sigma)^2 2^-46 and the expected
+// deviation is ~1/sqrt(N) of that.  gram_tensor_impl measures max/sigma per row and declines (the caller
+// falls back to the FP64 DMMA kernel) above 10; Gaussian-like data at N = 1e5 has max/sigma ~ 4.5
+// (measured deviation from the DMMA result 1.3e-13 of sigma_i sigma_j); heavy-tailed rows take DMMA.
 // Centring happens before the split, so the result is the same centred Gram the DMMA kernel
 // (gram.cu) computes, to ~1e-14 relative to sigma_i sigma_j N (tests compare the two).
 //
@@ -27,35 +33,54 @@
 
 namespace mcm {
 
-constexpr int OZ_S = 7;              // digits per value
+constexpr int OZ_S = 6;              // digits per value
 constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 32;   // tile rows, tile cols, k per block (== UMMA K for i8)
 constexpr int OZ_STAGES = 4;
 constexpr int OZ_THREADS = 256;
 constexpr int OZ_A_SLICE = OZ_TM * OZ_KB;            // 4096 B
 constexpr int OZ_B_SLICE = OZ_TN * OZ_KB;            // 2048 B
 constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);  // 43008 B
-constexpr int OZ_CHUNK_KB = 65536 / OZ_KB;           // k-blocks between flushes
+constexpr int OZ_CHUNK_KB = 16384 / OZ_KB;           // k-blocks between flushes
+constexpr int OZ_DBITS = 8;                          // bits per digit
+constexpr double OZ_MAX_RATIO = 10.0;                // max/sigma above which the caller must use DMMA
 constexpr int OZ_TMEM_COLS = 512;
 
 // ---- operand preparation ------------------------------------------------------------------
-// e[i] = exponent with max_k |x_i[k] - mu_i| < 2^e[i]  (e = INT_MIN/2 marks an all-zero row)
+// Per row: e[i] = exponent with max_k |x_i[k] - mu_i| * 256/255 < 2^e[i] (so that the leading 8-bit digit
+// cannot overflow), and ratio[i] = max / sigma (accuracy guard).  e = -2000 marks an all-zero row.
 template <typename T>
 __global__ void __launch_bounds__(256)
-k_rowmax(const T* const* __restrict__ vars, const double* __restrict__ means, size_t n, int* __restrict__ ex) {
+k_rowstats(const T* const* __restrict__ vars, const double* __restrict__ means, size_t n, int* __restrict__ ex,
+           double* __restrict__ ratio) {
   const T* x = vars[blockIdx.x];
   const double mu = means[blockIdx.x];
-  double m = 0.0;
-  for (size_t i = threadIdx.x; i < n; i += 256) m = fmax(m, fabs((double)x[i] - mu));
-  __shared__ double sh[8];
+  double m = 0.0, q = 0.0;
+  for (size_t i = threadIdx.x; i < n; i += 256) {
+    const double d = (double)x[i] - mu;
+    m = fmax(m, fabs(d));
+    q = fma(d, d, q);
+  }
+  __shared__ double shm[8], shq[8];
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, d));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  for (int d = 16; d >= 1; d >>= 1) {
+    m = fmax(m, __shfl_down_sync(0xffffffffu, m, d));
+    q += __shfl_down_sync(0xffffffffu, q, d);
+  }
+  if ((threadIdx.x & 31) == 0) { shm[threadIdx.x >> 5] = m; shq[threadIdx.x >> 5] = q; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) m = fmax(m, sh[w]);
-    int e = 0;
-    if (m > 0.0 && m < 1.7e308) { frexp(m, &e); } else e = (m > 0.0) ? 2000 : -2000;  // Inf/NaN rows: huge e -> zeros
+    for (int w = 1; w < 8; ++w) { m = fmax(m, shm[w]); q += shq[w]; }
+    int e = -2000;
+    double r = 0.0;
+    if (m > 0.0 && m < 1.7e308) {
+      double mant = frexp(m, &e);           // m = mant * 2^e, mant in [0.5, 1)
+      if (mant > 0.995) ++e;                // keep 256 * y below 127.5
+      r = m / sqrt(q / (double)n);
+    } else if (m > 0.0) {
+      e = 2000; r = 1e300;                  // Inf/NaN in the row: force the fallback
+    }
     ex[blockIdx.x] = e;
+    ratio[blockIdx.x] = r;
   }
 }
 
@@ -68,30 +93,40 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, const int* __restrict__ ex, int M,
         size_t n, size_t kpad, size_t mpad, int8_t* __restrict__ slices) {
-  const size_t chunks_per_row = kpad / 16;
-  const size_t total = (size_t)M * chunks_per_row;
-  const size_t stride = (size_t)gridDim.x * 256;
+  // work item w -> (kb, rg, c, r8) with r8 fastest: the 16 lanes of a half-warp write one 256-byte core block
   const size_t nkb = kpad / OZ_KB, nrg = mpad / 8;
+  const size_t total = nkb * nrg * 16;
+  const size_t stride = (size_t)gridDim.x * 256;
   for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < total; w += stride) {
-    const size_t row = w / chunks_per_row, ch = w % chunks_per_row;
-    const T* x = vars[row];
-    const double mu = means[row];
-    const int e = ex[row];
-    const double sc = (e > -1500 && e < 1500) ? scalbn(1.0, -(e + 1) + 7) : 0.0;  // y * 2^7
+    const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;     // blk = kb * nrg + rg
+    const size_t rg = blk % nrg, kb = blk / nrg;
+    const size_t row = rg * 8 + r8;
     alignas(16) int8_t dg[OZ_S][16];
+    if (row < (size_t)M) {
+      const T* x = vars[row];
+      const double mu = means[row];
+      const int e = ex[row];
+      // I = rint(y * 2^48), |I| < 2^47 (|y| < 127.4/256); balanced base-256 digits from the low end:
+      // every digit lands in [-128, 127] and the carries make sum_s d_s 256^(5-s) == I exactly.
+      const double sc = (e > -1500 && e < 1500) ? scalbn(1.0, -(e + 1) + OZ_DBITS * OZ_S) : 0.0;
+      const size_t k0 = kb * OZ_KB + c * 16;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const size_t k = ch * 16 + j;
-      double v = (k < n) ? ((double)x[k] - mu) * sc : 0.0;   // |v| <= 64, exact
+      for (int j = 0; j < 16; ++j) {
+        const size_t k = k0 + j;
+        long long I = (k < n) ? __double2ll_rn(((double)x[k] - mu) * sc) : 0ll;
 #pragma unroll
-      for (int s = 0; s < OZ_S; ++s) {
-        const double d = rint(v);
-        dg[s][j] = (int8_t)(int)d;
-        v = (v - d) * 128.0;                                    // exact
+        for (int s = OZ_S - 1; s >= 1; --s) {
+          const long long d = ((I + 128) & 255) - 128;
+          dg[s][j] = (int8_t)d;
+          I = (I - d) >> 8;
+        }
+        dg[0][j] = (int8_t)I;
       }
+    } else {
+#pragma unroll
+      for (int s = 0; s < OZ_S; ++s) *reinterpret_cast<int4*>(dg[s]) = make_int4(0, 0, 0, 0);
     }
-    const size_t kb = ch >> 1, c = ch & 1;
-    const size_t off = ((kb * nrg + (row >> 3)) * 2 + c) * 128 + (row & 7) * 16;
+    const size_t off = w * 16;   // ((kb*nrg + rg)*2 + c)*128 + r8*16
 #pragma unroll
     for (int s = 0; s < OZ_S; ++s)
       *reinterpret_cast<int4*>(slices + (size_t)s * (mpad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
@@ -244,7 +279,7 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
         const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
         const uint64_t dA0 = umma_desc_kmajor(sbase, 128, 256);
         const uint64_t dB0 = umma_desc_kmajor(sbase + OZ_S * OZ_A_SLICE, 128, 256);
-        uint32_t started = (it == c0) ? 0u : 0x7fu;
+        uint32_t started = (it == c0) ? 0u : 0xffu;
 #pragma unroll
         for (int s = 0; s < OZ_S; ++s) {
 #pragma unroll
@@ -271,7 +306,7 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
       const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(d * OZ_TN + (warp >> 2) * 32);
       tmem_ld32(taddr, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const double w = scalbn(1.0, -7 * (d + 2));
+      const double w = scalbn(1.0, -OZ_DBITS * (d + 2));
 #pragma unroll
       for (int j = 0; j < 32; ++j) facc[j] = fma((double)(int)v[j], w, facc[j]);
     }
@@ -339,15 +374,27 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   const size_t sbytes = (size_t)OZ_S * mpad * kpad;
   MCM_CUDA(cudaMallocAsync((void**)&slices, sbytes, c.stream));
   MCM_CUDA(cudaMallocAsync((void**)&ex, mpad * sizeof(int), c.stream));
-  if (mpad > (size_t)M) {
-    // padded rows interleave with real rows in the tile-ready layout: clear everything first
-    MCM_CUDA(cudaMemsetAsync(slices, 0, sbytes, c.stream));
-    MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
-  }
-  k_rowmax<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex);
+  if (mpad > (size_t)M) MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
+  double* d_ratio = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_ratio, (size_t)M * sizeof(double), c.stream));
+  k_rowstats<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex, d_ratio);
   MCM_CHECK_LAUNCH();
   {
-    const size_t total = (size_t)M * (kpad / 16);
+    // accuracy guard: (max/sigma)^2 * 2^-46 must stay below 1e-12
+    std::vector<double> h_ratio(M);
+    MCM_CUDA(cudaMemcpyAsync(h_ratio.data(), d_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    MCM_CUDA(cudaStreamSynchronize(c.stream));
+    MCM_CUDA(cudaFreeAsync(d_ratio, c.stream));
+    double worst = 0.0;
+    for (int i = 0; i < M; ++i) worst = std::max(worst, h_ratio[i]);
+    if (!(worst <= OZ_MAX_RATIO)) {
+      MCM_CUDA(cudaFreeAsync(slices, c.stream));
+      MCM_CUDA(cudaFreeAsync(ex, c.stream));
+      return -1;  // decline: heavy-tailed rows, the caller runs the DMMA kernel
+    }
+  }
+  {
+    const size_t total = (kpad / OZ_KB) * (mpad / 8) * 16;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)c.sm_count * 16;
     if (blocks > cap) blocks = cap;

@@ -27,5 +27,22 @@ def run(M, n, timing=False, offset=0.0):
 for (M, n) in [(256, 4096), (256, 5000), (300, 70001), (1024, 20000)]:
     run(M, n)
 run(512, 10000, offset=1e6)
+# heavy-tailed rows: t-distributed (ratio ~ 20-30, tensor path) and one extreme outlier (guard -> DMMA)
+import numpy as _np
+def heavy(M, n, outlier):
+    rng = _np.random.default_rng(3)
+    X = rng.standard_t(3, size=(M, n))
+    if outlier: X[7, 123] = 1e6
+    v = [mcm.Particles(_np.ascontiguousarray(X[j])) for j in range(M)]
+    ptrs = (C.c_void_p * M)(*[C.c_void_p(p.ptr) for p in v]); dC = mcm.particles._alloc(M * M * 8)
+    out = []
+    for mode in (0, 1):
+        lib.mcm_gram_use_tensor(mode)
+        L.check(lib.mcm_gram(L.F64, ptrs, M, n, 1, None, C.c_void_p(dC), None))
+        o = _np.empty((M, M)); L.check(lib.mcm_download(o.ctypes.data_as(C.c_void_p), C.c_void_p(dC), o.nbytes)); out.append((o, lib.mcm_gram_last_engine()))
+    d = _np.sqrt(_np.diag(out[0][0]))
+    ratio = _np.max(_np.abs(X - X.mean(axis=1, keepdims=True)), axis=1) / X.std(axis=1)
+    print(f"heavy-tailed M={M} N={n} outlier={outlier}: max ratio {ratio.max():.1f}  engine {out[1][1]}  dev {_np.max(_np.abs(out[0][0]-out[1][0])/_np.outer(d,d)):.3e}", flush=True)
+heavy(256, 20000, False); heavy(256, 20000, True)
 run(4096, 100_000, timing=True)
 run(1024, 1_000_000, timing=True)

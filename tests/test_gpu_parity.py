@@ -455,6 +455,39 @@ def test_pcov_pcor(mcm, orc, dt, M, n):
     assert abs(mcm.pcov(v[0]) - Cr[0, 0]) <= tol * Cr[0, 0]  # scalar pcov == variance
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_pcov_tcgen05_engine_vs_oracle_and_dmma(mcm, orc, dt):
+    """Large problems run on the tcgen05/TMEM int8 path (Ozaki split, exact int32 accumulation); it must agree
+    with the oracle and with the FP64 DMMA kernel, and must decline heavy-tailed rows."""
+    lib = mcm._lib.lib()
+    rng = np.random.default_rng(41)
+    for M, n in ((256, 4096), (300, 70001), (640, 20000)):       # second case: 5 flush chunks + row/k padding
+        X = rng.normal(3.0, 2.0, size=(M, n)).astype(dt)
+        X[2] = 2 * X[0] - X[1]
+        v = [mcm.Particles(X[j]) for j in range(M)]
+        Ct = mcm.pcov(v)
+        assert lib.mcm_gram_last_engine() == 1
+        lib.mcm_gram_use_tensor(0)
+        try:
+            Cd = mcm.pcov(v)
+            assert lib.mcm_gram_last_engine() == 0
+        finally:
+            lib.mcm_gram_use_tensor(1)
+        d = np.sqrt(np.diag(Cd))
+        tol = 1e-12 if dt == np.float64 else 1e-5
+        assert np.max(np.abs(Ct - Cd) / np.outer(d, d)) <= tol
+        assert np.array_equal(Ct, Ct.T)
+        sub = [0, 1, 2, 7, M // 2, M - 1]
+        Cr = orc.cov(X[sub])
+        assert np.max(np.abs(Ct[np.ix_(sub, sub)] - Cr)) <= tol * np.max(np.abs(Cr))
+    Xh = rng.standard_t(3, size=(256, 20000))                      # heavy tails: max/sigma >> 10 -> guard -> DMMA
+    mcm.pcov([mcm.Particles(r) for r in Xh])
+    assert lib.mcm_gram_last_engine() == 0
+    Xc = rng.normal(size=(256, 8192)); Xc[5] = 1.25                # a constant (zero-variance) row
+    Cc = mcm.pcov([mcm.Particles(r) for r in Xc])
+    assert np.all(Cc[5] == 0) and np.all(Cc[:, 5] == 0) and abs(Cc[0, 0] - Xc[0].var(ddof=1)) <= 1e-12
+
+
 def test_pcov_large_offset_is_centred_first(mcm, orc):
     rng = np.random.default_rng(15)
     X = 1e8 + rng.normal(size=(4, 5000))
