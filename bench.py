@@ -146,6 +146,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="particles per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-families", action="store_true")
+    ap.add_argument("--no-pcov", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -280,6 +281,10 @@ def main():
         "check": {"pmean": m.mean, "pstd": m.std(), "n": m.n},
     }
 
+    if not args.no_pcov:
+        pc = pcov_bench(mcm, L, lib, stream, rank, world)
+        if rank == 0:
+            line["pcov"] = pc
     if rank == 0 and world == 1 and not args.no_families:
         line["hbm_family"] = hbm_family(mcm, L, lib, stream, a, y, N, peak)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -294,6 +299,49 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def pcov_bench(mcm, L, lib, stream, rank, world):
+    """Config C4: pcov of M = 4096 uncertain variables x N = 1e5 Float64 particles per GPU (the particle index is
+    sharded: global N = world * 1e5).  TFLOP/s in the GEMM convention 2*M^2*N (the symmetric half is computed).
+    Engines: tcgen05/TMEM int8 tensor cores with an Ozaki split (default) and the FP64 tensor pipe (DMMA)."""
+    import torch
+    M, n = 4096, 100_000
+    base = [mcm.systematic_sample(n, mcm.Normal(0.0, 1.0), permute=True, seed=1 + j + 64 * rank, as_particles=True)
+            for j in range(64)]
+    v = [mcm.lincomb([1.0 + 0.001 * j, 0.5], [base[j % 64], base[(j * 7 + 3) % 64]]) for j in range(M)]
+    ptrs = (C.c_void_p * M)(*[C.c_void_p(p.ptr) for p in v])
+    dC = mcm.particles._alloc(M * M * 8)
+    out = {"config": f"C4: M={M} variables x N={n} Float64 particles per GPU, corrected covariance, {world} GPU(s)",
+           "flops_convention": "2*M^2*N_global (GEMM convention; only the upper triangle of tiles is computed)"}
+    with torch.cuda.stream(stream):
+        for name, mode in (("tcgen05_int8_ozaki", 1), ("fp64_dmma", 0)):
+            lib.mcm_gram_use_tensor(mode)
+
+            def run():
+                if world > 1:
+                    L.check(lib.mcm_gram_sharded(L.F64, ptrs, M, n, 1, C.c_void_p(dC)))
+                else:
+                    L.check(lib.mcm_gram(L.F64, ptrs, M, n, 1, None, C.c_void_p(dC), None))
+            run(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record(stream)
+            for _ in range(reps):
+                run()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            out[name] = {"ms": ms, "TFLOP/s": 2.0 * M * M * n * world / (ms * 1e-3) / 1e12,
+                         "engine_used": "tcgen05" if lib.mcm_gram_last_engine() == 1 else "dmma"}
+        lib.mcm_gram_use_tensor(1)
+    L.check(lib.mcm_free(C.c_void_p(dC)))
+    return out
 
 
 def hbm_family(mcm, L, lib, stream, a, y, N, peak):
