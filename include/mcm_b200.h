@@ -264,9 +264,32 @@ int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* sorted_out_
 /* pquantile(p, q) = Statistics.quantile(p.particles, q) type-7 (particles.jl:321);
  * q_host: nq probabilities in [0,1]; out_host: nq values.  pmedian == q=0.5. */
 int mcm_quantile(int dtype, const void* in, size_t n, const double* q_host, int nq, double* out_host);
-/* A/B switch: 1 (default) = MSD radix select (one 8 B/key read per pass), 0 = full sort + index.
- * Both return the exact order statistics. */
+/* A/B switch: 1 (default) = sampled brackets + one streaming read for n >= 131072 and <= 8 probabilities
+ * (select_batch.cu), MSD radix select otherwise; 2 = MSD radix select always (select.cu, one 8 B/key read
+ * per pass); 0 = full sort + index.  All return the exact order statistics. */
 int mcm_quantile_use_select(int on);
+
+/* pquantile of M variables of equal length in one call (particles.jl:316-323 per element of a
+ * Vector{Particles}): out_host[m*nq + i] = quantile(vars[m], q[i]).  Sampled pivots bracket every rank,
+ * one streaming read counts/collects, radix select on the candidates; one device->host copy in total
+ * (select_batch.cu).  M <= 16383. */
+int mcm_quantile_batch(int dtype, const void* const* vars, int M, size_t n, const double* q_host, int nq,
+                       double* out_host);
+/* exact order statistics: out_host[r] = sort(in)[ranks_host[r]] (0-based ranks) without sorting — what
+ * Statistics.median (central one / two order statistics, particles.jl:319) and partialsort need */
+int mcm_order_statistics(int dtype, const void* in, size_t n, const uint64_t* ranks_host, int nr, double* out_host);
+/* diagnostics: number of variables the batched path has handed to the general path so far
+ * (heavy ties around a rank, or a rank outside its sampled bracket) */
+int mcm_quantile_batch_fallbacks(void);
+
+/* ======================= constant matrix x particle vector ================= */
+/* outs[j][i] = bias[j] + sum_k A[j*Mi + k] * (xs[k][i] - shift[k])  for j < Mo, k < Mi, i < n.
+ * Replaces the `Matrix(b) * A'` GEMM of mul!(y, A, b::Vector{Particles}) (particles.jl:688-707),
+ * `A * p` (_pgemv, :620-631) and the transform_moments application (sigmapoints.jl:71).
+ * A_host: row-major Mo x Mi Float64 on the host; shift_host / bias_host may be NULL (zeros).
+ * xs / outs: host arrays of device pointers; outputs must not alias inputs. */
+int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const void* const* xs, const double* shift_host,
+              const double* bias_host, void* const* outs, size_t n);
 
 /* ======================= sampling / resampling ============================= */
 /* quantile(Normal(0,1), p) elementwise on device */
@@ -282,6 +305,16 @@ int mcm_systematic_uniform(int dtype, void* out, size_t n, double a, double b,
 /* randperm(rng, N) stand-in: device permutation from a counter-based generator
  * (Philox-4x32-10 keys + stable radix sort).  Stream differs from Julia's RNG (H5). */
 int mcm_randperm(int64_t* perm_out, size_t n, uint64_t seed);
+/* Keyed pseudo-random permutation of [0, n_total) evaluated per index (6-round Feistel network +
+ * cycle walking; no sort, no storage): out[j] = pi_{seed,column}(i0 + j).  The communication-free
+ * replacement for randperm at sampling.jl:11 when the sample is large or sharded. */
+int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, uint64_t i0, uint64_t n_total);
+/* M systematic columns in ONE launch (the multivariate systematic construction, docs index.md:141 +
+ * types.jl:67-90 per column): outs[v][j] = quantile(d_v, grid[pi_v(i0 + j)]), d_v = Normal(a[v], b[v])
+ * (kind 0) or Uniform(a[v], b[v]) (kind 1); a_host/b_host NULL = standard parameters; permute = 0
+ * keeps the grid order, 1 applies the keyed bijection of column v. */
+int mcm_systematic_batch(int dtype, int kind, void* const* outs, int M, size_t n, const double* a_host,
+                         const double* b_host, int permute, uint64_t seed, uint64_t i0, uint64_t n_total);
 /* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
 int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
 /* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */

@@ -20,11 +20,12 @@ from .particles import (
     maximum, minimum, mod, mod1, rem, div, hypot, add_sum, clamp, muladd, minmax, sincos, ratdiv,
     moments, pmean, psum, pvar, pstd, pminimum, pmaximum, pextrema, pmiddle, meanstd, meanvar,
     pquantile, pmedian, psort, psortperm, pcov, pcor, to_matrix,
+    pgemm, pgemv, mul_, pdot, paxpy_,
     unsafe_comparisons, set_comparison_function, approx, lesssim, gtrsim,
     check_domain, nparticles, particleeltype, flat_particles, is_particle_array,
 )
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
-                       mvnormal_particles)
+                       mvnormal_particles, systematic_batch, index_bijection)
 from .resampling import bootstrap, resample, resample_indices, rand_indices
 from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
 from . import sharded, tape

@@ -121,6 +121,12 @@ SIGNATURES = {
     "mcm_systematic_normal": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_systematic_uniform": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_randperm": (_i, [_vp, _sz, C.c_uint64]),
+    "mcm_index_bijection": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "mcm_systematic_batch": (_i, [_i, _i, _vpp, _i, _sz, _dp, _dp, _i, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "mcm_quantile_batch": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),
+    "mcm_quantile_batch_fallbacks": (_i, []),
+    "mcm_order_statistics": (_i, [_i, _vp, _sz, C.POINTER(C.c_uint64), _i, _dp]),
+    "mcm_pgemm": (_i, [_i, _dp, _i, _i, _vpp, _dp, _dp, _vpp, _sz]),
     "mcm_rand_indices": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_gather": (_i, [_i, _vp, _vp, _vp, _sz, _sz]),
     "mcm_gather_multi": (_i, [_i, _vpp, _vpp, _i, _vp, _sz, _sz]),

@@ -2,6 +2,9 @@
 // (src/resampling.jl:76-84) and systematic resampling (the dead reference code at
 // src/resampling.jl:45-67, restated with an exact integer scan).
 #include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
 #include "mcm_common.cuh"
 #include "mcm_norminv.cuh"
 
@@ -83,6 +86,90 @@ __global__ void __launch_bounds__(256) k_u32_to_i64_b(const uint32_t* __restrict
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) o[i] = (int64_t)v[i];
 }
 
+// ---- keyed index bijection ---------------------------------------------------------
+// randperm(rng, N) (sampling.jl:11) without materialising or sorting anything: a keyed
+// pseudo-random PERMUTATION of [0, n_total) evaluated per index — a 6-round alternating
+// Feistel network on ceil(log2 n_total) bits (left half floor(b/2) bits, right half the rest),
+// cycle-walked back into range (domain < 2 n_total, so < 2 evaluations on average).  Every rank of
+// a sharded sample evaluates its own index range with no communication.
+// The round function is a 32-bit multiply-xorshift mixer; round keys come from splitmix64 of
+// (seed, column).  oracle/mcm_oracle.c restates it bit for bit.  Rounds: 2 fail simple correlation
+// tests, 4 pass them (lag correlations, index correlation, pair chi-square, 3-column moments at
+// n = 1e3..1e6); 6 are used for margin (8 cost 16.3 ms per 1e9 samples).
+constexpr int kFeistelRounds = 6;
+struct FeistelKey {
+  uint32_t k[8];
+  uint32_t lbits, rbits;
+};
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t& s) {
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ FeistelKey feistel_key(uint64_t seed, uint64_t column, uint64_t n_total) {
+  FeistelKey fk;
+  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (column + 1));
+#pragma unroll
+  for (int r = 0; r < 8; ++r) fk.k[r] = (uint32_t)(splitmix64(s) >> 32);
+  uint32_t bits = 2;
+  while (bits < 64 && (1ull << bits) < n_total) ++bits;
+  fk.lbits = bits / 2;
+  fk.rbits = bits - fk.lbits;
+  return fk;
+}
+__host__ __device__ __forceinline__ uint32_t feistel_mix(uint32_t v, uint32_t k) {
+  uint32_t h = v + k;
+  h ^= h >> 16; h *= 0x7feb352du;
+  h ^= h >> 15; h *= 0x846ca68bu;
+  h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, const FeistelKey& fk, uint64_t n_total) {
+  const uint32_t lmask = fk.lbits >= 32 ? 0xffffffffu : ((1u << fk.lbits) - 1u);
+  const uint32_t rmask = fk.rbits >= 32 ? 0xffffffffu : ((1u << fk.rbits) - 1u);
+  do {
+    uint32_t L = (uint32_t)(x >> fk.rbits) & lmask, R = (uint32_t)x & rmask;
+#pragma unroll
+    for (int r = 0; r < kFeistelRounds; r += 2) {
+      L ^= feistel_mix(R, fk.k[r]) & lmask;
+      R ^= feistel_mix(L, fk.k[r + 1]) & rmask;
+    }
+    x = ((uint64_t)L << fk.rbits) | R;
+  } while (x >= n_total);
+  return x;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_index_bijection(int64_t* __restrict__ out, size_t n, FeistelKey fk, unsigned long long i0, unsigned long long n_total) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += stride)
+    out[j] = (int64_t)feistel_permute(i0 + j, fk, n_total);
+}
+
+// M systematic columns in one launch (grid.y = column): out_v[j] = a_v + b_v * Phi^-1(grid[pi_v(i0+j)]).
+// ab: [2M] doubles on device (a then b) or nullptr for (0, 1) / Uniform(0,1).
+template <typename T, bool NORMAL>
+__global__ void __launch_bounds__(kThreads)
+k_systematic_batch(T* const* __restrict__ outs, size_t n, const double* __restrict__ ab, int M, int permute,
+                   unsigned long long seed, unsigned long long i0, unsigned long long n_total) {
+  const int v = blockIdx.y;
+  T* __restrict__ out = outs[v];
+  const double a = ab ? ab[v] : 0.0, b = ab ? ab[M + v] : 1.0;
+  const FeistelKey fk = feistel_key(seed, (uint64_t)v, n_total);
+  const double two_n = 2.0 * (double)n_total;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += stride) {
+    const unsigned long long i = permute ? feistel_permute(i0 + j, fk, n_total) : i0 + j;
+    const double p = (double)(2ull * i + 1ull) / two_n;
+    double val;
+    if constexpr (NORMAL) val = a + b * norminv::norminvcdf(p);
+    else val = a + (b - a) * p;
+    __stcs(out + j, (T)val);
+  }
+}
+
 // ---- gather ----------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -95,19 +182,41 @@ k_gather(const T* __restrict__ src, const int64_t* __restrict__ idx, T* __restri
     out[j] = __ldg(src + i);
   }
 }
-// the SAME index vector applied to M variables (resampling.jl:80-84): each CTA row
-// reads its slice of idx once into registers and reuses it for a group of variables
+// the SAME index vector applied to M variables (resampling.jl:80-84).  grid.y walks the
+// variables four at a time, grid.x covers ALL draws (no grid-stride), and CTAs are scheduled
+// x-fastest: at any moment the resident CTAs work on one or two groups of variables, whose
+// source arrays (4 x 8 MB at N = 1e6) stay in the 126 MB L2 — the random 8-byte reads then
+// hit L2 and HBM sees each source once, sequentially (first version: every group in flight
+// at once, 8 GB working set, 686 GB/s).
+constexpr int GM_VARS = 4;
+constexpr int GM_IPT = 4;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_gather_multi(const T* const* __restrict__ srcs, T* const* __restrict__ outs, int M,
                const int64_t* __restrict__ idx, size_t n_draw, size_t n_src, uint32_t* flags) {
-  const size_t stride = (size_t)gridDim.x * kThreads;
-  const int v0 = blockIdx.y * 8;
-  const int v1 = min(v0 + 8, M);
-  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n_draw; j += stride) {
-    const int64_t i = idx[j];
-    if (i < 0 || (size_t)i >= n_src) { atomicOr(flags, 0x80000000u); continue; }
-    for (int v = v0; v < v1; ++v) outs[v][j] = __ldg(srcs[v] + i);
+  const int v0 = blockIdx.y * GM_VARS;
+  const size_t base = (size_t)blockIdx.x * (kThreads * GM_IPT) + threadIdx.x;
+  int64_t ii[GM_IPT];
+  bool ok[GM_IPT];
+#pragma unroll
+  for (int u = 0; u < GM_IPT; ++u) {
+    const size_t j = base + (size_t)u * kThreads;
+    ii[u] = j < n_draw ? __ldg(idx + j) : 0;
+    ok[u] = j < n_draw;
+    if (ok[u] && (ii[u] < 0 || (size_t)ii[u] >= n_src)) { atomicOr(flags, 0x80000000u); ok[u] = false; }  // BoundsError
+  }
+#pragma unroll
+  for (int dv = 0; dv < GM_VARS; ++dv) {
+    const int v = v0 + dv;
+    if (v >= M) break;
+    const T* __restrict__ src = srcs[v];
+    T* __restrict__ out = outs[v];
+    T val[GM_IPT];
+#pragma unroll
+    for (int u = 0; u < GM_IPT; ++u) val[u] = ok[u] ? __ldg(src + ii[u]) : T(0);
+#pragma unroll
+    for (int u = 0; u < GM_IPT; ++u)
+      if (ok[u]) __stcs(out + base + (size_t)u * kThreads, val[u]);
   }
 }
 
@@ -208,6 +317,53 @@ extern "C" int mcm_systematic_uniform(int dtype, void* out, size_t n, double a, 
   return systematic_impl<false>(dtype, out, n, a, b, perm_dev, i0, n_total);
 }
 
+extern "C" int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, uint64_t i0, uint64_t n_total) {
+  MCM_NEED_INIT();
+  if (n && !out) return fail(MCM_ERR_INVALID, "mcm_index_bijection: null pointer");
+  if (n_total == 0 || i0 + n > n_total) return fail(MCM_ERR_INVALID, "mcm_index_bijection: index range exceeds n_total");
+  if (n == 0) return MCM_OK;
+  Ctx& c = ctx();
+  k_index_bijection<<<stream_grid(n, 2, 8), kThreads, 0, c.stream>>>(out, n, feistel_key(seed, column, n_total), i0, n_total);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+extern "C" int mcm_systematic_batch(int dtype, int kind, void* const* outs, int M, size_t n, const double* a_host,
+                                    const double* b_host, int permute, uint64_t seed, uint64_t i0, uint64_t n_total) {
+  MCM_NEED_INIT();
+  if (M < 1 || !outs) return fail(MCM_ERR_INVALID, "mcm_systematic_batch: bad arguments");
+  if (M > 65535) return fail(MCM_ERR_UNSUPPORTED, "mcm_systematic_batch: at most 65535 columns per call");
+  if ((a_host == nullptr) != (b_host == nullptr)) return fail(MCM_ERR_INVALID, "mcm_systematic_batch: pass both parameter arrays or neither");
+  if (kind != 0 && kind != 1) return fail(MCM_ERR_INVALID, "mcm_systematic_batch: kind must be 0 (Normal) or 1 (Uniform)");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_systematic_batch: bad dtype %d", dtype);
+  if (n_total == 0 || i0 + n > n_total) return fail(MCM_ERR_INVALID, "mcm_systematic_batch: index range exceeds n_total");
+  if (n == 0) return MCM_OK;
+  Ctx& c = ctx();
+  std::vector<unsigned char> host((size_t)M * sizeof(void*) + (a_host ? 2 * (size_t)M * sizeof(double) : 0));
+  memcpy(host.data(), outs, (size_t)M * sizeof(void*));
+  if (a_host) {
+    memcpy(host.data() + (size_t)M * sizeof(void*), a_host, (size_t)M * sizeof(double));
+    memcpy(host.data() + (size_t)M * sizeof(void*) + (size_t)M * sizeof(double), b_host, (size_t)M * sizeof(double));
+  }
+  unsigned char* d_tab = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_tab, host.size(), c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_tab, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));  // host staging vector dies at return
+  const double* d_ab = a_host ? (const double*)(d_tab + (size_t)M * sizeof(void*)) : nullptr;
+  int gx = stream_grid(n, 2, 8);
+  const int cap = std::max(1, (8 * c.sm_count + M - 1) / M);
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)M);
+#define MCM_SYS_BATCH(T, NORMAL) \
+  k_systematic_batch<T, NORMAL><<<grid, kThreads, 0, c.stream>>>((T* const*)d_tab, n, d_ab, M, permute, seed, i0, n_total)
+  if (dtype == MCM_F64) { if (kind == 0) MCM_SYS_BATCH(double, true); else MCM_SYS_BATCH(double, false); }
+  else { if (kind == 0) MCM_SYS_BATCH(float, true); else MCM_SYS_BATCH(float, false); }
+#undef MCM_SYS_BATCH
+  MCM_CHECK_LAUNCH();
+  MCM_CUDA(cudaFreeAsync(d_tab, c.stream));
+  return MCM_OK;
+}
+
 extern "C" int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset) {
   MCM_NEED_INIT();
   if (n_draw && !idx_out) return fail(MCM_ERR_INVALID, "mcm_rand_indices: null pointer");
@@ -267,14 +423,10 @@ extern "C" int mcm_gather_multi(int dtype, const void* const* srcs, void* const*
   MCM_CUDA(cudaMallocAsync((void**)&d_tab, 2 * (size_t)M * sizeof(void*), c.stream));
   MCM_CUDA(cudaMemcpyAsync(d_tab, srcs, (size_t)M * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
   MCM_CUDA(cudaMemcpyAsync(d_tab + M, outs, (size_t)M * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
-  // grid.y walks groups of 8 variables; grid.x covers the draws (grid-stride), sized so
-  // that the whole grid is about 8 CTAs per SM
-  const int gy = (M + 7) / 8;
-  int gx = stream_grid(n_draw, 1, 8);
-  int cap = (8 * c.sm_count + gy - 1) / gy;
-  if (cap < 4) cap = 4;
-  if (gx > cap) gx = cap;
-  dim3 grid(gx, gy);
+  const unsigned gy = (unsigned)((M + GM_VARS - 1) / GM_VARS);
+  const size_t gx = (n_draw + (size_t)kThreads * GM_IPT - 1) / ((size_t)kThreads * GM_IPT);
+  if (gy > 65535u || gx > 0x7fffffffull) return fail(MCM_ERR_UNSUPPORTED, "mcm_gather_multi: problem too large for one launch");
+  dim3 grid((unsigned)gx, gy);
   if (dtype == MCM_F64)
     k_gather_multi<double><<<grid, kThreads, 0, c.stream>>>((const double* const*)d_tab, (double* const*)(d_tab + M), M, idx, n_draw, n_src, c.d_flags);
   else if (dtype == MCM_F32)

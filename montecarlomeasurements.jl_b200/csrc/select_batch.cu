@@ -1,0 +1,829 @@
+// select_batch.cu — pquantile / pmedian of M uncertain variables in one call
+// (src/particles.jl:316-323 applied per element of a Vector{Particles}: the ribbon / C5 case,
+// 1024 variables x 1e6 particles).
+//
+// Stage 1 (n >= 131072), BRACKETING — one read of the data at streaming speed, no histograms:
+//   k_bq_sample  one CTA per segment sorts a stratified sample (64 runs x 128 keys) in shared memory
+//                and publishes, for every group of requested ranks, two pivots lo <= hi taken
+//                4.5 standard deviations of the sampling error either side of the rank;
+//   k_bq_stream  grid (chunks, M): every key is compared with the pivots: per-thread register
+//                counters of keys below lo, keys inside [lo, hi] (a few % of the data) are appended
+//                to the bracket's candidate list (warp-aggregated atomics).
+//   The wanted order statistic of the segment is order statistic (rank - below) of its bracket; a
+//   rank that falls outside its bracket (probability ~1e-5, or adversarial data) is flagged and
+//   re-done by the general path, so results are always exact.
+// Stage 2, RADIX SELECT on the (small, L2-resident) candidate lists — or directly on the data when
+// n is small.  The single-variable path (select.cu) narrows the ranks on the host between passes;
+// with M segments that is M x passes round trips.  Here the narrowing state lives on the device:
+//   k_bs_hist    grid (chunks, M): 2048-bin histograms of the next 11 key bits for the keys of
+//                segment m that match one of its live prefixes (shared-memory histograms with
+//                warp-aggregated atomics, flushed with integer global atomics => exact and
+//                order-independent);
+//   k_bs_pick    one CTA per segment: block scan of each live histogram, every requested rank
+//                moves to its bin; bins with <= 2048 keys are final; histograms are re-zeroed;
+//   (repeated a FIXED number of times — segments whose ranks are all final skip the reads)
+//   k_bs_compact grid (chunks, M): keys matching a final prefix are appended to the segment's
+//                candidate lists;
+//   k_bs_final   grid (groups, M): one-CTA bitonic sort of <= 2048 candidates, ranks read off.
+// One device->host copy at the end returns M x nr order statistics; the type-7 interpolation is
+// done on the host (mcm_quantile.cuh).  A segment that cannot be resolved in the fixed pass count
+// (more than 2048 identical keys around a rank) is flagged and re-done by the single path, so
+// results are always the exact order statistics.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "mcm_common.cuh"
+#include "mcm_keys.cuh"
+#include "mcm_quantile.cuh"
+
+namespace mcm {
+
+constexpr int BS_BITS = 11;
+constexpr int BS_BINS = 1 << BS_BITS;
+constexpr int BS_MAXG = 8;       // live prefixes / ranks per segment
+constexpr int BS_THRESH = 2048;  // candidates per final group
+constexpr int BS_PASSES = 4;     // 44 key bits; 3 are enough for 32-bit keys
+
+static int g_bq_fallbacks = 0;  // segments re-done by the general path (diagnostics / tests)
+
+struct BSeg {
+  unsigned long long prefix[BS_MAXG];
+  uint32_t count[BS_MAXG];
+  int rem[BS_MAXG];             // low key bits of group g not fixed yet
+  uint32_t rank_group[BS_MAXG];
+  uint32_t rank_local[BS_MAXG];  // rank inside its group
+  int G;
+  int nr;            // requested ranks of this segment
+  uint32_t active;   // groups still being narrowed
+  uint32_t resolved; // groups whose key is fully determined (rem == 0): value = prefix
+  uint32_t flags;    // 1 = NaN seen, 2 = unresolved after BS_PASSES
+};
+
+// Segment descriptors for the radix stage.  Uniform mode: nseg == nullptr, every segment has n keys and
+// the same ranks.  Bracket mode: segment sidx = m*NB + b holds the candidates of bracket b of variable m:
+// nseg[sidx] keys (must be <= cap), its ranks are the parent's ranks of that bracket minus below[sidx];
+// all candidates share the key bits above `hb` = highest bit in which the two pivots differ.
+struct BInit {
+  int nb;                        // brackets per variable (1 in uniform mode)
+  int nr[4];                     // ranks per bracket
+  uint32_t rank[4][BS_MAXG];     // global ranks of bracket b
+  uint32_t cap[4];
+};
+__global__ void k_bs_init(BSeg* __restrict__ seg, int nsegs, int key_bits, uint32_t n_uniform, BInit bi,
+                          const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ below,
+                          const unsigned long long* __restrict__ pivots, uint32_t* __restrict__ parent_flags) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx >= nsegs) return;
+  const int b = sidx % bi.nb, m = sidx / bi.nb;
+  BSeg s;
+  memset(&s, 0, sizeof(s));
+  s.G = 1;
+  s.nr = bi.nr[b];
+  uint32_t n = n_uniform, sub = 0;
+  int rem = key_bits;
+  unsigned long long prefix = 0;
+  if (nseg) {
+    n = nseg[sidx];
+    sub = below[sidx];
+    const unsigned long long lo = pivots[2 * sidx], hi = pivots[2 * sidx + 1];
+    const unsigned long long diff = lo ^ hi;
+    rem = diff ? 64 - __clzll((long long)diff) : 0;
+    if (rem > key_bits) rem = key_bits;
+    prefix = rem >= 64 ? 0ull : (lo >> rem);
+    if (n > bi.cap[b]) { atomicOr(parent_flags + m, 2u); n = 0; }
+  }
+  s.count[0] = n;
+  s.rem[0] = rem;
+  s.prefix[0] = prefix;
+  for (int r = 0; r < bi.nr[b]; ++r) {
+    const uint32_t want = bi.rank[b][r];
+    if (want < sub || want - sub >= n) {         // the rank is not inside its bracket: general path
+      if (parent_flags) atomicOr(parent_flags + m, 2u);
+      s.flags |= 2u;
+    }
+    s.rank_group[r] = 0;
+    s.rank_local[r] = want - sub;
+  }
+  if (s.flags & 2u) n = 0;
+  if (rem == 0 && n > (uint32_t)BS_THRESH) s.resolved = 1u;
+  else s.active = (n > (uint32_t)BS_THRESH) ? 1u : 0u;
+  seg[sidx] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_bs_hist(const T* const* __restrict__ vars, size_t n_uniform, const uint32_t* __restrict__ nseg, BSeg* __restrict__ segs,
+          uint32_t* __restrict__ hist) {
+  using K = typename KeyOf<T>::type;
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  constexpr int UNROLL = 4;
+  extern __shared__ uint32_t sh[];  // [gmax][BS_BINS], indexed by group id
+  const int m = blockIdx.y;
+  BSeg* sg = segs + m;
+  const uint32_t active = sg->active;
+  if (active == 0) return;
+  const size_t n = nseg ? (size_t)nseg[m] : n_uniform;
+  if ((size_t)blockIdx.x * kThreads >= n && blockIdx.x > 0) return;   // more chunks than this segment needs
+  const int G = sg->G;
+  unsigned long long pre[BS_MAXG];
+  int rem = 0;
+#pragma unroll
+  for (int g = 0; g < BS_MAXG; ++g) {
+    const bool on = g < G && ((active >> g) & 1u);
+    pre[g] = on ? sg->prefix[g] : ~0ull;  // live groups share `rem`; an impossible prefix disables the rest
+    if (on) rem = sg->rem[g];
+  }
+  const int dbits = rem < BS_BITS ? rem : BS_BITS;
+  const int shift = rem - dbits;
+  const uint32_t dmask = (1u << dbits) - 1u;
+  const int nb_total = G * BS_BINS;
+  const bool first_pass = rem >= (int)(8 * sizeof(K));   // nothing fixed yet: every key belongs to group 0
+  for (int i = threadIdx.x; i < nb_total; i += kThreads) sh[i] = 0;
+  __syncthreads();
+  const T* __restrict__ in = vars[m];
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool nan = false;
+  // a prefix of ~0 can only be matched by rem == 0 keys of all ones, and live groups have rem > 0
+  auto account = [&](bool valid, T x) {
+    uint32_t code = 0xffffffffu - lane;
+    if (valid) {
+      const K key = to_key(x, nan);
+      const unsigned long long kp = first_pass ? 0ull : ((unsigned long long)key >> rem);
+#pragma unroll
+      for (int g = 0; g < BS_MAXG; ++g)
+        if (kp == pre[g]) code = (uint32_t)g * BS_BINS + (uint32_t)(((unsigned long long)key >> shift) & dmask);
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, code);
+    if (code < (uint32_t)nb_total && lane == __ffs(peers) - 1) atomicAdd(&sh[code], (uint32_t)__popc(peers));
+  };
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const size_t nvec = vec ? n / V : 0;
+  const P* pin = reinterpret_cast<const P*>(in);
+  const size_t rows = (nvec + stride * UNROLL - 1) / (stride * UNROLL);
+  for (size_t r = 0; r < rows; ++r) {
+    P x[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t j = (r * UNROLL + u) * stride + tid;
+      ok[u] = j < nvec;
+      if (ok[u]) x[u] = ld_stream(pin + j);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < V; ++e) account(ok[u], ok[u] ? x[u].v[e] : T(0));
+  }
+  const size_t tail0 = nvec * V;
+  const size_t trips = (n - tail0 + stride - 1) / stride;
+  for (size_t r = 0; r < trips; ++r) {
+    const size_t i = tail0 + r * stride + tid;
+    account(i < n, i < n ? in[i] : T(0));
+  }
+  __syncthreads();
+  uint32_t* gh = hist + (size_t)m * BS_MAXG * BS_BINS;
+  for (int i = threadIdx.x; i < nb_total; i += kThreads) {
+    const uint32_t v = sh[i];
+    if (v) atomicAdd(gh + i, v);
+  }
+  if (nan) atomicOr(&sg->flags, 1u);
+}
+
+// one CTA (256 threads) per segment: thread t owns bins 8t .. 8t+7
+__global__ void __launch_bounds__(256)
+k_bs_pick(BSeg* __restrict__ segs, uint32_t* __restrict__ hist, int last_pass) {
+  const int m = blockIdx.x;
+  BSeg* sg = segs + m;
+  __shared__ BSeg s;
+  __shared__ uint32_t warp_sum[8];
+  __shared__ uint32_t nbin[BS_MAXG], nlocal[BS_MAXG], ncount[BS_MAXG];
+  if (threadIdx.x == 0) s = *sg;
+  __syncthreads();
+  if (s.active == 0) return;
+  const int nr = s.nr;
+  uint32_t* gh = hist + (size_t)m * BS_MAXG * BS_BINS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int g = 0; g < s.G; ++g) {
+    if (!((s.active >> g) & 1u)) continue;
+    uint32_t b[8], tot = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      b[e] = gh[g * BS_BINS + threadIdx.x * 8 + e];
+      gh[g * BS_BINS + threadIdx.x * 8 + e] = 0;  // clean for the next pass
+      tot += b[e];
+    }
+    uint32_t inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_sum[w];
+    const uint32_t lo = base + inc - tot;  // keys in bins before mine
+    for (int r = 0; r < nr; ++r) {
+      if (s.rank_group[r] != (uint32_t)g) continue;
+      const uint32_t want = s.rank_local[r];
+      if (want >= lo && want < lo + tot) {
+        uint32_t cum = lo;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (want >= cum && want < cum + b[e]) { nbin[r] = threadIdx.x * 8 + e; nlocal[r] = want - cum; ncount[r] = b[e]; }
+          cum += b[e];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    BSeg o;
+    memset(&o, 0, sizeof(o));
+    o.flags = s.flags;
+    o.nr = s.nr;
+    int src_group[BS_MAXG];
+    uint32_t src_bin[BS_MAXG];
+    for (int r = 0; r < nr; ++r) {
+      const int og = (int)s.rank_group[r];
+      const bool live = (s.active >> og) & 1u;
+      const uint32_t bin = live ? nbin[r] : 0xffffffffu;
+      int ng = -1;
+      for (int q = 0; q < o.G; ++q)
+        if (src_group[q] == og && src_bin[q] == bin) ng = q;
+      if (ng < 0) {
+        ng = o.G++;
+        src_group[ng] = og; src_bin[ng] = bin;
+        if (live) {
+          const int rem = s.rem[og];
+          const int dbits = rem < BS_BITS ? rem : BS_BITS;
+          o.prefix[ng] = (s.prefix[og] << dbits) | (unsigned long long)bin;
+          o.rem[ng] = rem - dbits;
+          o.count[ng] = ncount[r];
+          if (o.rem[ng] == 0 && o.count[ng] > (uint32_t)BS_THRESH) o.resolved |= 1u << ng;
+          else if (o.count[ng] > (uint32_t)BS_THRESH) o.active |= 1u << ng;
+        } else {
+          o.prefix[ng] = s.prefix[og]; o.rem[ng] = s.rem[og]; o.count[ng] = s.count[og];
+          if ((s.resolved >> og) & 1u) o.resolved |= 1u << ng;
+        }
+      }
+      o.rank_group[r] = (uint32_t)ng;
+      o.rank_local[r] = live ? nlocal[r] : s.rank_local[r];
+    }
+    if (last_pass && o.active) { o.flags |= 2u; o.active = 0; }
+    *sg = o;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_bs_compact(const T* const* __restrict__ vars, size_t n_uniform, const uint32_t* __restrict__ nseg,
+             const BSeg* __restrict__ segs, unsigned long long* __restrict__ cand, uint32_t* __restrict__ cnt) {
+  using K = typename KeyOf<T>::type;
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  constexpr int UNROLL = 4;
+  const int m = blockIdx.y;
+  const BSeg* sg = segs + m;
+  if (sg->flags & 2u) return;
+  const size_t n = nseg ? (size_t)nseg[m] : n_uniform;
+  if ((size_t)blockIdx.x * kThreads >= n) return;
+  const int G = sg->G;
+  unsigned long long pre[BS_MAXG];
+  int rem[BS_MAXG];
+  bool any = false;
+#pragma unroll
+  for (int g = 0; g < BS_MAXG; ++g) {
+    const bool on = g < G && !((sg->resolved >> g) & 1u);
+    pre[g] = on ? sg->prefix[g] : ~0ull;
+    rem[g] = on ? sg->rem[g] : 0;   // (key >> 0) == ~0 only for NaN keys, which are never candidates of a live rank
+    any |= on;
+  }
+  if (!any) return;
+  const T* __restrict__ in = vars[m];
+  unsigned long long* mc = cand + (size_t)m * BS_MAXG * BS_THRESH;
+  uint32_t* mcnt = cnt + (size_t)m * BS_MAXG;
+  bool nan = false;
+  auto consider = [&](T x) {
+    const K key = to_key(x, nan);
+#pragma unroll
+    for (int g = 0; g < BS_MAXG; ++g) {
+      if (rem[g] < 64 ? (((unsigned long long)key >> rem[g]) == pre[g]) : (pre[g] == 0ull)) {
+        if (g < G && !((sg->resolved >> g) & 1u)) {
+          const uint32_t pos = atomicAdd(mcnt + g, 1u);
+          if (pos < (uint32_t)BS_THRESH) mc[(size_t)g * BS_THRESH + pos] = (unsigned long long)key;
+        }
+        break;
+      }
+    }
+  };
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const size_t nvec = vec ? n / V : 0;
+  const P* pin = reinterpret_cast<const P*>(in);
+  for (size_t i = tid; i < nvec; i += stride * UNROLL) {
+    P x[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t j = i + (size_t)u * stride;
+      if (j < nvec) x[u] = ld_stream(pin + j);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t j = i + (size_t)u * stride;
+      if (j < nvec) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) consider(x[u].v[e]);
+      }
+    }
+  }
+  for (size_t i = nvec * V + tid; i < n; i += stride) consider(in[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_bs_final(BSeg* __restrict__ segs, const unsigned long long* __restrict__ cand, const uint32_t* __restrict__ cnt,
+           double* __restrict__ out) {
+  using K = typename KeyOf<T>::type;
+  __shared__ unsigned long long s[BS_THRESH];
+  const int g = blockIdx.x, m = blockIdx.y;
+  BSeg* sg = segs + m;
+  if (g >= sg->G || (sg->flags & 2u)) return;
+  const int nr = sg->nr;
+  double* mo = out + (size_t)m * BS_MAXG;
+  if ((sg->resolved >> g) & 1u) {
+    if (threadIdx.x < nr && sg->rank_group[threadIdx.x] == (uint32_t)g) mo[threadIdx.x] = (double)from_key((K)sg->prefix[g]);
+    return;
+  }
+  const uint32_t have = cnt[(size_t)m * BS_MAXG + g];
+  if (have != sg->count[g] || have > (uint32_t)BS_THRESH) {  // cannot happen unless the data changed under us
+    if (threadIdx.x == 0) atomicOr(&sg->flags, 2u);
+    return;
+  }
+  const unsigned long long* mc = cand + ((size_t)m * BS_MAXG + g) * BS_THRESH;
+  for (int i = threadIdx.x; i < BS_THRESH; i += 1024) s[i] = i < (int)have ? mc[i] : ~0ull;
+  __syncthreads();
+  // sort only as many elements as needed (next power of two >= have)
+  int len = 2;
+  while (len < (int)have) len <<= 1;
+  for (int k = 2; k <= len; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < len; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = s[i], b = s[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { s[i] = b; s[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x < nr && sg->rank_group[threadIdx.x] == (uint32_t)g)
+    mo[threadIdx.x] = (double)from_key((K)s[sg->rank_local[threadIdx.x]]);
+}
+
+// ---- stage 1: bracketing ------------------------------------------------------------------------
+constexpr int BQ_SAMPLE = 8192;     // keys sampled per segment
+constexpr int BQ_RUN = 128;         // contiguous keys per sampled run
+constexpr int BQ_MAXB = 4;          // brackets per sweep
+constexpr size_t BQ_MIN_N = 131072; // below this the radix stage runs on the data directly
+
+struct BqParams {
+  int nb;
+  int a[BQ_MAXB], b[BQ_MAXB];  // sample positions of the pivots: a < 0 -> -inf, b >= BQ_SAMPLE -> +inf
+  uint32_t cap[BQ_MAXB];        // capacity of each candidate list
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned long long* __restrict__ pivots) {
+  using K = typename KeyOf<T>::type;
+  extern __shared__ unsigned long long sk[];  // BQ_SAMPLE keys
+  const int m = blockIdx.x;
+  const T* __restrict__ in = vars[m];
+  constexpr int RUNS = BQ_SAMPLE / BQ_RUN;
+  bool nan = false;
+  for (int i = threadIdx.x; i < BQ_SAMPLE; i += 1024) {
+    const int run = i / BQ_RUN, off = i % BQ_RUN;
+    const size_t start = (size_t)(((unsigned __int128)run * (n - BQ_RUN)) / (RUNS - 1));  // evenly spaced, both ends included
+    sk[i] = (unsigned long long)to_key(in[start + off], nan);
+  }
+  __syncthreads();
+  for (int k = 2; k <= BQ_SAMPLE; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < BQ_SAMPLE; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = sk[i], y = sk[l];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) { sk[i] = y; sk[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x < bp.nb) {
+    const int b = threadIdx.x;
+    const unsigned long long kmax = sizeof(K) == 8 ? ~0ull : 0xffffffffull;
+    pivots[2 * ((size_t)m * bp.nb + b)] = bp.a[b] < 0 ? 0ull : sk[bp.a[b]];
+    pivots[2 * ((size_t)m * bp.nb + b) + 1] = bp.b[b] >= BQ_SAMPLE ? kmax : sk[bp.b[b]];
+  }
+}
+
+// Candidates are staged per CTA in shared memory and flushed with ONE global atomic per bracket per
+// flush (first version: one global atomic per warp-step on 3 addresses per variable — 3.6 ms for
+// 1e8 keys, L2 same-address atomic throughput).
+constexpr int BQ_ITER_KEYS = kThreads * 4 * 2;       // keys per CTA iteration (both dtypes)
+constexpr int BQ_FLUSH = 512;                        // flush a list once it holds more than this
+constexpr int BQ_STAGE = BQ_ITER_KEYS + BQ_FLUSH;    // staging capacity per bracket
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(kThreads)
+k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsigned long long* __restrict__ pivots,
+            T* __restrict__ cand, size_t cand_stride, uint32_t* __restrict__ cnt, uint32_t* __restrict__ below,
+            uint32_t* __restrict__ flags) {
+  using K = typename KeyOf<T>::type;
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  constexpr int UNROLL = BQ_ITER_KEYS / (kThreads * V);   // 4 (f64) / 2 (f32)
+  extern __shared__ __align__(16) unsigned char bq_smem[];
+  T* stage = reinterpret_cast<T*>(bq_smem);                // [NB][BQ_STAGE]
+  __shared__ uint32_t s_cnt[NB], s_base[NB], s_n[NB];
+  __shared__ uint32_t sh[NB][kThreads / 32];
+  const int m = blockIdx.y;
+  const T* __restrict__ in = vars[m];
+  K lo[NB], hi[NB];
+  uint32_t nbelow[NB];
+  T* cb[NB];
+  size_t coff = 0;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    lo[b] = (K)pivots[2 * ((size_t)m * NB + b)];
+    hi[b] = (K)pivots[2 * ((size_t)m * NB + b) + 1];
+    nbelow[b] = 0;
+    cb[b] = cand + (size_t)m * cand_stride + coff;
+    coff += bp.cap[b];
+  }
+  if (threadIdx.x < NB) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t* mcnt = cnt + (size_t)m * NB;
+  const int lane = threadIdx.x & 31;
+  bool nan = false;
+  // classify one key: below-counters in registers, membership bit `bit` of the per-bracket masks
+  uint32_t inmask[NB];
+  auto classify = [&](bool valid, T x, int bit) {
+    const K key = to_key(x, nan);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      nbelow[b] += (valid && key < lo[b]) ? 1u : 0u;
+      inmask[b] |= (valid && key >= lo[b] && key <= hi[b]) ? (1u << bit) : 0u;
+    }
+  };
+  // scalar variant used by the tails: one key per thread
+  auto consider = [&](bool valid, T x) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) inmask[b] = 0;
+    classify(valid, x, 0);
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+      if (inmask[b]) stage[b * BQ_STAGE + atomicAdd(&s_cnt[b], 1u)] = x;
+  };
+  // flush every list holding more than `threshold` entries; called by all threads at a uniform point
+  auto flush = [&](uint32_t threshold) {
+    __syncthreads();
+    if (threadIdx.x < NB) {
+      const uint32_t c = s_cnt[threadIdx.x];
+      const bool go = c > threshold;
+      s_n[threadIdx.x] = go ? c : 0u;
+      if (go) { s_base[threadIdx.x] = atomicAdd(mcnt + threadIdx.x, c); s_cnt[threadIdx.x] = 0; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint32_t c = s_n[b];
+      if (c) {
+        const uint32_t base = s_base[b];
+        for (uint32_t i = threadIdx.x; i < c; i += kThreads)
+          if (base + i < bp.cap[b]) cb[b][base + i] = stage[b * BQ_STAGE + i];
+      }
+    }
+    __syncthreads();   // staging is reused by the next iteration
+  };
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+  const size_t nvec = vec ? n / V : 0;
+  const P* pin = reinterpret_cast<const P*>(in);
+  const size_t rows = (nvec + stride * UNROLL - 1) / (stride * UNROLL);   // CTA-uniform trip count
+  for (size_t r = 0; r < rows; ++r) {
+    P x[UNROLL];
+    bool ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const size_t j = (r * UNROLL + u) * stride + tid;
+      ok[u] = j < nvec;
+      if (ok[u]) x[u] = ld_stream(pin + j);
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) inmask[b] = 0;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+      for (int e = 0; e < V; ++e) classify(ok[u], ok[u] ? x[u].v[e] : T(0), u * V + e);
+    // one shared-memory atomic per thread per bracket, only for threads that hold candidates (~30 %)
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (inmask[b]) {
+        uint32_t pos = atomicAdd(&s_cnt[b], (uint32_t)__popc(inmask[b]));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if ((inmask[b] >> (u * V + e)) & 1u) stage[b * BQ_STAGE + pos++] = x[u].v[e];
+      }
+    }
+    flush(BQ_FLUSH);
+  }
+  const size_t tail0 = nvec * V;
+  const size_t trips = (n - tail0 + stride - 1) / stride;
+  for (size_t r = 0; r < trips; ++r) {
+    const size_t i = tail0 + r * stride + tid;
+    consider(i < n, i < n ? in[i] : T(0));
+    if ((r & 7) == 7) flush(BQ_FLUSH);   // 8 x 256 keys per flush check
+  }
+  flush(0);
+  // CTA totals of the below-counters, one atomic per bracket per CTA
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    uint32_t v = nbelow[b];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+    if (lane == 0) sh[b][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NB) {
+    uint32_t t = 0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[threadIdx.x][w];
+    if (t) atomicAdd(below + (size_t)m * NB + threadIdx.x, t);
+  }
+  if (nan) atomicOr(flags + m, 1u);
+}
+
+__global__ void k_bs_flags(const BSeg* __restrict__ segs, int nsegs, int nb, uint32_t* __restrict__ flags) {
+  const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sidx < nsegs && segs[sidx].flags) atomicOr(flags + sidx / nb, segs[sidx].flags);
+}
+
+template <typename T>
+int order_statistics(const T* in, size_t n, const unsigned long long* ranks, int nr, double* vals_host, int* has_nan);
+
+// vals_host[m*nr + r] = sorted(vars[m])[ranks[r]]; nr <= BS_MAXG
+template <typename T>
+static int order_statistics_batch(const T* const* vars_host, int M, size_t n, const unsigned long long* ranks, int nr,
+                                  double* vals_host, int* has_nan) {
+  using K = typename KeyOf<T>::type;
+  Ctx& c = ctx();
+  *has_nan = 0;
+  const bool bracket = n >= BQ_MIN_N;
+  // ---- host plan: brackets in sample space (data independent) --------------------------------
+  BqParams bp;
+  BInit bi;
+  memset(&bp, 0, sizeof(bp));
+  memset(&bi, 0, sizeof(bi));
+  int slot_bracket[BS_MAXG], slot_index[BS_MAXG];   // where rank r of the caller lives
+  if (bracket) {
+    struct Iv { int a, b; std::vector<int> ranks; };
+    std::vector<Iv> iv;
+    std::vector<int> order(nr);
+    for (int r = 0; r < nr; ++r) order[r] = r;
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return ranks[x] < ranks[y]; });
+    for (int oi = 0; oi < nr; ++oi) {
+      const int r = order[oi];
+      const double p = ((double)ranks[r] + 0.5) / (double)n;
+      const double pos = p * BQ_SAMPLE;
+      const double w = 4.5 * sqrt(BQ_SAMPLE * p * (1.0 - p)) + 3.0;
+      int a = (int)floor(pos - w), b = (int)ceil(pos + w);
+      if (a < 0) a = -1;
+      if (b >= BQ_SAMPLE) b = BQ_SAMPLE;
+      if (!iv.empty() && a <= iv.back().b + 1) { iv.back().b = std::max(iv.back().b, b); iv.back().ranks.push_back(r); }
+      else iv.push_back({a, b, {r}});
+    }
+    while ((int)iv.size() > BQ_MAXB) {  // cannot happen for <= 4 probabilities; merge the closest pair otherwise
+      size_t best = 0;
+      for (size_t i = 1; i + 1 < iv.size(); ++i)
+        if (iv[i + 1].a - iv[i].b < iv[best + 1].a - iv[best].b) best = i;
+      iv[best].b = iv[best + 1].b;
+      iv[best].ranks.insert(iv[best].ranks.end(), iv[best + 1].ranks.begin(), iv[best + 1].ranks.end());
+      iv.erase(iv.begin() + best + 1);
+    }
+    bp.nb = bi.nb = (int)iv.size();
+    for (int b = 0; b < bp.nb; ++b) {
+      bp.a[b] = iv[b].a; bp.b[b] = iv[b].b;
+      const double width = (double)(std::min(iv[b].b, BQ_SAMPLE) - std::max(iv[b].a, 0) + 2);
+      double cap = (width + 6.0 * sqrt(width) + 8.0) * (double)n / BQ_SAMPLE + 1024.0;
+      if (cap > (double)n) cap = (double)n;
+      bp.cap[b] = bi.cap[b] = ((uint32_t)cap + 3u) & ~3u;   // 16-byte aligned lists
+      bi.nr[b] = (int)iv[b].ranks.size();
+      for (int i = 0; i < bi.nr[b]; ++i) {
+        bi.rank[b][i] = (uint32_t)ranks[iv[b].ranks[i]];
+        slot_bracket[iv[b].ranks[i]] = b; slot_index[iv[b].ranks[i]] = i;
+      }
+    }
+  } else {
+    bi.nb = 1; bi.nr[0] = nr; bi.cap[0] = (uint32_t)n;
+    for (int r = 0; r < nr; ++r) { bi.rank[0][r] = (uint32_t)ranks[r]; slot_bracket[r] = 0; slot_index[r] = r; }
+  }
+  const int NB = bi.nb;
+  const int S = M * NB;  // radix-stage segments
+  size_t cand_stride = 0;
+  uint32_t max_cap = 0;
+  for (int b = 0; b < NB; ++b) { cand_stride += bi.cap[b]; max_cap = std::max(max_cap, bi.cap[b]); }
+
+  // ---- device workspace -----------------------------------------------------------------------
+  const size_t tab_bytes = (size_t)(M + S) * sizeof(void*);
+  const size_t seg_bytes = (size_t)S * sizeof(BSeg);
+  const size_t hist_bytes = (size_t)S * BS_MAXG * BS_BINS * sizeof(uint32_t);
+  const size_t cnt_bytes = (size_t)S * BS_MAXG * sizeof(uint32_t);
+  const size_t out_bytes = (size_t)S * BS_MAXG * sizeof(double);
+  const size_t piv_bytes = (size_t)S * 2 * sizeof(unsigned long long);
+  const size_t zero_bytes = hist_bytes + cnt_bytes + 3 * (size_t)S * 4 + (size_t)M * 4 + 64;  // hist, cnt, qcnt, below, pad, flags
+  unsigned char* d_all = nullptr;
+  const size_t total = tab_bytes + seg_bytes + zero_bytes + out_bytes + piv_bytes + 1024;
+  MCM_CUDA(cudaMallocAsync((void**)&d_all, total, c.stream));
+  size_t off = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = d_all + off; off += (bytes + 15) & ~(size_t)15; return p; };
+  unsigned char* d_zero0 = d_all;
+  uint32_t* d_hist = (uint32_t*)take(hist_bytes);
+  uint32_t* d_cnt = (uint32_t*)take(cnt_bytes);
+  uint32_t* d_qcnt = (uint32_t*)take((size_t)S * 4);    // bracket list lengths
+  uint32_t* d_below = (uint32_t*)take((size_t)S * 4);
+  uint32_t* d_flags = (uint32_t*)take((size_t)M * 4);
+  const size_t zero_span = off;
+  const T** d_tab = (const T**)take(tab_bytes);          // [M] data pointers, then [S] list pointers
+  BSeg* d_seg = (BSeg*)take(seg_bytes);
+  double* d_out = (double*)take(out_bytes);
+  unsigned long long* d_piv = (unsigned long long*)take(piv_bytes);
+  MCM_CUDA(cudaMemsetAsync(d_zero0, 0, zero_span, c.stream));
+  T* d_qcand = nullptr;
+  if (bracket) MCM_CUDA(cudaMallocAsync((void**)&d_qcand, (size_t)M * cand_stride * sizeof(T), c.stream));
+  unsigned long long* d_cand = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_cand, (size_t)S * BS_MAXG * BS_THRESH * sizeof(unsigned long long), c.stream));
+  std::vector<const T*> htab((size_t)M + S);
+  for (int m = 0; m < M; ++m) htab[m] = vars_host[m];
+  for (int m = 0; m < M; ++m) {
+    size_t o = 0;
+    for (int b = 0; b < NB; ++b) {
+      htab[(size_t)M + (size_t)m * NB + b] = bracket ? d_qcand + (size_t)m * cand_stride + o : vars_host[m];
+      o += bi.cap[b];
+    }
+  }
+  MCM_CUDA(cudaMemcpyAsync(d_tab, htab.data(), tab_bytes, cudaMemcpyHostToDevice, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));  // htab is a local
+  static bool attr = false;
+  if (!attr) {
+    MCM_CUDA(cudaFuncSetAttribute(k_bs_hist<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_MAXG * BS_BINS * 4));
+    MCM_CUDA(cudaFuncSetAttribute(k_bs_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_MAXG * BS_BINS * 4));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * BQ_STAGE * 8));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * BQ_STAGE * 8));
+    attr = true;
+  }
+  auto chunks = [&](size_t keys, int segs) {
+    size_t want = (keys + 8191) / 8192;
+    size_t cap = ((size_t)c.sm_count * 8 + segs - 1) / segs;
+    if (cap < 1) cap = 1;
+    return (unsigned)std::max<size_t>(1, std::min(want, cap));
+  };
+  // ---- stage 1 ------------------------------------------------------------------------------------
+  if (bracket) {
+    k_bq_sample<T><<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_tab, n, bp, d_piv);
+    MCM_CHECK_LAUNCH();
+    const dim3 g1(chunks(n, M), (unsigned)M);
+    switch (NB) {
+      case 1: k_bq_stream<T, 1><<<g1, kThreads, 1 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
+      case 2: k_bq_stream<T, 2><<<g1, kThreads, 2 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
+      case 3: k_bq_stream<T, 3><<<g1, kThreads, 3 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
+      default: k_bq_stream<T, 4><<<g1, kThreads, 4 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
+    }
+    MCM_CHECK_LAUNCH();
+  }
+  // ---- stage 2: radix select on S segments -------------------------------------------------------
+  const T* const* seg_tab = d_tab + M;
+  const uint32_t* d_nseg = bracket ? d_qcnt : nullptr;
+  const size_t seg_keys = bracket ? max_cap : n;
+  k_bs_init<<<(S + 127) / 128, 128, 0, c.stream>>>(d_seg, S, 8 * (int)sizeof(K), (uint32_t)n, bi, d_nseg, d_below, d_piv, d_flags);
+  MCM_CHECK_LAUNCH();
+  const dim3 grid(chunks(seg_keys, S), (unsigned)S);
+  const int passes = sizeof(K) == 8 ? BS_PASSES : 3;
+  int gmax = 1;
+  for (int b = 0; b < NB; ++b) gmax = std::max(gmax, std::min(BS_MAXG, bi.nr[b]));
+  for (int p = 0; p < passes; ++p) {
+    const size_t smem = (size_t)(p == 0 ? 1 : gmax) * BS_BINS * 4;
+    k_bs_hist<T><<<grid, kThreads, smem, c.stream>>>(seg_tab, n, d_nseg, d_seg, d_hist);
+    MCM_CHECK_LAUNCH();
+    k_bs_pick<<<S, 256, 0, c.stream>>>(d_seg, d_hist, p == passes - 1);
+    MCM_CHECK_LAUNCH();
+  }
+  k_bs_compact<T><<<grid, kThreads, 0, c.stream>>>(seg_tab, n, d_nseg, d_seg, d_cand, d_cnt);
+  MCM_CHECK_LAUNCH();
+  k_bs_final<T><<<dim3(gmax, S), 1024, 0, c.stream>>>(d_seg, d_cand, d_cnt, d_out);
+  MCM_CHECK_LAUNCH();
+  k_bs_flags<<<(S + 127) / 128, 128, 0, c.stream>>>(d_seg, S, NB, d_flags);
+  MCM_CHECK_LAUNCH();
+  std::vector<double> hout((size_t)S * BS_MAXG);
+  std::vector<uint32_t> hflags(M);
+  MCM_CUDA(cudaMemcpyAsync(hout.data(), d_out, out_bytes, cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, (size_t)M * 4, cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_cand, c.stream));
+  if (d_qcand) MCM_CUDA(cudaFreeAsync(d_qcand, c.stream));
+  MCM_CUDA(cudaFreeAsync(d_all, c.stream));
+  int rc = MCM_OK;
+  for (int m = 0; m < M && rc == MCM_OK; ++m) {
+    if (hflags[m] & 1u) *has_nan = 1;
+    if (hflags[m] & 2u) {  // heavy ties around a rank, or a rank outside its bracket: the general path resolves any input
+      int hn = 0;
+      rc = order_statistics<T>(vars_host[m], n, ranks, nr, vals_host + (size_t)m * nr, &hn);
+      *has_nan |= hn;
+      g_bq_fallbacks++;
+    } else {
+      for (int r = 0; r < nr; ++r)
+        vals_host[(size_t)m * nr + r] = hout[((size_t)m * NB + slot_bracket[r]) * BS_MAXG + slot_index[r]];
+    }
+  }
+  return rc;
+}
+
+}  // namespace mcm
+
+using namespace mcm;
+
+extern "C" int mcm_quantile_batch_fallbacks(void) { return g_bq_fallbacks; }
+
+extern "C" int mcm_order_statistics(int dtype, const void* in, size_t n, const uint64_t* ranks_host, int nr, double* out_host) {
+  MCM_NEED_INIT();
+  if (!in || !ranks_host || !out_host || nr < 1) return fail(MCM_ERR_INVALID, "mcm_order_statistics: bad arguments");
+  if (n == 0) return fail(MCM_ERR_INVALID, "mcm_order_statistics: empty particles");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_order_statistics: bad dtype %d", dtype);
+  if (n >= 0xFFFF0000ull) return fail(MCM_ERR_UNSUPPORTED, "mcm_order_statistics: n must be < 2^32");
+  if (reinterpret_cast<uintptr_t>(in) % (dtype == MCM_F64 ? 8 : 4)) return fail(MCM_ERR_INVALID, "mcm_order_statistics: misaligned input");
+  for (int r = 0; r < nr; ++r)
+    if (ranks_host[r] >= n) return fail(MCM_ERR_INVALID, "mcm_order_statistics: rank %llu out of range", (unsigned long long)ranks_host[r]);
+  int any_nan = 0;
+  for (int r0 = 0; r0 < nr; r0 += BS_MAXG) {
+    const int cnt = std::min(BS_MAXG, nr - r0);
+    unsigned long long rk[BS_MAXG];
+    for (int i = 0; i < cnt; ++i) rk[i] = ranks_host[r0 + i];
+    int hn = 0;
+    const int rc = dtype == MCM_F64 ? order_statistics_batch<double>((const double* const*)&in, 1, n, rk, cnt, out_host + r0, &hn)
+                                    : order_statistics_batch<float>((const float* const*)&in, 1, n, rk, cnt, out_host + r0, &hn);
+    if (rc) return rc;
+    any_nan |= hn;
+  }
+  if (any_nan) return fail(MCM_ERR_INVALID, "mcm_order_statistics: order is undefined in presence of NaNs");
+  return MCM_OK;
+}
+
+extern "C" int mcm_quantile_batch(int dtype, const void* const* vars, int M, size_t n, const double* q_host, int nq,
+                                  double* out_host) {
+  MCM_NEED_INIT();
+  if (!vars || !q_host || !out_host || nq < 1 || M < 1) return fail(MCM_ERR_INVALID, "mcm_quantile_batch: bad arguments");
+  if (n == 0) return fail(MCM_ERR_INVALID, "mcm_quantile_batch: empty particles");
+  if (M > 16383) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_batch: at most 16383 variables per call");
+  if (n >= 0xFFFF0000ull) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_batch: n must be < 2^32");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile_batch: bad dtype %d", dtype);
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  for (int m = 0; m < M; ++m)
+    if (!vars[m] || (reinterpret_cast<uintptr_t>(vars[m]) % esz) != 0)
+      return fail(MCM_ERR_INVALID, "mcm_quantile_batch: variable %d is null or misaligned", m);
+  for (int i = 0; i < nq; ++i)
+    if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
+      return fail(MCM_ERR_INVALID, "mcm_quantile_batch: input probability out of [0,1] range");
+  // 4 probabilities (8 ranks) per sweep
+  std::vector<double> vals((size_t)M * BS_MAXG);
+  int any_nan = 0;
+  for (int q0 = 0; q0 < nq; q0 += BS_MAXG / 2) {
+    const int cq = std::min(BS_MAXG / 2, nq - q0);
+    unsigned long long ranks[BS_MAXG];
+    double gam[BS_MAXG / 2];
+    for (int i = 0; i < cq; ++i) quantile_rank_pair(n, q_host[q0 + i], ranks[2 * i], ranks[2 * i + 1], gam[i]);
+    const int nr = 2 * cq;
+    int hn = 0;
+    const int rc = dtype == MCM_F64
+                       ? order_statistics_batch<double>((const double* const*)vars, M, n, ranks, nr, vals.data(), &hn)
+                       : order_statistics_batch<float>((const float* const*)vars, M, n, ranks, nr, vals.data(), &hn);
+    if (rc) return rc;
+    any_nan |= hn;
+    for (int m = 0; m < M; ++m)
+      for (int i = 0; i < cq; ++i)
+        out_host[(size_t)m * nq + q0 + i] =
+            quantile_combine(dtype, vals[(size_t)m * nr + 2 * i], vals[(size_t)m * nr + 2 * i + 1], gam[i]);
+  }
+  if (any_nan) return fail(MCM_ERR_INVALID, "mcm_quantile_batch: quantiles are undefined in presence of NaNs");
+  return MCM_OK;
+}

@@ -14,6 +14,7 @@
 #include <vector>
 #include "mcm_common.cuh"
 #include "mcm_keys.cuh"
+#include "mcm_quantile.cuh"
 
 namespace mcm {
 
@@ -360,20 +361,12 @@ extern "C" int mcm_quantile(int dtype, const void* in, size_t n, const double* q
     if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
       return fail(MCM_ERR_INVALID, "mcm_quantile: input probability out of [0,1] range");
   if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile: bad dtype %d", dtype);
+  // large inputs, few probabilities: sampled brackets + one streaming read (select_batch.cu)
+  if (g_use_select == 1 && n >= 131072 && nq <= 8 && (reinterpret_cast<uintptr_t>(in) % (dtype == MCM_F64 ? 8 : 4)) == 0)
+    return mcm_quantile_batch(dtype, &in, 1, n, q_host, nq, out_host);
   std::vector<double> gam(nq), vals(2 * (size_t)nq);
   std::vector<unsigned long long> ranks(2 * (size_t)nq);
-  for (int i = 0; i < nq; ++i) {
-    const double p = q_host[i];
-    const double aleph = (double)n * p + (1.0 - p);
-    long long j = (long long)trunc(aleph);
-    if (j > (long long)n - 1) j = (long long)n - 1;
-    if (j < 1) j = 1;
-    double g = aleph - (double)j;
-    g = g < 0.0 ? 0.0 : (g > 1.0 ? 1.0 : g);
-    gam[i] = g;
-    if (n == 1) { ranks[2 * i] = 0; ranks[2 * i + 1] = 0; }
-    else { ranks[2 * i] = (unsigned long long)(j - 1); ranks[2 * i + 1] = (unsigned long long)j; }
-  }
+  for (int i = 0; i < nq; ++i) quantile_rank_pair(n, q_host[i], ranks[2 * i], ranks[2 * i + 1], gam[i]);
   int has_nan = 0, rc = MCM_OK;
   const int nr = 2 * nq;
   if (g_use_select && (reinterpret_cast<uintptr_t>(in) % (dtype == MCM_F64 ? 8 : 4)) == 0) {
@@ -395,17 +388,6 @@ extern "C" int mcm_quantile(int dtype, const void* in, size_t n, const double* q
   }
   if (rc) return rc;
   if (has_nan) return fail(MCM_ERR_INVALID, "mcm_quantile: quantiles are undefined in presence of NaNs");
-  for (int i = 0; i < nq; ++i) {
-    const double g = gam[i];
-    if (dtype == MCM_F64) {
-      const double a = vals[2 * i], b = vals[2 * i + 1];
-      out_host[i] = (isfinite(a) && isfinite(b)) ? a + g * (b - a) : (1.0 - g) * a + g * b;
-    } else {
-      const float a = (float)vals[2 * i], b = (float)vals[2 * i + 1];
-      // Float32 data, Float64 probability: (b-a) rounds in Float32, the rest promotes
-      out_host[i] = (isfinite(a) && isfinite(b)) ? (double)a + g * (double)(b - a)
-                                                 : (1.0 - g) * (double)a + g * (double)b;
-    }
-  }
+  for (int i = 0; i < nq; ++i) out_host[i] = quantile_combine(dtype, vals[2 * i], vals[2 * i + 1], gam[i]);
   return MCM_OK;
 }

@@ -522,22 +522,44 @@ def meanvar(p): return pvar(p) / p.N               # particles.jl:486
 
 
 def pquantile(p, q):
-    """pquantile(p, q) = Statistics.quantile(p.particles, q) (particles.jl:321); q scalar or vector."""
+    """pquantile(p, q) = Statistics.quantile(p.particles, q) (particles.jl:321); q scalar or vector.
+    p may be a vector of Particles: one batched device call (mcm_quantile_batch), result [M] or [M, nq]."""
     scalar = isinstance(q, numbers.Real)
     qs = np.ascontiguousarray(np.atleast_1d(np.asarray(q, dtype=np.float64)))
+    if not isinstance(p, Particles):
+        v = _check_mv(p)
+        M = len(v)
+        ptrs = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in v])
+        out = np.zeros((M, len(qs)))
+        L.check(L.lib().mcm_quantile_batch(v[0].dtype, ptrs, M, v[0].N, qs.ctypes.data_as(L._dp), len(qs),
+                                           out.ctypes.data_as(L._dp)))
+        return out[:, 0].copy() if scalar else out
     out = np.zeros(len(qs))
     L.check(L.lib().mcm_quantile(p.dtype, C.c_void_p(p.ptr), p.N, qs.ctypes.data_as(L._dp), len(qs),
                                  out.ctypes.data_as(L._dp)))
     return float(out[0]) if scalar else out
 
 
+def order_statistics(p: Particles, ranks) -> np.ndarray:
+    """sort(p.particles)[ranks] (0-based) without sorting (mcm_order_statistics)."""
+    rk = np.ascontiguousarray(np.atleast_1d(np.asarray(ranks, dtype=np.uint64)))
+    out = np.zeros(len(rk))
+    L.check(L.lib().mcm_order_statistics(p.dtype, C.c_void_p(p.ptr), p.N, rk.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                         len(rk), out.ctypes.data_as(L._dp)))
+    return out
+
+
 def pmedian(p):
-    """Statistics.median: middle of the one/two central order statistics."""
+    """Statistics.median: middle of the one/two central order statistics (no full sort)."""
     n = p.N
-    srt = psort(p)
+    if n == 0:
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "median of an empty collection")
     if n % 2 == 1:
-        return float(_pick(srt, [n // 2])[0])
-    a, b = _pick(srt, [n // 2 - 1, n // 2])
+        return float(order_statistics(p, [n // 2])[0])
+    a, b = order_statistics(p, [n // 2 - 1, n // 2])
+    if p.np_dtype == np.float32:
+        a, b = np.float32(a), np.float32(b)
+        return float(a / np.float32(2) + b / np.float32(2))
     return float(a / 2 + b / 2)  # Statistics.middle(x, y) = x/2 + y/2
 
 
@@ -624,6 +646,55 @@ def pcov(v, corrected: bool = True) -> np.ndarray:
     finally:
         L.lib().mcm_free(C.c_void_p(dC))
     return out
+
+
+# ---- Particle BLAS (src/particles.jl:614-707) ------------------------------------------------
+def pgemm(A, xs, shift=None, bias=None):
+    """y_j = bias_j + sum_k A[j,k] (x_k - shift_k) on device (mcm_pgemm): the GEMM behind
+    mul!(y, A, b::Vector{Particles}) (particles.jl:688-707), A*p (_pgemv, :620-631) and the
+    transform_moments application (sigmapoints.jl:71).  Returns a list of Mo new Particles."""
+    xs = _check_mv(xs)
+    A = np.ascontiguousarray(np.atleast_2d(np.asarray(A, dtype=np.float64)))
+    Mo, Mi = A.shape
+    if Mi != len(xs):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, f"DimensionMismatch: A has {Mi} columns, vector has {len(xs)} entries")
+    sh = None if shift is None else np.ascontiguousarray(np.broadcast_to(np.asarray(shift, dtype=np.float64), (Mi,)))
+    bi = None if bias is None else np.ascontiguousarray(np.broadcast_to(np.asarray(bias, dtype=np.float64), (Mo,)))
+    outs = [_empty_like(xs[0]) for _ in range(Mo)]
+    xin = (C.c_void_p * Mi)(*[C.c_void_p(x.ptr) for x in xs])
+    xout = (C.c_void_p * Mo)(*[C.c_void_p(y.ptr) for y in outs])
+    L.check(L.lib().mcm_pgemm(xs[0].dtype, A.ctypes.data_as(L._dp), Mo, Mi, xin,
+                              None if sh is None else sh.ctypes.data_as(L._dp),
+                              None if bi is None else bi.ctypes.data_as(L._dp), xout, xs[0].N))
+    return outs
+
+
+def pgemv(A, p):
+    """A * p::Vector{Particles} (particles.jl:620-633)."""
+    return pgemm(A, p)
+
+
+def mul_(y, A, b):
+    """mul!(y, A, b) (particles.jl:688-707): fills the list y in place with A*b and returns it."""
+    res = pgemm(A, b)
+    if len(y) != len(res):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "DimensionMismatch: y has the wrong length")
+    y[:] = res
+    return y
+
+
+def pdot(v, p):
+    """dot(v, p::Vector{Particles}) (_pdot, particles.jl:641-654)."""
+    return pgemm(np.asarray(v, dtype=np.float64)[None, :], p)[0]
+
+
+def paxpy_(a, x, y):
+    """axpy!(a, x, y) on particle vectors (_paxpy!, particles.jl:657-673): y .= a*x + y, returns y."""
+    x, yv = _check_mv(x), _check_mv(y)
+    if len(x) != len(yv):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "DimensionMismatch")
+    y[:] = [muladd(float(a), xi, yi) for xi, yi in zip(x, yv)]
+    return y
 
 
 def pcor(v) -> np.ndarray:

@@ -16,6 +16,12 @@ import numpy as np
 from . import _lib as L
 from . import particles as P
 
+try:  # LAPACK trtrs; numpy alone only offers a general LU solve (3x the flops at d = 1024)
+    from scipy.linalg import solve_triangular as _solve_triangular
+except ImportError:  # pragma: no cover
+    def _solve_triangular(a, b, lower=False):
+        return np.linalg.solve(a, b)
+
 
 # ---- minimal Distributions.jl stand-ins (only what the hot path constructs) -----------------
 class Normal:
@@ -140,35 +146,67 @@ def dotdot(a, b, N: int = P.DEFAULT_NUM_PARTICLES, seed: int | None = None):
 # ---- multivariate construction (types.jl:92-100; systematic route docs/index.md:141 + sigmapoints.jl:63-72)
 def transform_moments(X, m, S, preserve_latin: bool = False):
     """transform_moments(X, m, Σ) (sigmapoints.jl:63-72) on a list of M device Particles (the N x M sample):
-    centre, xl = chol(cov X).L (or Diagonal(std)), Y = m + (chol(Σ).L / xl) X'.  The Gram runs on device
-    (mcm_gram); the two M x M Cholesky factorisations and the triangular solve are host-size."""
+    centre, xl = chol(cov X).L (or Diagonal(std)), Y = m + (chol(Σ).L / xl) X'.  The Gram (mcm_gram) and the
+    application (mcm_pgemm, centring fused as its shift) run on device; the two M x M Cholesky factorisations
+    and the triangular solve are host-size."""
     X = P._check_mv(X)
-    M = len(X)
     m = np.asarray(m, dtype=np.float64)
     S = np.asarray(S, dtype=np.float64)
-    means = np.array([P.pmean(x) for x in X])
-    Xc = [x - float(mu) for x, mu in zip(X, means)]
+    M = len(X)
+    ptrs = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in X])
+    means = np.empty(M)
+    L.check(L.lib().mcm_colmeans(X[0].dtype, ptrs, M, X[0].N, means.ctypes.data_as(L._dp)))
+    cov = P.pcov(X)   # centring is internal to the Gram kernel; cov(X .- mean) == cov(X)
     if preserve_latin:
-        xl = np.diag([P.pstd(x) for x in Xc])
+        xl = np.diag(np.sqrt(np.diag(cov)))
     else:
-        xl = np.linalg.cholesky(P.pcov(Xc))
-    A = np.linalg.solve(xl.T, np.linalg.cholesky(S).T).T  # chol(Σ).L / xl
-    out = []
-    for i in range(M):
-        nz = [(float(A[i, j]), Xc[j]) for j in range(M) if A[i, j] != 0.0]
-        acc = None
-        for k in range(0, len(nz), 8):
-            part = P.lincomb([c for c, _ in nz[k:k + 8]], [x for _, x in nz[k:k + 8]])
-            acc = part if acc is None else acc + part
-        out.append((acc if acc is not None else P.fill(0.0, X[0].N, X[0].np_dtype)) + float(m[i]))
+        xl = np.linalg.cholesky(cov)
+    # chol(Σ).L / xl: a triangular solve (A xl = L_S  <=>  xl' A' = L_S'), so A is lower triangular by construction
+    A = _solve_triangular(xl.T, np.linalg.cholesky(S).T, lower=False).T
+    A = np.tril(A)
+    return P.pgemm(A, X, shift=means, bias=m)
+
+
+def index_bijection(n: int, seed: int = 0, column: int = 0, i0: int = 0, n_total: int | None = None) -> P.DeviceIndex:
+    """Keyed pseudo-random permutation pi(i0 .. i0+n) of [0, n_total) evaluated on device with no sort and no
+    communication (mcm_index_bijection) — the sharding-friendly stand-in for randperm (sampling.jl:11)."""
+    n_total = int(n if n_total is None else n_total)
+    out = P.DeviceIndex(int(n))
+    L.check(L.lib().mcm_index_bijection(C.c_void_p(out.ptr), int(n), int(seed), int(column), int(i0), n_total))
     return out
+
+
+def systematic_batch(N: int, dists, *, permute=True, seed: int = 0, i0: int = 0, n_total: int | None = None,
+                     n_local: int | None = None, dtype=np.float64):
+    """M systematic columns in one launch (mcm_systematic_batch): column v is systematic_sample(N, dists[v])
+    permuted by the keyed bijection of (seed, v).  `dists`: an int M (standard normals) or a list of Normal /
+    Uniform (one family per call)."""
+    if isinstance(dists, numbers.Integral):
+        M, kind, a, b = int(dists), 0, None, None
+    else:
+        dists = list(dists)
+        M = len(dists)
+        if all(isinstance(d, Normal) for d in dists):
+            kind, a, b = 0, np.array([float(d.mu) for d in dists]), np.array([float(d.sigma) for d in dists])
+        elif all(isinstance(d, Uniform) for d in dists):
+            kind, a, b = 1, np.array([float(d.a) for d in dists]), np.array([float(d.b) for d in dists])
+        else:
+            raise L.MethodError(L.MCM_ERR_UNSUPPORTED, "systematic_batch: all Normal or all Uniform")
+    n_total = int(N if n_total is None else n_total)
+    n_loc = int(N if n_local is None else n_local)
+    code = P._dtype_code(dtype)
+    outs = [P._empty(n_loc, code) for _ in range(M)]
+    ptrs = (C.c_void_p * M)(*[C.c_void_p(o.ptr) for o in outs])
+    L.check(L.lib().mcm_systematic_batch(code, kind, ptrs, M, n_loc,
+                                         None if a is None else a.ctypes.data_as(L._dp),
+                                         None if b is None else b.ctypes.data_as(L._dp),
+                                         1 if permute else 0, int(seed), int(i0), n_total))
+    return outs
 
 
 def mvnormal_particles(N: int, d: MvNormal, seed: int | None = None):
     """Systematic multivariate Normal: independent permuted systematic columns (docs index.md:141) moved to
     (μ, Σ) by transform_moments.  (The reference default for MvNormal draws iid randn — a host RNG stream
     that cannot be reproduced here, H5; this is its documented systematic alternative.)"""
-    seed = 0 if seed is None else int(seed)
-    cols = [systematic_sample(N, Normal(), permute=True, seed=seed + 1000003 * j, as_particles=True)
-            for j in range(len(d.mu))]
+    cols = systematic_batch(N, len(d.mu), permute=True, seed=0 if seed is None else int(seed))
     return transform_moments(cols, d.mu, d.S)

@@ -597,3 +597,57 @@ ORC_API int orc_resample_systematic(const double* w, size_t n, double u, int64_t
   free(C);
   return MCM_OK;
 }
+
+/* ---- keyed index bijection (restates csrc/sampling.cu feistel_permute; the reference uses
+ * randperm(rng, N) at src/sampling.jl:11, whose stream cannot be reproduced — H5).  Test
+ * infrastructure: checks that the device evaluates exactly this permutation. ---- */
+static uint64_t orc_splitmix64(uint64_t* s) {
+  *s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = *s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static uint32_t orc_feistel_mix(uint32_t v, uint32_t k) {
+  uint32_t h = v + k;
+  h ^= h >> 16; h *= 0x7feb352du;
+  h ^= h >> 15; h *= 0x846ca68bu;
+  h ^= h >> 16;
+  return h;
+}
+ORC_API void orc_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, uint64_t i0, uint64_t n_total) {
+  uint32_t key[8];
+  uint64_t s = seed ^ (0xD1B54A32D192ED03ull * (column + 1));
+  for (int r = 0; r < 8; ++r) key[r] = (uint32_t)(orc_splitmix64(&s) >> 32);
+  uint32_t bits = 2;
+  while (bits < 64 && (1ull << bits) < n_total) ++bits;
+  const uint32_t lbits = bits / 2, rbits = bits - lbits;
+  const uint32_t lmask = lbits >= 32 ? 0xffffffffu : ((1u << lbits) - 1u);
+  const uint32_t rmask = rbits >= 32 ? 0xffffffffu : ((1u << rbits) - 1u);
+  for (size_t j = 0; j < n; ++j) {
+    uint64_t x = i0 + j;
+    do {
+      uint32_t L = (uint32_t)(x >> rbits) & lmask, R = (uint32_t)x & rmask;
+      for (int r = 0; r < 6; r += 2) {   /* kFeistelRounds */
+        L ^= orc_feistel_mix(R, key[r]) & lmask;
+        R ^= orc_feistel_mix(L, key[r + 1]) & rmask;
+      }
+      x = ((uint64_t)L << rbits) | R;
+    } while (x >= n_total);
+    out[j] = (int64_t)x;
+  }
+}
+
+/* ---- constant matrix x particle vector (src/particles.jl:688-707 `Matrix(b) * A'`,
+ * src/sigmapoints.jl:71): y[j][i] = bias[j] + sum_k A[j,k] (x[k][i] - shift[k]) in long double.
+ * xs: Mi x n row-major (variable-major), ys: Mo x n. ---- */
+ORC_API void orc_pgemm(const double* A, int Mo, int Mi, const double* xs, const double* shift, const double* bias,
+               double* ys, size_t n) {
+  for (int j = 0; j < Mo; ++j)
+    for (size_t i = 0; i < n; ++i) {
+      long double acc = 0.0L;
+      for (int k = 0; k < Mi; ++k)
+        acc += (long double)A[(size_t)j * Mi + k] * ((long double)xs[(size_t)k * n + i] - (shift ? (long double)shift[k] : 0.0L));
+      ys[(size_t)j * n + i] = (double)(acc + (bias ? (long double)bias[j] : 0.0L));
+    }
+}

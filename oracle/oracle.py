@@ -209,6 +209,29 @@ def randperm(n: int, seed: int = 0) -> np.ndarray:
     return out
 
 
+def index_bijection(n: int, seed: int = 0, column: int = 0, i0: int = 0, n_total=None) -> np.ndarray:
+    n_total = n if n_total is None else n_total
+    out = np.empty(n, dtype=np.int64)
+    lib().orc_index_bijection.restype = None
+    lib().orc_index_bijection(_p(out), C.c_size_t(n), C.c_uint64(seed), C.c_uint64(column), C.c_uint64(i0),
+                              C.c_uint64(n_total))
+    return out
+
+
+def pgemm(A: np.ndarray, xs: np.ndarray, shift=None, bias=None) -> np.ndarray:
+    """ys[j] = bias[j] + sum_k A[j,k] (xs[k] - shift[k]); xs is Mi x n (variable-major); long-double accumulation."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    xs = np.ascontiguousarray(xs, dtype=np.float64)
+    Mo, Mi = A.shape
+    n = xs.shape[1]
+    sh = None if shift is None else np.ascontiguousarray(shift, dtype=np.float64)
+    bi = None if bias is None else np.ascontiguousarray(bias, dtype=np.float64)
+    ys = np.empty((Mo, n))
+    lib().orc_pgemm.restype = None
+    lib().orc_pgemm(_p(A), C.c_int(Mo), C.c_int(Mi), _p(xs), _p(sh), _p(bi), _p(ys), C.c_size_t(n))
+    return ys
+
+
 def resample_systematic(w: np.ndarray, u: float) -> np.ndarray:
     w = np.ascontiguousarray(w, dtype=np.float64)
     out = np.empty(w.size, dtype=np.int64)

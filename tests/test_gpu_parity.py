@@ -350,8 +350,9 @@ def test_sort_sortperm_quantile_bit_exact(mcm, orc, dt):
         mcm._lib.lib().mcm_quantile_use_select(1)
     assert mcm.pquantile(p, 0.5) == orc.quantile(x, 0.5)[0]
     even = mcm.Particles(x[:-1])
-    s = orc.sort(x[:-1]).astype(np.float64)
-    assert mcm.pmedian(even) == s[(N - 1) // 2 - 1] / 2 + s[(N - 1) // 2] / 2 and mcm.pmedian(p) == orc.sort(x)[N // 2]
+    s = orc.sort(x[:-1])                                                   # middle(x, y) = x/2 + y/2 in the particle eltype
+    assert mcm.pmedian(even) == float(s[(N - 1) // 2 - 1] / dt(2) + s[(N - 1) // 2] / dt(2)) and mcm.pmedian(p) == orc.sort(x)[N // 2]
+    assert np.array_equal(mcm.particles.order_statistics(p, [0, 5, N // 3, N - 1]), orc.sort(x)[[0, 5, N // 3, N - 1]].astype(np.float64))
     with pytest.raises(mcm.ArgumentError):
         mcm.pquantile(p, 1.5)
     xn = x.copy(); xn[5] = np.nan
