@@ -429,140 +429,182 @@ k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned l
   if (threadIdx.x < bp.nb) {
     const int b = threadIdx.x;
     const unsigned long long kmax = sizeof(K) == 8 ? ~0ull : 0xffffffffull;
-    pivots[2 * ((size_t)m * bp.nb + b)] = bp.a[b] < 0 ? 0ull : sk[bp.a[b]];
-    pivots[2 * ((size_t)m * bp.nb + b) + 1] = bp.b[b] >= BQ_SAMPLE ? kmax : sk[bp.b[b]];
+    // 64-bit keys: the pivots are widened to boundaries of the HIGH key word, so the streaming pass classifies
+    // with 32-bit compares only (the bracket grows by < 2^32 key units, i.e. by ~1e-6 of the value)
+    unsigned long long lo = bp.a[b] < 0 ? 0ull : sk[bp.a[b]];
+    unsigned long long hi = bp.b[b] >= BQ_SAMPLE ? kmax : sk[bp.b[b]];
+    if (sizeof(K) == 8) { lo &= 0xffffffff00000000ull; hi |= 0x00000000ffffffffull; }
+    pivots[2 * ((size_t)m * bp.nb + b)] = lo;
+    pivots[2 * ((size_t)m * bp.nb + b) + 1] = hi;
   }
 }
 
-// Candidates are staged per CTA in shared memory and flushed with ONE global atomic per bracket per
-// flush (first version: one global atomic per warp-step on 3 addresses per variable — 3.6 ms for
-// 1e8 keys, L2 same-address atomic throughput).
-constexpr int BQ_ITER_KEYS = kThreads * 4 * 2;       // keys per CTA iteration (both dtypes)
-constexpr int BQ_FLUSH = 512;                        // flush a list once it holds more than this
-constexpr int BQ_STAGE = BQ_ITER_KEYS + BQ_FLUSH;    // staging capacity per bracket
+// The classification only needs the high word of each 64-bit key, and ptxas narrows a 128-bit load whose low
+// words are dead into two strided 4-byte loads that fetch every sector twice (ncu: 14.6 GB of DRAM reads for
+// 8.19 GB of data).  Folding the low words into a live value (one LOP3 per pack) keeps the load whole.
+template <typename T>
+__device__ __forceinline__ uint32_t low_words(const Pack<T>& p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&p);
+  return sizeof(T) == 8 ? (w[0] | w[2]) : 0u;
+}
+
+// Candidates are staged PER WARP in shared memory — as 32-bit element INDICES — and flushed by the warp
+// with one global atomic per flush; the flush gathers the values (L1/L2 hits) into the bracket's list.
+// There is no CTA barrier and no shared-memory atomic anywhere in the loop: the per-lane counts of all brackets
+// are scanned at once (16-bit fields of a 64-bit word, 5 shuffle steps) and the warp's fill counts live in
+// registers.  History (C5, 8.19 GB of keys): one global atomic per warp-step 7.1 ms -> CTA staging of values
+// 5.1 ms (97 instructions per key, 3 barriers per iteration, no load/compute overlap) -> CTA staging of
+// indices + prefetch + one barrier 3.6 ms (flush every 4th iteration stalls all 8 warps) -> this version.
+constexpr int BQ_WARP_KEYS = 32 * 4 * 2;                   // keys per warp iteration (both dtypes)
 
 template <typename T, int NB>
 __global__ void __launch_bounds__(kThreads)
 k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsigned long long* __restrict__ pivots,
             T* __restrict__ cand, size_t cand_stride, uint32_t* __restrict__ cnt, uint32_t* __restrict__ below,
-            uint32_t* __restrict__ flags) {
+            uint32_t* __restrict__ flags, int flush_at) {
   using K = typename KeyOf<T>::type;
   using P = Pack<T>;
   constexpr int V = P::N;
-  constexpr int UNROLL = BQ_ITER_KEYS / (kThreads * V);   // 4 (f64) / 2 (f32)
+  constexpr int UNROLL = BQ_WARP_KEYS / (32 * V);          // 4 (f64) / 2 (f32)
   extern __shared__ __align__(16) unsigned char bq_smem[];
-  T* stage = reinterpret_cast<T*>(bq_smem);                // [NB][BQ_STAGE]
-  __shared__ uint32_t s_cnt[NB], s_base[NB], s_n[NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int capw = flush_at + BQ_WARP_KEYS;                // staging entries per (warp, bracket)
+  uint32_t* wstage = reinterpret_cast<uint32_t*>(bq_smem) + (size_t)warp * NB * capw;
   __shared__ uint32_t sh[NB][kThreads / 32];
   const int m = blockIdx.y;
   const T* __restrict__ in = vars[m];
-  K lo[NB], hi[NB];
-  uint32_t nbelow[NB];
+  uint32_t lo[NB], span[NB];    // pivots as high key words (the whole key for Float32): in bracket <=> k - lo <= span
+  uint32_t nbelow[NB], wcnt[NB];
   T* cb[NB];
   size_t coff = 0;
+  constexpr int PSH = sizeof(K) == 8 ? 32 : 0;
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
-    lo[b] = (K)pivots[2 * ((size_t)m * NB + b)];
-    hi[b] = (K)pivots[2 * ((size_t)m * NB + b) + 1];
+    lo[b] = (uint32_t)(pivots[2 * ((size_t)m * NB + b)] >> PSH);
+    span[b] = (uint32_t)(pivots[2 * ((size_t)m * NB + b) + 1] >> PSH) - lo[b];
     nbelow[b] = 0;
+    wcnt[b] = 0;
     cb[b] = cand + (size_t)m * cand_stride + coff;
     coff += bp.cap[b];
   }
-  if (threadIdx.x < NB) s_cnt[threadIdx.x] = 0;
-  __syncthreads();
   uint32_t* mcnt = cnt + (size_t)m * NB;
-  const int lane = threadIdx.x & 31;
-  bool nan = false;
-  // classify one key: below-counters in registers, membership bit `bit` of the per-bracket masks
+  // high key word of x: order-preserving on the sign/exponent/top-mantissa bits.  NaNs are the keys above
+  // +Inf or below -Inf: tracked with a running min/max instead of a per-key test.
+  uint32_t kmin = 0xffffffffu, kmax = 0u, lowor = 0u;
   uint32_t inmask[NB];
-  auto classify = [&](bool valid, T x, int bit) {
-    const K key = to_key(x, nan);
+  auto classify = [&](T x, int bit) {
+    uint32_t w;
+    if constexpr (sizeof(T) == 8) w = (uint32_t)__double2hiint(x); else w = __float_as_uint(x);
+    const uint32_t k = w ^ ((uint32_t)((int32_t)w >> 31) | 0x80000000u);
+    kmin = min(kmin, k); kmax = max(kmax, k);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      nbelow[b] += (valid && key < lo[b]) ? 1u : 0u;
-      inmask[b] |= (valid && key >= lo[b] && key <= hi[b]) ? (1u << bit) : 0u;
+      nbelow[b] += (k < lo[b]) ? 1u : 0u;
+      inmask[b] |= ((k - lo[b]) <= span[b]) ? (1u << bit) : 0u;
     }
   };
-  // scalar variant used by the tails: one key per thread
-  auto consider = [&](bool valid, T x) {
-#pragma unroll
-    for (int b = 0; b < NB; ++b) inmask[b] = 0;
-    classify(valid, x, 0);
-#pragma unroll
-    for (int b = 0; b < NB; ++b)
-      if (inmask[b]) stage[b * BQ_STAGE + atomicAdd(&s_cnt[b], 1u)] = x;
+  // warp flush of bracket b: one global atomic, gather of the staged elements, coalesced stores
+  auto warp_flush = [&](int b) {
+    const uint32_t c = wcnt[b];
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(mcnt + b, c);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    const uint32_t* st = wstage + b * capw;
+    for (uint32_t i = lane; i < c; i += 32)
+      if (base + i < bp.cap[b]) cb[b][base + i] = __ldg(in + st[i]);
+    __syncwarp();
+    wcnt[b] = 0;
   };
-  // flush every list holding more than `threshold` entries; called by all threads at a uniform point
-  auto flush = [&](uint32_t threshold) {
-    __syncthreads();
-    if (threadIdx.x < NB) {
-      const uint32_t c = s_cnt[threadIdx.x];
-      const bool go = c > threshold;
-      s_n[threadIdx.x] = go ? c : 0u;
-      if (go) { s_base[threadIdx.x] = atomicAdd(mcnt + threadIdx.x, c); s_cnt[threadIdx.x] = 0; }
+  // Append the candidates flagged in inmask[] (bit (u*V + e) = element row0 + u*ustride + e).  Warp-uniform call.
+  auto append = [&](uint32_t row0, uint32_t ustride) {
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) packed |= (unsigned long long)__popc(inmask[b]) << (16 * b);
+    if (!__any_sync(0xffffffffu, packed != 0)) return;
+    unsigned long long incl = packed;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
     }
-    __syncthreads();
+    const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned long long excl = incl - packed;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      const uint32_t c = s_n[b];
-      if (c) {
-        const uint32_t base = s_base[b];
-        for (uint32_t i = threadIdx.x; i < c; i += kThreads)
-          if (base + i < bp.cap[b]) cb[b][base + i] = stage[b * BQ_STAGE + i];
+      uint32_t mk = inmask[b];
+      if (mk) {
+        uint32_t* p = wstage + b * capw + wcnt[b] + ((uint32_t)(excl >> (16 * b)) & 0xffffu);
+        do {
+          const int bit = __ffs(mk) - 1;
+          mk &= mk - 1;
+          *p++ = row0 + (uint32_t)(bit / V) * ustride + (uint32_t)(bit % V);
+        } while (mk);
       }
+      wcnt[b] += (uint32_t)(total >> (16 * b)) & 0xffffu;
+      if (wcnt[b] > (uint32_t)flush_at) warp_flush(b);
     }
-    __syncthreads();   // staging is reused by the next iteration
   };
   const size_t stride = (size_t)gridDim.x * kThreads;
   const size_t tid = (size_t)blockIdx.x * kThreads + threadIdx.x;
   const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
   const size_t nvec = vec ? n / V : 0;
   const P* pin = reinterpret_cast<const P*>(in);
-  const size_t rows = (nvec + stride * UNROLL - 1) / (stride * UNROLL);   // CTA-uniform trip count
-  for (size_t r = 0; r < rows; ++r) {
-    P x[UNROLL];
-    bool ok[UNROLL];
+  const size_t full_rows = nvec / (stride * UNROLL);   // rows in which every thread of the grid has UNROLL packs
+  P cur[UNROLL], nxt[UNROLL];
+  if (full_rows) {
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      const size_t j = (r * UNROLL + u) * stride + tid;
-      ok[u] = j < nvec;
-      if (ok[u]) x[u] = ld_stream(pin + j);
+    for (int u = 0; u < UNROLL; ++u) cur[u] = ld_stream(pin + (size_t)u * stride + tid);
+  }
+  for (size_t r = 0; r < full_rows; ++r) {
+    if (r + 1 < full_rows) {     // next row's loads are in flight while this row is classified
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) nxt[u] = ld_stream(pin + ((r + 1) * UNROLL + u) * stride + tid);
     }
 #pragma unroll
     for (int b = 0; b < NB; ++b) inmask[b] = 0;
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u)
+    for (int u = 0; u < UNROLL; ++u) {
+      lowor |= low_words(cur[u]);
 #pragma unroll
-      for (int e = 0; e < V; ++e) classify(ok[u], ok[u] ? x[u].v[e] : T(0), u * V + e);
-    // one shared-memory atomic per thread per bracket, only for threads that hold candidates (~30 %)
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      if (inmask[b]) {
-        uint32_t pos = atomicAdd(&s_cnt[b], (uint32_t)__popc(inmask[b]));
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-#pragma unroll
-          for (int e = 0; e < V; ++e)
-            if ((inmask[b] >> (u * V + e)) & 1u) stage[b * BQ_STAGE + pos++] = x[u].v[e];
-      }
+      for (int e = 0; e < V; ++e) classify(cur[u].v[e], u * V + e);
     }
-    flush(BQ_FLUSH);
+    append((uint32_t)((r * UNROLL * stride + tid) * V), (uint32_t)(stride * V));
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) cur[u] = nxt[u];
+  }
+  // remaining packs: fewer than UNROLL per thread, uniform trip count, bounds-checked
+  for (size_t j0 = full_rows * UNROLL * stride; j0 < nvec; j0 += stride) {
+    const size_t j = j0 + tid;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) inmask[b] = 0;
+    if (j < nvec) {
+      const P x = ld_stream(pin + j);
+      lowor |= low_words(x);
+#pragma unroll
+      for (int e = 0; e < V; ++e) classify(x.v[e], e);
+    }
+    append((uint32_t)(j * V), 0u);
   }
   const size_t tail0 = nvec * V;
   const size_t trips = (n - tail0 + stride - 1) / stride;
   for (size_t r = 0; r < trips; ++r) {
     const size_t i = tail0 + r * stride + tid;
-    consider(i < n, i < n ? in[i] : T(0));
-    if ((r & 7) == 7) flush(BQ_FLUSH);   // 8 x 256 keys per flush check
+#pragma unroll
+    for (int b = 0; b < NB; ++b) inmask[b] = 0;
+    if (i < n) classify(in[i], 0);
+    append((uint32_t)i, 0u);
   }
-  flush(0);
+#pragma unroll
+  for (int b = 0; b < NB; ++b)
+    if (wcnt[b]) warp_flush(b);
   // CTA totals of the below-counters, one atomic per bracket per CTA
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     uint32_t v = nbelow[b];
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
-    if (lane == 0) sh[b][threadIdx.x >> 5] = v;
+    if (lane == 0) sh[b][warp] = v;
   }
   __syncthreads();
   if (threadIdx.x < NB) {
@@ -570,7 +612,11 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
     for (int w = 0; w < kThreads / 32; ++w) t += sh[threadIdx.x][w];
     if (t) atomicAdd(below + (size_t)m * NB + threadIdx.x, t);
   }
-  if (nan) atomicOr(flags + m, 1u);
+  // NaN keys lie above +Inf / below -Inf
+  constexpr uint32_t kPosInf = sizeof(T) == 8 ? 0xfff00000u : 0xff800000u;
+  constexpr uint32_t kNegInf = sizeof(T) == 8 ? 0x000fffffu : 0x007fffffu;
+  if (kmax > kPosInf || kmin < kNegInf) atomicOr(flags + m, 1u);
+  if (lowor == 0x5a5a5a5au && kmax == 0u) atomicOr(flags + m, 0u);   // keeps `lowor` (hence the full loads) alive
 }
 
 __global__ void k_bs_flags(const BSeg* __restrict__ segs, int nsegs, int nb, uint32_t* __restrict__ flags) {
@@ -689,8 +735,13 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     MCM_CUDA(cudaFuncSetAttribute(k_bs_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_MAXG * BS_BINS * 4));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
-    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * BQ_STAGE * 8));
-    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * BQ_STAGE * 8));
+    constexpr int kStreamSmem = (kThreads / 32) * 4 * (512 + BQ_WARP_KEYS) * 4;
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<float, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<float, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
     attr = true;
   }
   auto chunks = [&](size_t keys, int segs) {
@@ -704,11 +755,14 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     k_bq_sample<T><<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_tab, n, bp, d_piv);
     MCM_CHECK_LAUNCH();
     const dim3 g1(chunks(n, M), (unsigned)M);
+    // few variables: many warps flush into the same three counters -> flush rarely; many variables: small staging
+    const int flush_at = M >= 64 ? 128 : 512;
+    const size_t smem1 = (size_t)(kThreads / 32) * NB * (flush_at + BQ_WARP_KEYS) * sizeof(uint32_t);
     switch (NB) {
-      case 1: k_bq_stream<T, 1><<<g1, kThreads, 1 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
-      case 2: k_bq_stream<T, 2><<<g1, kThreads, 2 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
-      case 3: k_bq_stream<T, 3><<<g1, kThreads, 3 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
-      default: k_bq_stream<T, 4><<<g1, kThreads, 4 * BQ_STAGE * sizeof(T), c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags); break;
+      case 1: k_bq_stream<T, 1><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
+      case 2: k_bq_stream<T, 2><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
+      case 3: k_bq_stream<T, 3><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
+      default: k_bq_stream<T, 4><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
     }
     MCM_CHECK_LAUNCH();
   }

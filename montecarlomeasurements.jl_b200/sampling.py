@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import numbers
+import threading
 
 import numpy as np
 
@@ -154,15 +155,25 @@ def transform_moments(X, m, S, preserve_latin: bool = False):
     S = np.asarray(S, dtype=np.float64)
     M = len(X)
     ptrs = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in X])
-    means = np.empty(M)
-    L.check(L.lib().mcm_colmeans(X[0].dtype, ptrs, M, X[0].N, means.ctypes.data_as(L._dp)))
-    cov = P.pcov(X)   # centring is internal to the Gram kernel; cov(X .- mean) == cov(X)
+    # chol(Σ) does not depend on the sample: factor it on a host thread while the device computes means and Gram
+    # (LAPACK releases the GIL)
+    box = {}
+    th = threading.Thread(target=lambda: box.__setitem__("ls", np.linalg.cholesky(S)))
+    th.start()
+    try:
+        means = np.empty(M)
+        L.check(L.lib().mcm_colmeans(X[0].dtype, ptrs, M, X[0].N, means.ctypes.data_as(L._dp)))
+        cov = P.pcov(X)   # centring is internal to the Gram kernel; cov(X .- mean) == cov(X)
+    finally:
+        th.join()
+    if "ls" not in box:
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "transform_moments: Σ is not positive definite")
     if preserve_latin:
         xl = np.diag(np.sqrt(np.diag(cov)))
     else:
         xl = np.linalg.cholesky(cov)
     # chol(Σ).L / xl: a triangular solve (A xl = L_S  <=>  xl' A' = L_S'), so A is lower triangular by construction
-    A = _solve_triangular(xl.T, np.linalg.cholesky(S).T, lower=False).T
+    A = _solve_triangular(xl.T, box["ls"].T, lower=False).T
     A = np.tril(A)
     return P.pgemm(A, X, shift=means, bias=m)
 
