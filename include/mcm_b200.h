@@ -250,7 +250,8 @@ int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale,
 /* Gram engine for large problems (M >= 256, N >= 4096): 1 (default) = tcgen05/TMEM int8 tensor cores
  * with an Ozaki error-free split of the centred Float64 data (exact int32 accumulation, 48 bits kept;
  * rows with max/sigma > 10 make it decline and the FP64 kernel runs instead), 0 = always the FP64
- * tensor pipe (DMMA).  Both meet the 1e-12 tolerance; small problems always use DMMA.
+ * tensor pipe (DMMA), 2 = tcgen05 with the A operand read from shared memory instead of staged in TMEM
+ * (A/B runs; bit-identical results).  All meet the 1e-12 tolerance; small problems always use DMMA.
  * mcm_gram_last_engine: 0 = DMMA, 1 = tcgen05 for the most recent mcm_gram call. */
 int mcm_gram_use_tensor(int on);
 int mcm_gram_last_engine(void);
@@ -290,6 +291,11 @@ int mcm_quantile_batch_fallbacks(void);
  * xs / outs: host arrays of device pointers; outputs must not alias inputs. */
 int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const void* const* xs, const double* shift_host,
               const double* bias_host, void* const* outs, size_t n);
+/* A/B switch: 1 (default) = tcgen05/TMEM int8 path (7-digit Ozaki split, exact int32 accumulation) for
+ * Mo >= 64, Mi >= 128, n >= 8192 with automatic fallback; 0 = FP64 DMMA kernel always.
+ * mcm_pgemm_last_engine: 0 = DMMA, 1 = tcgen05. */
+int mcm_pgemm_use_tensor(int on);
+int mcm_pgemm_last_engine(void);
 
 /* ======================= sampling / resampling ============================= */
 /* quantile(Normal(0,1), p) elementwise on device */

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <vector>
 #include "mcm_common.cuh"
+#include "mcm_tcgen05.cuh"
 
 namespace mcm {
 
@@ -44,45 +45,6 @@ constexpr int OZ_CHUNK_KB = 16384 / OZ_KB;           // k-blocks between flushes
 constexpr int OZ_DBITS = 8;                          // bits per digit
 constexpr double OZ_MAX_RATIO = 10.0;                // max/sigma above which the caller must use DMMA
 constexpr int OZ_TMEM_COLS = 512;
-
-// ---- operand preparation ------------------------------------------------------------------
-// Per row: e[i] = exponent with max_k |x_i[k] - mu_i| * 256/255 < 2^e[i] (so that the leading 8-bit digit
-// cannot overflow), and ratio[i] = max / sigma (accuracy guard).  e = -2000 marks an all-zero row.
-template <typename T>
-__global__ void __launch_bounds__(256)
-k_rowstats(const T* const* __restrict__ vars, const double* __restrict__ means, size_t n, int* __restrict__ ex,
-           double* __restrict__ ratio) {
-  const T* x = vars[blockIdx.x];
-  const double mu = means[blockIdx.x];
-  double m = 0.0, q = 0.0;
-  for (size_t i = threadIdx.x; i < n; i += 256) {
-    const double d = (double)x[i] - mu;
-    m = fmax(m, fabs(d));
-    q = fma(d, d, q);
-  }
-  __shared__ double shm[8], shq[8];
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) {
-    m = fmax(m, __shfl_down_sync(0xffffffffu, m, d));
-    q += __shfl_down_sync(0xffffffffu, q, d);
-  }
-  if ((threadIdx.x & 31) == 0) { shm[threadIdx.x >> 5] = m; shq[threadIdx.x >> 5] = q; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) { m = fmax(m, shm[w]); q += shq[w]; }
-    int e = -2000;
-    double r = 0.0;
-    if (m > 0.0 && m < 1.7e308) {
-      double mant = frexp(m, &e);           // m = mant * 2^e, mant in [0.5, 1)
-      if (mant > 0.995) ++e;                // keep 256 * y below 127.5
-      r = m / sqrt(q / (double)n);
-    } else if (m > 0.0) {
-      e = 2000; r = 1e300;                  // Inf/NaN in the row: force the fallback
-    }
-    ex[blockIdx.x] = e;
-    ratio[blockIdx.x] = r;
-  }
-}
 
 // digits in TILE-READY order: slices[s][kb][rg][c][r8][16] (kb = k / 32, rg = row / 8, c = (k % 32) / 16,
 // r8 = row % 8): the 8-row x 16-byte core matrices of the canonical K-major no-swizzle UMMA layout are
@@ -133,64 +95,6 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
   }
 }
 
-// ---- tcgen05 helpers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices; LBO = byte distance between the two
-// core matrices along K, SBO = byte distance between consecutive 8-row groups.  version = 1 (sm_100).
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-// instruction descriptor, kind::i8: D = s32, A = B = signed int8, both K-major, M x N
-__device__ __forceinline__ uint32_t umma_idesc_i8(int Mt, int Nt) {
-  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Nt >> 3) << 17) | ((uint32_t)(Mt >> 4) << 24);
-}
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_init_tc(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait_tc(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "TC_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra TC_DONE_%=;\n"
-      "bra TC_WAIT_%=;\n"
-      "TC_DONE_%=:\n"
-      "}\n" ::"r"(smem_addr(bar)), "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void cp_async16_tc(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-
 // tile t -> (bi over 128-row blocks, bj over 64-col blocks) with bj >= 2*bi (upper part incl. the diagonal)
 __device__ __forceinline__ void oz_tile_decode(int t, int mb, int nbk, int& bi, int& bj) {
   int i = 0, rem = t;
@@ -198,21 +102,12 @@ __device__ __forceinline__ void oz_tile_decode(int t, int mb, int nbk, int& bi, 
   bi = i; bj = 2 * i + rem;
 }
 
-__device__ __forceinline__ void mbar_expect_tx_tc(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_tc(uint32_t dst, const void* src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_addr(bar))
-               : "memory");
-}
-
 // Warp-specialised: warp 0 lane 0 = TMA producer (14 bulk copies per k-block), warp 1 lane 0 = MMA issuer
 // (28 tcgen05.mma per k-block), all 8 warps = TMEM flush + epilogue.  K range [kb_begin, kb_end) of this CTA
 // (split-K when there are fewer tiles than SMs); `out` is C (ksplit == 1) or the split workspace.
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
 k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, size_t mpad, size_t kpad,
-          int ksplit, int kb_per_split, double scale, double* __restrict__ C, double* __restrict__ ws) {
+          int ksplit, int kb_per_split, double scale, double* __restrict__ C, double* __restrict__ ws, int a_in_tmem) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_full[OZ_STAGES];
   __shared__ __align__(8) unsigned long long bar_free[OZ_STAGES];
@@ -236,13 +131,16 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   }
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < OZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 1); }
+    // bar_free counts the MMA commits of BOTH CTAs of the pair: the A planes of a stage are multicast into both
+    for (int s = 0; s < OZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 2); }
     mbar_init_tc(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers exist before any multicast copy or commit targets them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t crank = cluster_ctarank();
   const uint32_t tmem_base = tmem_base_sh;
   const uint32_t idesc = umma_idesc_i8(OZ_TM, OZ_TN);
   const uint32_t smem0 = smem_addr(smem);
@@ -254,46 +152,72 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   int chunk = 0;
   for (int c0 = 0; c0 < nkb; c0 += OZ_CHUNK_KB, ++chunk) {
     const int c1 = min(nkb, c0 + OZ_CHUNK_KB);
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
       // ---- producer: digit planes of k-block kb -> stage (it % STAGES); `it` counts k-blocks of this CTA
       for (int it = c0; it < c1; ++it) {
         const int st = it % OZ_STAGES;
         if (it >= OZ_STAGES) mbar_wait_tc(&bar_free[st], (unsigned)((it / OZ_STAGES - 1) & 1));
-        mbar_expect_tx_tc(&bar_full[st], OZ_STAGE_BYTES);
-        const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
-        const size_t kb = (size_t)(kb_begin + it);
-        const int8_t* srcA = slices + (kb * nrg + (size_t)bi * (OZ_TM / 8)) * 256;
-        const int8_t* srcB = slices + (kb * nrg + (size_t)bj * (OZ_TN / 8)) * 256;
+        if (elect_one()) {
+          mbar_expect_tx_tc(&bar_full[st], OZ_STAGE_BYTES);
+          const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
+          const size_t kb = (size_t)(kb_begin + it);
+          const int8_t* srcA = slices + (kb * nrg + (size_t)bi * (OZ_TM / 8)) * 256;
+          const int8_t* srcB = slices + (kb * nrg + (size_t)bj * (OZ_TN / 8)) * 256;
+          // the pair (tiles 2p, 2p+1) has the same row block bi: each CTA fetches every other A plane and
+          // multicasts it to both, so an A plane crosses the L2 -> SM fabric once per pair
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) {
-          bulk_g2s_tc(sbase + s * OZ_A_SLICE, srcA + (size_t)s * plane, OZ_A_SLICE, &bar_full[st]);
-          bulk_g2s_tc(sbase + OZ_S * OZ_A_SLICE + s * OZ_B_SLICE, srcB + (size_t)s * plane, OZ_B_SLICE, &bar_full[st]);
+          for (int s = 0; s < OZ_S; ++s) {
+            if ((uint32_t)(s & 1) == crank)
+              bulk_g2s_mc(sbase + s * OZ_A_SLICE, srcA + (size_t)s * plane, OZ_A_SLICE, &bar_full[st], (uint16_t)0x3);
+            bulk_g2s_tc(sbase + OZ_S * OZ_A_SLICE + s * OZ_B_SLICE, srcB + (size_t)s * plane, OZ_B_SLICE, &bar_full[st]);
+          }
         }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
-      // ---- MMA issuer
+    } else if (warp == 1) {
+      // ---- MMA issuer: the whole warp walks the loop, one elected lane issues
       for (int it = c0; it < c1; ++it) {
         const int st = it % OZ_STAGES;
         mbar_wait_tc(&bar_full[st], (unsigned)((it / OZ_STAGES) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
-        const uint64_t dA0 = umma_desc_kmajor(sbase, 128, 256);
-        const uint64_t dB0 = umma_desc_kmajor(sbase + OZ_S * OZ_A_SLICE, 128, 256);
-        uint32_t started = (it == c0) ? 0u : 0xffu;
+        if (elect_one()) {
+          const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
+          const uint64_t dA0 = umma_desc_kmajor(sbase, 128, 256);
+          const uint64_t dB0 = umma_desc_kmajor(sbase + OZ_S * OZ_A_SLICE, 128, 256);
+          // pair (s, t) feeds accumulator d = s + t; the first pair of every accumulator is (0, d), so only the
+          // s == 0 row of the first k-block of a chunk overwrites
+          const uint32_t acc0 = (it == c0) ? 0u : 1u;
+          if (a_in_tmem) {
+            // stage the 6 A planes of this k-block in TMEM (8 columns each, two alternating buffers behind the
+            // 6 x 64 accumulator columns); tcgen05.cp and tcgen05.mma execute in issue order
+            const uint32_t abuf = tmem_base + (uint32_t)(OZ_S * OZ_TN) + (uint32_t)(it & 1) * (OZ_S * 8);
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) {
+            for (int s = 0; s < OZ_S; ++s) tmem_cp_128x256b(abuf + s * 8, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4));
 #pragma unroll
-          for (int t = 0; t < OZ_S; ++t) {
-            if (s + t < OZ_S) {
-              const int d = s + t;
-              umma_i8(tmem_base + (uint32_t)d * OZ_TN, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4),
-                      dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc, (started >> d) & 1u);
-              started |= 1u << d;
+            for (int s = 0; s < OZ_S; ++s) {
+#pragma unroll
+              for (int t = 0; t < OZ_S; ++t) {
+                if (s + t < OZ_S)
+                  umma_i8_ts(tmem_base + (uint32_t)(s + t) * OZ_TN, abuf + s * 8, dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc,
+                             s == 0 ? acc0 : 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) {
+#pragma unroll
+              for (int t = 0; t < OZ_S; ++t) {
+                if (s + t < OZ_S) {
+                  umma_i8(tmem_base + (uint32_t)(s + t) * OZ_TN, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4),
+                          dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc, s == 0 ? acc0 : 1u);
+                }
+              }
             }
           }
+          umma_commit_mc(&bar_free[st], (uint16_t)0x3);   // stage reusable in BOTH CTAs once these MMAs have read it
+          if (it == c1 - 1) umma_commit(&bar_acc);        // chunk accumulated
         }
-        umma_commit(&bar_free[st]);                 // stage reusable once these MMAs have read it
-        if (it == c1 - 1) umma_commit(&bar_acc);    // chunk accumulated
+        __syncwarp();
       }
     }
     __syncwarp();
@@ -343,6 +267,7 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   }
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(OZ_TMEM_COLS));
+  cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
 }
 
 __global__ void __launch_bounds__(256)
@@ -363,6 +288,8 @@ k_gram_i8_reduce(const double* __restrict__ ws, const int* __restrict__ ex, int 
     }
   }
 }
+
+int g_a_in_tmem = 1;   // A operand staged in TMEM (default); mcm_gram_use_tensor(2) selects the shared-memory (SS) form for A/B runs
 
 template <typename T>
 int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C) {
@@ -422,7 +349,7 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   ksplit = (nkb_total + kb_per_split - 1) / kb_per_split;
   double* ws = nullptr;
   if (ksplit > 1) MCM_CUDA(cudaMallocAsync((void**)&ws, (size_t)ksplit * ntiles * OZ_TM * OZ_TN * sizeof(double), c.stream));
-  k_gram_i8<<<dim3(ntiles, ksplit), OZ_THREADS, kSmem, c.stream>>>(slices, ex, M, mpad, kpad, ksplit, kb_per_split, scale, C, ws);
+  k_gram_i8<<<dim3(ntiles, ksplit), OZ_THREADS, kSmem, c.stream>>>(slices, ex, M, mpad, kpad, ksplit, kb_per_split, scale, C, ws, g_a_in_tmem);
   MCM_CHECK_LAUNCH();
   if (ksplit > 1) {
     k_gram_i8_reduce<<<ntiles, 256, 0, c.stream>>>(ws, ex, M, mb, nbk, ntiles, ksplit, scale, C);

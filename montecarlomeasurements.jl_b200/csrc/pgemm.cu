@@ -182,9 +182,18 @@ k_pgemm(const double* __restrict__ A, int lda, const int* __restrict__ kend, con
     }
 }
 
+template <typename T>
+int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_host, const double* shift_host,
+                      const double* bias_host, T* const* outs_host, size_t n);
+static int g_pgemm_use_tensor = 1;
+static int g_pgemm_last_engine = 0;   // 0 = FP64 DMMA, 1 = tcgen05 int8 (Ozaki)
+
 }  // namespace mcm
 
 using namespace mcm;
+
+extern "C" int mcm_pgemm_use_tensor(int on) { g_pgemm_use_tensor = on; return MCM_OK; }
+extern "C" int mcm_pgemm_last_engine(void) { return g_pgemm_last_engine; }
 
 extern "C" int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const void* const* xs, const double* shift_host,
                          const double* bias_host, void* const* outs, size_t n) {
@@ -205,6 +214,15 @@ extern "C" int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const 
     aligned &= (reinterpret_cast<uintptr_t>(outs[j]) & 15u) == 0;
     for (int k = 0; k < Mi; ++k)
       if (outs[j] == xs[k]) return fail(MCM_ERR_INVALID, "mcm_pgemm: outputs must not alias inputs");
+  }
+  // large problems: tcgen05 / TMEM path (pgemm_tc.cu); it declines inputs it cannot represent safely
+  g_pgemm_last_engine = 0;
+  if (g_pgemm_use_tensor && Mo >= 64 && Mi >= 128 && n >= 8192) {
+    const int rc = dtype == MCM_F64
+                       ? pgemm_tensor_impl<double>(A_host, Mo, Mi, (const double* const*)xs, shift_host, bias_host, (double* const*)outs, n)
+                       : pgemm_tensor_impl<float>(A_host, Mo, Mi, (const float* const*)xs, shift_host, bias_host, (float* const*)outs, n);
+    if (rc == MCM_OK) { g_pgemm_last_engine = 1; return MCM_OK; }
+    if (rc != -1) return rc;
   }
   Ctx& c = ctx();
   const int njt = (Mo + PG_BM - 1) / PG_BM;

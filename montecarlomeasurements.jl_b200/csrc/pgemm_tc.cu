@@ -1,0 +1,446 @@
+// pgemm_tc.cu — constant matrix x vector of uncertain variables on tcgen05 + TMEM (Float64 in, Float64 out).
+//
+//   y_j[i] = bias_j + sum_k A[j,k] (x_k[i] - shift_k)        (sigmapoints.jl:71, particles.jl:688-707)
+//
+// Same Ozaki-style error-free split as the Gram kernel (gram_tc.cu), with 7 digits because the result is a
+// per-particle value, not an average:
+//   x'_k[i]  = (x_k[i] - shift_k) 2^-(e_k+1)        |x'| < 1/2,  e_k from max_i |x_k[i] - shift_k|  (k_rowstats)
+//   a''_jk   = A[j,k] 2^(e_k+1) 2^-(f_j+1)          |a''| < 1/2, f_j from max_k |A[j,k]| 2^(e_k+1)  (k_pz_rows)
+//   both cut into 7 balanced base-256 digits (56 bits); digit-plane products are exact int32 dot products on
+//   tcgen05.mma kind::i8; the 28 plane pairs with s + t <= 6 accumulate into 7 TMEM accumulators (one per
+//   weight 256^-(s+t+2)); y = bias + 2^(f_j+1) sum_d 256^-(d+2) acc_d.
+// Dropped terms are below 2^-55 |x'|max |a''|max per product: the deviation from the FP64 DMMA kernel
+// (pgemm.cu) is ~1e-15 of the row scale sum_k |A[j,k]| max|x_k - shift_k| (tests compare both with the
+// long-double oracle).  Inputs whose max/sigma exceeds 40 for some variable, or K > 16384, are declined and run
+// on the DMMA kernel.
+//
+// Tile: 128 particles (TMEM lanes, so the epilogue writes 256 contiguous bytes of one output per warp store) x
+// 64 outputs; k-blocks of 32 variables.  PERSISTENT kernel, one CTA per SM: two CTAs share a particle tile and
+// split its output tiles, so the 148 CTAs keep 74 digit tiles (7 planes x 128 x K bytes) hot in L2 while they
+// sweep all output tiles; the TMA producer runs ahead across tile boundaries.
+//   warp 0 lane 0 : producer, 14 cp.async.bulk per k-block (digit planes are stored tile-ready) -> 4-stage ring
+//   warp 1 lane 0 : 28 tcgen05.mma (M128 N64 K32) per k-block, tcgen05.commit -> mbarriers
+//   warps 2..5    : tcgen05.ld of the 7 accumulators, exact int64 recombination, 3 conversions, then release
+//                   TMEM (the next tile's MMAs start) and store 256 contiguous bytes per warp per output
+// Output tiles whose rows of A end early (triangular factors) stop their k loop early.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+#include "mcm_common.cuh"
+#include "mcm_tcgen05.cuh"
+
+namespace mcm {
+
+constexpr int PZ_S = 7;                               // digits per value
+constexpr int PZ_TM = 128, PZ_TN = 64, PZ_KB = 32;    // particles per tile, outputs per tile, variables per k-block
+constexpr int PZ_STAGES = 4;
+constexpr int PZ_THREADS = 192;
+constexpr int PZ_X_SLICE = PZ_TM * PZ_KB;             // 4096 B
+constexpr int PZ_A_SLICE = PZ_TN * PZ_KB;             // 2048 B
+constexpr int PZ_STAGE_BYTES = PZ_S * (PZ_X_SLICE + PZ_A_SLICE);   // 43008 B
+constexpr int PZ_TMEM_COLS = 512;
+constexpr int PZ_MAX_K = 16384;                       // int32 headroom: 7 pairs x 128 x 128 x K < 2^31
+constexpr double PZ_MAX_RATIO = 40.0;
+
+// digits of the particle operand in TILE-READY order: planes[s][kb][rg][c][r8][16]  (kb = k / 32, rg = particle / 8,
+// c = (k % 32) / 16, r8 = particle % 8) — the canonical K-major no-swizzle UMMA layout, so the 128 particles of one
+// k-block of one plane are ONE contiguous 4096-byte run.  One thread = 16 consecutive variables of one particle:
+// it reads 16 arrays at the same particle index (8 consecutive particles per 8 lanes = 64-byte segments) and
+// writes 16 bytes per plane (fully coalesced).
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pslice(const T* const* __restrict__ xs, const double* __restrict__ shift, const double* __restrict__ scale56, int K,
+         size_t n, size_t npad, size_t kpad, int8_t* __restrict__ planes) {
+  const size_t nrg = npad / 8;
+  const size_t total = (kpad / PZ_KB) * nrg * 16;
+  const size_t stride = (size_t)gridDim.x * 256;
+  for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < total; w += stride) {
+    const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;
+    const size_t rg = blk % nrg, kb = blk / nrg;
+    const size_t row = rg * 8 + r8;
+    const int k0 = (int)(kb * PZ_KB + c * 16);
+    alignas(16) int8_t dg[PZ_S][16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int k = k0 + j;
+      long long I = 0;
+      if (k < K && row < n) I = __double2ll_rn(((double)xs[k][row] - shift[k]) * scale56[k]);
+#pragma unroll
+      for (int s = PZ_S - 1; s >= 1; --s) {
+        const long long d = ((I + 128) & 255) - 128;
+        dg[s][j] = (int8_t)d;
+        I = (I - d) >> 8;
+      }
+      dg[0][j] = (int8_t)I;
+    }
+    const size_t off = w * 16;
+#pragma unroll
+    for (int s = 0; s < PZ_S; ++s)
+      *reinterpret_cast<int4*>(planes + (size_t)s * (npad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
+  }
+}
+
+// ---- coefficient operand (device side) -------------------------------------------------------
+// per-variable powers: sc56[k] = 2^(-(e_k+1)+56) for the particle digits, apow[k] = 2^(e_k+1) folded into A
+__global__ void k_pz_scales(const int* __restrict__ ex, int K, size_t kpad, double* __restrict__ sc56, double* __restrict__ apow) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kpad) return;
+  const bool live = k < (size_t)K && ex[k] != -2000;
+  sc56[k] = live ? scalbn(1.0, -(ex[k] + 1) + 8 * PZ_S) : 0.0;
+  apow[k] = live ? scalbn(1.0, ex[k] + 1) : 0.0;
+}
+// one CTA per output row j: f_j from max_k |A[j,k]| apow[k]; rowscale = 2^(f_j+1), cscale = 2^(-(f_j+1)+56);
+// kend[j/64] = columns needed by the output tile (multiple of 32); flag bit 0 = out-of-range scale
+__global__ void __launch_bounds__(256)
+k_pz_rows(const double* __restrict__ A, int Mi, const double* __restrict__ apow, double* __restrict__ rowscale,
+          double* __restrict__ cscale, int* __restrict__ kend, uint32_t* __restrict__ flag) {
+  const int j = blockIdx.x;
+  double amax = 0.0;
+  int last = 0;
+  for (int k = threadIdx.x; k < Mi; k += 256) {
+    const double v = fabs(A[(size_t)j * Mi + k] * apow[k]);
+    if (v != 0.0) last = k + 1;
+    amax = fmax(amax, v);    // NaN-free maximum is enough: a NaN product is caught through amax below
+    if (!(v <= 1.7e308)) amax = INFINITY;
+  }
+  __shared__ double shm[8];
+  __shared__ int shl[8];
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    amax = fmax(amax, __shfl_down_sync(0xffffffffu, amax, d));
+    last = max(last, __shfl_down_sync(0xffffffffu, last, d));
+  }
+  if ((threadIdx.x & 31) == 0) { shm[threadIdx.x >> 5] = amax; shl[threadIdx.x >> 5] = last; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) { amax = fmax(amax, shm[w]); last = max(last, shl[w]); }
+    double rs = 0.0, cs = 0.0;
+    if (amax > 0.0) {
+      int f;
+      const double mant = frexp(amax, &f);
+      if (mant > 0.995) ++f;
+      if (!(amax <= 1.7e308) || f < -900 || f > 900) atomicOr(flag, 1u);
+      else { rs = scalbn(1.0, f + 1); cs = scalbn(1.0, -(f + 1) + 8 * PZ_S); }
+    }
+    rowscale[j] = rs;
+    cscale[j] = cs;
+    atomicMax(&kend[j / PZ_TN], (last + PZ_KB - 1) / PZ_KB * PZ_KB);
+  }
+}
+// digits of a''_jk in tile-ready order aplanes[t][kb][jg][c][r8][16] (same layout as the particle operand)
+__global__ void __launch_bounds__(256)
+k_pz_coef(const double* __restrict__ A, int Mo, int Mi, const double* __restrict__ apow, const double* __restrict__ cscale,
+          size_t mopad, size_t kpad, int8_t* __restrict__ planes) {
+  const size_t njg = mopad / 8;
+  const size_t total = (kpad / PZ_KB) * njg * 16;
+  const size_t w = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (w >= total) return;
+  const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;
+  const size_t jg = blk % njg, kb = blk / njg;
+  const size_t j = jg * 8 + r8;
+  const int k0 = (int)(kb * PZ_KB + c * 16);
+  alignas(16) int8_t dg[PZ_S][16];
+  const double cs = j < (size_t)Mo ? cscale[j] : 0.0;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int k = k0 + q;
+    long long I = 0;
+    if (k < Mi && cs != 0.0) I = __double2ll_rn(A[j * (size_t)Mi + k] * apow[k] * cs);
+#pragma unroll
+    for (int s = PZ_S - 1; s >= 1; --s) {
+      const long long d = ((I + 128) & 255) - 128;
+      dg[s][q] = (int8_t)d;
+      I = (I - d) >> 8;
+    }
+    dg[0][q] = (int8_t)I;
+  }
+#pragma unroll
+  for (int s = 0; s < PZ_S; ++s)
+    *reinterpret_cast<int4*>(planes + (size_t)s * (mopad * kpad) + w * 16) = *reinterpret_cast<const int4*>(dg[s]);
+}
+
+struct PzSchedule {
+  int nptiles, njt, share, slots;   // share = CTAs per particle tile, slots = particle tiles in flight
+};
+
+// tile sequence of CTA c: particle tiles slot, slot + slots, ...; for each, output tiles njt-1-part, -share, ...
+#define PZ_TILE_LOOP(sch)                                                                      \
+  for (int ptile = (int)blockIdx.x / (sch).share; ptile < (sch).nptiles; ptile += (sch).slots) \
+    for (int jt = (sch).njt - 1 - ((int)blockIdx.x % (sch).share); jt >= 0; jt -= (sch).share)
+
+// warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane group = warp % 4)
+constexpr int PZ_EPI_WARPS = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(PZ_THREADS, 1)
+k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplanes, const int* __restrict__ kend,
+           const double* __restrict__ rowscale, const double* __restrict__ bias, T* const* __restrict__ outs, int Mo,
+           size_t n, size_t npad, size_t kpad, size_t mopad, PzSchedule sch) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar_full[PZ_STAGES];
+  __shared__ __align__(8) unsigned long long bar_free[PZ_STAGES];
+  __shared__ __align__(8) unsigned long long bar_acc;     // accumulators of a tile complete
+  __shared__ __align__(8) unsigned long long bar_drained; // accumulators read back: TMEM reusable
+  __shared__ uint32_t tmem_base_sh;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const size_t xplane = npad * kpad, aplane = mopad * kpad;
+  const size_t nrg = npad / 8, njg = mopad / 8;
+  if ((int)blockIdx.x / sch.share >= sch.nptiles) return;   // more CTAs than work (uniform per CTA)
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&tmem_base_sh)), "r"(PZ_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < PZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 1); }
+    mbar_init_tc(&bar_acc, 1);
+    mbar_init_tc(&bar_drained, PZ_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_sh;
+  const uint32_t idesc = umma_idesc_i8(PZ_TM, PZ_TN);
+  const uint32_t smem0 = smem_addr(smem);
+
+  if (warp == 0) {
+    // ---- producer: runs ahead over the whole tile sequence; `it` counts k-blocks of this CTA.  The whole warp
+    // walks the loop and one elected lane issues (see elect_one in mcm_tcgen05.cuh).
+    int it = 0;
+    PZ_TILE_LOOP(sch) {
+      const int nkb = kend[jt] / PZ_KB;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % PZ_STAGES;
+        if (it >= PZ_STAGES) mbar_wait_tc(&bar_free[st], (unsigned)((it / PZ_STAGES - 1) & 1));
+        if (elect_one()) {
+          mbar_expect_tx_tc(&bar_full[st], PZ_STAGE_BYTES);
+          const uint32_t sbase = smem0 + (uint32_t)st * PZ_STAGE_BYTES;
+          const int8_t* srcX = xplanes + ((size_t)kb * nrg + (size_t)ptile * (PZ_TM / 8)) * 256;
+          const int8_t* srcA = aplanes + ((size_t)kb * njg + (size_t)jt * (PZ_TN / 8)) * 256;
+#pragma unroll
+          for (int s = 0; s < PZ_S; ++s) {
+            bulk_g2s_tc(sbase + s * PZ_X_SLICE, srcX + (size_t)s * xplane, PZ_X_SLICE, &bar_full[st]);
+            bulk_g2s_tc(sbase + PZ_S * PZ_X_SLICE + s * PZ_A_SLICE, srcA + (size_t)s * aplane, PZ_A_SLICE, &bar_full[st]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    int it = 0;
+    int tile = 0;
+    PZ_TILE_LOOP(sch) {
+      const int nkb = kend[jt] / PZ_KB;
+      if (tile > 0) {   // the previous tile's accumulators must have been read back
+        mbar_wait_tc(&bar_drained, (unsigned)((tile - 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = it % PZ_STAGES;
+        mbar_wait_tc(&bar_full[st], (unsigned)((it / PZ_STAGES) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+          const uint32_t sbase = smem0 + (uint32_t)st * PZ_STAGE_BYTES;
+          const uint64_t dX0 = umma_desc_kmajor(sbase, 128, 256);
+          const uint64_t dA0 = umma_desc_kmajor(sbase + PZ_S * PZ_X_SLICE, 128, 256);
+          // pair (s, t) feeds accumulator d = s + t; the first pair of every accumulator is (0, d), so only the
+          // s == 0 row of the tile's first k-block overwrites
+          const uint32_t acc0 = kb == 0 ? 0u : 1u;
+#pragma unroll
+          for (int s = 0; s < PZ_S; ++s) {
+#pragma unroll
+            for (int t = 0; t < PZ_S; ++t) {
+              if (s + t < PZ_S)
+                umma_i8(tmem_base + (uint32_t)(s + t) * PZ_TN, dX0 + (uint64_t)((s * PZ_X_SLICE) >> 4),
+                        dA0 + (uint64_t)((t * PZ_A_SLICE) >> 4), idesc, s == 0 ? acc0 : 1u);
+            }
+          }
+          umma_commit(&bar_free[st]);
+          if (kb == nkb - 1) umma_commit(&bar_acc);
+        }
+        __syncwarp();
+      }
+      if (nkb == 0) {   // nothing to accumulate: release the epilogue at once
+        if (elect_one()) umma_commit(&bar_acc);
+        __syncwarp();
+      }
+      ++tile;
+    }
+  } else if (warp < 2 + PZ_EPI_WARPS) {
+    // ---- epilogue warps: TMEM lane = particle; 64 output columns per thread in two halves of 32
+    const int lg = warp & 3;   // TMEM lane group this warp may access
+    int tile = 0;
+    PZ_TILE_LOOP(sch) {
+      const int nkb = kend[jt] / PZ_KB;
+      mbar_wait_tc(&bar_acc, (unsigned)(tile & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // one half (32 output columns) of this thread's particle: TMEM -> exact int64 recombination of the diagonals
+      // (0,1,2), (3,4,5), (6) (|acc_d| < 2^31, 16 extra bits) -> 3 conversions
+      auto read_half = [&](int h, double (&f)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = 0.0;
+        if (nkb > 0) {
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            long long comb[32];
+            const int dn = g < 2 ? 3 : 1;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              if (q < dn) {
+                uint32_t v[32];
+                const int d = g * 3 + q;
+                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * PZ_TN + h * 32), v);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) comb[j] = (q == 0) ? (long long)(int)v[j] : comb[j] * 256 + (long long)(int)v[j];
+              }
+            }
+            const double w = scalbn(1.0, -8 * (g * 3 + dn - 1 + 2));   // weight of the group's last diagonal
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fma((double)comb[j], w, f[j]);
+          }
+        }
+      };
+      const size_t i = (size_t)ptile * PZ_TM + lg * 32 + lane;
+      auto store_half = [&](int h, const double (&f)[32]) {
+        if (i < n) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int jj = jt * PZ_TN + h * 32 + j;
+            if (jj < Mo) __stcs(outs[jj] + i, (T)fma(f[j], rowscale[jj], bias ? bias[jj] : 0.0));
+          }
+        }
+      };
+      double f0[32], f1[32];
+      read_half(0, f0);
+      read_half(1, f1);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_drained)) : "memory");
+      store_half(0, f0);
+      store_half(1, f1);
+      ++tile;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PZ_TMEM_COLS));
+}
+
+// returns MCM_OK, an error, or -1 = declined (caller runs the DMMA kernel)
+template <typename T>
+int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_host, const double* shift_host,
+                      const double* bias_host, T* const* outs_host, size_t n) {
+  Ctx& c = ctx();
+  const size_t kpad = ((size_t)Mi + PZ_KB - 1) / PZ_KB * PZ_KB;
+  const size_t npad = (n + PZ_TM - 1) / PZ_TM * PZ_TM;
+  const size_t mopad = ((size_t)Mo + PZ_TN - 1) / PZ_TN * PZ_TN;
+  if (kpad > (size_t)PZ_MAX_K) return -1;
+  const int njt = (int)(mopad / PZ_TN);
+  const size_t nptiles = npad / PZ_TM;
+  if (nptiles > 0x7fffffffull) return -1;
+  for (size_t q = 0; q < (size_t)Mo * Mi; ++q)
+    if (!std::isfinite(A_host[q])) return -1;
+
+  // ---- one upload: input/output pointer tables, shift, bias, A
+  auto al = [](size_t b) { return (b + 15) / 16 * 16; };
+  const size_t o_xs = 0, o_outs = al((size_t)Mi * sizeof(void*)), o_shift = o_outs + al((size_t)Mo * sizeof(void*));
+  const size_t o_bias = o_shift + kpad * sizeof(double), o_A = o_bias + mopad * sizeof(double);
+  const size_t up_bytes = o_A + (size_t)Mo * Mi * sizeof(double);
+  std::vector<unsigned char> up(up_bytes, 0);
+  memcpy(up.data() + o_xs, xs_host, (size_t)Mi * sizeof(void*));
+  memcpy(up.data() + o_outs, outs_host, (size_t)Mo * sizeof(void*));
+  if (shift_host) memcpy(up.data() + o_shift, shift_host, (size_t)Mi * sizeof(double));
+  if (bias_host) memcpy(up.data() + o_bias, bias_host, (size_t)Mo * sizeof(double));
+  memcpy(up.data() + o_A, A_host, (size_t)Mo * Mi * sizeof(double));
+  // ---- device workspace: ex, ratio, sc56, apow, rowscale, cscale, kend, flag, coefficient planes
+  const size_t w_ex = 0, w_ratio = al((size_t)Mi * sizeof(int)), w_sc = w_ratio + al((size_t)Mi * sizeof(double));
+  const size_t w_apow = w_sc + kpad * sizeof(double), w_rows = w_apow + kpad * sizeof(double);
+  const size_t w_cs = w_rows + mopad * sizeof(double), w_kend = w_cs + mopad * sizeof(double);
+  const size_t w_flag = w_kend + al((size_t)njt * sizeof(int)), w_planes = w_flag + 16;
+  const size_t ws_bytes = w_planes + (size_t)PZ_S * mopad * kpad;
+  unsigned char *d_up = nullptr, *d_ws = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_up, up_bytes, c.stream));
+  MCM_CUDA(cudaMallocAsync((void**)&d_ws, ws_bytes, c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_up, up.data(), up_bytes, cudaMemcpyHostToDevice, c.stream));
+  MCM_CUDA(cudaMemsetAsync(d_ws + w_rows, 0, w_planes - w_rows, c.stream));   // rowscale, cscale, kend, flag
+  const T* const* d_xs = reinterpret_cast<const T* const*>(d_up + o_xs);
+  const double* d_shift = reinterpret_cast<const double*>(d_up + o_shift);
+  const double* d_A = reinterpret_cast<const double*>(d_up + o_A);
+  int* d_ex = reinterpret_cast<int*>(d_ws + w_ex);
+  double* d_ratio = reinterpret_cast<double*>(d_ws + w_ratio);
+  double* d_sc = reinterpret_cast<double*>(d_ws + w_sc);
+  double* d_apow = reinterpret_cast<double*>(d_ws + w_apow);
+  double* d_rows = reinterpret_cast<double*>(d_ws + w_rows);
+  double* d_cs = reinterpret_cast<double*>(d_ws + w_cs);
+  int* d_kend = reinterpret_cast<int*>(d_ws + w_kend);
+  uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_ws + w_flag);
+  int8_t* d_aplanes = reinterpret_cast<int8_t*>(d_ws + w_planes);
+  auto release = [&]() { cudaFreeAsync(d_up, c.stream); cudaFreeAsync(d_ws, c.stream); };
+
+  k_rowstats<T><<<Mi, 256, 0, c.stream>>>(d_xs, d_shift, n, d_ex, d_ratio);
+  MCM_CHECK_LAUNCH();
+  std::vector<int> ex(Mi);
+  std::vector<double> ratio(Mi);
+  MCM_CUDA(cudaMemcpyAsync(ex.data(), d_ex, (size_t)Mi * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaMemcpyAsync(ratio.data(), d_ratio, (size_t)Mi * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));   // also: `up` has been consumed
+  bool ok = true;
+  for (int k = 0; k < Mi; ++k) ok &= (ratio[k] <= PZ_MAX_RATIO) && (ex[k] == -2000 || (ex[k] > -900 && ex[k] < 900));
+  if (!ok) { release(); return -1; }
+
+  k_pz_scales<<<(unsigned)((kpad + 255) / 256), 256, 0, c.stream>>>(d_ex, Mi, kpad, d_sc, d_apow);
+  MCM_CHECK_LAUNCH();
+  k_pz_rows<<<Mo, 256, 0, c.stream>>>(d_A, Mi, d_apow, d_rows, d_cs, d_kend, d_flag);
+  MCM_CHECK_LAUNCH();
+  {
+    const size_t total = (kpad / PZ_KB) * (mopad / 8) * 16;
+    k_pz_coef<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(d_A, Mo, Mi, d_apow, d_cs, mopad, kpad, d_aplanes);
+    MCM_CHECK_LAUNCH();
+  }
+  int8_t* d_xplanes = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_xplanes, (size_t)PZ_S * npad * kpad, c.stream));
+  {
+    const size_t total = (kpad / PZ_KB) * (npad / 8) * 16;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)c.sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    k_pslice<T><<<(unsigned)blocks, 256, 0, c.stream>>>(d_xs, d_shift, d_sc, Mi, n, npad, kpad, d_xplanes);
+    MCM_CHECK_LAUNCH();
+  }
+  PzSchedule sch;
+  sch.nptiles = (int)nptiles;
+  sch.njt = njt;
+  sch.share = njt >= 2 ? 2 : 1;
+  int ncta = c.sm_count;
+  if ((size_t)ncta > nptiles * sch.share) ncta = (int)(nptiles * sch.share);
+  ncta = std::max(sch.share, ncta / sch.share * sch.share);
+  sch.slots = ncta / sch.share;
+  constexpr size_t kSmem = (size_t)PZ_STAGES * PZ_STAGE_BYTES;
+  static bool attr = false;
+  if (!attr) {
+    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    attr = true;
+  }
+  k_pgemm_i8<T><<<ncta, PZ_THREADS, kSmem, c.stream>>>(
+      d_xplanes, d_aplanes, d_kend, d_rows, bias_host ? reinterpret_cast<const double*>(d_up + o_bias) : nullptr,
+      reinterpret_cast<T* const*>(d_up + o_outs), Mo, n, npad, kpad, mopad, sch);
+  MCM_CHECK_LAUNCH();
+  uint32_t flag = 0;
+  MCM_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_xplanes, c.stream));
+  release();
+  return flag ? -1 : MCM_OK;   // out-of-range coefficient scale: the caller recomputes on the DMMA kernel
+}
+
+template int pgemm_tensor_impl<double>(const double*, int, int, const double* const*, const double*, const double*, double* const*, size_t);
+template int pgemm_tensor_impl<float>(const double*, int, int, const float* const*, const double*, const double*, float* const*, size_t);
+
+}  // namespace mcm

@@ -47,14 +47,21 @@ t_host = time.perf_counter() - t0
 outs = [mcm.particles._empty(n, L.F64) for _ in range(d)]
 optr = (C.c_void_p * d)(*[C.c_void_p(p.ptr) for p in outs])
 Ac = np.ascontiguousarray(A)
-t_apply, _ = best(lambda: L.check(lib.mcm_pgemm(L.F64, Ac.ctypes.data_as(L._dp), d, d, ptrs, means.ctypes.data_as(L._dp),
-                                               m.ctypes.data_as(L._dp), optr, n)))
 Af = np.ascontiguousarray(A + np.triu(np.full((d, d), 1e-300), 1))     # same values, no structural zeros
-t_apply_full, _ = best(lambda: L.check(lib.mcm_pgemm(L.F64, Af.ctypes.data_as(L._dp), d, d, ptrs, means.ctypes.data_as(L._dp),
-                                                    m.ctypes.data_as(L._dp), optr, n)), reps=2)
-print(f"C5 transform_moments: colmeans {t_mu*1e3:.2f} ms | Gram {t_gram*1e3:.2f} ms ({2*d*d*n/t_gram/1e12:.1f} TFLOP/s, engine {eng}) | "
-      f"host 2x potrf + trsm {t_host*1e3:.1f} ms | apply (lower-triangular A) {t_apply*1e3:.2f} ms "
-      f"({d*d*n/t_apply/1e12:.1f} TFLOP/s executed) | apply dense A {t_apply_full*1e3:.2f} ms ({2*d*d*n/t_apply_full/1e12:.1f} TFLOP/s)")
+apply = lambda M_: L.check(lib.mcm_pgemm(L.F64, M_.ctypes.data_as(L._dp), d, d, ptrs, means.ctypes.data_as(L._dp),
+                                        m.ctypes.data_as(L._dp), optr, n))
+res_apply = {}
+for eng, name in ((1, "tcgen05 int8 (7-digit Ozaki)"), (0, "FP64 DMMA")):
+    lib.mcm_pgemm_use_tensor(eng)
+    t_tri, _ = best(lambda: apply(Ac), reps=3)
+    used = lib.mcm_pgemm_last_engine()
+    t_full, _ = best(lambda: apply(Af), reps=2)
+    res_apply[eng] = (t_tri, t_full)
+    print(f"C5 apply Y = m + A (X - mu), {name} (engine used {used}): lower-triangular A {t_tri*1e3:.2f} ms "
+          f"({d*d*n/t_tri/1e12:.1f} TFLOP/s executed) | dense A {t_full*1e3:.2f} ms ({2*d*d*n/t_full/1e12:.1f} TFLOP/s)")
+lib.mcm_pgemm_use_tensor(1)
+print(f"C5 transform_moments pieces: colmeans {t_mu*1e3:.2f} ms | Gram {t_gram*1e3:.2f} ms ({2*d*d*n/t_gram/1e12:.1f} TFLOP/s, engine {eng}) | "
+      f"host 2x potrf + solve {t_host*1e3:.1f} ms")
 t_tm, Y = best(lambda: mcm.transform_moments(cols, m, S), reps=2)
 total["transform_moments"] = t_tm
 print(f"C5 transform_moments, one call (colmeans + Gram + host factorisations + apply): {t_tm*1e3:.1f} ms")

@@ -114,6 +114,70 @@ def test_pgemm_triangular_unaligned_float32_and_offset(mcm, orc):
         mcm.pgemm(np.ones((2, 3)), xs[:2])
 
 
+def _ozaki_floor(A, X, shift):
+    """Absolute error floor of the 7-digit int8 split: operands are kept to 2^-56 of the row maximum
+    max_k |A_jk| max_i |x_k - s_k| (x 4 for the two power-of-two roundings), K products per output."""
+    Xc = np.abs(X - (0 if shift is None else np.asarray(shift)[:, None]))
+    rowmax = np.max(np.abs(A) * Xc.max(axis=1)[None, :], axis=1)
+    return (8 * A.shape[1] * 2.0 ** -56 * 4 * rowmax)[:, None]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("Mo,Mi,n,tri", [(64, 128, 8192, False), (130, 200, 10001, False), (257, 300, 20000, True)])
+def test_pgemm_tcgen05_engine_vs_oracle_and_dmma(mcm, orc, dt, Mo, Mi, n, tri):
+    """Large problems run on the tcgen05/TMEM int8 path (7 balanced 8-bit digits, exact int32 accumulation); both
+    engines must agree with the long-double oracle, the tensor path additionally within its stated floor."""
+    lib = mcm._lib.lib()
+    rng = np.random.default_rng(Mo + Mi)
+    A = rng.normal(size=(Mo, Mi)) * np.exp(rng.normal(size=(Mo, 1)))          # rows of different magnitude
+    if tri:
+        A = np.tril(A)
+    X = (rng.normal(size=(Mi, n)) * np.exp(2 * rng.normal(size=(Mi, 1))) + rng.normal(size=(Mi, 1))).astype(dt)
+    shift = X.astype(np.float64).mean(axis=1)
+    bias = rng.normal(size=Mo)
+    xs = [mcm.Particles(r) for r in X]
+    Yt = np.stack([y.to_numpy() for y in mcm.pgemm(A, xs, shift=shift, bias=bias)])
+    assert lib.mcm_pgemm_last_engine() == 1
+    lib.mcm_pgemm_use_tensor(0)
+    try:
+        Yd = np.stack([y.to_numpy() for y in mcm.pgemm(A, xs, shift=shift, bias=bias)])
+        assert lib.mcm_pgemm_last_engine() == 0
+    finally:
+        lib.mcm_pgemm_use_tensor(1)
+    sub = sorted({0, 1, 63, min(64, Mo - 1), Mo // 2, Mo - 1})
+    cols = np.r_[0:300, n - 300:n]
+    X64 = X.astype(np.float64)
+    ref = orc.pgemm(A[sub], X64[:, cols], shift, bias[sub])
+    bound = _pgemm_bound(A[sub], X64[:, cols], shift)
+    if dt == np.float32:
+        bound = bound + 6e-8 * np.abs(ref)                                     # one rounding to Float32 on store
+    assert np.all(np.abs(Yd[np.ix_(sub, cols)] - ref) <= bound + 1e-300)
+    assert np.all(np.abs(Yt[np.ix_(sub, cols)] - ref) <= bound + _ozaki_floor(A[sub], X64, shift))
+    # whole result: the two engines agree to the same floor
+    full_floor = _ozaki_floor(A, X64, shift) + (Mi + 4) * 2.3e-16 * (np.abs(A) @ np.abs(X64 - shift[:, None]))
+    if dt == np.float32:
+        full_floor = full_floor + 1.2e-7 * np.abs(Yd)
+    assert np.all(np.abs(Yt.astype(np.float64) - Yd) <= full_floor)
+
+
+def test_pgemm_tcgen05_declines_what_it_cannot_represent(mcm, orc):
+    lib = mcm._lib.lib()
+    rng = np.random.default_rng(77)
+    A = rng.normal(size=(64, 128))
+    Xh = rng.standard_t(2, size=(128, 8192))                                   # heavy tails: max/sigma >> 40
+    Y = np.stack([y.to_numpy() for y in mcm.pgemm(A, [mcm.Particles(r) for r in Xh])])
+    assert lib.mcm_pgemm_last_engine() == 0
+    assert np.all(np.abs(Y[:2, :200] - orc.pgemm(A[:2], Xh[:, :200])) <= _pgemm_bound(A[:2], Xh[:, :200], None))
+    Xc = rng.normal(size=(128, 8192)); Xc[7] = 2.5                             # a constant variable is fine (digits 0)
+    Yc = np.stack([y.to_numpy() for y in mcm.pgemm(A, [mcm.Particles(r) for r in Xc], shift=Xc.mean(axis=1))])
+    assert lib.mcm_pgemm_last_engine() == 1
+    refc = orc.pgemm(A[:3], Xc[:, :300], Xc.mean(axis=1), None)
+    assert np.all(np.abs(Yc[:3, :300] - refc) <= _pgemm_bound(A[:3], Xc[:, :300], Xc.mean(axis=1)) + _ozaki_floor(A[:3], Xc, Xc.mean(axis=1)))
+    Az = A.copy(); Az[5] = 0.0                                                 # an all-zero output row -> exactly the bias
+    Yz = mcm.pgemm(Az, [mcm.Particles(r) for r in Xc], bias=np.full(64, 1.5))
+    assert lib.mcm_pgemm_last_engine() == 1 and np.all(Yz[5].to_numpy() == 1.5)
+
+
 def test_particle_blas_wrappers(mcm, orc):
     """mul!(y, A, b), A*p, dot(v, p), axpy!(a, x, y) (particles.jl:620-707; runtests.jl:735-753 pattern)."""
     rng = np.random.default_rng(8)
