@@ -297,6 +297,20 @@ int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const void* const
 int mcm_pgemm_use_tensor(int on);
 int mcm_pgemm_last_engine(void);
 
+/* ======================= M x M dense steps + transform_moments ============= */
+/* In-place lower Cholesky factor of a symmetric positive definite M x M matrix in device memory (row-major,
+ * lower triangle referenced, strict upper triangle zeroed) — `cholesky(C).L` of sigmapoints.jl:38,69.
+ * *info_host = 0, or the 1-based column of the first non-positive pivot (then MCM_ERR_INVALID). */
+int mcm_potrf(double* a_dev, int M, int* info_host);
+/* X L = B solved in place in b_dev (nrows x M, row-major) for lower-triangular L (M x M): the `/` of
+ * `cholesky(S).L / xl` (sigmapoints.jl:71). */
+int mcm_trsm_right_lower(const double* l_dev, double* b_dev, int M, int nrows);
+/* transform_moments(X, m, S; preserve_latin) (sigmapoints.jl:63-72) entirely on device:
+ * outs[j] = m[j] + sum_k A[j,k] (xs[k] - mean(xs[k])),  A = cholesky(S).L / xl,
+ * xl = cholesky(cov(X)).L  or  Diagonal(std(X)) when preserve_latin != 0.  S_host: row-major M x M. */
+int mcm_transform_moments(int dtype, const void* const* xs, int M, size_t n, const double* m_host,
+                          const double* S_host, int preserve_latin, void* const* outs);
+
 /* ======================= sampling / resampling ============================= */
 /* quantile(Normal(0,1), p) elementwise on device */
 int mcm_norminvcdf(int dtype, const void* p_in, void* out, size_t n);

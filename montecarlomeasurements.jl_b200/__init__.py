@@ -25,7 +25,7 @@ from .particles import (
     check_domain, nparticles, particleeltype, flat_particles, is_particle_array,
 )
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
-                       mvnormal_particles, systematic_batch, index_bijection)
+                       mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower)
 from .resampling import bootstrap, resample, resample_indices, rand_indices
 from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
 from . import sharded, tape

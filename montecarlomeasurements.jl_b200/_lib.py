@@ -127,6 +127,9 @@ SIGNATURES = {
     "mcm_quantile_batch_fallbacks": (_i, []),
     "mcm_order_statistics": (_i, [_i, _vp, _sz, C.POINTER(C.c_uint64), _i, _dp]),
     "mcm_pgemm": (_i, [_i, _dp, _i, _i, _vpp, _dp, _dp, _vpp, _sz]),
+    "mcm_potrf": (_i, [_vp, _i, C.POINTER(C.c_int)]),
+    "mcm_trsm_right_lower": (_i, [_vp, _vp, _i, _i]),
+    "mcm_transform_moments": (_i, [_i, _vpp, _i, _sz, _dp, _dp, _i, _vpp]),
     "mcm_pgemm_use_tensor": (_i, [_i]),
     "mcm_pgemm_last_engine": (_i, []),
     "mcm_rand_indices": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64]),

@@ -10,18 +10,11 @@ from __future__ import annotations
 
 import ctypes as C
 import numbers
-import threading
 
 import numpy as np
 
 from . import _lib as L
 from . import particles as P
-
-try:  # LAPACK trtrs; numpy alone only offers a general LU solve (3x the flops at d = 1024)
-    from scipy.linalg import solve_triangular as _solve_triangular
-except ImportError:  # pragma: no cover
-    def _solve_triangular(a, b, lower=False):
-        return np.linalg.solve(a, b)
 
 
 # ---- minimal Distributions.jl stand-ins (only what the hot path constructs) -----------------
@@ -147,35 +140,54 @@ def dotdot(a, b, N: int = P.DEFAULT_NUM_PARTICLES, seed: int | None = None):
 # ---- multivariate construction (types.jl:92-100; systematic route docs/index.md:141 + sigmapoints.jl:63-72)
 def transform_moments(X, m, S, preserve_latin: bool = False):
     """transform_moments(X, m, Σ) (sigmapoints.jl:63-72) on a list of M device Particles (the N x M sample):
-    centre, xl = chol(cov X).L (or Diagonal(std)), Y = m + (chol(Σ).L / xl) X'.  The Gram (mcm_gram) and the
-    application (mcm_pgemm, centring fused as its shift) run on device; the two M x M Cholesky factorisations
-    and the triangular solve are host-size."""
+    centre, xl = chol(cov X).L (or Diagonal(std)), Y = m + (chol(Σ).L / xl) X' — one C-ABI call, all on device:
+    Gram (mcm_gram), blocked Cholesky and triangular solve (dense.cu), application (mcm_pgemm with the centring
+    fused as its shift)."""
     X = P._check_mv(X)
-    m = np.asarray(m, dtype=np.float64)
-    S = np.asarray(S, dtype=np.float64)
     M = len(X)
-    ptrs = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in X])
-    # chol(Σ) does not depend on the sample: factor it on a host thread while the device computes means and Gram
-    # (LAPACK releases the GIL)
-    box = {}
-    th = threading.Thread(target=lambda: box.__setitem__("ls", np.linalg.cholesky(S)))
-    th.start()
+    m = np.ascontiguousarray(np.broadcast_to(np.asarray(m, dtype=np.float64), (M,)))
+    S = np.ascontiguousarray(np.asarray(S, dtype=np.float64))
+    if S.shape != (M, M):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, f"DimensionMismatch: Σ must be {M} x {M}")
+    outs = [P._empty_like(X[0]) for _ in range(M)]
+    pin = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in X])
+    pout = (C.c_void_p * M)(*[C.c_void_p(y.ptr) for y in outs])
+    L.check(L.lib().mcm_transform_moments(X[0].dtype, pin, M, X[0].N, m.ctypes.data_as(L._dp), S.ctypes.data_as(L._dp),
+                                          1 if preserve_latin else 0, pout))
+    return outs
+
+
+def cholesky_lower(A) -> np.ndarray:
+    """cholesky(A).L computed on device (mcm_potrf); raises ArgumentError if A is not positive definite."""
+    A = np.ascontiguousarray(np.asarray(A, dtype=np.float64))
+    M = A.shape[0]
+    d = P._alloc(A.nbytes)
     try:
-        means = np.empty(M)
-        L.check(L.lib().mcm_colmeans(X[0].dtype, ptrs, M, X[0].N, means.ctypes.data_as(L._dp)))
-        cov = P.pcov(X)   # centring is internal to the Gram kernel; cov(X .- mean) == cov(X)
+        L.check(L.lib().mcm_upload(C.c_void_p(d), A.ctypes.data_as(C.c_void_p), A.nbytes))
+        info = C.c_int(0)
+        L.check(L.lib().mcm_potrf(C.c_void_p(d), M, C.byref(info)))
+        out = np.empty_like(A)
+        L.check(L.lib().mcm_download(out.ctypes.data_as(C.c_void_p), C.c_void_p(d), out.nbytes))
     finally:
-        th.join()
-    if "ls" not in box:
-        raise L.ArgumentError(L.MCM_ERR_INVALID, "transform_moments: Σ is not positive definite")
-    if preserve_latin:
-        xl = np.diag(np.sqrt(np.diag(cov)))
-    else:
-        xl = np.linalg.cholesky(cov)
-    # chol(Σ).L / xl: a triangular solve (A xl = L_S  <=>  xl' A' = L_S'), so A is lower triangular by construction
-    A = _solve_triangular(xl.T, box["ls"].T, lower=False).T
-    A = np.tril(A)
-    return P.pgemm(A, X, shift=means, bias=m)
+        L.lib().mcm_free(C.c_void_p(d))
+    return out
+
+
+def solve_right_lower(Lm, B) -> np.ndarray:
+    """B / L for lower-triangular L (X L = B) on device (mcm_trsm_right_lower)."""
+    Lm = np.ascontiguousarray(np.asarray(Lm, dtype=np.float64))
+    B = np.ascontiguousarray(np.atleast_2d(np.asarray(B, dtype=np.float64)))
+    M = Lm.shape[0]
+    dl, db = P._alloc(Lm.nbytes), P._alloc(B.nbytes)
+    try:
+        L.check(L.lib().mcm_upload(C.c_void_p(dl), Lm.ctypes.data_as(C.c_void_p), Lm.nbytes))
+        L.check(L.lib().mcm_upload(C.c_void_p(db), B.ctypes.data_as(C.c_void_p), B.nbytes))
+        L.check(L.lib().mcm_trsm_right_lower(C.c_void_p(dl), C.c_void_p(db), M, B.shape[0]))
+        out = np.empty_like(B)
+        L.check(L.lib().mcm_download(out.ctypes.data_as(C.c_void_p), C.c_void_p(db), out.nbytes))
+    finally:
+        L.lib().mcm_free(C.c_void_p(dl)); L.lib().mcm_free(C.c_void_p(db))
+    return out
 
 
 def index_bijection(n: int, seed: int = 0, column: int = 0, i0: int = 0, n_total: int | None = None) -> P.DeviceIndex:

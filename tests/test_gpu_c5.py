@@ -282,3 +282,51 @@ def test_quantile_batch_errors(mcm):
         mcm.pquantile(v[1:], 1.5)
     with pytest.raises(mcm.ArgumentError):
         mcm.pquantile([mcm.Particles(np.zeros(3)), mcm.Particles(np.zeros(4))], 0.5)
+
+
+# ---- M x M dense steps (dense.cu) ------------------------------------------------------------------------
+@pytest.mark.parametrize("M", [1, 5, 64, 65, 200, 517])
+def test_device_cholesky_and_triangular_solve(mcm, M):
+    """cholesky(C).L and B / L on device against LAPACK (numpy): same factor up to rounding."""
+    rng = np.random.default_rng(M)
+    Q = rng.normal(size=(M, M + 3))
+    A = Q @ Q.T / M + 0.5 * np.eye(M)
+    Ld = mcm.cholesky_lower(A)
+    Lh = np.linalg.cholesky(A)
+    scale = np.abs(Lh).max()
+    assert np.all(np.triu(Ld, 1) == 0)
+    assert np.max(np.abs(Ld - Lh)) <= 1e-13 * M * scale
+    assert np.max(np.abs(Ld @ Ld.T - A)) <= 1e-14 * M * np.abs(A).max()
+    B = np.tril(rng.normal(size=(M, M)))
+    X = mcm.solve_right_lower(Lh, B)
+    assert np.max(np.abs(X @ Lh - B)) <= 1e-12 * M * max(1.0, np.abs(X).max())
+    Xr = mcm.solve_right_lower(Lh, rng.normal(size=(3, M)))                      # general right-hand sides
+    assert Xr.shape == (3, M)
+    with pytest.raises(mcm.MCMError):
+        Bad = A.copy(); Bad[M // 2, M // 2] = -1.0
+        mcm.cholesky_lower(Bad)                                                   # not positive definite -> error, like LAPACK
+
+
+def test_transform_moments_device_matches_host_linear_algebra(mcm):
+    """mcm_transform_moments (all on device) against the same algebra done with LAPACK on the host."""
+    d, n = 70, 9000
+    rng = np.random.default_rng(21)
+    cols = mcm.systematic_batch(n, d, seed=5)
+    Aq = rng.normal(size=(d, d)); S = Aq @ Aq.T / d + np.eye(d); m = rng.normal(size=d)
+    Y = mcm.transform_moments(cols, m, S)
+    X = np.stack([c.to_numpy() for c in cols])
+    mu = X.mean(axis=1)
+    xl = np.linalg.cholesky(np.cov(X))
+    A = np.linalg.solve(xl.T, np.linalg.cholesky(S).T).T
+    ref = m[:, None] + A @ (X - mu[:, None])
+    Yh = np.stack([y.to_numpy() for y in Y])
+    assert np.max(np.abs(Yh - ref)) <= 1e-11 * np.abs(ref).max()
+    assert np.max(np.abs(np.cov(Yh) - S)) <= 1e-11 and np.max(np.abs(Yh.mean(axis=1) - m)) <= 1e-12
+    Yl = mcm.transform_moments(cols, m, S, preserve_latin=True)                   # xl = Diagonal(std): sigmapoints.jl:66-67
+    Al = np.linalg.cholesky(S) / X.std(axis=1, ddof=1)[None, :]
+    refl = m[:, None] + Al @ (X - mu[:, None])
+    assert np.max(np.abs(np.stack([y.to_numpy() for y in Yl]) - refl)) <= 1e-11 * np.abs(refl).max()
+    with pytest.raises(mcm.MCMError):
+        mcm.transform_moments(cols, m, -S)
+    with pytest.raises(mcm.ArgumentError):
+        mcm.transform_moments(cols, m, S[:5, :5])
