@@ -361,6 +361,13 @@ int mcm_comm_allreduce_sum_f64(double* dptr, size_t count);
 int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_host);
 /* merge host-resident per-rank moments (e.g. mcm_chain's fused statistics) across ranks, in place */
 int mcm_moments_allmerge(double* inout_host6);
+/* sharded pquantile (particles.jl:316-323 over a particle index spread across GPUs): every rank passes its
+ * shard (balanced to 1 %, >= 8192 particles, power-of-two rank count); all ranks return the quantiles of the
+ * GLOBAL particle set, out_host[m*nq + i].  Sampled pivots (all-gather of 8192 sample keys per variable),
+ * local streaming count/collect, radix select on all-reduced histograms; only the <= 2048 finalists per rank
+ * group ever leave a GPU.  With a single rank this is mcm_quantile_batch. */
+int mcm_quantile_sharded(int dtype, const void* const* vars, int M, size_t n_local, const double* q_host, int nq,
+                         double* out_host);
 /* sharded pcov: global means by all-reduce, local centred Gram, all-reduce of the
  * M x M block, scaled by 1/(N_global - corrected) */
 int mcm_gram_sharded(int dtype, const void* const* vars, int M, size_t n_local, int corrected,

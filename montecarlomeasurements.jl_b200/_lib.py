@@ -125,6 +125,7 @@ SIGNATURES = {
     "mcm_systematic_batch": (_i, [_i, _i, _vpp, _i, _sz, _dp, _dp, _i, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_quantile_batch": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),
     "mcm_quantile_batch_fallbacks": (_i, []),
+    "mcm_quantile_sharded": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),
     "mcm_order_statistics": (_i, [_i, _vp, _sz, C.POINTER(C.c_uint64), _i, _dp]),
     "mcm_pgemm": (_i, [_i, _dp, _i, _i, _vpp, _dp, _dp, _vpp, _sz]),
     "mcm_potrf": (_i, [_vp, _i, C.POINTER(C.c_int)]),

@@ -69,6 +69,32 @@ int read_back(double* host_dst, const double* dev_src, size_t count);
 int gram_dispatch(int dtype, const void* const* vars, int M, size_t n, double scale, const double* center_host,
                   double* cov_out_dev, double* means_out_dev);
 
+// ---- internal collectives for other translation units (select_batch.cu) ----------------------------
+// ncclDataType_t values: uint8 = 1, uint32 = 3, uint64 = 5
+int comm_world(int* nranks, int* rank) {
+  *nranks = g_nccl.comm ? g_nccl.nranks : 1;
+  *rank = g_nccl.comm ? g_nccl.rank : 0;
+  return MCM_OK;
+}
+int comm_allreduce_sum_u32(uint32_t* d, size_t count) {
+  if (!g_nccl.comm) return MCM_OK;
+  MCM_NCCL(g_nccl.AllReduce(d, d, count, 3, ncclSum, g_nccl.comm, ctx().stream));
+  return MCM_OK;
+}
+int comm_allreduce_sum_u64(unsigned long long* d, size_t count) {
+  if (!g_nccl.comm) return MCM_OK;
+  MCM_NCCL(g_nccl.AllReduce(d, d, count, 5, ncclSum, g_nccl.comm, ctx().stream));
+  return MCM_OK;
+}
+int comm_allgather_bytes(const void* send, void* recv, size_t bytes_per_rank) {
+  if (!g_nccl.comm) {
+    if (send != recv) MCM_CUDA(cudaMemcpyAsync(recv, send, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx().stream));
+    return MCM_OK;
+  }
+  MCM_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, 1, g_nccl.comm, ctx().stream));
+  return MCM_OK;
+}
+
 __global__ void k_scale(double* a, size_t n, double s) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a[i] *= s;

@@ -43,7 +43,7 @@ constexpr int BS_BITS = 11;
 constexpr int BS_BINS = 1 << BS_BITS;
 constexpr int BS_MAXG = 8;       // live prefixes / ranks per segment
 constexpr int BS_THRESH = 2048;  // candidates per final group
-constexpr int BS_PASSES = 4;     // 44 key bits; 3 are enough for 32-bit keys
+constexpr int BS_PASSES = 6;     // 66 >= 64 key bits: every group ends final or fully resolved; 3 are enough for 32-bit keys
 
 static int g_bq_fallbacks = 0;  // segments re-done by the general path (diagnostics / tests)
 
@@ -71,8 +71,9 @@ struct BInit {
   uint32_t cap[4];
 };
 __global__ void k_bs_init(BSeg* __restrict__ seg, int nsegs, int key_bits, uint32_t n_uniform, BInit bi,
-                          const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ below,
-                          const unsigned long long* __restrict__ pivots, uint32_t* __restrict__ parent_flags) {
+                          const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ nseg_global,
+                          const uint32_t* __restrict__ below, const unsigned long long* __restrict__ pivots,
+                          uint32_t* __restrict__ parent_flags) {
   const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx >= nsegs) return;
   const int b = sidx % bi.nb, m = sidx / bi.nb;
@@ -84,14 +85,14 @@ __global__ void k_bs_init(BSeg* __restrict__ seg, int nsegs, int key_bits, uint3
   int rem = key_bits;
   unsigned long long prefix = 0;
   if (nseg) {
-    n = nseg[sidx];
+    n = nseg_global ? nseg_global[sidx] : nseg[sidx];   // sharded: counts and ranks are global, lists are local
     sub = below[sidx];
     const unsigned long long lo = pivots[2 * sidx], hi = pivots[2 * sidx + 1];
     const unsigned long long diff = lo ^ hi;
     rem = diff ? 64 - __clzll((long long)diff) : 0;
     if (rem > key_bits) rem = key_bits;
     prefix = rem >= 64 ? 0ull : (lo >> rem);
-    if (n > bi.cap[b]) { atomicOr(parent_flags + m, 2u); n = 0; }
+    if (nseg[sidx] > bi.cap[b]) { atomicOr(parent_flags + m, 2u); n = 0; }
   }
   s.count[0] = n;
   s.rem[0] = rem;
@@ -401,7 +402,8 @@ struct BqParams {
 
 template <typename T>
 __global__ void __launch_bounds__(1024)
-k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned long long* __restrict__ pivots) {
+k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned long long* __restrict__ pivots,
+            unsigned long long* __restrict__ sub_out, int world) {
   using K = typename KeyOf<T>::type;
   extern __shared__ unsigned long long sk[];  // BQ_SAMPLE keys
   const int m = blockIdx.x;
@@ -426,6 +428,13 @@ k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned l
       }
       __syncthreads();
     }
+  if (sub_out) {
+    // sharded: this rank contributes every world-th key of its sorted sample (a stratified subsample); the union
+    // over the ranks is the 8192-key sample every rank derives the SAME pivots from (k_bq_pivots)
+    const int per = BQ_SAMPLE / world;
+    for (int i = threadIdx.x; i < per; i += 1024) sub_out[(size_t)m * per + i] = sk[i * world + world / 2];
+    return;
+  }
   if (threadIdx.x < bp.nb) {
     const int b = threadIdx.x;
     const unsigned long long kmax = sizeof(K) == 8 ? ~0ull : 0xffffffffull;
@@ -434,6 +443,37 @@ k_bq_sample(const T* const* __restrict__ vars, size_t n, BqParams bp, unsigned l
     unsigned long long lo = bp.a[b] < 0 ? 0ull : sk[bp.a[b]];
     unsigned long long hi = bp.b[b] >= BQ_SAMPLE ? kmax : sk[bp.b[b]];
     if (sizeof(K) == 8) { lo &= 0xffffffff00000000ull; hi |= 0x00000000ffffffffull; }
+    pivots[2 * ((size_t)m * bp.nb + b)] = lo;
+    pivots[2 * ((size_t)m * bp.nb + b) + 1] = hi;
+  }
+}
+
+// sharded: pivots from the union of the per-rank subsamples ([rank][M][per] keys, identical on every rank)
+__global__ void __launch_bounds__(1024)
+k_bq_pivots(const unsigned long long* __restrict__ uni, int world, int M, BqParams bp, int key64,
+            unsigned long long* __restrict__ pivots) {
+  extern __shared__ unsigned long long sk[];
+  const int m = blockIdx.x;
+  const int per = BQ_SAMPLE / world;
+  for (int e = threadIdx.x; e < BQ_SAMPLE; e += 1024) sk[e] = uni[((size_t)(e / per) * M + m) * per + e % per];
+  __syncthreads();
+  for (int k = 2; k <= BQ_SAMPLE; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < BQ_SAMPLE; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long x = sk[i], y = sk[l];
+          const bool up = ((i & k) == 0);
+          if ((x > y) == up) { sk[i] = y; sk[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  if (threadIdx.x < bp.nb) {
+    const int b = threadIdx.x;
+    unsigned long long lo = bp.a[b] < 0 ? 0ull : sk[bp.a[b]];
+    unsigned long long hi = bp.b[b] >= BQ_SAMPLE ? (key64 ? ~0ull : 0xffffffffull) : sk[bp.b[b]];
+    if (key64) { lo &= 0xffffffff00000000ull; hi |= 0x00000000ffffffffull; }
     pivots[2 * ((size_t)m * bp.nb + b)] = lo;
     pivots[2 * ((size_t)m * bp.nb + b) + 1] = hi;
   }
@@ -619,6 +659,28 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
   if (lowor == 0x5a5a5a5au && kmax == 0u) atomicOr(flags + m, 0u);   // keeps `lowor` (hence the full loads) alive
 }
 
+// sharded merge of the final candidates: rank r's keys of group (sidx, g) go to offset sum_{q<r} cnt[q] of a zeroed
+// global-size list; an all-reduce (sum) of the lists then equals their concatenation
+__global__ void __launch_bounds__(256)
+k_bs_place(const unsigned long long* __restrict__ cand_local, const uint32_t* __restrict__ cnt_all, int world, int rank,
+           int ngroups, unsigned long long* __restrict__ cand_global, uint32_t* __restrict__ cnt_total) {
+  const int gidx = blockIdx.x;   // sidx * BS_MAXG + g
+  uint32_t off = 0, tot = 0;
+  for (int r = 0; r < world; ++r) {
+    const uint32_t c = cnt_all[(size_t)r * ngroups + gidx];
+    if (r < rank) off += c;
+    tot += c;
+  }
+  const uint32_t mine = cnt_all[(size_t)rank * ngroups + gidx];
+  for (uint32_t i = threadIdx.x; i < mine && i < (uint32_t)BS_THRESH; i += 256)
+    if (off + i < (uint32_t)BS_THRESH) cand_global[(size_t)gidx * BS_THRESH + off + i] = cand_local[(size_t)gidx * BS_THRESH + i];
+  if (threadIdx.x == 0) cnt_total[gidx] = tot;
+}
+__global__ void k_split_flags(const uint32_t* __restrict__ flags, int M, uint32_t* __restrict__ out2) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < M) { out2[m] = flags[m] & 1u; out2[M + m] = (flags[m] >> 1) & 1u; }
+}
+
 __global__ void k_bs_flags(const BSeg* __restrict__ segs, int nsegs, int nb, uint32_t* __restrict__ flags) {
   const int sidx = blockIdx.x * blockDim.x + threadIdx.x;
   if (sidx < nsegs && segs[sidx].flags) atomicOr(flags + sidx / nb, segs[sidx].flags);
@@ -628,13 +690,39 @@ template <typename T>
 int order_statistics(const T* in, size_t n, const unsigned long long* ranks, int nr, double* vals_host, int* has_nan);
 
 // vals_host[m*nr + r] = sorted(vars[m])[ranks[r]]; nr <= BS_MAXG
+int comm_world(int* nranks, int* rank);
+int comm_allreduce_sum_u32(uint32_t* d, size_t count);
+int comm_allreduce_sum_u64(unsigned long long* d, size_t count);
+int comm_allgather_bytes(const void* send, void* recv, size_t bytes_per_rank);
+
+struct ShardInfo {
+  int world, rank;
+  size_t n_global;
+  bool full;                   // skip the bracketing stage: radix select over the whole (sharded) data
+  std::vector<int>* flagged;   // out: variables whose ranks escaped their bracket (same list on every rank)
+};
+
+// sharded radix select without brackets: the "candidate list" of a variable is its whole local shard
+__global__ void k_fill_full(uint32_t* __restrict__ qcnt, uint32_t* __restrict__ qcnt_g, unsigned long long* __restrict__ piv,
+                            int S, uint32_t n_local, uint32_t n_global, int key64) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S) return;
+  qcnt[i] = n_local;
+  qcnt_g[i] = n_global;
+  piv[2 * i] = 0ull;
+  piv[2 * i + 1] = key64 ? ~0ull : 0xffffffffull;
+}
+
+// n = number of LOCAL keys per variable.  sh != nullptr: the variables are sharded over sh->world ranks (every rank
+// calls with its shard), `ranks` are ranks in the GLOBAL order, every rank returns the same values.
 template <typename T>
 static int order_statistics_batch(const T* const* vars_host, int M, size_t n, const unsigned long long* ranks, int nr,
-                                  double* vals_host, int* has_nan) {
+                                  double* vals_host, int* has_nan, const ShardInfo* sh = nullptr) {
   using K = typename KeyOf<T>::type;
   Ctx& c = ctx();
   *has_nan = 0;
-  const bool bracket = n >= BQ_MIN_N;
+  const size_t n_plan = sh ? sh->n_global : n;     // the order statistics refer to this many keys
+  const bool bracket = sh ? !sh->full : n >= BQ_MIN_N;
   // ---- host plan: brackets in sample space (data independent) --------------------------------
   BqParams bp;
   BInit bi;
@@ -649,7 +737,7 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     std::sort(order.begin(), order.end(), [&](int x, int y) { return ranks[x] < ranks[y]; });
     for (int oi = 0; oi < nr; ++oi) {
       const int r = order[oi];
-      const double p = ((double)ranks[r] + 0.5) / (double)n;
+      const double p = ((double)ranks[r] + 0.5) / (double)n_plan;
       const double pos = p * BQ_SAMPLE;
       const double w = 4.5 * sqrt(BQ_SAMPLE * p * (1.0 - p)) + 3.0;
       int a = (int)floor(pos - w), b = (int)ceil(pos + w);
@@ -670,7 +758,9 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     for (int b = 0; b < bp.nb; ++b) {
       bp.a[b] = iv[b].a; bp.b[b] = iv[b].b;
       const double width = (double)(std::min(iv[b].b, BQ_SAMPLE) - std::max(iv[b].a, 0) + 2);
-      double cap = (width + 6.0 * sqrt(width) + 8.0) * (double)n / BQ_SAMPLE + 1024.0;
+      // sharded: one rank may hold ALL candidates of a bracket (e.g. a globally sorted array), so the bound is
+      // the global candidate count, clipped to the local size
+      double cap = (width + 6.0 * sqrt(width) + 8.0) * (double)n_plan / BQ_SAMPLE + 1024.0;
       if (cap > (double)n) cap = (double)n;
       bp.cap[b] = bi.cap[b] = ((uint32_t)cap + 3u) & ~3u;   // 16-byte aligned lists
       bi.nr[b] = (int)iv[b].ranks.size();
@@ -696,9 +786,13 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
   const size_t cnt_bytes = (size_t)S * BS_MAXG * sizeof(uint32_t);
   const size_t out_bytes = (size_t)S * BS_MAXG * sizeof(double);
   const size_t piv_bytes = (size_t)S * 2 * sizeof(unsigned long long);
+  const int world = sh ? sh->world : 1;
+  const size_t per = BQ_SAMPLE / (size_t)world;                       // subsample keys per rank per variable
+  const size_t shard_bytes = sh ? ((size_t)S * 4 + 2 * (size_t)M * 4 + (size_t)world * cnt_bytes + cnt_bytes +
+                                   (size_t)M * per * 8 + (size_t)world * M * per * 8 + 256) : 0;
   const size_t zero_bytes = hist_bytes + cnt_bytes + 3 * (size_t)S * 4 + (size_t)M * 4 + 64;  // hist, cnt, qcnt, below, pad, flags
   unsigned char* d_all = nullptr;
-  const size_t total = tab_bytes + seg_bytes + zero_bytes + out_bytes + piv_bytes + 1024;
+  const size_t total = tab_bytes + seg_bytes + zero_bytes + out_bytes + piv_bytes + shard_bytes + 1024;
   MCM_CUDA(cudaMallocAsync((void**)&d_all, total, c.stream));
   size_t off = 0;
   auto take = [&](size_t bytes) { unsigned char* p = d_all + off; off += (bytes + 15) & ~(size_t)15; return p; };
@@ -713,11 +807,24 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
   BSeg* d_seg = (BSeg*)take(seg_bytes);
   double* d_out = (double*)take(out_bytes);
   unsigned long long* d_piv = (unsigned long long*)take(piv_bytes);
+  uint32_t *d_qcnt_g = nullptr, *d_flags2 = nullptr, *d_cnt_all = nullptr, *d_cnt_tot = nullptr;
+  unsigned long long *d_sub = nullptr, *d_uni = nullptr;
+  if (sh) {
+    d_qcnt_g = (uint32_t*)take((size_t)S * 4);
+    d_flags2 = (uint32_t*)take(2 * (size_t)M * 4);
+    d_cnt_all = (uint32_t*)take((size_t)world * cnt_bytes);
+    d_cnt_tot = (uint32_t*)take(cnt_bytes);
+    d_sub = (unsigned long long*)take((size_t)M * per * 8);
+    d_uni = (unsigned long long*)take((size_t)world * M * per * 8);
+  }
   MCM_CUDA(cudaMemsetAsync(d_zero0, 0, zero_span, c.stream));
   T* d_qcand = nullptr;
   if (bracket) MCM_CUDA(cudaMallocAsync((void**)&d_qcand, (size_t)M * cand_stride * sizeof(T), c.stream));
   unsigned long long* d_cand = nullptr;
-  MCM_CUDA(cudaMallocAsync((void**)&d_cand, (size_t)S * BS_MAXG * BS_THRESH * sizeof(unsigned long long), c.stream));
+  const size_t cand_keys = (size_t)S * BS_MAXG * BS_THRESH;
+  MCM_CUDA(cudaMallocAsync((void**)&d_cand, cand_keys * sizeof(unsigned long long) * (sh ? 2 : 1), c.stream));
+  unsigned long long* d_cand_g = sh ? d_cand + cand_keys : nullptr;   // merged lists (sharded)
+  if (sh) MCM_CUDA(cudaMemsetAsync(d_cand_g, 0, cand_keys * sizeof(unsigned long long), c.stream));
   std::vector<const T*> htab((size_t)M + S);
   for (int m = 0; m < M; ++m) htab[m] = vars_host[m];
   for (int m = 0; m < M; ++m) {
@@ -735,6 +842,7 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     MCM_CUDA(cudaFuncSetAttribute(k_bs_hist<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_MAXG * BS_BINS * 4));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
+    MCM_CUDA(cudaFuncSetAttribute(k_bq_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
     constexpr int kStreamSmem = (kThreads / 32) * 4 * (512 + BQ_WARP_KEYS) * 4;
     MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
@@ -752,8 +860,16 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
   };
   // ---- stage 1 ------------------------------------------------------------------------------------
   if (bracket) {
-    k_bq_sample<T><<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_tab, n, bp, d_piv);
-    MCM_CHECK_LAUNCH();
+    if (!sh) {
+      k_bq_sample<T><<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_tab, n, bp, d_piv, nullptr, 1);
+      MCM_CHECK_LAUNCH();
+    } else {
+      k_bq_sample<T><<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_tab, n, bp, d_piv, d_sub, world);
+      MCM_CHECK_LAUNCH();
+      if (int rc = comm_allgather_bytes(d_sub, d_uni, (size_t)M * per * 8)) return rc;
+      k_bq_pivots<<<M, 1024, BQ_SAMPLE * 8, c.stream>>>(d_uni, world, M, bp, sizeof(K) == 8 ? 1 : 0, d_piv);
+      MCM_CHECK_LAUNCH();
+    }
     const dim3 g1(chunks(n, M), (unsigned)M);
     // few variables: many warps flush into the same three counters -> flush rarely; many variables: small staging
     const int flush_at = M >= 64 ? 128 : 512;
@@ -765,12 +881,21 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
       default: k_bq_stream<T, 4><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
     }
     MCM_CHECK_LAUNCH();
+    if (sh) {   // global below-counts and candidate counts (the lists themselves stay where they are)
+      MCM_CUDA(cudaMemcpyAsync(d_qcnt_g, d_qcnt, (size_t)S * 4, cudaMemcpyDeviceToDevice, c.stream));
+      if (int rc = comm_allreduce_sum_u32(d_qcnt_g, S)) return rc;
+      if (int rc = comm_allreduce_sum_u32(d_below, S)) return rc;
+    }
+  }
+  if (sh && !bracket) {
+    k_fill_full<<<(S + 127) / 128, 128, 0, c.stream>>>(d_qcnt, d_qcnt_g, d_piv, S, (uint32_t)n, (uint32_t)sh->n_global, sizeof(K) == 8 ? 1 : 0);
+    MCM_CHECK_LAUNCH();
   }
   // ---- stage 2: radix select on S segments -------------------------------------------------------
   const T* const* seg_tab = d_tab + M;
-  const uint32_t* d_nseg = bracket ? d_qcnt : nullptr;
+  const uint32_t* d_nseg = (bracket || sh) ? d_qcnt : nullptr;
   const size_t seg_keys = bracket ? max_cap : n;
-  k_bs_init<<<(S + 127) / 128, 128, 0, c.stream>>>(d_seg, S, 8 * (int)sizeof(K), (uint32_t)n, bi, d_nseg, d_below, d_piv, d_flags);
+  k_bs_init<<<(S + 127) / 128, 128, 0, c.stream>>>(d_seg, S, 8 * (int)sizeof(K), (uint32_t)n, bi, d_nseg, d_qcnt_g, d_below, d_piv, d_flags);
   MCM_CHECK_LAUNCH();
   const dim3 grid(chunks(seg_keys, S), (unsigned)S);
   const int passes = sizeof(K) == 8 ? BS_PASSES : 3;
@@ -780,27 +905,52 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     const size_t smem = (size_t)(p == 0 ? 1 : gmax) * BS_BINS * 4;
     k_bs_hist<T><<<grid, kThreads, smem, c.stream>>>(seg_tab, n, d_nseg, d_seg, d_hist);
     MCM_CHECK_LAUNCH();
+    if (sh) {   // every rank narrows on the GLOBAL histograms, so the narrowing state stays identical everywhere
+      if (int rc = comm_allreduce_sum_u32(d_hist, (size_t)S * BS_MAXG * BS_BINS)) return rc;
+    }
     k_bs_pick<<<S, 256, 0, c.stream>>>(d_seg, d_hist, p == passes - 1);
     MCM_CHECK_LAUNCH();
   }
   k_bs_compact<T><<<grid, kThreads, 0, c.stream>>>(seg_tab, n, d_nseg, d_seg, d_cand, d_cnt);
   MCM_CHECK_LAUNCH();
-  k_bs_final<T><<<dim3(gmax, S), 1024, 0, c.stream>>>(d_seg, d_cand, d_cnt, d_out);
+  const unsigned long long* fin_cand = d_cand;
+  const uint32_t* fin_cnt = d_cnt;
+  if (sh) {   // the <= 2048 finalists of every group are the only keys that ever cross NVLink
+    const int ngroups = S * BS_MAXG;
+    if (int rc = comm_allgather_bytes(d_cnt, d_cnt_all, cnt_bytes)) return rc;
+    k_bs_place<<<ngroups, 256, 0, c.stream>>>(d_cand, d_cnt_all, world, sh->rank, ngroups, d_cand_g, d_cnt_tot);
+    MCM_CHECK_LAUNCH();
+    if (int rc = comm_allreduce_sum_u64(d_cand_g, cand_keys)) return rc;
+    fin_cand = d_cand_g;
+    fin_cnt = d_cnt_tot;
+  }
+  k_bs_final<T><<<dim3(gmax, S), 1024, 0, c.stream>>>(d_seg, fin_cand, fin_cnt, d_out);
   MCM_CHECK_LAUNCH();
   k_bs_flags<<<(S + 127) / 128, 128, 0, c.stream>>>(d_seg, S, NB, d_flags);
   MCM_CHECK_LAUNCH();
+  if (sh) {   // a NaN or an escaped rank seen by any rank is seen by all
+    k_split_flags<<<(M + 127) / 128, 128, 0, c.stream>>>(d_flags, M, d_flags2);
+    MCM_CHECK_LAUNCH();
+    if (int rc = comm_allreduce_sum_u32(d_flags2, 2 * (size_t)M)) return rc;
+  }
   std::vector<double> hout((size_t)S * BS_MAXG);
-  std::vector<uint32_t> hflags(M);
+  std::vector<uint32_t> hflags(M), hflags2(sh ? 2 * (size_t)M : 0);
   MCM_CUDA(cudaMemcpyAsync(hout.data(), d_out, out_bytes, cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, (size_t)M * 4, cudaMemcpyDeviceToHost, c.stream));
+  if (sh) MCM_CUDA(cudaMemcpyAsync(hflags2.data(), d_flags2, 2 * (size_t)M * 4, cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaStreamSynchronize(c.stream));
+  if (sh)
+    for (int m = 0; m < M; ++m) hflags[m] = (hflags2[m] ? 1u : 0u) | (hflags2[(size_t)M + m] ? 2u : 0u);
   MCM_CUDA(cudaFreeAsync(d_cand, c.stream));
   if (d_qcand) MCM_CUDA(cudaFreeAsync(d_qcand, c.stream));
   MCM_CUDA(cudaFreeAsync(d_all, c.stream));
   int rc = MCM_OK;
   for (int m = 0; m < M && rc == MCM_OK; ++m) {
     if (hflags[m] & 1u) *has_nan = 1;
-    if (hflags[m] & 2u) {  // heavy ties around a rank, or a rank outside its bracket: the general path resolves any input
+    if ((hflags[m] & 2u) && sh) {
+      if (sh->full || !sh->flagged) rc = fail(MCM_ERR_CUDA, "sharded order statistics: variable %d did not resolve", m);
+      else sh->flagged->push_back(m);   // heavy ties or an escaped rank: the caller re-runs these without brackets
+    } else if (hflags[m] & 2u) {  // a rank outside its bracket: the general path resolves any input
       int hn = 0;
       rc = order_statistics<T>(vars_host[m], n, ranks, nr, vals_host + (size_t)m * nr, &hn);
       *has_nan |= hn;
@@ -879,5 +1029,89 @@ extern "C" int mcm_quantile_batch(int dtype, const void* const* vars, int M, siz
             quantile_combine(dtype, vals[(size_t)m * nr + 2 * i], vals[(size_t)m * nr + 2 * i + 1], gam[i]);
   }
   if (any_nan) return fail(MCM_ERR_INVALID, "mcm_quantile_batch: quantiles are undefined in presence of NaNs");
+  return MCM_OK;
+}
+
+// pquantile over a particle index sharded across the ranks of the library communicator: every
+// rank passes its shard of each variable; all ranks return the same quantiles of the GLOBAL particle set.
+// Communication: 8192 sample keys per variable (all-gather), the below/candidate counts and the per-pass
+// histograms (all-reduce), and the <= 2048 finalists per rank group — no other key leaves its GPU.
+extern "C" int mcm_quantile_sharded(int dtype, const void* const* vars, int M, size_t n_local, const double* q_host, int nq,
+                                    double* out_host) {
+  MCM_NEED_INIT();
+  int world = 1, rank = 0;
+  comm_world(&world, &rank);
+  if (world == 1) return mcm_quantile_batch(dtype, vars, M, n_local, q_host, nq, out_host);
+  if (!vars || !q_host || !out_host || nq < 1 || M < 1) return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: bad arguments");
+  if (M > 16383) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: at most 16383 variables per call");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: bad dtype %d", dtype);
+  if (world > 64 || (world & (world - 1))) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: the number of ranks must be a power of two <= 64");
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  for (int m = 0; m < M; ++m)
+    if (!vars[m] || (reinterpret_cast<uintptr_t>(vars[m]) % esz) != 0)
+      return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: variable %d is null or misaligned", m);
+  for (int i = 0; i < nq; ++i)
+    if (!(q_host[i] >= 0.0 && q_host[i] <= 1.0))
+      return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: input probability out of [0,1] range");
+  Ctx& c = ctx();
+  // shard sizes of all ranks
+  unsigned long long* d_n = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_n, (size_t)(world + 1) * 8, c.stream));
+  const unsigned long long nl = n_local;
+  MCM_CUDA(cudaMemcpyAsync(d_n + world, &nl, 8, cudaMemcpyHostToDevice, c.stream));
+  if (int rc = comm_allgather_bytes(d_n + world, d_n, 8)) return rc;
+  std::vector<unsigned long long> hn(world);
+  MCM_CUDA(cudaMemcpyAsync(hn.data(), d_n, (size_t)world * 8, cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_n, c.stream));
+  size_t n_global = 0;
+  for (int r = 0; r < world; ++r) n_global += hn[r];
+  for (int r = 0; r < world; ++r) {
+    if (hn[r] < (unsigned long long)BQ_SAMPLE) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: every shard needs at least %d particles (rank %d has %llu)", BQ_SAMPLE, r, hn[r]);
+    const double ideal = (double)n_global / world;
+    if (fabs((double)hn[r] - ideal) > 0.01 * ideal + 2.0)
+      return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: shards must be balanced to 1 %% (rank %d has %llu of %zu)", r, hn[r], n_global);
+  }
+  if (n_global >= 0xFFFF0000ull) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: global N must be < 2^32");
+  std::vector<int> flagged;
+  ShardInfo sh{world, rank, n_global, false, &flagged};
+  std::vector<double> vals((size_t)M * BS_MAXG);
+  int any_nan = 0;
+  for (int q0 = 0; q0 < nq; q0 += BS_MAXG / 2) {
+    const int cq = std::min(BS_MAXG / 2, nq - q0);
+    unsigned long long ranks[BS_MAXG];
+    double gam[BS_MAXG / 2];
+    for (int i = 0; i < cq; ++i) quantile_rank_pair(n_global, q_host[q0 + i], ranks[2 * i], ranks[2 * i + 1], gam[i]);
+    const int nr = 2 * cq;
+    int h = 0;
+    const int rc = dtype == MCM_F64
+                       ? order_statistics_batch<double>((const double* const*)vars, M, n_local, ranks, nr, vals.data(), &h, &sh)
+                       : order_statistics_batch<float>((const float* const*)vars, M, n_local, ranks, nr, vals.data(), &h, &sh);
+    if (rc) return rc;
+    any_nan |= h;
+    if (!flagged.empty()) {
+      // variables with more ties around a rank than a bracket can hold (or, with probability ~1e-5, an escaped
+      // rank): radix select over their whole shards with all-reduced histograms — 64 key bits in 6 passes
+      std::vector<const void*> sub(flagged.size());
+      for (size_t i = 0; i < flagged.size(); ++i) sub[i] = vars[flagged[i]];
+      std::vector<double> v2(flagged.size() * BS_MAXG);
+      ShardInfo full{world, rank, n_global, true, nullptr};
+      int h2 = 0;
+      const int rc2 = dtype == MCM_F64
+                          ? order_statistics_batch<double>((const double* const*)sub.data(), (int)sub.size(), n_local, ranks, nr, v2.data(), &h2, &full)
+                          : order_statistics_batch<float>((const float* const*)sub.data(), (int)sub.size(), n_local, ranks, nr, v2.data(), &h2, &full);
+      if (rc2) return rc2;
+      any_nan |= h2;
+      for (size_t i = 0; i < flagged.size(); ++i)
+        for (int r = 0; r < nr; ++r) vals[(size_t)flagged[i] * nr + r] = v2[i * nr + r];
+      g_bq_fallbacks += (int)flagged.size();
+      flagged.clear();
+    }
+    for (int m = 0; m < M; ++m)
+      for (int i = 0; i < cq; ++i)
+        out_host[(size_t)m * nq + q0 + i] =
+            quantile_combine(dtype, vals[(size_t)m * nr + 2 * i], vals[(size_t)m * nr + 2 * i + 1], gam[i]);
+  }
+  if (any_nan) return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: quantiles are undefined in presence of NaNs");
   return MCM_OK;
 }

@@ -121,3 +121,28 @@ def pcov(v_local, corrected: bool = True) -> np.ndarray:
     finally:
         L.lib().mcm_free(C.c_void_p(dC))
     return out
+
+
+def pquantile(p_local, q):
+    """Global pquantile of a sharded Particles (or a list of M sharded variables): every rank passes its shard and
+    gets the quantiles of the whole particle set (mcm_quantile_sharded: sampled pivots, local count/collect, radix
+    select on all-reduced histograms; only <= 2048 finalists per rank group cross NVLink)."""
+    import numbers
+    scalar = isinstance(q, numbers.Real)
+    qs = np.ascontiguousarray(np.atleast_1d(np.asarray(q, dtype=np.float64)))
+    single = isinstance(p_local, P.Particles)
+    v = [p_local] if single else P._check_mv(p_local)
+    M = len(v)
+    ptrs = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in v])
+    out = np.zeros((M, len(qs)))
+    L.check(L.lib().mcm_quantile_sharded(v[0].dtype, ptrs, M, v[0].N, qs.ctypes.data_as(L._dp), len(qs),
+                                         out.ctypes.data_as(L._dp)))
+    if single:
+        return float(out[0, 0]) if scalar else out[0]
+    return out[:, 0].copy() if scalar else out
+
+
+def pmedian(p_local):
+    """Global median = middle of the one / two central order statistics of the whole particle set.  (Computed as the
+    type-7 quantile at 0.5, which interpolates the same two order statistics: a + (b - a)/2.)"""
+    return pquantile(p_local, 0.5)

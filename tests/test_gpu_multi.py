@@ -37,8 +37,15 @@ def _worker(rank, world, port, N, M, ret):
     lo, hi = mcm.sharded.shard_range(N, rank, world)
     v = [mcm.Particles(np.ascontiguousarray(X[j, lo:hi])) for j in range(M)]
     Cg = mcm.sharded.pcov(v)
+    # sharded quantiles: exact order statistics of the GLOBAL particle set; variable 3 is globally sorted, so each
+    # bracket's candidates all live on one rank; variable 4 has heavy ties
+    X[3] = np.sort(X[3]); X[4] = np.round(X[4])
+    vq = [mcm.Particles(np.ascontiguousarray(X[j, lo:hi])) for j in range(M)]
+    Q = mcm.sharded.pquantile(vq, [0.025, 0.5, 0.975])
+    Q5 = mcm.sharded.pquantile(vq[0], [0.0, 0.1, 0.5, 0.9, 1.0])
+    qy = mcm.sharded.pquantile(y, 0.5)
     ret[rank] = {"fused": [g.n, g.mean, g.m2, g.min, g.max], "pm": [gm.n, gm.mean, gm.m2, gm.min, gm.max], "cov": Cg,
-                 "local_n": a.N}
+                 "local_n": a.N, "Q": Q, "Q5": Q5, "qy": qy}
     dist.barrier()
     dist.destroy_process_group()
 
@@ -73,3 +80,9 @@ def test_sharded_statistics_and_pcov_match_oracle(orc):
     for r in range(world):
         assert np.max(np.abs(ret[r]["cov"] - Cr)) <= 1e-12 * np.max(np.abs(Cr))
         assert np.array_equal(ret[r]["cov"], ret[0]["cov"])
+    X[3] = np.sort(X[3]); X[4] = np.round(X[4])
+    for r in range(world):
+        for j in range(M):
+            assert np.array_equal(ret[r]["Q"][j], orc.quantile(X[j], [0.025, 0.5, 0.975])), (r, j)   # bit-exact, every rank
+        assert np.array_equal(ret[r]["Q5"], orc.quantile(X[0], [0.0, 0.1, 0.5, 0.9, 1.0]))
+        assert ret[r]["qy"] == orc.quantile(orc.chain10(a), 0.5)[0]
