@@ -335,6 +335,13 @@ int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, 
  * keeps the grid order, 1 applies the keyed bijection of column v. */
 int mcm_systematic_batch(int dtype, int kind, void* const* outs, int M, size_t n, const double* a_host,
                          const double* b_host, int permute, uint64_t seed, uint64_t i0, uint64_t n_total);
+/* iid draws: out[j] = a + b*Phi^-1(u_j) (kind 0, Normal(a,b)) or a + (b-a)*u_j (kind 1, Uniform(a,b)) with
+ * u_j = (top 53 bits of Philox(seed, offset+j) + 1/2) 2^-53 — the device stand-in for rand(rng, d, N)
+ * (types.jl:71,79,93,97; optimize.jl:5).  Julia's stream is not reproducible (H5). */
+int mcm_rand_real(int dtype, int kind, void* out, size_t n, double a, double b, uint64_t seed, uint64_t offset);
+/* StatsBase.autocor(p.particles, 1:maxlag) (demean = true): out_host[k-1] = lag-k autocorrelation, maxlag <= 256
+ * — the reduction behind ess (sampling.jl:26-38). */
+int mcm_autocor(int dtype, const void* in, size_t n, int maxlag, double* out_host);
 /* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
 int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
 /* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */

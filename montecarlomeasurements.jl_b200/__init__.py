@@ -27,6 +27,7 @@ from .particles import (
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
                        mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower)
 from .resampling import bootstrap, resample, resample_indices, rand_indices
+from .optimize import optimize, perturb, wasserstein, ess, rand_particles
 from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
 from . import sharded, tape
 

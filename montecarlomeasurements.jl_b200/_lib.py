@@ -121,6 +121,8 @@ SIGNATURES = {
     "mcm_systematic_normal": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_systematic_uniform": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_randperm": (_i, [_vp, _sz, C.c_uint64]),
+    "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),
+    "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
     "mcm_index_bijection": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_systematic_batch": (_i, [_i, _i, _vpp, _i, _sz, _dp, _dp, _i, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_quantile_batch": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),

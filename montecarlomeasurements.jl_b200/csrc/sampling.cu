@@ -71,6 +71,24 @@ k_rand_indices(int64_t* __restrict__ out, size_t n, unsigned long long N, unsign
     out[j] = (int64_t)__umul64hi(u, N);
   }
 }
+// iid uniforms in (0,1) and standard normals from the same counters: u = (k + 1/2) 2^-53 with k the top 53 bits
+// of a Philox draw (never 0 or 1), z = Phi^-1(u).  rand(rng, Normal(), N) stand-in for the iid constructors
+// (types.jl:67-82 with systematic=false, types.jl:92-100) and optimize's perturb (optimize.jl:3-6).
+template <typename T, bool NORMAL>
+__global__ void __launch_bounds__(kThreads)
+k_rand_real(T* __restrict__ out, size_t n, unsigned long long seed, unsigned long long offset, double a, double b) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += stride) {
+    uint32_t r[4];
+    philox4x32(offset + j, seed, r);
+    const unsigned long long k = ((((unsigned long long)r[1] << 32) | r[0]) >> 11);
+    const double u = ((double)k + 0.5) * 0x1p-53;
+    double v;
+    if constexpr (NORMAL) v = a + b * norminv::norminvcdf(u); else v = a + (b - a) * u;
+    out[j] = (T)v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_rand_keys(uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, size_t n, unsigned long long seed) {
   const size_t stride = (size_t)gridDim.x * kThreads;
@@ -371,6 +389,25 @@ extern "C" int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uin
   if (n_draw == 0) return MCM_OK;
   Ctx& c = ctx();
   k_rand_indices<<<stream_grid(n_draw, 2, 8), kThreads, 0, c.stream>>>(idx_out, n_draw, N, seed, offset);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+extern "C" int mcm_rand_real(int dtype, int kind, void* out, size_t n, double a, double b, uint64_t seed, uint64_t offset) {
+  MCM_NEED_INIT();
+  if (n && !out) return fail(MCM_ERR_INVALID, "mcm_rand_real: null pointer");
+  if (kind != 0 && kind != 1) return fail(MCM_ERR_INVALID, "mcm_rand_real: kind must be 0 (Normal) or 1 (Uniform)");
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_rand_real: bad dtype %d", dtype);
+  if (n == 0) return MCM_OK;
+  Ctx& c = ctx();
+  const int grid = stream_grid(n, 2, 8);
+  if (dtype == MCM_F64) {
+    if (kind == 0) k_rand_real<double, true><<<grid, kThreads, 0, c.stream>>>((double*)out, n, seed, offset, a, b);
+    else k_rand_real<double, false><<<grid, kThreads, 0, c.stream>>>((double*)out, n, seed, offset, a, b);
+  } else {
+    if (kind == 0) k_rand_real<float, true><<<grid, kThreads, 0, c.stream>>>((float*)out, n, seed, offset, a, b);
+    else k_rand_real<float, false><<<grid, kThreads, 0, c.stream>>>((float*)out, n, seed, offset, a, b);
+  }
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }

@@ -651,3 +651,30 @@ ORC_API void orc_pgemm(const double* A, int Mo, int Mi, const double* xs, const 
       ys[(size_t)j * n + i] = (double)(acc + (bias ? (long double)bias[j] : 0.0L));
     }
 }
+
+/* ---- iid uniforms of mcm_rand_real (csrc/sampling.cu k_rand_real): u = (top 53 Philox bits + 1/2) 2^-53.
+ * The reference draws rand(rng, d, N) from Julia's task-local generator (types.jl:71,79,93,97), whose stream
+ * cannot be reproduced (H5); this restates the device stand-in for bit-exact tests. ---- */
+ORC_API void orc_rand_uniform(double* out, size_t n, uint64_t seed, uint64_t offset) {
+  for (size_t j = 0; j < n; ++j) {
+    uint32_t r[4];
+    philox(offset + j, seed, r);
+    const uint64_t k = ((((uint64_t)r[1] << 32) | r[0]) >> 11);
+    out[j] = ((double)k + 0.5) * 0x1p-53;
+  }
+}
+
+/* ---- StatsBase.autocor(x, 1:maxlag; demean=true) [upstream StatsBase, called at src/sampling.jl:27]:
+ * ac[k] = sum_{i<N-k} (x_i - m)(x_{i+k} - m) / sum_i (x_i - m)^2, long double accumulation. ---- */
+ORC_API void orc_autocor(const double* x, size_t n, int maxlag, double* out) {
+  long double m = 0.0L;
+  for (size_t i = 0; i < n; ++i) m += x[i];
+  m /= (long double)n;
+  long double den = 0.0L;
+  for (size_t i = 0; i < n; ++i) den += ((long double)x[i] - m) * ((long double)x[i] - m);
+  for (int k = 1; k <= maxlag; ++k) {
+    long double acc = 0.0L;
+    for (size_t i = 0; i + (size_t)k < n; ++i) acc += ((long double)x[i] - m) * ((long double)x[i + k] - m);
+    out[k - 1] = (double)(acc / den);
+  }
+}

@@ -232,6 +232,37 @@ def pgemm(A: np.ndarray, xs: np.ndarray, shift=None, bias=None) -> np.ndarray:
     return ys
 
 
+def rand_uniform(n: int, seed: int = 0, offset: int = 0) -> np.ndarray:
+    out = np.empty(n)
+    lib().orc_rand_uniform.restype = None
+    lib().orc_rand_uniform(_p(out), C.c_size_t(n), C.c_uint64(seed), C.c_uint64(offset))
+    return out
+
+
+def autocor(x: np.ndarray, maxlag: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(maxlag)
+    lib().orc_autocor.restype = None
+    lib().orc_autocor(_p(x), C.c_size_t(x.size), C.c_int(maxlag), _p(out))
+    return out
+
+
+def ess(x: np.ndarray) -> float:
+    """src/sampling.jl:26-38 restated."""
+    N = len(x)
+    ac = autocor(x, min(250, N // 2))
+    n = len(ac)
+    tau_inv = 1 + 2 * ac[0]
+    K = 2
+    while K < n - 2:
+        d = ac[K - 1] + ac[K]
+        if d < 0:
+            break
+        tau_inv += 2 * d
+        K += 2
+    return min(1 / tau_inv, 1.0) * N
+
+
 def resample_systematic(w: np.ndarray, u: float) -> np.ndarray:
     w = np.ascontiguousarray(w, dtype=np.float64)
     out = np.empty(w.size, dtype=np.int64)
