@@ -353,6 +353,9 @@ int mcm_gather_multi(int dtype, const void* const* srcs, void* const* outs, int 
  * resampling.jl:45-67): weights w (f64, >=0), offset u in [0,1):
  * idx_out[i] = smallest b with cumsum(w)[b] > (i+u)*sum(w)/n.  Exact fixed-point scan. */
 int mcm_resample_systematic(const double* w, size_t n, double u, int64_t* idx_out);
+/* A/B switch: 0 (default) = expansion (each source writes its run of outputs; one exact 128-bit division per
+ * source), 1 = one binary search per output over the scan (first version).  Identical indices. */
+int mcm_resample_use_search(int on);
 
 /* ======================= multi-GPU (one process per GPU) ==================== */
 /* NCCL is dlopen'ed; the 128-byte unique id is created on rank 0 and distributed

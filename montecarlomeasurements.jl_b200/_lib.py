@@ -121,6 +121,7 @@ SIGNATURES = {
     "mcm_systematic_normal": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_systematic_uniform": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_randperm": (_i, [_vp, _sz, C.c_uint64]),
+    "mcm_resample_use_search": (_i, [_i]),
     "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),
     "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
     "mcm_index_bijection": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),

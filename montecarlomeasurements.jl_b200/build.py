@@ -30,6 +30,8 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
     "-diag-suppress", "177,550",
 ]
+# experiments: e.g. MCM_NVCC_EXTRA="-DMCM_CHAIN_W=2 -DMCM_CHAIN_MIN_CTAS=2"
+NVCC_FLAGS += os.environ.get("MCM_NVCC_EXTRA", "").split()
 
 
 def _sources():

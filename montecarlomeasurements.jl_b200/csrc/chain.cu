@@ -130,18 +130,32 @@ __device__ __forceinline__ void sget(const T (&r)[S][V], const ChainParams& p, T
   }
 }
 
-template <class TP, int PC, int END, typename T, int V>
-__device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, size_t j, int nvalid, bool& bad) {
+// W packs per thread (pack indices j[0..W)): W independent dependency chains per lane-pair for the FP64 pipe
+template <int W> struct PackIdx { size_t j[W]; int nvalid[W]; };
+
+template <class TP, int PC, int END, typename T, int V, int W>
+__device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, const PackIdx<W>& ix, int nvalid, bool& bad) {
+  constexpr int PV = V / W;
   if constexpr (PC < END) {
     constexpr SIns I = TP::ins[PC];
     T x[V], y[V], z[V];
     if constexpr (I.op == MCM_TAPE_LOAD) {
-      load_input<T, V>(p.in[I.a], j, nvalid, x);
 #pragma unroll
-      for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
+      for (int w = 0; w < W; ++w) {
+        T t[PV];
+        load_input<T, PV>(p.in[I.a], ix.j[w], ix.nvalid[w], t);
+#pragma unroll
+        for (int v = 0; v < PV; ++v) r[I.dst][w * PV + v] = t[v];
+      }
     } else if constexpr (I.op == MCM_TAPE_STORE) {
       sget<I.a, T, V>(r, p, x);
-      store_output<T, V>(p.out[I.dst], j, nvalid, x);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        T t[PV];
+#pragma unroll
+        for (int v = 0; v < PV; ++v) t[v] = x[w * PV + v];
+        if (ix.nvalid[w] > 0) store_output<T, PV>(p.out[I.dst], ix.j[w], ix.nvalid[w], t);
+      }
     } else if constexpr (I.op == MCM_TAPE_MOV) {
       sget<I.a, T, V>(r, p, x);
 #pragma unroll
@@ -154,32 +168,45 @@ __device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, 
 #pragma unroll
       for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
     }
-    exec_static<TP, PC + 1, END, T, V>(r, p, j, nvalid, bad);
+    exec_static<TP, PC + 1, END, T, V, W>(r, p, ix, nvalid, bad);
   }
 }
+
+#ifndef MCM_CHAIN_W
+#define MCM_CHAIN_W 1   // packs per thread in the registered-chain kernel
+#endif
 
 template <class TP, typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads, MCM_CHAIN_MIN_CTAS)
 k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
                uint32_t* flags) {
-  constexpr int V = Pack<T>::N;
+  constexpr int W = MCM_CHAIN_W;
+  constexpr int PV = Pack<T>::N;
+  constexpr int V = W * PV;
   const size_t n = p.n;
-  const size_t nvec = (n + V - 1) / V;
+  const size_t nvec = (n + PV - 1) / PV;
   const size_t stride = (size_t)gridDim.x * kThreads;
   bool bad = false;
   Mom m = mom_empty();
-  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += stride) {
-    const int nvalid = (j + 1) * V <= n ? V : (int)(n - j * V);
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += W * stride) {
+    PackIdx<W> ix;
+    int nvalid = 0;   // valid lanes form a prefix of the V lanes of this thread only when W == 1; used for the domain flag
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      ix.j[w] = j + (size_t)w * stride;
+      ix.nvalid[w] = ix.j[w] >= nvec ? 0 : ((ix.j[w] + 1) * PV <= n ? PV : (int)(n - ix.j[w] * PV));
+      nvalid += ix.nvalid[w];
+    }
     T r[S][V];
 #pragma unroll
     for (int k = 0; k < S; ++k)
 #pragma unroll
       for (int v = 0; v < V; ++v) r[k][v] = T(0);
-    exec_static<TP, 0, TP::loop_begin, T, V>(r, p, j, nvalid, bad);
+    exec_static<TP, 0, TP::loop_begin, T, V, W>(r, p, ix, nvalid, bad);
     if constexpr (TP::loop_end > TP::loop_begin) {
-      for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V>(r, p, j, nvalid, bad);
+      for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V, W>(r, p, ix, nvalid, bad);
     }
-    exec_static<TP, TP::loop_end, TP::n, T, V>(r, p, j, nvalid, bad);
+    exec_static<TP, TP::loop_end, TP::n, T, V, W>(r, p, ix, nvalid, bad);
     if constexpr (STATS) {
       T x[V];
       // stats slot is a runtime choice among 8 registers: resolved by a uniform switch once per vector
@@ -189,7 +216,13 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
         MCM_SS(10) MCM_SS(11) MCM_SS(12) MCM_SS(13) MCM_SS(14) default: MCM_SS(15)
 #undef MCM_SS
       }
-      stats_push<T, V>(m, x, nvalid);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        T t[PV];
+#pragma unroll
+        for (int v = 0; v < PV; ++v) t[v] = x[w * PV + v];
+        if (ix.nvalid[w] > 0) stats_push<T, PV>(m, t, ix.nvalid[w]);
+      }
     }
   }
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);

@@ -269,6 +269,73 @@ k_resample_search(const unsigned long long* __restrict__ Cs, size_t n, unsigned 
     idx_out[i] = (int64_t)lo;
   }
 }
+// Expansion form of the same rule (first version: one 27-step binary search per output over the 800 MB scan,
+// 50 ms at n = 1e8).  Source b owns the outputs [E(C_{b-1}), E(C_b)) with
+//   E(C) = #{ i in [0,n) : (i 2^32 + U) S < C n 2^32 } = min(n, max(0, floor((ceil(C n 2^32 / S) - 1 - U) / 2^32) + 1)),
+// one exact 128-bit division per source, streaming reads of the scan and (almost) streaming writes of the indices.
+__device__ __forceinline__ unsigned long long resample_end(unsigned long long C, unsigned long long n, unsigned long long U,
+                                                           unsigned long long S) {
+  const unsigned __int128 X = (unsigned __int128)C * ((unsigned __int128)n << 32);
+  const unsigned __int128 Q = (X + (S - 1)) / S;          // ceil; < 2^63 because C <= S
+  if (Q < (unsigned __int128)U + 1) return 0ull;
+  const unsigned long long e = (unsigned long long)((Q - 1 - U) >> 32) + 1ull;
+  return e < n ? e : n;
+}
+constexpr unsigned RS_SMALL = 8;          // runs up to this length are written by the owning thread
+constexpr unsigned RS_CHUNK = 1u << 16;   // longer-than-a-warp-job runs are cut into chunks for k_resample_fill
+struct RsBig { unsigned long long start; unsigned len; unsigned src; };
+
+__global__ void __launch_bounds__(kThreads)
+k_resample_expand(const unsigned long long* __restrict__ Cs, size_t n, unsigned long long U, int64_t* __restrict__ idx_out,
+                  RsBig* __restrict__ big, unsigned* __restrict__ nbig, unsigned big_cap) {
+  const unsigned long long S = Cs[n - 1];
+  const int lane = threadIdx.x & 31;
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const size_t rounds = (n + stride - 1) / stride;   // warp-uniform trip count (shuffles inside)
+  for (size_t r = 0; r < rounds; ++r) {
+    const size_t b = r * stride + (size_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool live = b < n;
+    const unsigned long long eb = live ? resample_end(Cs[b], n, U, S) : n;
+    unsigned long long ea = __shfl_up_sync(0xffffffffu, eb, 1);
+    if (lane == 0) ea = (live && b > 0) ? resample_end(Cs[b - 1], n, U, S) : 0ull;
+    const unsigned long long cnt = live ? eb - ea : 0ull;
+    if (cnt && cnt <= RS_SMALL) {
+      for (unsigned k = 0; k < (unsigned)cnt; ++k) idx_out[ea + k] = (int64_t)b;
+    }
+    // medium runs: the warp fills them together, coalesced
+    unsigned med = __ballot_sync(0xffffffffu, cnt > RS_SMALL && cnt <= RS_CHUNK);
+    while (med) {
+      const int src = __ffs(med) - 1;
+      med &= med - 1;
+      const unsigned long long s0 = __shfl_sync(0xffffffffu, ea, src);
+      const unsigned len = (unsigned)__shfl_sync(0xffffffffu, cnt, src);
+      const long long who = (long long)__shfl_sync(0xffffffffu, (unsigned long long)b, src);
+      for (unsigned k = lane; k < len; k += 32) idx_out[s0 + k] = who;
+    }
+    // long runs (a few dominant weights): queued in chunks for a grid-wide fill
+    if (cnt > RS_CHUNK) {
+      const unsigned nch = (unsigned)((cnt + RS_CHUNK - 1) / RS_CHUNK);
+      const unsigned at = atomicAdd(nbig, nch);
+      for (unsigned q = 0; q < nch; ++q) {
+        if (at + q < big_cap) {
+          const unsigned long long off = (unsigned long long)q * RS_CHUNK;
+          big[at + q].start = ea + off;
+          big[at + q].len = (unsigned)min((unsigned long long)RS_CHUNK, cnt - off);
+          big[at + q].src = (unsigned)b;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(kThreads)
+k_resample_fill(const RsBig* __restrict__ big, const unsigned* __restrict__ nbig, int64_t* __restrict__ idx_out) {
+  const unsigned total = *nbig;
+  for (unsigned q = blockIdx.x; q < total; q += gridDim.x) {
+    const RsBig e = big[q];
+    for (unsigned k = threadIdx.x; k < e.len; k += kThreads) idx_out[e.start + k] = (int64_t)e.src;
+  }
+}
+
 __global__ void k_max_abs(const double* __restrict__ w, size_t n, double* out) {
   // single CTA max reduction (n reads, tiny vs the scan); 1024 threads
   __shared__ double sh[32];
@@ -288,6 +355,7 @@ template <typename U, bool INCLUSIVE> int device_scan(U* a, size_t n, U* grand_t
 template <typename K, bool HAS_VAL> int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n);
 int read_back(double* host_dst, const double* dev_src, size_t count);
 double* moments_result_slot();
+int moments_device(int dtype, const void* in, size_t n, double* d_out6);
 
 }  // namespace mcm
 
@@ -474,18 +542,23 @@ extern "C" int mcm_gather_multi(int dtype, const void* const* srcs, void* const*
   return MCM_OK;
 }
 
+static int g_resample_search = 0;   // A/B: 1 = one binary search per output (first version)
+extern "C" int mcm_resample_use_search(int on) { g_resample_search = on; return MCM_OK; }
+
 extern "C" int mcm_resample_systematic(const double* w, size_t n, double u, int64_t* idx_out) {
   MCM_NEED_INIT();
   if (!w || !idx_out || n == 0) return fail(MCM_ERR_INVALID, "mcm_resample_systematic: bad arguments");
   if (!(u >= 0.0 && u < 1.0)) return fail(MCM_ERR_INVALID, "mcm_resample_systematic: u must be in [0,1)");
   if (n > (1ull << 30)) return fail(MCM_ERR_UNSUPPORTED, "mcm_resample_systematic: n must be <= 2^30");
   Ctx& c = ctx();
-  double* d_max = moments_result_slot() + 10;
-  k_max_abs<<<1, 1024, 0, c.stream>>>(w, n, d_max);
-  MCM_CHECK_LAUNCH();
-  double wmax;
-  int rc = read_back(&wmax, d_max, 1);
+  // largest weight: the grid-wide one-pass moments kernel (first version: a single-CTA max loop, 45 of the 50 ms)
+  double m6[6];
+  int rc = moments_device(MCM_F64, w, n, moments_result_slot());
   if (rc) return rc;
+  rc = read_back(m6, moments_result_slot(), 6);
+  if (rc) return rc;
+  const double wmax = m6[4];
+  if (m6[3] < 0.0) return fail(MCM_ERR_INVALID, "mcm_resample_systematic: weights must be non-negative");
   if (!(wmax > 0.0) || !isfinite(wmax)) return fail(MCM_ERR_INVALID, "mcm_resample_systematic: weights must be finite with a positive maximum");
   // scale = 2^s with wmax*2^s < 2^(62 - ceil(log2 n))  ->  sum < 2^62
   int e;
@@ -502,8 +575,24 @@ extern "C" int mcm_resample_systematic(const double* w, size_t n, double u, int6
   rc = device_scan<unsigned long long, true>(W, n, nullptr);
   if (rc) return rc;
   const unsigned long long U = (unsigned long long)floor(u * 4294967296.0);
-  k_resample_search<<<grid, kThreads, 0, c.stream>>>(W, n, U, idx_out);
-  MCM_CHECK_LAUNCH();
+  if (g_resample_search) {
+    k_resample_search<<<grid, kThreads, 0, c.stream>>>(W, n, U, idx_out);
+    MCM_CHECK_LAUNCH();
+  } else {
+    // every output belongs to exactly one run; runs longer than RS_CHUNK are split, so at most n / RS_CHUNK + n_runs
+    // chunks exist and n / RS_CHUNK + 2 * (number of long runs) <= 3 n / RS_CHUNK + 1 bounds the queue
+    const unsigned big_cap = (unsigned)(3 * (n / RS_CHUNK) + 64);
+    RsBig* d_big = nullptr;
+    unsigned* d_nbig = nullptr;
+    MCM_CUDA(cudaMallocAsync((void**)&d_big, (size_t)big_cap * sizeof(RsBig) + 16, c.stream));
+    d_nbig = reinterpret_cast<unsigned*>(d_big + big_cap);
+    MCM_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), c.stream));
+    k_resample_expand<<<grid, kThreads, 0, c.stream>>>(W, n, U, idx_out, d_big, d_nbig, big_cap);
+    MCM_CHECK_LAUNCH();
+    k_resample_fill<<<c.sm_count * 4, kThreads, 0, c.stream>>>(d_big, d_nbig, idx_out);
+    MCM_CHECK_LAUNCH();
+    MCM_CUDA(cudaFreeAsync(d_big, c.stream));
+  }
   MCM_CUDA(cudaFreeAsync(W, c.stream));
   return MCM_OK;
 }

@@ -83,3 +83,29 @@ def test_perturb_has_the_requested_moments(mcm):
     q = mcm.perturb(p, Cp, seed=5)
     assert np.max(np.abs(np.array(mcm.pmean(q)) - np.array(mcm.pmean(p)))) < 0.05
     assert np.max(np.abs(mcm.pcov(q) - 1.1 * Cp)) < 0.05 * np.abs(Cp).max()
+
+
+@pytest.mark.parametrize("n", [1, 7, 1000, 200003, 3_000_001])
+def test_systematic_resampling_expansion_is_exact(mcm, orc, n):
+    """Weighted systematic resampling (the weighted `sample(...; ordered=true)` + gather of optimize.jl:22-23,
+    resampling.jl:45-67): identical indices from the expansion form, the per-output search and the oracle, for flat,
+    zero-containing and extremely peaked weights (one source owning almost every output)."""
+    lib = mcm._lib.lib()
+    rng = np.random.default_rng(n)
+    cases = {
+        "flat": np.ones(n),
+        "lognormal": np.exp(3 * rng.normal(size=n)),
+        "zeros": np.where(rng.random(n) < 0.7, 0.0, rng.random(n)) + (np.arange(n) == n // 2),
+        "peaked": np.exp(-0.5 * ((np.arange(n) - 0.3 * n) / max(1.0, 1e-4 * n)) ** 2) + 1e-300,
+        "one": (np.arange(n) == n - 1).astype(np.float64),
+    }
+    for name, w in cases.items():
+        for u in (0.0, 0.5, 0.999999):
+            want = orc.resample_systematic(w, u)
+            got = mcm.resample_indices(w, u).to_numpy()
+            assert np.array_equal(got, want), (name, u)
+        lib.mcm_resample_use_search(1)
+        try:
+            assert np.array_equal(mcm.resample_indices(w, 0.25).to_numpy(), orc.resample_systematic(w, 0.25)), name
+        finally:
+            lib.mcm_resample_use_search(0)
