@@ -24,6 +24,7 @@
 //                   TMEM (the next tile's MMAs start) and store 256 contiguous bytes per warp per output
 // Output tiles whose rows of A end early (triangular factors) stop their k loop early.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
@@ -416,7 +417,14 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   PzSchedule sch;
   sch.nptiles = (int)nptiles;
   sch.njt = njt;
-  sch.share = njt >= 2 ? 2 : 1;
+  {
+    // CTAs per particle tile: more sharing = fewer digit tiles alive in L2 (74 x 917 KB at share 2 straddles the two L2
+    // partitions: ncu showed a 40 % hit rate); MCM_PGEMM_SHARE overrides for experiments
+    const char* e = getenv("MCM_PGEMM_SHARE");
+    int want = e ? atoi(e) : 2;
+    while (want > 1 && (njt < want || c.sm_count % want != 0)) want >>= 1;
+    sch.share = want;
+  }
   int ncta = c.sm_count;
   if ((size_t)ncta > nptiles * sch.share) ncta = (int)(nptiles * sch.share);
   ncta = std::max(sch.share, ncta / sch.share * sch.share);
