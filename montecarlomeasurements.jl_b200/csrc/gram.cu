@@ -289,7 +289,10 @@ int read_back(double* host_dst, const double* dev_src, size_t count);
 
 // tcgen05 / TMEM path (gram_tc.cu)
 template <typename T>
-int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C);
+int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C,
+                     const int* pre_ex, const double* pre_ratio);
+template <typename T>
+int varstats_device(const T* const* d_vars, int M, size_t n, double* d_means, int* d_ex, double* d_ratio);
 static int g_use_tensor = 1;  // mcm_gram_use_tensor: 0 = FP64 DMMA kernel only, 1 = Ozaki int8 on tcgen05 for large problems
 static int g_last_engine = 0; // 0 = DMMA, 1 = tcgen05
 
@@ -303,8 +306,17 @@ static int gram_impl(const void* const* vars_host, int M, size_t n, double scale
   MCM_CUDA(cudaMallocAsync((void**)&d_means, (size_t)M * sizeof(double), c.stream));
   // pageable -> device copy is staged before return, so vars_host may be transient
   MCM_CUDA(cudaMemcpyAsync(d_vars, vars_host, (size_t)M * sizeof(void*), cudaMemcpyHostToDevice, c.stream));
+  const bool tensor_ok = g_use_tensor && M >= 256 && n >= 4096;
+  int* d_ex = nullptr;
+  double* d_ratio = nullptr;
   if (center_host) {
     MCM_CUDA(cudaMemcpyAsync(d_means, center_host, (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  } else if (tensor_ok) {
+    // one read gives the means AND the row statistics the digit split needs
+    MCM_CUDA(cudaMallocAsync((void**)&d_ex, (size_t)M * sizeof(int), c.stream));
+    MCM_CUDA(cudaMallocAsync((void**)&d_ratio, (size_t)M * sizeof(double), c.stream));
+    int rc = varstats_device<T>(d_vars, M, n, d_means, d_ex, d_ratio);
+    if (rc) return rc;
   } else {
     int rc = colmeans_device<T>(d_vars, M, n, d_means);
     if (rc) return rc;
@@ -313,8 +325,9 @@ static int gram_impl(const void* const* vars_host, int M, size_t n, double scale
     MCM_CUDA(cudaMemcpyAsync(means_out_dev, d_means, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
 
   g_last_engine = 0;
-  if (g_use_tensor && M >= 256 && n >= 4096) {
-    int rc = gram_tensor_impl<T>(d_vars, d_means, M, n, scale, cov_out_dev);
+  if (tensor_ok) {
+    int rc = gram_tensor_impl<T>(d_vars, d_means, M, n, scale, cov_out_dev, d_ex, d_ratio);
+    if (d_ex) { MCM_CUDA(cudaFreeAsync(d_ex, c.stream)); MCM_CUDA(cudaFreeAsync(d_ratio, c.stream)); }
     if (rc >= 0) {  // -1: declined by the accuracy guard (heavy-tailed rows) -> DMMA below
       g_last_engine = 1;
       MCM_CUDA(cudaFreeAsync(d_vars, c.stream));

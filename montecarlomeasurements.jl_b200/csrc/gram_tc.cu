@@ -31,6 +31,7 @@
 #include <vector>
 #include "mcm_common.cuh"
 #include "mcm_tcgen05.cuh"
+#include "mcm_moments.cuh"
 
 namespace mcm {
 
@@ -45,6 +46,77 @@ constexpr int OZ_CHUNK_KB = 16384 / OZ_KB;           // k-blocks between flushes
 constexpr int OZ_DBITS = 8;                          // bits per digit
 constexpr double OZ_MAX_RATIO = 10.0;                // max/sigma above which the caller must use DMMA
 constexpr int OZ_TMEM_COLS = 512;
+
+// ---- one-pass row statistics ----------------------------------------------------------------------------
+// mean, exponent of max |x - mean| and max/sigma of every variable from ONE read (the one-pass moments of
+// mcm_moments.cuh: {n, mean, M2, min, max}); replaces a column-mean pass followed by a centred max/sum-of-squares
+// pass (0.46 ms each at C4).  max |x - mean| = max(max - mean, mean - min).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_varstats(const T* const* __restrict__ vars, size_t n, size_t slice, Mom* __restrict__ partial) {
+  using P = Pack<T>;
+  constexpr int V = P::N;
+  const T* x = vars[blockIdx.x];
+  const size_t b = (size_t)blockIdx.y * slice;          // slice is a multiple of V and vars are 16-byte aligned
+  size_t e = b + slice;
+  if (e > n) e = n;
+  Mom m = mom_empty();
+  const size_t nvec = (e - b) / V;
+  const P* px = reinterpret_cast<const P*>(x + b);
+  for (size_t i = threadIdx.x; i < nvec; i += kThreads) {
+    const P t = ld_stream(px + i);
+    double d[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) d[v] = (double)t.v[v];
+    mom_push_chunk<V>(m, d);
+  }
+  for (size_t i = b + nvec * V + threadIdx.x; i < e; i += kThreads) mom_push_one(m, (double)x[i]);
+  m = mom_block_reduce(m);
+  if (threadIdx.x == 0) partial[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = m;
+}
+__global__ void k_varstats_finish(const Mom* __restrict__ partial, int M, int nsplit, double* __restrict__ means,
+                                  int* __restrict__ ex, double* __restrict__ ratio) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  Mom a = mom_empty();
+  for (int s = 0; s < nsplit; ++s) a = mom_merge(a, partial[(size_t)j * nsplit + s]);
+  const double mu = a.K + a.dm;
+  means[j] = mu;
+  const double m = fmax(a.mx - mu, mu - a.mn);
+  int e = -2000;
+  double r = 0.0;
+  if (m > 0.0 && m < 1.7e308) {
+    const double mant = frexp(m, &e);
+    if (mant > 0.99) ++e;                 // the max is formed from rounded differences: a little more headroom than k_rowstats
+    r = m / sqrt(a.m2 / a.n);
+  } else if (!(m == 0.0)) {
+    e = 2000; r = 1e300;                  // Inf / NaN in the row: force the fallback
+  }
+  ex[j] = e;
+  ratio[j] = r;
+}
+template <typename T>
+int varstats_device(const T* const* d_vars, int M, size_t n, double* d_means, int* d_ex, double* d_ratio) {
+  Ctx& c = ctx();
+  constexpr size_t V = Pack<T>::N;
+  int nsplit = (4 * c.sm_count + M - 1) / M;
+  const size_t max_split = (n + 65535) / 65536;
+  if ((size_t)nsplit > max_split) nsplit = (int)max_split;
+  if (nsplit < 1) nsplit = 1;
+  size_t slice = (n + nsplit - 1) / nsplit;
+  slice = (slice + V - 1) / V * V;
+  nsplit = (int)((n + slice - 1) / slice);
+  Mom* partial = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&partial, (size_t)M * nsplit * sizeof(Mom), c.stream));
+  k_varstats<T><<<dim3(M, nsplit), kThreads, 0, c.stream>>>(d_vars, n, slice, partial);
+  MCM_CHECK_LAUNCH();
+  k_varstats_finish<<<(M + 127) / 128, 128, 0, c.stream>>>(partial, M, nsplit, d_means, d_ex, d_ratio);
+  MCM_CHECK_LAUNCH();
+  MCM_CUDA(cudaFreeAsync(partial, c.stream));
+  return MCM_OK;
+}
+template int varstats_device<double>(const double* const*, int, size_t, double*, int*, double*);
+template int varstats_device<float>(const float* const*, int, size_t, double*, int*, double*);
 
 // digits in TILE-READY order: slices[s][kb][rg][c][r8][16] (kb = k / 32, rg = row / 8, c = (k % 32) / 16,
 // r8 = row % 8): the 8-row x 16-byte core matrices of the canonical K-major no-swizzle UMMA layout are
@@ -72,10 +144,26 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
       // every digit lands in [-128, 127] and the carries make sum_s d_s 256^(5-s) == I exactly.
       const double sc = (e > -1500 && e < 1500) ? scalbn(1.0, -(e + 1) + OZ_DBITS * OZ_S) : 0.0;
       const size_t k0 = kb * OZ_KB + c * 16;
+      // 16 consecutive particles of this row: 128-bit loads when the whole run is inside the data (the lanes of a
+      // warp read 32 different 128-byte runs, so wider requests halve the LSU wavefronts per byte)
+      T xv[16];
+      if (k0 + 16 <= n && (reinterpret_cast<uintptr_t>(x + k0) & 15u) == 0) {
+        using P = Pack<T>;
+        constexpr int V = P::N;
+#pragma unroll
+        for (int q = 0; q < 16 / V; ++q) {
+          const P t = *reinterpret_cast<const P*>(x + k0 + q * V);
+#pragma unroll
+          for (int v = 0; v < V; ++v) xv[q * V + v] = t.v[v];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) xv[j] = (k0 + j < n) ? x[k0 + j] : (T)mu;
+      }
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const size_t k = k0 + j;
-        long long I = (k < n) ? __double2ll_rn(((double)x[k] - mu) * sc) : 0ll;
+        long long I = (k < n) ? __double2ll_rn(((double)xv[j] - mu) * sc) : 0ll;
 #pragma unroll
         for (int s = OZ_S - 1; s >= 1; --s) {
           const long long d = ((I + 128) & 255) - 128;
@@ -291,8 +379,11 @@ k_gram_i8_reduce(const double* __restrict__ ws, const int* __restrict__ ex, int 
 
 int g_a_in_tmem = 1;   // A operand staged in TMEM (default); mcm_gram_use_tensor(2) selects the shared-memory (SS) form for A/B runs
 
+// pre_ex / pre_ratio: row statistics already on device (varstats_device), or nullptr to compute them here about
+// the given means (k_rowstats: the centre was supplied by the caller, e.g. the global means of a sharded pcov)
 template <typename T>
-int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C) {
+int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C,
+                     const int* pre_ex, const double* pre_ratio) {
   Ctx& c = ctx();
   const size_t mpad = ((size_t)M + OZ_TM - 1) / OZ_TM * OZ_TM;
   const size_t kpad = (n + OZ_KB - 1) / OZ_KB * OZ_KB;
@@ -304,8 +395,13 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   if (mpad > (size_t)M) MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
   double* d_ratio = nullptr;
   MCM_CUDA(cudaMallocAsync((void**)&d_ratio, (size_t)M * sizeof(double), c.stream));
-  k_rowstats<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex, d_ratio);
-  MCM_CHECK_LAUNCH();
+  if (pre_ex) {
+    MCM_CUDA(cudaMemcpyAsync(ex, pre_ex, (size_t)M * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    MCM_CUDA(cudaMemcpyAsync(d_ratio, pre_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  } else {
+    k_rowstats<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex, d_ratio);
+    MCM_CHECK_LAUNCH();
+  }
   {
     // accuracy guard: (max/sigma)^2 * 2^-46 must stay below 1e-12
     std::vector<double> h_ratio(M);
@@ -340,10 +436,20 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   // split-K when the tiles alone cannot fill the GPU
   const int nkb_total = (int)(kpad / OZ_KB);
   int ksplit = 1;
+  const int max_split = std::max(1, nkb_total / 256);   // keep >= 8192 particles per split
   if (ntiles < c.sm_count) {
     ksplit = (2 * c.sm_count + ntiles - 1) / ntiles;
-    const int max_split = std::max(1, nkb_total / 256);   // keep >= 8192 particles per split
     if (ksplit > max_split) ksplit = max_split;
+  } else {
+    // wave quantisation: 1056 tiles on 148 SMs are 7.1 waves = 8 rounds (89 % efficient); cutting K in 3 gives
+    // 21.4 -> 22 rounds of a third the length (97 %).  Pick the split (<= 4) with the best efficiency, if it
+    // gains more than the ~1 % the extra workspace pass costs.
+    double best = 0.0;
+    for (int k = 1; k <= std::min(4, max_split); ++k) {
+      const double waves = (double)ntiles * k / c.sm_count;
+      const double eff = waves / ceil(waves) - (k > 1 ? 0.01 : 0.0);
+      if (eff > best + 1e-9) { best = eff; ksplit = k; }
+    }
   }
   int kb_per_split = (nkb_total + ksplit - 1) / ksplit;
   ksplit = (nkb_total + kb_per_split - 1) / kb_per_split;
@@ -361,7 +467,7 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   return MCM_OK;
 }
 
-template int gram_tensor_impl<double>(const double* const*, const double*, int, size_t, double, double*);
-template int gram_tensor_impl<float>(const float* const*, const double*, int, size_t, double, double*);
+template int gram_tensor_impl<double>(const double* const*, const double*, int, size_t, double, double*, const int*, const double*);
+template int gram_tensor_impl<float>(const float* const*, const double*, int, size_t, double, double*, const int*, const double*);
 
 }  // namespace mcm
