@@ -250,8 +250,8 @@ int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale,
 /* Gram engine for large problems (M >= 256, N >= 4096): 1 (default) = tcgen05/TMEM int8 tensor cores
  * with an Ozaki error-free split of the centred Float64 data (exact int32 accumulation, 48 bits kept;
  * rows with max/sigma > 10 make it decline and the FP64 kernel runs instead), 0 = always the FP64
- * tensor pipe (DMMA), 2 = tcgen05 with the A operand read from shared memory instead of staged in TMEM
- * (A/B runs; bit-identical results).  All meet the 1e-12 tolerance; small problems always use DMMA.
+ * tensor pipe (DMMA), 2 = tcgen05 with the A operand staged in TMEM (tcgen05.cp + TS-form MMAs) instead of
+ * read from shared memory (A/B runs; bit-identical results).  All meet the 1e-12 tolerance; small problems always use DMMA.
  * mcm_gram_last_engine: 0 = DMMA, 1 = tcgen05 for the most recent mcm_gram call. */
 int mcm_gram_use_tensor(int on);
 int mcm_gram_last_engine(void);

@@ -37,7 +37,10 @@ namespace mcm {
 
 constexpr int OZ_S = 6;              // digits per value
 constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 32;   // tile rows, tile cols, k per block (== UMMA K for i8)
-constexpr int OZ_STAGES = 4;
+#ifndef MCM_OZ_STAGES
+#define MCM_OZ_STAGES 4
+#endif
+constexpr int OZ_STAGES = MCM_OZ_STAGES;
 constexpr int OZ_THREADS = 256;
 constexpr int OZ_A_SLICE = OZ_TM * OZ_KB;            // 4096 B
 constexpr int OZ_B_SLICE = OZ_TN * OZ_KB;            // 2048 B
@@ -220,7 +223,11 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   if (tid == 0) {
 #pragma unroll
     // bar_free counts the MMA commits of BOTH CTAs of the pair: the A planes of a stage are multicast into both
+#ifdef MCM_EXP_NO_MC
+    for (int s = 0; s < OZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 1); }
+#else
     for (int s = 0; s < OZ_STAGES; ++s) { mbar_init_tc(&bar_full[s], 1); mbar_init_tc(&bar_free[s], 2); }
+#endif
     mbar_init_tc(&bar_acc, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,76 +248,115 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   for (int c0 = 0; c0 < nkb; c0 += OZ_CHUNK_KB, ++chunk) {
     const int c1 = min(nkb, c0 + OZ_CHUNK_KB);
     if (warp == 0) {
-      // ---- producer: digit planes of k-block kb -> stage (it % STAGES); `it` counts k-blocks of this CTA
-      for (int it = c0; it < c1; ++it) {
-        const int st = it % OZ_STAGES;
-        if (it >= OZ_STAGES) mbar_wait_tc(&bar_free[st], (unsigned)((it / OZ_STAGES - 1) & 1));
-        if (elect_one()) {
+      // ---- producer: digit planes of k-block kb -> stage (it % STAGES); `it` counts k-blocks of this CTA.
+      // One elected thread owns the loop; the next stage's free-barrier is tested while this stage's copies are issued.
+      if (elect_one()) {
+        const int8_t* srcA0 = slices + ((size_t)bi * (OZ_TM / 8)) * 256;
+        const int8_t* srcB0 = slices + ((size_t)bj * (OZ_TN / 8)) * 256;
+        const size_t kb_stride = nrg * 256;                 // bytes between consecutive k-blocks of one plane
+        bool ready = true;
+        if (c0 >= OZ_STAGES) ready = mbar_try_tc(&bar_free[c0 % OZ_STAGES], (unsigned)((c0 / OZ_STAGES - 1) & 1));
+        for (int it = c0; it < c1; ++it) {
+          const int st = it % OZ_STAGES;
+          if (!ready) mbar_wait_tc(&bar_free[st], (unsigned)((it / OZ_STAGES - 1) & 1));
+          // test the NEXT stage now; the answer is needed only after this stage's copies have been issued
+          ready = (it + 1 >= OZ_STAGES && it + 1 < c1)
+                      ? mbar_try_tc(&bar_free[(it + 1) % OZ_STAGES], (unsigned)(((it + 1) / OZ_STAGES - 1) & 1))
+                      : true;
+#ifdef MCM_EXP_HALF_B
+          mbar_expect_tx_tc(&bar_full[st], OZ_STAGE_BYTES - 3 * OZ_B_SLICE);   // EXPERIMENT: timing sensitivity to operand bytes
+#else
           mbar_expect_tx_tc(&bar_full[st], OZ_STAGE_BYTES);
+#endif
           const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
+#ifdef MCM_EXP_SAME_KB
+          const size_t kb = (size_t)kb_begin;   // EXPERIMENT: every k-block re-reads the same (L2-hot) planes
+#else
           const size_t kb = (size_t)(kb_begin + it);
-          const int8_t* srcA = slices + (kb * nrg + (size_t)bi * (OZ_TM / 8)) * 256;
-          const int8_t* srcB = slices + (kb * nrg + (size_t)bj * (OZ_TN / 8)) * 256;
+#endif
+          const int8_t* srcA = srcA0 + kb * kb_stride;
+          const int8_t* srcB = srcB0 + kb * kb_stride;
           // the pair (tiles 2p, 2p+1) has the same row block bi: each CTA fetches every other A plane and
           // multicasts it to both, so an A plane crosses the L2 -> SM fabric once per pair
 #pragma unroll
           for (int s = 0; s < OZ_S; ++s) {
+#ifdef MCM_EXP_NO_MC
+            bulk_g2s_tc(sbase + s * OZ_A_SLICE, srcA + (size_t)s * plane, OZ_A_SLICE, &bar_full[st]);
+#else
             if ((uint32_t)(s & 1) == crank)
               bulk_g2s_mc(sbase + s * OZ_A_SLICE, srcA + (size_t)s * plane, OZ_A_SLICE, &bar_full[st], (uint16_t)0x3);
+#endif
+#ifdef MCM_EXP_HALF_B
+            if (s < 3)
+#endif
             bulk_g2s_tc(sbase + OZ_S * OZ_A_SLICE + s * OZ_B_SLICE, srcB + (size_t)s * plane, OZ_B_SLICE, &bar_full[st]);
           }
         }
-        __syncwarp();
       }
     } else if (warp == 1) {
-      // ---- MMA issuer: the whole warp walks the loop, one elected lane issues
-      for (int it = c0; it < c1; ++it) {
-        const int st = it % OZ_STAGES;
-        mbar_wait_tc(&bar_full[st], (unsigned)((it / OZ_STAGES) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t sbase = smem0 + (uint32_t)st * OZ_STAGE_BYTES;
-          const uint64_t dA0 = umma_desc_kmajor(sbase, 128, 256);
-          const uint64_t dB0 = umma_desc_kmajor(sbase + OZ_S * OZ_A_SLICE, 128, 256);
+      // ---- MMA issuer.  tcgen05.mma issue is nearly synchronous with execution (the queue holds only a couple of
+      // these 128-cycle MMAs), so every cycle the issuing thread spends between k-blocks is a cycle the tensor pipe
+      // idles.  Measured on an isolated replica of this pipeline (scripts/micro/pipe.cu): wait-then-issue per k-block
+      // = 1009 cycles, against 696 for the MMAs alone.  Hence: ONE elected thread owns the loop (no per-k-block
+      // elect / __syncwarp), the NEXT stage's barrier is TESTED before the current k-block's MMAs are issued (its
+      // latency hides behind the blocking issue), no tcgen05.fence inside the loop (TMA -> MMA needs none), and the
+      // shared-memory descriptors advance by a constant per stage: 740 cycles per k-block on the replica.
+      if (elect_one()) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   // TMEM was read by the flush before this chunk
+        const uint64_t dA00 = umma_desc_kmajor(smem0, 128, 256);
+        const uint64_t dB00 = umma_desc_kmajor(smem0 + OZ_S * OZ_A_SLICE, 128, 256);
+        if (c0 < c1) mbar_wait_tc(&bar_full[c0 % OZ_STAGES], (unsigned)((c0 / OZ_STAGES) & 1));
+        for (int it = c0; it < c1; ++it) {
+          const int st = it % OZ_STAGES;
+          const int nst = (it + 1) % OZ_STAGES;
+          const unsigned npar = (unsigned)(((it + 1) / OZ_STAGES) & 1);
+          const bool nready = (it + 1 < c1) ? mbar_try_tc(&bar_full[nst], npar) : true;   // consumed after the MMAs
+          const uint64_t dA0 = dA00 + (uint64_t)(((uint32_t)st * OZ_STAGE_BYTES) >> 4);
+          const uint64_t dB0 = dB00 + (uint64_t)(((uint32_t)st * OZ_STAGE_BYTES) >> 4);
           // pair (s, t) feeds accumulator d = s + t; the first pair of every accumulator is (0, d), so only the
           // s == 0 row of the first k-block of a chunk overwrites
           const uint32_t acc0 = (it == c0) ? 0u : 1u;
+          // WIDE-N issue: the accumulators of diagonals d, d+1, ... are adjacent TMEM column blocks and the B planes
+          // t, t+1, ... are adjacent 64-row blocks of one K-major tile, so for a fixed A plane s ONE MMA with
+          // N = 64 (6 - s) (cut at 256) updates all its diagonals: 8 MMAs per k-block instead of 21, and the
+          // 4 KiB A plane is read from shared memory once per MMA instead of once per diagonal
+          // (microbenchmark: M128 N64 SS costs 48 cycles, smem-bound; N >= 128 runs at the 32-cycles-per-64-columns floor)
+          uint32_t abuf = 0;
           if (a_in_tmem) {
-            // stage the 6 A planes of this k-block in TMEM (8 columns each, two alternating buffers behind the
-            // 6 x 64 accumulator columns); tcgen05.cp and tcgen05.mma execute in issue order
-            const uint32_t abuf = tmem_base + (uint32_t)(OZ_S * OZ_TN) + (uint32_t)(it & 1) * (OZ_S * 8);
+            abuf = tmem_base + (uint32_t)(OZ_S * OZ_TN) + (uint32_t)(it & 1) * (OZ_S * 8);
 #pragma unroll
             for (int s = 0; s < OZ_S; ++s) tmem_cp_128x256b(abuf + s * 8, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4));
-#pragma unroll
-            for (int s = 0; s < OZ_S; ++s) {
-#pragma unroll
-              for (int t = 0; t < OZ_S; ++t) {
-                if (s + t < OZ_S)
-                  umma_i8_ts(tmem_base + (uint32_t)(s + t) * OZ_TN, abuf + s * 8, dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc,
-                             s == 0 ? acc0 : 1u);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int s = 0; s < OZ_S; ++s) {
-#pragma unroll
-              for (int t = 0; t < OZ_S; ++t) {
-                if (s + t < OZ_S) {
-                  umma_i8(tmem_base + (uint32_t)(s + t) * OZ_TN, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4),
-                          dB0 + (uint64_t)((t * OZ_B_SLICE) >> 4), idesc, s == 0 ? acc0 : 1u);
-                }
-              }
-            }
           }
+          // issue order: plane 0 first (it alone may overwrite), the LONGEST MMAs last, so that the tensor queue still
+          // holds ~250 cycles of work while this thread commits, loops and builds the next descriptors
+          auto issue = [&](int s, int c0n, int nn) {
+            const uint32_t idn = umma_idesc_i8(OZ_TM, nn);
+            const uint32_t dcol = tmem_base + (uint32_t)(s * OZ_TN + c0n);
+            const uint64_t db = dB0 + (uint64_t)(((c0n / OZ_TN) * OZ_B_SLICE) >> 4);   // B planes start at t = c0n/64
+            if (a_in_tmem) umma_i8_ts(dcol, abuf + s * 8, db, idn, s == 0 ? acc0 : 1u);
+            else umma_i8(dcol, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4), db, idn, s == 0 ? acc0 : 1u);
+          };
+          static_assert(OZ_S == 6 && OZ_TN == 64, "issue schedule is written for 6 digits and 64-column accumulators");
+          issue(0, 0, 256); issue(0, 256, 128);     // diagonals 0..3, 4..5
+          issue(5, 0, 64);                          // 5
+          issue(4, 0, 128);                         // 4..5
+          issue(3, 0, 192);                         // 3..5
+          issue(1, 256, 64);                        // plane 1 x plane 4 -> diagonal 5
+          issue(2, 0, 256);                         // 2..5
+          issue(1, 0, 256);                         // 1..4
+#ifdef MCM_EXP_NO_MC
+          umma_commit(&bar_free[st]);
+#else
           umma_commit_mc(&bar_free[st], (uint16_t)0x3);   // stage reusable in BOTH CTAs once these MMAs have read it
+#endif
           if (it == c1 - 1) umma_commit(&bar_acc);        // chunk accumulated
+          if (!nready) mbar_wait_tc(&bar_full[nst], npar);
         }
-        __syncwarp();
       }
     }
     __syncwarp();
     // ---- flush: int32 accumulators -> Float64 registers (all warps)
-    mbar_wait_tc(&bar_acc, (unsigned)(chunk & 1));
+    mbar_wait_backoff(&bar_acc, (unsigned)(chunk & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
     for (int d = 0; d < OZ_S; ++d) {
@@ -377,7 +423,7 @@ k_gram_i8_reduce(const double* __restrict__ ws, const int* __restrict__ ex, int 
   }
 }
 
-int g_a_in_tmem = 1;   // A operand staged in TMEM (default); mcm_gram_use_tensor(2) selects the shared-memory (SS) form for A/B runs
+int g_a_in_tmem = 0;   // 0 (default): A planes read from shared memory by wide-N MMAs; mcm_gram_use_tensor(2): staged in TMEM (A/B runs)
 
 // pre_ex / pre_ratio: row statistics already on device (varstats_device), or nullptr to compute them here about
 // the given means (k_rowstats: the centre was supplied by the caller, e.g. the global means of a sharded pcov)

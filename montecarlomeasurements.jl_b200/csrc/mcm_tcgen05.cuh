@@ -51,6 +51,26 @@ __device__ __forceinline__ void mbar_wait_tc(unsigned long long* bar, unsigned p
       "}\n" ::"r"(smem_addr(bar)), "r"(parity)
       : "memory");
 }
+// Wait used by warps that have nothing to do for a long time (the epilogue warps during a tile's MMA phase): a
+// bare try_wait spin from 6 idle warps hammers the mbarrier in shared memory while UMMA operand fetches and TMA
+// writes need the same port; back off between polls.
+__device__ __forceinline__ bool mbar_try_tc(unsigned long long* bar, unsigned parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(unsigned long long* bar, unsigned parity) {
+  while (!mbar_try_tc(bar, parity)) __nanosleep(512);
+}
+
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "

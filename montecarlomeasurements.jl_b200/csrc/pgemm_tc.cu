@@ -209,76 +209,87 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
   const uint32_t smem0 = smem_addr(smem);
 
   if (warp == 0) {
-    // ---- producer: runs ahead over the whole tile sequence; `it` counts k-blocks of this CTA.  The whole warp
-    // walks the loop and one elected lane issues (see elect_one in mcm_tcgen05.cuh).
-    int it = 0;
-    PZ_TILE_LOOP(sch) {
-      const int nkb = kend[jt] / PZ_KB;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int st = it % PZ_STAGES;
-        if (it >= PZ_STAGES) mbar_wait_tc(&bar_free[st], (unsigned)((it / PZ_STAGES - 1) & 1));
-        if (elect_one()) {
+    // ---- producer: runs ahead over the whole tile sequence; `it` counts k-blocks of this CTA.  One elected thread
+    // owns the loop; the next stage's free-barrier is tested while this stage's copies are issued.
+    if (elect_one()) {
+      int it = 0;
+      bool ready = true;
+      PZ_TILE_LOOP(sch) {
+        const int nkb = kend[jt] / PZ_KB;
+        const int8_t* srcX0 = xplanes + ((size_t)ptile * (PZ_TM / 8)) * 256;
+        const int8_t* srcA0 = aplanes + ((size_t)jt * (PZ_TN / 8)) * 256;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % PZ_STAGES;
+          if (it >= PZ_STAGES && !ready) mbar_wait_tc(&bar_free[st], (unsigned)((it / PZ_STAGES - 1) & 1));
+          ready = (it + 1 >= PZ_STAGES) ? mbar_try_tc(&bar_free[(it + 1) % PZ_STAGES], (unsigned)(((it + 1) / PZ_STAGES - 1) & 1)) : true;
           mbar_expect_tx_tc(&bar_full[st], PZ_STAGE_BYTES);
           const uint32_t sbase = smem0 + (uint32_t)st * PZ_STAGE_BYTES;
-          const int8_t* srcX = xplanes + ((size_t)kb * nrg + (size_t)ptile * (PZ_TM / 8)) * 256;
-          const int8_t* srcA = aplanes + ((size_t)kb * njg + (size_t)jt * (PZ_TN / 8)) * 256;
+          const int8_t* srcX = srcX0 + (size_t)kb * nrg * 256;
+          const int8_t* srcA = srcA0 + (size_t)kb * njg * 256;
 #pragma unroll
           for (int s = 0; s < PZ_S; ++s) {
             bulk_g2s_tc(sbase + s * PZ_X_SLICE, srcX + (size_t)s * xplane, PZ_X_SLICE, &bar_full[st]);
             bulk_g2s_tc(sbase + PZ_S * PZ_X_SLICE + s * PZ_A_SLICE, srcA + (size_t)s * aplane, PZ_A_SLICE, &bar_full[st]);
           }
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
-    // ---- MMA issuer
-    int it = 0;
-    int tile = 0;
-    PZ_TILE_LOOP(sch) {
-      const int nkb = kend[jt] / PZ_KB;
-      if (tile > 0) {   // the previous tile's accumulators must have been read back
-        mbar_wait_tc(&bar_drained, (unsigned)((tile - 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int st = it % PZ_STAGES;
-        mbar_wait_tc(&bar_full[st], (unsigned)((it / PZ_STAGES) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
-          const uint32_t sbase = smem0 + (uint32_t)st * PZ_STAGE_BYTES;
-          const uint64_t dX0 = umma_desc_kmajor(sbase, 128, 256);
-          const uint64_t dA0 = umma_desc_kmajor(sbase + PZ_S * PZ_X_SLICE, 128, 256);
-          // pair (s, t) feeds accumulator d = s + t; the first pair of every accumulator is (0, d), so only the
-          // s == 0 row of the tile's first k-block overwrites
+    // ---- MMA issuer (see gram_tc.cu for the measurements behind this shape): one elected thread owns the loop, the
+    // next stage's barrier is tested before the current k-block's MMAs are issued, WIDE-N MMAs (for a fixed particle
+    // plane s one MMA covers the adjacent accumulators of diagonals s..6 and the adjacent coefficient planes 0..6-s:
+    // 10 MMAs per k-block instead of 28), plane 0 first (it alone may overwrite), the longest MMAs last.
+    if (elect_one()) {
+      const uint64_t dX00 = umma_desc_kmajor(smem0, 128, 256);
+      const uint64_t dA00 = umma_desc_kmajor(smem0 + PZ_S * PZ_X_SLICE, 128, 256);
+      int it = 0;
+      int tile = 0;
+      PZ_TILE_LOOP(sch) {
+        const int nkb = kend[jt] / PZ_KB;
+        if (tile > 0) {   // the previous tile's accumulators must have been read back
+          mbar_wait_tc(&bar_drained, (unsigned)((tile - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        if (nkb > 0) mbar_wait_tc(&bar_full[it % PZ_STAGES], (unsigned)((it / PZ_STAGES) & 1));
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = it % PZ_STAGES;
+          const int nst = (it + 1) % PZ_STAGES;
+          const unsigned npar = (unsigned)(((it + 1) / PZ_STAGES) & 1);
+          const bool nready = (kb + 1 < nkb) ? mbar_try_tc(&bar_full[nst], npar) : true;   // consumed after the MMAs
+          const uint64_t dX0 = dX00 + (uint64_t)(((uint32_t)st * PZ_STAGE_BYTES) >> 4);
+          const uint64_t dA0 = dA00 + (uint64_t)(((uint32_t)st * PZ_STAGE_BYTES) >> 4);
           const uint32_t acc0 = kb == 0 ? 0u : 1u;
-#pragma unroll
-          for (int s = 0; s < PZ_S; ++s) {
-#pragma unroll
-            for (int t = 0; t < PZ_S; ++t) {
-              if (s + t < PZ_S)
-                umma_i8(tmem_base + (uint32_t)(s + t) * PZ_TN, dX0 + (uint64_t)((s * PZ_X_SLICE) >> 4),
-                        dA0 + (uint64_t)((t * PZ_A_SLICE) >> 4), idesc, s == 0 ? acc0 : 1u);
-            }
-          }
+          auto issue = [&](int s, int c0n, int nn) {
+            umma_i8(tmem_base + (uint32_t)(s * PZ_TN + c0n), dX0 + (uint64_t)((s * PZ_X_SLICE) >> 4),
+                    dA0 + (uint64_t)(((c0n / PZ_TN) * PZ_A_SLICE) >> 4), umma_idesc_i8(PZ_TM, nn), s == 0 ? acc0 : 1u);
+          };
+          static_assert(PZ_S == 7 && PZ_TN == 64, "issue schedule is written for 7 digits and 64-column accumulators");
+          issue(0, 0, 256); issue(0, 256, 192);     // diagonals 0..3, 4..6
+          issue(6, 0, 64);                          // 6
+          issue(5, 0, 128);                         // 5..6
+          issue(4, 0, 192);                         // 4..6
+          issue(2, 256, 64);                        // plane 2 x coefficient plane 4 -> 6
+          issue(1, 256, 128);                       // plane 1 x coefficient planes 4..5 -> 5..6
+          issue(3, 0, 256);                         // 3..6
+          issue(2, 0, 256);                         // 2..5
+          issue(1, 0, 256);                         // 1..4
           umma_commit(&bar_free[st]);
           if (kb == nkb - 1) umma_commit(&bar_acc);
+          if (!nready) mbar_wait_tc(&bar_full[nst], npar);
         }
-        __syncwarp();
+        if (nkb == 0) umma_commit(&bar_acc);   // nothing to accumulate: release the epilogue at once
+        ++tile;
       }
-      if (nkb == 0) {   // nothing to accumulate: release the epilogue at once
-        if (elect_one()) umma_commit(&bar_acc);
-        __syncwarp();
-      }
-      ++tile;
     }
+    __syncwarp();
   } else if (warp < 2 + PZ_EPI_WARPS) {
     // ---- epilogue warps: TMEM lane = particle; 64 output columns per thread in two halves of 32
     const int lg = warp & 3;   // TMEM lane group this warp may access
     int tile = 0;
     PZ_TILE_LOOP(sch) {
       const int nkb = kend[jt] / PZ_KB;
-      mbar_wait_tc(&bar_acc, (unsigned)(tile & 1));
+      mbar_wait_backoff(&bar_acc, (unsigned)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // one half (32 output columns) of this thread's particle: TMEM -> exact int64 recombination of the diagonals
       // (0,1,2), (3,4,5), (6) (|acc_d| < 2^31, 16 extra bits) -> 3 conversions

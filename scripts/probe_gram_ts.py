@@ -19,5 +19,6 @@ for M, n in ((256, 8192), (512, 40000), (4096, 100000)):
         out[mode] = (min(ts), h)
     lib.mcm_gram_use_tensor(1)
     d = np.sqrt(np.diag(out[1][1]))
-    print(f"M={M} N={n}: SS {out[1][0]*1e3:.2f} ms ({2*M*M*n/out[1][0]/1e12:.1f} TF)  TS {out[2][0]*1e3:.2f} ms ({2*M*M*n/out[2][0]/1e12:.1f} TF)  "
-          f"max |TS - SS| / (sigma_i sigma_j) = {np.max(np.abs(out[2][1] - out[1][1]) / np.outer(d, d)):.3e}  bit-equal={np.array_equal(out[1][1], out[2][1])}")
+    # mode 1 = library default (A operand staged in TMEM when g_a_in_tmem), mode 2 = A read from shared memory
+    print(f"M={M} N={n}: mode1 (A in TMEM) {out[1][0]*1e3:.2f} ms ({2*M*M*n/out[1][0]/1e12:.1f} TF)  mode2 (A from smem) {out[2][0]*1e3:.2f} ms ({2*M*M*n/out[2][0]/1e12:.1f} TF)  "
+          f"max |diff| / (sigma_i sigma_j) = {np.max(np.abs(out[2][1] - out[1][1]) / np.outer(d, d)):.3e}  bit-equal={np.array_equal(out[1][1], out[2][1])}")
