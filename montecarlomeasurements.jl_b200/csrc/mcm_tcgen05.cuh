@@ -128,6 +128,24 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// L2 residency hints for bulk copies: operand tiles that are re-read by later output tiles should outlive the
+// streaming traffic (result stores, other CTAs' tiles) in L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, unsigned bytes, unsigned long long* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
+               : "memory");
+}
+
 // ---- thread-block clusters: TMA multicast + multicast commit -----------------------------------------
 // A CTA pair that needs the same operand tile loads half of it each and multicasts: the data lands at the
 // same shared-memory offset in every CTA of `mask` and completes bytes on the mbarrier at the same offset.

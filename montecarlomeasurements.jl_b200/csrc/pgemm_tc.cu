@@ -35,7 +35,10 @@ namespace mcm {
 
 constexpr int PZ_S = 7;                               // digits per value
 constexpr int PZ_TM = 128, PZ_TN = 64, PZ_KB = 32;    // particles per tile, outputs per tile, variables per k-block
-constexpr int PZ_STAGES = 4;
+#ifndef MCM_PZ_STAGES
+#define MCM_PZ_STAGES 4
+#endif
+constexpr int PZ_STAGES = MCM_PZ_STAGES;
 constexpr int PZ_THREADS = 192;
 constexpr int PZ_X_SLICE = PZ_TM * PZ_KB;             // 4096 B
 constexpr int PZ_A_SLICE = PZ_TN * PZ_KB;             // 2048 B
