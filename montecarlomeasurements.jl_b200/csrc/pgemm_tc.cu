@@ -39,7 +39,7 @@ constexpr int PZ_TM = 128, PZ_TN = 64, PZ_KB = 32;    // particles per tile, out
 #define MCM_PZ_STAGES 4
 #endif
 constexpr int PZ_STAGES = MCM_PZ_STAGES;
-constexpr int PZ_THREADS = 192;
+constexpr int PZ_THREADS = 320;     // producer warp, MMA warp, 8 epilogue warps
 constexpr int PZ_X_SLICE = PZ_TM * PZ_KB;             // 4096 B
 constexpr int PZ_A_SLICE = PZ_TN * PZ_KB;             // 2048 B
 constexpr int PZ_STAGE_BYTES = PZ_S * (PZ_X_SLICE + PZ_A_SLICE);   // 43008 B
@@ -174,7 +174,7 @@ struct PzSchedule {
     for (int jt = (sch).njt - 1 - ((int)blockIdx.x % (sch).share); jt >= 0; jt -= (sch).share)
 
 // warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane group = warp % 4)
-constexpr int PZ_EPI_WARPS = 4;
+constexpr int PZ_EPI_WARPS = 8;     // two per TMEM lane group: 32 of the 64 output columns each
 
 template <typename T>
 __global__ void __launch_bounds__(PZ_THREADS, 1)
@@ -287,58 +287,54 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
     }
     __syncwarp();
   } else if (warp < 2 + PZ_EPI_WARPS) {
-    // ---- epilogue warps: TMEM lane = particle; 64 output columns per thread in two halves of 32
-    const int lg = warp & 3;   // TMEM lane group this warp may access
+    // ---- epilogue warps: TMEM lane = particle; warps (2 + lg) and (6 + lg) share lane group lg and take 32 output
+    // columns each.  The tile's MMAs cannot be followed by the next tile's until all 448 accumulator columns have been
+    // read (no TMEM left for a second set), so this read-back is on the critical path: 8 warps halve it (per-tile
+    // overhead measured at 12-14 k cycles with 4 warps and a sleeping wait).
+    const int lg = warp & 3;             // TMEM lane group this warp may access (warp id modulo 4)
+    const int h = (warp - 2) >> 2;       // which half of the 64 output columns
     int tile = 0;
     PZ_TILE_LOOP(sch) {
       const int nkb = kend[jt] / PZ_KB;
-      mbar_wait_backoff(&bar_acc, (unsigned)(tile & 1));
+      mbar_wait_tc(&bar_acc, (unsigned)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // one half (32 output columns) of this thread's particle: TMEM -> exact int64 recombination of the diagonals
-      // (0,1,2), (3,4,5), (6) (|acc_d| < 2^31, 16 extra bits) -> 3 conversions
-      auto read_half = [&](int h, double (&f)[32]) {
+      // TMEM -> exact int64 recombination of the diagonals (0,1,2), (3,4,5), (6) (|acc_d| < 2^31, 16 extra bits)
+      // -> 3 conversions per output
+      double f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = 0.0;
-        if (nkb > 0) {
+      for (int j = 0; j < 32; ++j) f[j] = 0.0;
+      if (nkb > 0) {
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            long long comb[32];
-            const int dn = g < 2 ? 3 : 1;
+        for (int g = 0; g < 3; ++g) {
+          long long comb[32];
+          const int dn = g < 2 ? 3 : 1;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              if (q < dn) {
-                uint32_t v[32];
-                const int d = g * 3 + q;
-                tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * PZ_TN + h * 32), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int q = 0; q < 3; ++q) {
+            if (q < dn) {
+              uint32_t v[32];
+              const int d = g * 3 + q;
+              tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(d * PZ_TN + h * 32), v);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 32; ++j) comb[j] = (q == 0) ? (long long)(int)v[j] : comb[j] * 256 + (long long)(int)v[j];
-              }
+              for (int j = 0; j < 32; ++j) comb[j] = (q == 0) ? (long long)(int)v[j] : comb[j] * 256 + (long long)(int)v[j];
             }
-            const double w = scalbn(1.0, -8 * (g * 3 + dn - 1 + 2));   // weight of the group's last diagonal
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fma((double)comb[j], w, f[j]);
           }
-        }
-      };
-      const size_t i = (size_t)ptile * PZ_TM + lg * 32 + lane;
-      auto store_half = [&](int h, const double (&f)[32]) {
-        if (i < n) {
+          const double w = scalbn(1.0, -8 * (g * 3 + dn - 1 + 2));   // weight of the group's last diagonal
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int jj = jt * PZ_TN + h * 32 + j;
-            if (jj < Mo) __stcs(outs[jj] + i, (T)fma(f[j], rowscale[jj], bias ? bias[jj] : 0.0));
-          }
+          for (int j = 0; j < 32; ++j) f[j] = fma((double)comb[j], w, f[j]);
         }
-      };
-      double f0[32], f1[32];
-      read_half(0, f0);
-      read_half(1, f1);
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_drained)) : "memory");
-      store_half(0, f0);
-      store_half(1, f1);
+      const size_t i = (size_t)ptile * PZ_TM + lg * 32 + lane;
+      if (i < n) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int jj = jt * PZ_TN + h * 32 + j;
+          if (jj < Mo) __stcs(outs[jj] + i, (T)fma(f[j], rowscale[jj], bias ? bias[jj] : 0.0));
+        }
+      }
       ++tile;
     }
   }
