@@ -335,6 +335,9 @@ int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, 
  * keeps the grid order, 1 applies the keyed bijection of column v. */
 int mcm_systematic_batch(int dtype, int kind, void* const* outs, int M, size_t n, const double* a_host,
                          const double* b_host, int permute, uint64_t seed, uint64_t i0, uint64_t n_total);
+/* A/B switch: 1 (default) = whole permuted columns of <= 32 MB are written in scatter form (grid order in,
+ * pi^-1 out: branch-coherent Phi^-1), 0 = always the gather form.  Identical results. */
+int mcm_systematic_use_scatter(int on);
 /* iid draws: out[j] = a + b*Phi^-1(u_j) (kind 0, Normal(a,b)) or a + (b-a)*u_j (kind 1, Uniform(a,b)) with
  * u_j = (top 53 bits of Philox(seed, offset+j) + 1/2) 2^-53 — the device stand-in for rand(rng, d, N)
  * (types.jl:71,79,93,97; optimize.jl:5).  Julia's stream is not reproducible (H5). */

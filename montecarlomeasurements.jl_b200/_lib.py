@@ -126,6 +126,7 @@ SIGNATURES = {
     "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
     "mcm_index_bijection": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_systematic_batch": (_i, [_i, _i, _vpp, _i, _sz, _dp, _dp, _i, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "mcm_systematic_use_scatter": (_i, [_i]),
     "mcm_quantile_batch": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),
     "mcm_quantile_batch_fallbacks": (_i, []),
     "mcm_quantile_sharded": (_i, [_i, _vpp, _i, _sz, _dp, _i, _dp]),

@@ -159,6 +159,22 @@ __host__ __device__ __forceinline__ uint64_t feistel_permute(uint64_t x, const F
   return x;
 }
 
+// inverse of feistel_permute: the rounds backwards, walked along the same cycle until the value is in range
+__host__ __device__ __forceinline__ uint64_t feistel_inverse(uint64_t x, const FeistelKey& fk, uint64_t n_total) {
+  const uint32_t lmask = fk.lbits >= 32 ? 0xffffffffu : ((1u << fk.lbits) - 1u);
+  const uint32_t rmask = fk.rbits >= 32 ? 0xffffffffu : ((1u << fk.rbits) - 1u);
+  do {
+    uint32_t L = (uint32_t)(x >> fk.rbits) & lmask, R = (uint32_t)x & rmask;
+#pragma unroll
+    for (int r = kFeistelRounds - 2; r >= 0; r -= 2) {
+      R ^= feistel_mix(L, fk.k[r + 1]) & rmask;
+      L ^= feistel_mix(R, fk.k[r]) & lmask;
+    }
+    x = ((uint64_t)L << fk.rbits) | R;
+  } while (x >= n_total);
+  return x;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_index_bijection(int64_t* __restrict__ out, size_t n, FeistelKey fk, unsigned long long i0, unsigned long long n_total) {
   const size_t stride = (size_t)gridDim.x * kThreads;
@@ -185,6 +201,36 @@ k_systematic_batch(T* const* __restrict__ outs, size_t n, const double* __restri
     if constexpr (NORMAL) val = a + b * norminv::norminvcdf(p);
     else val = a + (b - a) * p;
     __stcs(out + j, (T)val);
+  }
+}
+
+// Whole columns (i0 == 0, n == n_total): SCATTER form.  Thread i evaluates grid point i — consecutive lanes take
+// consecutive probabilities, so a warp is either entirely in the central region of AS 241 or entirely in a tail (the
+// gather form, with permuted probabilities, runs both branches in almost every warp: 15 % of the lanes need the
+// log/sqrt tail) — and stores the value at j = pi^-1(i).  grid.x covers a whole column and is the fast grid index, so
+// only one or two columns (8 MB each at n = 1e6) are being written at any time: the scattered 8-byte stores merge in
+// L2 and reach HBM as full lines.  Same values at the same positions as the gather form.
+constexpr int SB_IPT = 4;
+template <typename T, bool NORMAL>
+__global__ void __launch_bounds__(kThreads)
+k_systematic_batch_scatter(T* const* __restrict__ outs, size_t n, const double* __restrict__ ab, int M, int permute,
+                           unsigned long long seed) {
+  const int v = blockIdx.y;
+  T* __restrict__ out = outs[v];
+  const double a = ab ? ab[v] : 0.0, b = ab ? ab[M + v] : 1.0;
+  const FeistelKey fk = feistel_key(seed, (uint64_t)v, n);
+  const double two_n = 2.0 * (double)n;
+#pragma unroll
+  for (int u = 0; u < SB_IPT; ++u) {
+    const size_t i = (size_t)blockIdx.x * (kThreads * SB_IPT) + (size_t)u * kThreads + threadIdx.x;
+    if (i < n) {
+      const double p = (double)(2ull * i + 1ull) / two_n;
+      double val;
+      if constexpr (NORMAL) val = a + b * norminv::norminvcdf(p);
+      else val = a + (b - a) * p;
+      const size_t j = permute ? (size_t)feistel_inverse(i, fk, n) : i;
+      out[j] = (T)val;
+    }
   }
 }
 
@@ -414,6 +460,9 @@ extern "C" int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64
   return MCM_OK;
 }
 
+static int g_sys_scatter = 1;   // A/B: 0 = always the gather form
+extern "C" int mcm_systematic_use_scatter(int on) { g_sys_scatter = on; return MCM_OK; }
+
 extern "C" int mcm_systematic_batch(int dtype, int kind, void* const* outs, int M, size_t n, const double* a_host,
                                     const double* b_host, int permute, uint64_t seed, uint64_t i0, uint64_t n_total) {
   MCM_NEED_INIT();
@@ -436,15 +485,26 @@ extern "C" int mcm_systematic_batch(int dtype, int kind, void* const* outs, int 
   MCM_CUDA(cudaMemcpyAsync(d_tab, host.data(), host.size(), cudaMemcpyHostToDevice, c.stream));
   MCM_CUDA(cudaStreamSynchronize(c.stream));  // host staging vector dies at return
   const double* d_ab = a_host ? (const double*)(d_tab + (size_t)M * sizeof(void*)) : nullptr;
-  int gx = stream_grid(n, 2, 8);
-  const int cap = std::max(1, (8 * c.sm_count + M - 1) / M);
-  if (gx > cap) gx = cap;
-  dim3 grid((unsigned)gx, (unsigned)M);
+  const size_t gx_full = (n + (size_t)kThreads * SB_IPT - 1) / ((size_t)kThreads * SB_IPT);
+  if (g_sys_scatter && permute && i0 == 0 && n == n_total && n * (dtype == MCM_F64 ? 8 : 4) <= (32u << 20) && gx_full <= 0x7fffffffull) {
+    // whole columns that fit in L2 several times over: scatter form (coherent Phi^-1 branches)
+    dim3 grid((unsigned)gx_full, (unsigned)M);
+#define MCM_SYS_SCATTER(T, NORMAL) \
+  k_systematic_batch_scatter<T, NORMAL><<<grid, kThreads, 0, c.stream>>>((T* const*)d_tab, n, d_ab, M, permute, seed)
+    if (dtype == MCM_F64) { if (kind == 0) MCM_SYS_SCATTER(double, true); else MCM_SYS_SCATTER(double, false); }
+    else { if (kind == 0) MCM_SYS_SCATTER(float, true); else MCM_SYS_SCATTER(float, false); }
+#undef MCM_SYS_SCATTER
+  } else {
+    int gx = stream_grid(n, 2, 8);
+    const int cap = std::max(1, (8 * c.sm_count + M - 1) / M);
+    if (gx > cap) gx = cap;
+    dim3 grid((unsigned)gx, (unsigned)M);
 #define MCM_SYS_BATCH(T, NORMAL) \
   k_systematic_batch<T, NORMAL><<<grid, kThreads, 0, c.stream>>>((T* const*)d_tab, n, d_ab, M, permute, seed, i0, n_total)
-  if (dtype == MCM_F64) { if (kind == 0) MCM_SYS_BATCH(double, true); else MCM_SYS_BATCH(double, false); }
-  else { if (kind == 0) MCM_SYS_BATCH(float, true); else MCM_SYS_BATCH(float, false); }
+    if (dtype == MCM_F64) { if (kind == 0) MCM_SYS_BATCH(double, true); else MCM_SYS_BATCH(double, false); }
+    else { if (kind == 0) MCM_SYS_BATCH(float, true); else MCM_SYS_BATCH(float, false); }
 #undef MCM_SYS_BATCH
+  }
   MCM_CHECK_LAUNCH();
   MCM_CUDA(cudaFreeAsync(d_tab, c.stream));
   return MCM_OK;
