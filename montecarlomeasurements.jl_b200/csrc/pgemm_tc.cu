@@ -187,6 +187,8 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
   __shared__ __align__(8) unsigned long long bar_acc;     // accumulators of a tile complete
   __shared__ __align__(8) unsigned long long bar_drained; // accumulators read back: TMEM reusable
   __shared__ uint32_t tmem_base_sh;
+  __shared__ T* s_out[2][PZ_TN];          // per-tile output pointers / row scales / biases (double-buffered by tile parity)
+  __shared__ double s_rs[2][PZ_TN], s_bi[2][PZ_TN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t xplane = npad * kpad, aplane = mopad * kpad;
@@ -293,9 +295,25 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
     // overhead measured at 12-14 k cycles with 4 warps and a sleeping wait).
     const int lg = warp & 3;             // TMEM lane group this warp may access (warp id modulo 4)
     const int h = (warp - 2) >> 2;       // which half of the 64 output columns
+    const int et = tid - 64;             // index among the 256 epilogue threads
     int tile = 0;
     PZ_TILE_LOOP(sch) {
       const int nkb = kend[jt] / PZ_KB;
+      // Output pointers, row scales and biases of the tile's 64 columns go to shared memory BEFORE the wait for the
+      // accumulators.  While the tensor cores stream operands from shared memory every ordinary load / store of the
+      // SM crawls (traced: ~130 cycles per LDS, ~250 per STG; constant-bank loads are no better): the 32 stores per
+      // thread of a tile take ~20 k cycles, which hides behind the 31 k-cycle MMA phase of a dense tile but not
+      // behind a triangular one's.  Global loads inside the store loop made it 29 k.
+      {
+        const int buf = tile & 1;
+        if (et < PZ_TN) {
+          const int jj = jt * PZ_TN + et;
+          s_out[buf][et] = jj < Mo ? outs[jj] : nullptr;
+          s_rs[buf][et] = jj < Mo ? rowscale[jj] : 0.0;
+          s_bi[buf][et] = (jj < Mo && bias) ? bias[jj] : 0.0;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+      }
       mbar_wait_tc(&bar_acc, (unsigned)(tile & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // TMEM -> exact int64 recombination of the diagonals (0,1,2), (3,4,5), (6) (|acc_d| < 2^31, 16 extra bits)
@@ -329,10 +347,11 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_drained)) : "memory");
       const size_t i = (size_t)ptile * PZ_TM + lg * 32 + lane;
       if (i < n) {
+        const int buf = tile & 1;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int jj = jt * PZ_TN + h * 32 + j;
-          if (jj < Mo) __stcs(outs[jj] + i, (T)fma(f[j], rowscale[jj], bias ? bias[jj] : 0.0));
+          T* o = s_out[buf][h * 32 + j];
+          if (o) __stcs(o + i, (T)fma(f[j], s_rs[buf][h * 32 + j], s_bi[buf][h * 32 + j]));
         }
       }
       ++tile;
