@@ -345,6 +345,19 @@ int mcm_rand_real(int dtype, int kind, void* out, size_t n, double a, double b, 
 /* StatsBase.autocor(p.particles, 1:maxlag) (demean = true): out_host[k-1] = lag-k autocorrelation, maxlag <= 256
  * — the reduction behind ess (sampling.jl:26-38). */
 int mcm_autocor(int dtype, const void* in, size_t n, int maxlag, double* out_host);
+/* ---- decision layer leftovers ----------------------------------------------------------
+ * argmin(abs.(p.particles .- val)) (nominal.jl:21): 0-based FIRST index of the minimum; a NaN distance beats every
+ * number, as in Julia's findmin. */
+int mcm_argmin_absdiff(int dtype, const void* in, size_t n, double val, uint64_t* idx_host);
+/* argmin_i sum_j (x_ij - val_j)^2 over M variables, row sums accumulated left to right (the joint nearest
+ * particle; nominal.jl:26 sums over dims=1 instead — see with_nominal in the host mirror). */
+int mcm_argmin_sqdist(int dtype, const void* const* vars, int M, size_t n, const double* val_host, uint64_t* idx_host);
+/* shuffle_and_insert (nominal.jl:1-6): out = copy(in); out[ind] = in[0]; out[0] = val.  in may equal out. */
+int mcm_shuffle_insert(int dtype, const void* in, size_t n, uint64_t ind, double val, void* out);
+/* filter(x -> lo <= x <= hi, p.particles) (particles.jl:375-380, Base.intersect), order preserved: survivors
+ * are written to out[out_offset ...]; *count_host = how many.  out needs room for out_offset + n elements. */
+int mcm_filter_range(int dtype, const void* in, size_t n, double lo, double hi, void* out, size_t out_offset,
+                     size_t* count_host);
 /* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
 int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
 /* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */

@@ -12,7 +12,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmcm_b200.so")
+LIB_PATH = os.environ.get("MCM_B200_LIB") or os.path.join(HERE, "libmcm_b200.so")   # override: A/B builds in scripts/
 HEADER_PATH = os.path.join(HERE, "..", "include", "mcm_b200.h")
 
 
@@ -124,6 +124,10 @@ SIGNATURES = {
     "mcm_resample_use_search": (_i, [_i]),
     "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),
     "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
+    "mcm_argmin_absdiff": (_i, [_i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
+    "mcm_argmin_sqdist": (_i, [_i, _vpp, _i, _sz, _dp, C.POINTER(C.c_uint64)]),
+    "mcm_shuffle_insert": (_i, [_i, _vp, _sz, C.c_uint64, _d, _vp]),
+    "mcm_filter_range": (_i, [_i, _vp, _sz, _d, _d, _vp, _sz, C.POINTER(C.c_size_t)]),
     "mcm_index_bijection": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_systematic_batch": (_i, [_i, _i, _vpp, _i, _sz, _dp, _dp, _i, C.c_uint64, C.c_uint64, C.c_uint64]),
     "mcm_systematic_use_scatter": (_i, [_i]),

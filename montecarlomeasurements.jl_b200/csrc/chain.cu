@@ -73,6 +73,19 @@ __device__ __forceinline__ void store_output(void* base, size_t j, int nvalid, c
 }
 
 template <typename T, int V>
+__device__ __forceinline__ void stats_push(MomStream& m, const T (&x)[V], int nvalid) {
+  double d[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) d[v] = (double)x[v];
+  if (nvalid == V) {
+    ms_push<V>(m, d);
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      if (v < nvalid) { const double o[1] = {d[v]}; ms_push<1>(m, o); }
+  }
+}
+template <typename T, int V>
 __device__ __forceinline__ void stats_push(Mom& m, const T (&x)[V], int nvalid) {
   if (nvalid == V) {
     double d[V];
@@ -175,6 +188,27 @@ __device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, 
 #ifndef MCM_CHAIN_W
 #define MCM_CHAIN_W 1   // packs per thread in the registered-chain kernel
 #endif
+#ifndef MCM_CHAIN_PREFETCH
+#define MCM_CHAIN_PREFETCH 1   // 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2 of the next iteration's inputs
+#endif
+
+// The register budget (64 at 4 CTAs/SM) leaves no room to hold the next iteration's inputs, and the pc samples put
+// 18 % of all warp stalls on the first use of the loaded pack: ask the cache for it one iteration ahead instead.
+template <class TP, int PC, typename T>
+__device__ __forceinline__ void prefetch_static(const ChainParams& p, size_t jn) {
+  if constexpr (PC < TP::n) {
+    constexpr SIns I = TP::ins[PC];
+    if constexpr (I.op == MCM_TAPE_LOAD) {
+      const char* a = reinterpret_cast<const char*>(p.in[I.a]) + jn * sizeof(Pack<T>);
+#if MCM_CHAIN_PREFETCH == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+#elif MCM_CHAIN_PREFETCH == 2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#endif
+    }
+    prefetch_static<TP, PC + 1, T>(p, jn);
+  }
+}
 
 template <class TP, typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads, MCM_CHAIN_MIN_CTAS)
@@ -187,7 +221,7 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
   const size_t nvec = (n + PV - 1) / PV;
   const size_t stride = (size_t)gridDim.x * kThreads;
   bool bad = false;
-  Mom m = mom_empty();
+  MomStream acc = ms_empty();
   for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += W * stride) {
     PackIdx<W> ix;
     int nvalid = 0;   // valid lanes form a prefix of the V lanes of this thread only when W == 1; used for the domain flag
@@ -197,6 +231,13 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
       ix.nvalid[w] = ix.j[w] >= nvec ? 0 : ((ix.j[w] + 1) * PV <= n ? PV : (int)(n - ix.j[w] * PV));
       nvalid += ix.nvalid[w];
     }
+#if MCM_CHAIN_PREFETCH
+    if (j + W * stride < nvec) {
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (j + (W + w) * stride < nvec) prefetch_static<TP, 0, T>(p, j + (W + w) * stride);
+    }
+#endif
     T r[S][V];
 #pragma unroll
     for (int k = 0; k < S; ++k)
@@ -221,13 +262,13 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
         T t[PV];
 #pragma unroll
         for (int v = 0; v < PV; ++v) t[v] = x[w * PV + v];
-        if (ix.nvalid[w] > 0) stats_push<T, PV>(m, t, ix.nvalid[w]);
+        if (ix.nvalid[w] > 0) stats_push<T, PV>(acc, t, ix.nvalid[w]);
       }
     }
   }
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
   if constexpr (STATS) {
-    m = mom_block_reduce(m);
+    Mom m = mom_block_reduce(ms_finish(acc));
     mom_grid_finish(m, partials, ticket, stats_out);
   }
 }

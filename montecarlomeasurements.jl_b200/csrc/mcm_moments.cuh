@@ -104,6 +104,61 @@ __device__ __forceinline__ void mom_push_one(Mom& m, double x) {
   mom_push_chunk<1>(m, v);
 }
 
+// Accumulator for kernels that see only a pack per loop iteration (the fused chains): mom_push_chunk would pay a
+// full pairwise merge, with its division, for every two values.  Here the hot step is a shifted power sum
+// (d = v - K; s1 += d; s2 += d*d), folded into running (n, mean, m2) every MS_FOLD values by the same merge formula;
+// at every fold the shift K moves onto the running mean, so from the second fold on the in-chunk cancellation
+// s2 - s1^2/c loses log2(1 + (mean_chunk - K)^2 / var_chunk) bits of at most MS_FOLD values.
+constexpr int MS_FOLD = 16;
+struct MomStream {
+  double n, K, m2, mn, mx, sum, s1, s2;
+  int c;             // values in the open chunk; -1 until the first value fixed K
+  unsigned nanw;     // max over values of (high word << 1): > 0xffe00000 iff a NaN was pushed
+};
+__device__ __forceinline__ MomStream ms_empty() {
+  MomStream a;
+  a.n = 0.0; a.K = 0.0; a.m2 = 0.0; a.mn = __builtin_huge_val(); a.mx = -__builtin_huge_val(); a.sum = 0.0;
+  a.s1 = 0.0; a.s2 = 0.0; a.c = -1; a.nanw = 0u;
+  return a;
+}
+__device__ __forceinline__ void ms_fold(MomStream& a) {
+  const double cc = (double)a.c;
+  const double cm = a.s1 / cc;                 // chunk mean relative to K
+  double q = fma(-a.s1, cm, a.s2);
+  q = q < 0.0 ? 0.0 : q;
+  const double nn = a.n + cc;
+  const double f = cc / nn;
+  a.m2 = (a.m2 + q) + (cm * cm) * (a.n * f);
+  a.K += cm * f;                               // K is the running mean from here on
+  a.n = nn; a.s1 = 0.0; a.s2 = 0.0; a.c = 0;
+}
+template <int C>
+__device__ __forceinline__ void ms_push(MomStream& a, const double (&v)[C]) {
+  if (a.c < 0) {
+    a.K = (fabs(v[0]) <= 1.7976931348623157e308) ? v[0] : 0.0;
+    a.c = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < C; ++i) {
+    const double d = v[i] - a.K;
+    a.s1 += d;
+    a.s2 = fma(d, d, a.s2);
+    a.sum += v[i];
+    a.mn = fmin(a.mn, v[i]);
+    a.mx = fmax(a.mx, v[i]);
+    a.nanw = max(a.nanw, (unsigned)__double2hiint(v[i]) << 1);
+  }
+  a.c += C;
+  if (a.c >= MS_FOLD) ms_fold(a);
+}
+__device__ __forceinline__ Mom ms_finish(MomStream& a) {
+  if (a.c > 0) ms_fold(a);
+  Mom m;
+  m.n = a.n; m.K = a.K; m.dm = 0.0; m.m2 = a.m2; m.mn = a.mn; m.mx = a.mx; m.sum = a.sum;
+  if (a.nanw > 0xffe00000u) m.mn = m.mx = a.sum;   // a NaN was pushed: sum is NaN
+  return m;
+}
+
 __device__ __forceinline__ Mom mom_shfl_down(const Mom& a, int d) {
   Mom b;
   b.n = shfl_down_d(a.n, d); b.K = shfl_down_d(a.K, d); b.dm = shfl_down_d(a.dm, d); b.m2 = shfl_down_d(a.m2, d);

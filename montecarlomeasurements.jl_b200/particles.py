@@ -99,6 +99,8 @@ class Particles:
 
     def to_numpy(self) -> np.ndarray:
         out = np.empty(self.N, dtype=self.np_dtype)
+        if self.N == 0:
+            return out
         L.check(L.lib().mcm_download(out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), out.nbytes))
         return out
 

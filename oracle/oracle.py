@@ -358,3 +358,52 @@ def ref_chain10(a: np.ndarray, threads: int = 1):
     r.ref_chain10(_p(a), _p(y), _p(w1), _p(w2), _p(w3), C.c_long(n), C.c_int(threads), C.byref(m), C.byref(s))
     dt = time.perf_counter() - t0
     return y, m.value, s.value, dt
+
+
+# ---- decision layer leftovers (numpy restatements; index/byte work => bit-exact comparisons) ------------------
+def union(x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
+    """src/particles.jl:366-368: [p1.particles; p2.particles]."""
+    return np.concatenate([x1, x2])
+
+
+def intersect(x1: np.ndarray, x2: np.ndarray) -> np.ndarray:
+    """src/particles.jl:375-380: common support [max of minima, min of maxima], both filtered in order."""
+    mi = max(x1.min(), x2.min())
+    ma = min(x1.max(), x2.max())
+    keep = lambda x: x[(mi <= x) & (x <= ma)]
+    return np.concatenate([keep(x1), keep(x2)])
+
+
+def julia_argmin(d: np.ndarray) -> int:
+    """Base.argmin: first index of the minimum; NaN is smaller than everything (0-based here)."""
+    nan = np.isnan(d)
+    if nan.any():
+        return int(np.argmax(nan))
+    return int(np.argmin(d))
+
+
+def shuffle_and_insert(x: np.ndarray, ind: int, val) -> np.ndarray:
+    """src/nominal.jl:1-6 (0-based ind)."""
+    y = x.copy()
+    y[ind] = y[0]
+    y[0] = val
+    return y
+
+
+def with_nominal(x: np.ndarray, val) -> np.ndarray:
+    """src/nominal.jl:20-23."""
+    return shuffle_and_insert(x, julia_argmin(np.abs(x.astype(np.float64) - val)), val)
+
+
+def with_nominal_mv(X: np.ndarray, vals: np.ndarray, joint: bool = False):
+    """src/nominal.jl:25-29 with X the N x d sample matrix.  Literal form: argmin over the d column sums
+    (dims=1); joint=True: argmin over the N row sums (left-to-right accumulation)."""
+    D = X.astype(np.float64) - vals[None, :]
+    if joint:
+        acc = np.zeros(X.shape[0])
+        for j in range(X.shape[1]):
+            acc = acc + D[:, j] * D[:, j]
+        k = julia_argmin(acc)
+    else:
+        k = julia_argmin((D * D).sum(axis=0))
+    return [shuffle_and_insert(X[:, j], k, vals[j]) for j in range(X.shape[1])], k

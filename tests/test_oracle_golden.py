@@ -153,3 +153,16 @@ def test_resampling_restatement(orc):
         ref.append(b); s += S / n
     assert got.tolist() == ref
     assert orc.resample_systematic(np.array([0.0, 0.0, 5.0, 0.0]), 0.9).tolist() == [2, 2, 2, 2]
+
+
+def test_oracle_decision_restatements(orc):
+    """oracle.union / intersect / with_nominal against the reference's own assertions (test/runtests.jl:525-527,
+    :930-937) and Julia's argmin rules (first minimum; NaN wins)."""
+    o = orc
+    x = o.systematic_normal(2000, 1.0, 0.1)
+    assert np.array_equal(o.intersect(x, x), o.union(x, x))
+    assert o.intersect(x, 1 + x).size < 2 * x.size and o.union(x, 1 + x).size == 2 * x.size
+    pn = o.with_nominal(x, 0.0)
+    assert pn[0] == 0.0 and x[0] != 0.0 and np.sum(pn != x) <= 2
+    assert o.julia_argmin(np.array([2.0, 1.0, 1.0])) == 1
+    assert o.julia_argmin(np.array([2.0, np.nan, 1.0, np.nan])) == 1
