@@ -358,6 +358,25 @@ int mcm_shuffle_insert(int dtype, const void* in, size_t n, uint64_t ind, double
  * are written to out[out_offset ...]; *count_host = how many.  out needs room for out_offset + n elements. */
 int mcm_filter_range(int dtype, const void* in, size_t n, double lo, double hi, void* out, size_t out_offset,
                      size_t* count_host);
+/* ---- per-particle small-matrix operations ---------------------------------------------------
+ * Device replacement for the host loops of R^n2R^n_function / R^n2C^n_function (particles.jl:241-282), eigvals
+ * (:395-406), exp / exp! / lyap (:603-607) and `\` on particle matrices: entry (r,c) of the uncertain nmat x nmat
+ * matrix is the length-n device vector A[r*nmat + c]; particle i of every entry forms matrix i.  One thread per
+ * particle.  nmat <= 8 (lyap: <= 4).  Results agree with LAPACK to rounding (tolerance tier), not bit for bit.
+ *   SOLVE        out[r*m + c] = (A \ B)[r,c], B = nmat x m table (LU, partial pivoting)
+ *   INV, EXP     out[r*nmat + c]; EXP is Higham's scaling and squaring as LinearAlgebra.exp!, without balancing
+ *   DET          out[0]
+ *   EIGVALS      out[k] + i out_im[k], k < nmat, ordered by (real, imaginary) — LAPACK's order is not reproducible
+ *   EIGVALS_SYM  out[k] ascending (the upper triangle is read)
+ *   LYAP         out = X with A X + X A' + C = 0, C = B (nmat x nmat table)
+ *   SVDVALS      out[k] descending
+ * A singular system or a non-converged iteration raises MCM_FLAG_DOMAIN (LAPACKException in the reference). */
+enum mcm_la_op {
+  MCM_LA_SOLVE = 0, MCM_LA_INV = 1, MCM_LA_DET = 2, MCM_LA_EXP = 3, MCM_LA_EIGVALS = 4, MCM_LA_EIGVALS_SYM = 5,
+  MCM_LA_LYAP = 6, MCM_LA_SVDVALS = 7
+};
+int mcm_batched_linalg(int op, int dtype, int nmat, int m, const void* const* A, const void* const* B,
+                       void* const* out, void* const* out_im, size_t n);
 /* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
 int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
 /* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */

@@ -124,6 +124,7 @@ SIGNATURES = {
     "mcm_resample_use_search": (_i, [_i]),
     "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),
     "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
+    "mcm_batched_linalg": (_i, [_i, _i, _i, _i, _vpp, _vpp, _vpp, _vpp, _sz]),
     "mcm_argmin_absdiff": (_i, [_i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
     "mcm_argmin_sqdist": (_i, [_i, _vpp, _i, _sz, _dp, C.POINTER(C.c_uint64)]),
     "mcm_shuffle_insert": (_i, [_i, _vp, _sz, C.c_uint64, _d, _vp]),
