@@ -345,6 +345,31 @@ int mcm_rand_real(int dtype, int kind, void* out, size_t n, double a, double b, 
 /* StatsBase.autocor(p.particles, 1:maxlag) (demean = true): out_host[k-1] = lag-k autocorrelation, maxlag <= 256
  * — the reduction behind ess (sampling.jl:26-38). */
 int mcm_autocor(int dtype, const void* in, size_t n, int maxlag, double* out_host);
+/* ---- sharded bootstrap over peer memory (resampling.jl:76-84 on particle-sharded variables) -----
+ * A window is peer-visible device memory (plain cudaMalloc + CUDA IPC, handles exchanged through the library's
+ * communicator).  mcm_window_create / mcm_window_free are COLLECTIVE (every rank, same order, same size).
+ * mcm_comm_fence is a stream-ordered fence across ranks: work enqueued after it on any rank runs after the work
+ * enqueued before it on every rank (no-op without a communicator). */
+int mcm_window_create(size_t bytes, int* id_out, void** local_out);
+int mcm_window_free(int id);
+int mcm_comm_fence(void);
+/* Window layout: variables interleaved in groups of four, so the four values one remote read needs share a 32-byte
+ * sector (NVLink moves sectors).  mcm_window_bytes = size to create for M variables of `per` elements per rank;
+ * mcm_window_fill interleaves this rank's slices vars[v][0..n_local) into its window. */
+size_t mcm_window_bytes(int M, uint64_t per, int dtype);
+int mcm_window_fill(int dtype, int window, const void* const* vars, int M, size_t n_local, uint64_t per);
+/* outs[v][j] = variable v of GLOBAL particle idx[j] (0-based, < n_global), loaded straight from the HBM of its owner
+ * idx[j] / per over NVLink.  Bracket with mcm_comm_fence (after the fills, and before the next fill). */
+int mcm_gather_peer(int dtype, int window, int M, uint64_t per, uint64_t n_global, const int64_t* idx, size_t n_out,
+                    void* const* outs);
+/* Systematic resampling of a particle-sharded weight vector: this rank holds w[global_lo ..
+ * global_lo + n_local) of n_global weights.  Same rule and the same fixed-point scale (from the GLOBAL maximum and
+ * n_global) as mcm_resample_systematic, so the indices equal the single-process ones.  2 doubles + 1 integer per rank
+ * are all-gathered; then every source writes its run of output positions (GLOBAL source indices, int64) into the
+ * index window of the rank that owns them: output k lives at slot k % per_out of rank k / per_out's window.
+ * Collective.  Follow with mcm_comm_fence() before reading the window. */
+int mcm_resample_systematic_sharded(const double* w_local, size_t n_local, uint64_t n_global, uint64_t global_lo,
+                                    uint64_t n_out, double u, int window, uint64_t per_out);
 /* ---- decision layer leftovers ----------------------------------------------------------
  * argmin(abs.(p.particles .- val)) (nominal.jl:21): 0-based FIRST index of the minimum; a NaN distance beats every
  * number, as in Julia's findmin. */

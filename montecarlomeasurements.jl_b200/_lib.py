@@ -124,6 +124,13 @@ SIGNATURES = {
     "mcm_resample_use_search": (_i, [_i]),
     "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),
     "mcm_autocor": (_i, [_i, _vp, _sz, _i, _dp]),
+    "mcm_window_create": (_i, [_sz, C.POINTER(_i), _vpp]),
+    "mcm_window_free": (_i, [_i]),
+    "mcm_comm_fence": (_i, []),
+    "mcm_gather_peer": (_i, [_i, _i, _i, C.c_uint64, C.c_uint64, _vp, _sz, _vpp]),
+    "mcm_window_fill": (_i, [_i, _i, _vpp, _i, _sz, C.c_uint64]),
+    "mcm_window_bytes": (_sz, [_i, C.c_uint64, _i]),
+    "mcm_resample_systematic_sharded": (_i, [_vp, _sz, C.c_uint64, C.c_uint64, C.c_uint64, _d, _i, C.c_uint64]),
     "mcm_batched_linalg": (_i, [_i, _i, _i, _i, _vpp, _vpp, _vpp, _vpp, _sz]),
     "mcm_argmin_absdiff": (_i, [_i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
     "mcm_argmin_sqdist": (_i, [_i, _vpp, _i, _sz, _dp, C.POINTER(C.c_uint64)]),

@@ -331,22 +331,39 @@ constexpr unsigned RS_SMALL = 8;          // runs up to this length are written 
 constexpr unsigned RS_CHUNK = 1u << 16;   // longer-than-a-warp-job runs are cut into chunks for k_resample_fill
 struct RsBig { unsigned long long start; unsigned len; unsigned src; };
 
+// Where the indices go: this rank's array, or (sharded) the index windows of the ranks that own the
+// output positions — plain P2P stores over NVLink, runs are contiguous so they coalesce.
+struct RsOutLocal {
+  int64_t* p;
+  __device__ __forceinline__ void put(unsigned long long k, long long v) const { p[k] = v; }
+};
+struct RsOutPeer {
+  int64_t* win[16];
+  unsigned long long per;          // output positions per rank
+  __device__ __forceinline__ void put(unsigned long long k, long long v) const {
+    const unsigned d = (unsigned)(k / per);
+    win[d][k - (unsigned long long)d * per] = v;
+  }
+};
+// Sharded form: this rank holds sources [src0, src0 + n) of the global weight vector; C0 = sum of the fixed-point weights
+// of all lower ranks, S = global total, n_out = global number of outputs.  Single rank: src0 = C0 = 0, n_out = n.
+template <class Out>
 __global__ void __launch_bounds__(kThreads)
-k_resample_expand(const unsigned long long* __restrict__ Cs, size_t n, unsigned long long U, int64_t* __restrict__ idx_out,
-                  RsBig* __restrict__ big, unsigned* __restrict__ nbig, unsigned big_cap) {
-  const unsigned long long S = Cs[n - 1];
+k_resample_expand(const unsigned long long* __restrict__ Cs, size_t n, unsigned long long U, const __grid_constant__ Out out,
+                  RsBig* __restrict__ big, unsigned* __restrict__ nbig, unsigned big_cap, unsigned long long C0,
+                  unsigned long long S, unsigned long long n_out, unsigned long long src0) {
   const int lane = threadIdx.x & 31;
   const size_t stride = (size_t)gridDim.x * kThreads;
   const size_t rounds = (n + stride - 1) / stride;   // warp-uniform trip count (shuffles inside)
   for (size_t r = 0; r < rounds; ++r) {
     const size_t b = r * stride + (size_t)blockIdx.x * kThreads + threadIdx.x;
     const bool live = b < n;
-    const unsigned long long eb = live ? resample_end(Cs[b], n, U, S) : n;
+    const unsigned long long eb = live ? resample_end(C0 + Cs[b], n_out, U, S) : n_out;
     unsigned long long ea = __shfl_up_sync(0xffffffffu, eb, 1);
-    if (lane == 0) ea = (live && b > 0) ? resample_end(Cs[b - 1], n, U, S) : 0ull;
+    if (lane == 0) ea = live ? resample_end(C0 + (b > 0 ? Cs[b - 1] : 0ull), n_out, U, S) : 0ull;
     const unsigned long long cnt = live ? eb - ea : 0ull;
     if (cnt && cnt <= RS_SMALL) {
-      for (unsigned k = 0; k < (unsigned)cnt; ++k) idx_out[ea + k] = (int64_t)b;
+      for (unsigned k = 0; k < (unsigned)cnt; ++k) out.put(ea + k, (long long)(src0 + b));
     }
     // medium runs: the warp fills them together, coalesced
     unsigned med = __ballot_sync(0xffffffffu, cnt > RS_SMALL && cnt <= RS_CHUNK);
@@ -355,8 +372,8 @@ k_resample_expand(const unsigned long long* __restrict__ Cs, size_t n, unsigned 
       med &= med - 1;
       const unsigned long long s0 = __shfl_sync(0xffffffffu, ea, src);
       const unsigned len = (unsigned)__shfl_sync(0xffffffffu, cnt, src);
-      const long long who = (long long)__shfl_sync(0xffffffffu, (unsigned long long)b, src);
-      for (unsigned k = lane; k < len; k += 32) idx_out[s0 + k] = who;
+      const long long who = (long long)(src0 + __shfl_sync(0xffffffffu, (unsigned long long)b, src));
+      for (unsigned k = lane; k < len; k += 32) out.put(s0 + k, who);
     }
     // long runs (a few dominant weights): queued in chunks for a grid-wide fill
     if (cnt > RS_CHUNK) {
@@ -373,12 +390,14 @@ k_resample_expand(const unsigned long long* __restrict__ Cs, size_t n, unsigned 
     }
   }
 }
+template <class Out>
 __global__ void __launch_bounds__(kThreads)
-k_resample_fill(const RsBig* __restrict__ big, const unsigned* __restrict__ nbig, int64_t* __restrict__ idx_out) {
+k_resample_fill(const RsBig* __restrict__ big, const unsigned* __restrict__ nbig, const __grid_constant__ Out out,
+                unsigned long long src0) {
   const unsigned total = *nbig;
   for (unsigned q = blockIdx.x; q < total; q += gridDim.x) {
     const RsBig e = big[q];
-    for (unsigned k = threadIdx.x; k < e.len; k += kThreads) idx_out[e.start + k] = (int64_t)e.src;
+    for (unsigned k = threadIdx.x; k < e.len; k += kThreads) out.put(e.start + k, (long long)(src0 + e.src));
   }
 }
 
@@ -647,12 +666,120 @@ extern "C" int mcm_resample_systematic(const double* w, size_t n, double u, int6
     MCM_CUDA(cudaMallocAsync((void**)&d_big, (size_t)big_cap * sizeof(RsBig) + 16, c.stream));
     d_nbig = reinterpret_cast<unsigned*>(d_big + big_cap);
     MCM_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), c.stream));
-    k_resample_expand<<<grid, kThreads, 0, c.stream>>>(W, n, U, idx_out, d_big, d_nbig, big_cap);
+    unsigned long long S = 0;
+    MCM_CUDA(cudaMemcpyAsync(&S, W + (n - 1), sizeof(S), cudaMemcpyDeviceToHost, c.stream));
+    MCM_CUDA(cudaStreamSynchronize(c.stream));
+    const RsOutLocal out{idx_out};
+    k_resample_expand<RsOutLocal><<<grid, kThreads, 0, c.stream>>>(W, n, U, out, d_big, d_nbig, big_cap, 0ull, S, n, 0ull);
     MCM_CHECK_LAUNCH();
-    k_resample_fill<<<c.sm_count * 4, kThreads, 0, c.stream>>>(d_big, d_nbig, idx_out);
+    k_resample_fill<RsOutLocal><<<c.sm_count * 4, kThreads, 0, c.stream>>>(d_big, d_nbig, out, 0ull);
     MCM_CHECK_LAUNCH();
     MCM_CUDA(cudaFreeAsync(d_big, c.stream));
   }
   MCM_CUDA(cudaFreeAsync(W, c.stream));
+  return MCM_OK;
+}
+
+namespace mcm {
+int window_lookup(int id, void** peers16, int* world, int* rank, size_t* bytes);
+int comm_world(int* nranks, int* rank);
+int comm_allgather_bytes(const void* send, void* recv, size_t bytes_per_rank);
+}
+
+// Systematic resampling of a particle-sharded weight vector: this rank holds w[global_lo ..
+// global_lo + n_local) of n_global weights.  The rule is mcm_resample_systematic's (same fixed-point scale from the
+// GLOBAL maximum and n_global, so the indices are identical to the single-process ones); only 2 doubles and 1 integer
+// per rank cross NVLink for the scale and the scan offsets.  Every source writes its run of output positions into the
+// index window of whichever rank owns them (`window`: per_out int64 per rank, output k lives on rank k / per_out).
+// Collective; bracket the later read of the window with mcm_comm_fence().
+extern "C" int mcm_resample_systematic_sharded(const double* w_local, size_t n_local, uint64_t n_global, uint64_t global_lo,
+                                               uint64_t n_out, double u, int window, uint64_t per_out) {
+  MCM_NEED_INIT();
+  if ((n_local && !w_local) || n_global == 0 || n_out == 0 || per_out == 0)
+    return fail(MCM_ERR_INVALID, "mcm_resample_systematic_sharded: bad arguments");
+  if (!(u >= 0.0 && u < 1.0)) return fail(MCM_ERR_INVALID, "mcm_resample_systematic_sharded: u must be in [0,1)");
+  if (n_global > (1ull << 30) || n_out > (1ull << 30)) return fail(MCM_ERR_UNSUPPORTED, "mcm_resample_systematic_sharded: sizes must be <= 2^30");
+  Ctx& c = ctx();
+  int world, rank;
+  comm_world(&world, &rank);
+  void* peers[16];
+  int wworld, wrank;
+  size_t wbytes;
+  int rc = window_lookup(window, peers, &wworld, &wrank, &wbytes);
+  if (rc) return rc;
+  if (wworld != world || per_out * sizeof(int64_t) > wbytes || (n_out + per_out - 1) / per_out > (uint64_t)world)
+    return fail(MCM_ERR_INVALID, "mcm_resample_systematic_sharded: window does not fit the output layout");
+  // 1. global extrema of the weights: local one-pass moments, 16 bytes per rank all-gathered
+  double m6[6] = {0, 0, 0, __builtin_huge_val(), -__builtin_huge_val(), 0};
+  if (n_local) {
+    rc = moments_device(MCM_F64, w_local, n_local, moments_result_slot());
+    if (rc) return rc;
+    rc = read_back(m6, moments_result_slot(), 6);
+    if (rc) return rc;
+  }
+  unsigned long long* d_x = nullptr;     // exchange buffer: [mine(2)] [all(2*world)]
+  MCM_CUDA(cudaMallocAsync((void**)&d_x, sizeof(double) * 2 * (size_t)(world + 1), c.stream));
+  std::vector<double> hx(2 * (size_t)world);
+  const double mine[2] = {m6[3], m6[4]};
+  MCM_CUDA(cudaMemcpyAsync(d_x, mine, 16, cudaMemcpyHostToDevice, c.stream));
+  rc = comm_allgather_bytes(d_x, d_x + 2, 16);
+  if (rc) return rc;
+  MCM_CUDA(cudaMemcpyAsync(hx.data(), d_x + 2, 16 * (size_t)world, cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  double wmin = __builtin_huge_val(), wmax = -__builtin_huge_val();
+  for (int r = 0; r < world; ++r) {
+    if (hx[2 * r] != hx[2 * r] || hx[2 * r + 1] != hx[2 * r + 1]) { wmax = nan(""); break; }
+    wmin = fmin(wmin, hx[2 * r]); wmax = fmax(wmax, hx[2 * r + 1]);
+  }
+  if (wmin < 0.0) return fail(MCM_ERR_INVALID, "mcm_resample_systematic_sharded: weights must be non-negative");
+  if (!(wmax > 0.0) || !isfinite(wmax)) return fail(MCM_ERR_INVALID, "mcm_resample_systematic_sharded: weights must be finite with a positive maximum");
+  int e;
+  frexp(wmax, &e);
+  int lg = 0;
+  while ((1ull << lg) < n_global) ++lg;
+  const double scale = ldexp(1.0, 62 - lg - e);
+  // 2. local fixed-point scan and this rank's total
+  unsigned long long* W = nullptr;
+  unsigned long long S_local = 0;
+  const int grid = stream_grid(n_local ? n_local : 1, 2, 8);
+  if (n_local) {
+    MCM_CUDA(cudaMallocAsync((void**)&W, n_local * sizeof(unsigned long long), c.stream));
+    k_weights_to_fixed<<<grid, kThreads, 0, c.stream>>>(w_local, W, n_local, scale, c.d_flags);
+    MCM_CHECK_LAUNCH();
+    rc = device_scan<unsigned long long, true>(W, n_local, nullptr);
+    if (rc) return rc;
+    MCM_CUDA(cudaMemcpyAsync(d_x, W + (n_local - 1), 8, cudaMemcpyDeviceToDevice, c.stream));
+  } else {
+    MCM_CUDA(cudaMemsetAsync(d_x, 0, 8, c.stream));
+  }
+  // 3. totals of all ranks -> offset of this rank and the global total
+  rc = comm_allgather_bytes(d_x, d_x + 2, 8);
+  if (rc) return rc;
+  std::vector<unsigned long long> tot(world);
+  MCM_CUDA(cudaMemcpyAsync(tot.data(), d_x + 2, 8 * (size_t)world, cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_x, c.stream));
+  unsigned long long C0 = 0, S = 0;
+  for (int r = 0; r < world; ++r) { if (r < rank) C0 += tot[r]; S += tot[r]; }
+  S_local = tot[rank];
+  (void)S_local;
+  // 4. every source writes its run of outputs to the owners of those positions
+  if (n_local) {
+    const unsigned long long U = (unsigned long long)floor(u * 4294967296.0);
+    const unsigned big_cap = (unsigned)(3 * (n_out / RS_CHUNK) + 64);
+    RsBig* d_big = nullptr;
+    MCM_CUDA(cudaMallocAsync((void**)&d_big, (size_t)big_cap * sizeof(RsBig) + 16, c.stream));
+    unsigned* d_nbig = reinterpret_cast<unsigned*>(d_big + big_cap);
+    MCM_CUDA(cudaMemsetAsync(d_nbig, 0, sizeof(unsigned), c.stream));
+    RsOutPeer out{};
+    for (int r = 0; r < world; ++r) out.win[r] = static_cast<int64_t*>(peers[r]);
+    out.per = per_out;
+    k_resample_expand<RsOutPeer><<<grid, kThreads, 0, c.stream>>>(W, n_local, U, out, d_big, d_nbig, big_cap, C0, S, n_out, global_lo);
+    MCM_CHECK_LAUNCH();
+    k_resample_fill<RsOutPeer><<<c.sm_count * 4, kThreads, 0, c.stream>>>(d_big, d_nbig, out, global_lo);
+    MCM_CHECK_LAUNCH();
+    MCM_CUDA(cudaFreeAsync(d_big, c.stream));
+    MCM_CUDA(cudaFreeAsync(W, c.stream));
+  }
   return MCM_OK;
 }

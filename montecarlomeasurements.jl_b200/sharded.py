@@ -146,3 +146,110 @@ def pmedian(p_local):
     """Global median = middle of the one / two central order statistics of the whole particle set.  (Computed as the
     type-7 quantile at 0.5, which interpolates the same two order statistics: a + (b - a)/2.)"""
     return pquantile(p_local, 0.5)
+
+
+# ---- bootstrap across shards (SURVEY.md §8e): P2P loads from the owners' windows ---------------------------------
+_windows: dict[int, tuple[int, int]] = {}     # bytes -> (window id, local device pointer); windows are reused
+
+
+def _window(nbytes: int):
+    """Collective: every rank must ask for the same size in the same order."""
+    nbytes = int(nbytes)
+    if nbytes not in _windows:
+        wid, ptr = C.c_int(-1), C.c_void_p()
+        L.check(L.lib().mcm_window_create(nbytes, C.byref(wid), C.byref(ptr)))
+        _windows[nbytes] = (wid.value, int(ptr.value))
+    return _windows[nbytes]
+
+
+def free_windows():
+    """Collective: release every cached peer window."""
+    for wid, _ in _windows.values():
+        L.check(L.lib().mcm_window_free(wid))
+    _windows.clear()
+
+
+def bootstrap(p_local, N_global: int, n: int | None = None, *, seed: int = 0, force_window: bool = False):
+    """bootstrap(p, n = N) (resampling.jl:76-88) on particle-sharded variables.
+
+    p_local: this rank's slice (shard_range(N_global, rank, world)) of one Particles or of a list of Particles — ONE
+    global index vector is applied to every variable (resampling.jl:80-84).  Output: this rank's slice
+    (shard_range(n, rank, world)) of the resampled variables.  The indices are the same Philox stream as the
+    single-process `bootstrap(p, n, seed=seed)`, so the sharded result is that result, sliced.  Source elements are read
+    straight from their owners' HBM over NVLink (variables interleaved four to a 32-byte sector in the owners' windows);
+    nothing else moves.  One rank: the ordinary shared-index gather (force_window=True exercises the window path)."""
+    single = isinstance(p_local, P.Particles)
+    ps = [p_local] if single else list(p_local)
+    rank_, world = _comm["rank"], _comm["world"]
+    N_global = int(N_global)
+    n = N_global if n is None else int(n)
+    lo, hi = shard_range(N_global, rank_, world)
+    dt = ps[0].dtype
+    if any(q.N != hi - lo or q.dtype != dt for q in ps):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "sharded.bootstrap: every variable must hold this rank's slice of N_global particles")
+    from . import resampling as R
+    if world == 1 and not force_window:
+        out = R.bootstrap(ps, n, seed=seed)
+        return out[0] if single else out
+    olo, ohi = shard_range(n, rank_, world)
+    idx = R.rand_indices(ohi - olo, N_global, seed, offset=olo)
+    outs = _gather_global(ps, idx, N_global, ohi - olo)
+    return outs[0] if single else outs
+
+
+def _gather_global(ps, idx, N_global: int, n_out_local: int):
+    """outs[v][j] = variable v of GLOBAL particle idx[j]; ps = this rank's slices.  Collective."""
+    rank_, world = _comm["rank"], _comm["world"]
+    lo, hi = shard_range(N_global, rank_, world)
+    dt = ps[0].dtype
+    per = shard_range(N_global, 0, world)[1]                    # elements per rank (the last shard may be shorter)
+    lib = L.lib()
+    es = P._NP[dt].itemsize
+    chunk = max(4, min(-(-len(ps) // 4) * 4, ((8 << 30) // max(per * es, 1)) // 4 * 4))    # variables per fill (<= 8 GB)
+    wid, _ = _window(lib.mcm_window_bytes(chunk, per, dt))
+    outs = [P._empty(n_out_local, dt) for _ in ps]
+    for v0 in range(0, len(ps), chunk):
+        grp = ps[v0:v0 + chunk]
+        sptr = (C.c_void_p * len(grp))(*[C.c_void_p(q.ptr) for q in grp])
+        L.check(lib.mcm_window_fill(dt, wid, sptr, len(grp), hi - lo, per))
+        L.check(lib.mcm_comm_fence())                                   # every owner has filled its window
+        optr = (C.c_void_p * len(grp))(*[C.c_void_p(o.ptr) for o in outs[v0:v0 + chunk]])
+        L.check(lib.mcm_gather_peer(dt, wid, len(grp), per, N_global, C.c_void_p(idx.ptr), n_out_local, optr))
+        L.check(lib.mcm_comm_fence())                                   # every reader is done before the next fill
+    return outs
+
+
+def resample_indices(w_local, N_global: int, u: float = 0.5, n: int | None = None) -> P.DeviceIndex:
+    """Systematic resampling indices for particle-sharded unnormalised weights: this rank's slice
+    (shard_range(n, rank, world)) of the n GLOBAL source indices the single-process `resample_indices(weights, u)`
+    returns.  Each rank scans its own weights; the run of outputs of every source is written straight into the index
+    window of the rank that owns those output positions (P2P stores).  Collective."""
+    rank_, world = _comm["rank"], _comm["world"]
+    N_global = int(N_global)
+    n = N_global if n is None else int(n)
+    w = w_local if isinstance(w_local, P.Particles) else P.Particles(np.asarray(w_local, dtype=np.float64))
+    w = w.astype(np.float64)
+    lo, hi = shard_range(N_global, rank_, world)
+    if w.N != hi - lo:
+        raise L.ArgumentError(L.MCM_ERR_INVALID, "sharded.resample_indices: weights must be this rank's slice of N_global")
+    per_out = max(shard_range(n, 0, world)[1], 1)
+    olo, ohi = shard_range(n, rank_, world)
+    wid, wptr = _window(per_out * 8 + (1 << 20))       # distinct size class from the data windows
+    lib = L.lib()
+    L.check(lib.mcm_comm_fence())                        # nobody is still reading an earlier result from the window
+    L.check(lib.mcm_resample_systematic_sharded(C.c_void_p(w.ptr), w.N, N_global, lo, n, float(u), wid, per_out))
+    L.check(lib.mcm_comm_fence())                        # every owner's runs have landed
+    d = P.DeviceIndex(ohi - olo)
+    if ohi > olo:
+        L.check(lib.mcm_copy(C.c_void_p(d.ptr), C.c_void_p(wptr), (ohi - olo) * 8))
+    return d
+
+
+def resample(p_local, w_local, N_global: int, u: float = 0.5):
+    """Weighted systematic resample of particle-sharded variables (the sharded form of `resample(p, weights, u)`):
+    indices by `resample_indices`, values through the peer-window gather of `bootstrap`."""
+    single = isinstance(p_local, P.Particles)
+    ps = [p_local] if single else list(p_local)
+    idx = resample_indices(w_local, N_global, u)
+    outs = _gather_global(ps, idx, int(N_global), idx.n)
+    return outs[0] if single else outs

@@ -44,8 +44,42 @@ def _worker(rank, world, port, N, M, ret):
     Q = mcm.sharded.pquantile(vq, [0.025, 0.5, 0.975])
     Q5 = mcm.sharded.pquantile(vq[0], [0.0, 0.1, 0.5, 0.9, 1.0])
     qy = mcm.sharded.pquantile(y, 0.5)
+    # sharded bootstrap: one global index vector, sources read from their owners over NVLink; equals the
+    # single-process bootstrap (same Philox stream), sliced
+    boot_ok = True
+    for n_out, seed in ((N, 3), (N // 2 + 3, 4)):
+        outs = mcm.sharded.bootstrap(v[:3], N, n_out, seed=seed)
+        full_idx = mcm.rand_indices(n_out, N, seed).to_numpy()
+        olo, ohi = mcm.sharded.shard_range(n_out, rank, world)
+        for j in range(3):
+            boot_ok &= bool(np.array_equal(outs[j].to_numpy(), X[j][full_idx[olo:ohi]]))
+    one = mcm.sharded.bootstrap(vq[3], N, seed=9)
+    full_idx = mcm.rand_indices(N, N, 9).to_numpy()
+    boot_ok &= bool(np.array_equal(one.to_numpy(), X[3][full_idx[lo:hi]]))
+    x32 = mcm.Particles(np.ascontiguousarray(X[0, lo:hi].astype(np.float32)))
+    o32 = mcm.sharded.bootstrap(x32, N, seed=9)
+    boot_ok &= bool(np.array_equal(o32.to_numpy(), X[0].astype(np.float32)[full_idx[lo:hi]]))
+    # sharded systematic resampling: identical to the single-process indices (same fixed-point scale), sliced;
+    # weights with zeros, a run longer than a warp job and one dominant weight (queued fill path)
+    wrng = np.random.default_rng(11)
+    wfull = wrng.random(N) ** 4
+    wfull[wrng.integers(0, N, N // 10)] = 0.0
+    wfull[N // 3] = 5e3
+    wfull[N - 7] = 0.6 * wfull.sum()
+    res_ok = True
+    for uu in (0.5, 0.0, 0.999):
+        want_idx = mcm.resample_indices(wfull, uu).to_numpy()
+        got = mcm.sharded.resample_indices(np.ascontiguousarray(wfull[lo:hi]), N, uu)
+        olo, ohi = mcm.sharded.shard_range(N, rank, world)
+        res_ok &= bool(np.array_equal(got.to_numpy(), want_idx[olo:ohi]))
+    rs = mcm.sharded.resample(v[:3], np.ascontiguousarray(wfull[lo:hi]), N, 0.999)
+    for j in range(3):
+        res_ok &= bool(np.array_equal(rs[j].to_numpy(), X[j][want_idx[olo:ohi]]))
+    boot_ok &= res_ok
+    mcm.check_domain()
+    mcm.sharded.free_windows()
     ret[rank] = {"fused": [g.n, g.mean, g.m2, g.min, g.max], "pm": [gm.n, gm.mean, gm.m2, gm.min, gm.max], "cov": Cg,
-                 "local_n": a.N, "Q": Q, "Q5": Q5, "qy": qy}
+                 "local_n": a.N, "Q": Q, "Q5": Q5, "qy": qy, "boot_ok": boot_ok}
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +108,7 @@ def test_sharded_statistics_and_pcov_match_oracle(orc):
             assert got[0] == N
             assert abs(got[1] - want[1]) <= 1e-12 * abs(want[1]) and abs(got[2] - want[2]) <= 1e-11 * want[2], (r, key)
         assert ret[r]["fused"] == ret[0]["fused"]                  # identical on every rank
+        assert ret[r]["boot_ok"], r
     rng = np.random.default_rng(5)
     X = rng.normal(1.0, 2.0, size=(M, N)); X[2] = X[0] - 3 * X[1]
     Cr = orc.cov(X)

@@ -109,3 +109,22 @@ def test_systematic_resampling_expansion_is_exact(mcm, orc, n):
             assert np.array_equal(mcm.resample_indices(w, 0.25).to_numpy(), orc.resample_systematic(w, 0.25)), name
         finally:
             lib.mcm_resample_use_search(0)
+
+
+def test_sharded_bootstrap_single_rank_equals_bootstrap(mcm):
+    """world = 1: the peer-window path (window = own memory) reproduces bootstrap(p, n, seed) bit for bit."""
+    rng = np.random.default_rng(2)
+    X = rng.normal(size=(5, 100_001))
+    ps = [mcm.Particles(np.ascontiguousarray(x)) for x in X]
+    for n in (None, 40_000):
+        a = mcm.sharded.bootstrap(ps, X.shape[1], n, seed=11, force_window=True)
+        b = mcm.bootstrap(ps, n, seed=11)
+        assert all(np.array_equal(p.to_numpy(), q.to_numpy()) for p, q in zip(a, b))
+    w = rng.random(X.shape[1]) ** 3
+    for u in (0.25, 0.0):
+        a = mcm.sharded.resample_indices(w, X.shape[1], u).to_numpy()
+        assert np.array_equal(a, mcm.resample_indices(w, u).to_numpy())
+    mcm.sharded.free_windows()
+    lib = mcm._lib.lib()
+    assert lib.mcm_window_free(12345) == mcm._lib.MCM_ERR_INVALID
+    assert lib.mcm_comm_fence() == 0
