@@ -509,7 +509,9 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
   extern __shared__ __align__(16) unsigned char bq_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int capw = flush_at + BQ_WARP_KEYS;                // staging entries per (warp, bracket)
-  uint32_t* wstage = reinterpret_cast<uint32_t*>(bq_smem) + (size_t)warp * NB * capw;
+  // candidates are staged BY VALUE: staging their indices and re-reading the keys at flush time cost 47 % of the
+  // kernel's DRAM sectors (ncu: 8-byte re-reads are fetched as 64-byte pairs of sectors long after the line left L2)
+  T* wstage = reinterpret_cast<T*>(bq_smem) + (size_t)warp * NB * capw;
   __shared__ uint32_t sh[NB][kThreads / 32];
   const int m = blockIdx.y;
   const T* __restrict__ in = vars[m];
@@ -550,14 +552,14 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
     if (lane == 0) base = atomicAdd(mcnt + b, c);
     base = __shfl_sync(0xffffffffu, base, 0);
     __syncwarp();
-    const uint32_t* st = wstage + b * capw;
+    const T* st = wstage + b * capw;
     for (uint32_t i = lane; i < c; i += 32)
-      if (base + i < bp.cap[b]) cb[b][base + i] = __ldg(in + st[i]);
+      if (base + i < bp.cap[b]) cb[b][base + i] = st[i];
     __syncwarp();
     wcnt[b] = 0;
   };
-  // Append the candidates flagged in inmask[] (bit (u*V + e) = element row0 + u*ustride + e).  Warp-uniform call.
-  auto append = [&](uint32_t row0, uint32_t ustride) {
+  // Append the candidates flagged in inmask[] (bit (u*V + e) = vals[u].v[e]).  Warp-uniform call.
+  auto append = [&](const P (&vals)[UNROLL]) {
     unsigned long long packed = 0;
 #pragma unroll
     for (int b = 0; b < NB; ++b) packed |= (unsigned long long)__popc(inmask[b]) << (16 * b);
@@ -574,12 +576,12 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
     for (int b = 0; b < NB; ++b) {
       uint32_t mk = inmask[b];
       if (mk) {
-        uint32_t* p = wstage + b * capw + wcnt[b] + ((uint32_t)(excl >> (16 * b)) & 0xffffu);
-        do {
-          const int bit = __ffs(mk) - 1;
-          mk &= mk - 1;
-          *p++ = row0 + (uint32_t)(bit / V) * ustride + (uint32_t)(bit % V);
-        } while (mk);
+        T* p = wstage + b * capw + wcnt[b] + ((uint32_t)(excl >> (16 * b)) & 0xffffu);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (mk & (1u << (u * V + e))) *p++ = vals[u].v[e];     // static register names: no local memory
       }
       wcnt[b] += (uint32_t)(total >> (16 * b)) & 0xffffu;
       if (wcnt[b] > (uint32_t)flush_at) warp_flush(b);
@@ -609,7 +611,7 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
 #pragma unroll
       for (int e = 0; e < V; ++e) classify(cur[u].v[e], u * V + e);
     }
-    append((uint32_t)((r * UNROLL * stride + tid) * V), (uint32_t)(stride * V));
+    append(cur);
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) cur[u] = nxt[u];
   }
@@ -619,12 +621,12 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
 #pragma unroll
     for (int b = 0; b < NB; ++b) inmask[b] = 0;
     if (j < nvec) {
-      const P x = ld_stream(pin + j);
-      lowor |= low_words(x);
+      cur[0] = ld_stream(pin + j);
+      lowor |= low_words(cur[0]);
 #pragma unroll
-      for (int e = 0; e < V; ++e) classify(x.v[e], e);
+      for (int e = 0; e < V; ++e) classify(cur[0].v[e], e);
     }
-    append((uint32_t)(j * V), 0u);
+    append(cur);
   }
   const size_t tail0 = nvec * V;
   const size_t trips = (n - tail0 + stride - 1) / stride;
@@ -632,8 +634,8 @@ k_bq_stream(const T* const* __restrict__ vars, size_t n, BqParams bp, const unsi
     const size_t i = tail0 + r * stride + tid;
 #pragma unroll
     for (int b = 0; b < NB; ++b) inmask[b] = 0;
-    if (i < n) classify(in[i], 0);
-    append((uint32_t)i, 0u);
+    if (i < n) { cur[0].v[0] = in[i]; classify(cur[0].v[0], 0); }
+    append(cur);
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b)
@@ -843,7 +845,7 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_sample<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_pivots, cudaFuncAttributeMaxDynamicSharedMemorySize, BQ_SAMPLE * 8));
-    constexpr int kStreamSmem = (kThreads / 32) * 4 * (512 + BQ_WARP_KEYS) * 4;
+    constexpr int kStreamSmem = (kThreads / 32) * 4 * (256 + BQ_WARP_KEYS) * 8;
     MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
     MCM_CUDA(cudaFuncSetAttribute(k_bq_stream<double, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmem));
@@ -872,8 +874,8 @@ static int order_statistics_batch(const T* const* vars_host, int M, size_t n, co
     }
     const dim3 g1(chunks(n, M), (unsigned)M);
     // few variables: many warps flush into the same three counters -> flush rarely; many variables: small staging
-    const int flush_at = M >= 64 ? 128 : 512;
-    const size_t smem1 = (size_t)(kThreads / 32) * NB * (flush_at + BQ_WARP_KEYS) * sizeof(uint32_t);
+    const int flush_at = M >= 64 ? 128 : 256;
+    const size_t smem1 = (size_t)(kThreads / 32) * NB * (flush_at + BQ_WARP_KEYS) * sizeof(T);
     switch (NB) {
       case 1: k_bq_stream<T, 1><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
       case 2: k_bq_stream<T, 2><<<g1, kThreads, smem1, c.stream>>>(d_tab, n, bp, d_piv, d_qcand, cand_stride, d_qcnt, d_below, d_flags, flush_at); break;
