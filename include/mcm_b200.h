@@ -402,6 +402,18 @@ enum mcm_la_op {
 };
 int mcm_batched_linalg(int op, int dtype, int nmat, int m, const void* const* A, const void* const* B,
                        void* const* out, void* const* out_im, size_t n);
+/* ---- Complex{Particles} (src/complex.jl:1-93) ----------------------------------------------------------------
+ * A complex uncertain number is two device vectors (re, im).  One streaming kernel per operation replaces the host
+ * loop of C2C_function (complex.jl:30-67).  Operand components: a null pointer selects the constant beside it, so
+ * real particles (im = NULL, 0.0), real and complex scalars are all expressible.  + - * follow Base bit for bit
+ * ((ac - bd) + (ad + bc)i, no contraction); / ^ and the functions are tolerance tier (1e-13 relative). */
+enum mcm_complex_opcode {
+  MCM_C_ADD = 0, MCM_C_SUB = 1, MCM_C_MUL = 2, MCM_C_DIV = 3, MCM_C_POW = 4,
+  MCM_C_EXP = 16, MCM_C_LOG = 17, MCM_C_SQRT = 18, MCM_C_SIN = 19, MCM_C_COS = 20, MCM_C_TAN = 21,
+  MCM_C_EXP10 = 22, MCM_C_LOG10 = 23
+};
+int mcm_complex_op(int op, int dtype, const void* a_re, const void* a_im, double sa_re, double sa_im,
+                   const void* b_re, const void* b_im, double sb_re, double sb_im, void* out_re, void* out_im, size_t n);
 /* [rand(rng,1:N) for _ in 1:n] stand-in (resampling.jl:77,81): 0-based indices in [0,N) */
 int mcm_rand_indices(int64_t* idx_out, size_t n_draw, uint64_t N, uint64_t seed, uint64_t offset);
 /* p.particles[inds] (resampling.jl:77,82): out[j] = src[idx[j]] */

@@ -29,7 +29,8 @@ from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dot
 from .resampling import bootstrap, resample, resample_indices, rand_indices
 from .optimize import optimize, perturb, wasserstein, ess, rand_particles
 from .decision import union, intersect, with_nominal, nominal
-from . import linalg
+from . import linalg, complexp
+from .complexp import ComplexParticles, complex_particles
 from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
 from . import sharded, tape
 
