@@ -268,7 +268,16 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "k_chain_static<Chain10,double,stats>",
                 "kernel_ms": kernel_ms,
-                "note": "algorithmic 16 B/particle; this chain is FP64-pipe-bound (see DESIGN.md), the HBM-bound family is in hbm_family"}
+                "note": "algorithmic 16 B/particle; this chain is FP64-latency-bound (see DESIGN.md), the HBM-bound family is in hbm_family"}
+    # the pipe that actually limits chain10: FP64 warp instructions per particle counted from the SASS by ncu
+    # (profiles/r1_chain10_final_ncu_summary.txt: 47.0 % of the FP64 pipe's issue slots over 1.040 ms = 284e6 FP64 warp instructions for 1e8 particles) against the measured issue
+    # rate of the pipe (scripts/micro/fp64_rate.cu: one warp instruction per 2 cycles per SM sub-partition)
+    fp64_inst = 90.9 * N
+    sm_hz = 1.965e9
+    fp64_peak = 148 * 4 * 16 * sm_hz                      # FP64 lanes per second
+    roofline["fp64_pipe"] = {"inst_per_particle": 90.9, "achieved_lanes_per_s": fp64_inst / (kernel_ms * 1e-3),
+                             "peak_lanes_per_s": fp64_peak, "frac": fp64_inst / (kernel_ms * 1e-3) / fp64_peak,
+                             "peak_source": "148 SMs x 4 sub-partitions x 16 lanes x 1.965 GHz (measured issue rate, scripts/micro/fp64_rate.cu)"}
 
     line = {
         "metric": "Gparticle-ops/s", "value": value, "unit": "Gparticle-ops/s", "n_gpus": world, "steps": args.steps,

@@ -15,7 +15,7 @@
 #include <math.h>
 
 #ifdef __CUDACC__
-#define MCM_SLA __host__ __device__ __forceinline__
+#define MCM_SLA __device__ __forceinline__
 #define MCM_SLA_UNROLL _Pragma("unroll")
 #else
 #define MCM_SLA inline
