@@ -36,7 +36,7 @@ struct ChainParams {
 
 constexpr int S = MCM_TAPE_SLOTS;
 #ifndef MCM_CHAIN_MIN_CTAS
-#define MCM_CHAIN_MIN_CTAS 4  // 64 registers/thread -> 32 resident warps per SM (latency-bound FP64 chains)
+#define MCM_CHAIN_MIN_CTAS 3  // 80 registers/thread, 24 resident warps per SM: measured 1.036 ms vs 1.052 (4 CTAs, 64 registers, spills) and 1.289 (2 CTAs)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -100,21 +100,35 @@ __device__ __forceinline__ void stats_push(Mom& m, const T (&x)[V], int nvalid) 
 }
 
 // apply opcode OP (compile-time) to V lanes; result in x
-template <int OP, typename T, int V>
-__device__ __forceinline__ void apply_op(T (&x)[V], const T (&y)[V], const T (&z)[V], int imm, int nvalid, bool& bad) {
+// Domain errors (NaN out of non-NaN in, H7).  EXACT: the per-lane test.  !EXACT (the registered-chain hot loop): only
+// the running maximum of the results' NaN keys is kept — two integer instructions per checked value instead of ~8 —
+// and the pack is replayed through the EXACT instantiation in the rare case that the maximum says "a NaN appeared".
+__device__ __forceinline__ unsigned nan_key(double v) { return (unsigned)__double2hiint(v) << 1; }
+__device__ __forceinline__ unsigned nan_key(float v) { return __float_as_uint(v) << 1; }
+template <typename T> __device__ __forceinline__ bool nan_key_hit(unsigned k) {
+  return k > (sizeof(T) == 8 ? 0xffe00000u : 0xff000000u);
+}
+template <int OP, typename T, int V, bool EXACT = true>
+__device__ __forceinline__ void apply_op(T (&x)[V], const T (&y)[V], const T (&z)[V], int imm, int nvalid, bool& bad,
+                                         unsigned& susp) {
   if constexpr (OP < MCM_TAPE_BINARY) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const T t = math::unary_apply<OP - MCM_TAPE_UNARY, T>(x[v]);
-      if constexpr (math::UnaryCanDomainError<OP - MCM_TAPE_UNARY>::value) bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && (v < nvalid);
+      if constexpr (math::UnaryCanDomainError<OP - MCM_TAPE_UNARY>::value) {
+        if constexpr (EXACT) bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && (v < nvalid);
+        else susp = max(susp, nan_key(t));
+      }
       x[v] = t;
     }
   } else if constexpr (OP < MCM_TAPE_TERNARY) {
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       const T t = math::binary_apply<OP - MCM_TAPE_BINARY, T>(x[v], y[v]);
-      if constexpr (math::BinaryCanDomainError<OP - MCM_TAPE_BINARY>::value)
-        bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && !is_nan_fast(y[v]) && (v < nvalid);
+      if constexpr (math::BinaryCanDomainError<OP - MCM_TAPE_BINARY>::value) {
+        if constexpr (EXACT) bad |= is_nan_fast(t) && !is_nan_fast(x[v]) && !is_nan_fast(y[v]) && (v < nvalid);
+        else susp = max(susp, nan_key(t));
+      }
       x[v] = t;
     }
   } else if constexpr (OP < MCM_TAPE_LOAD) {
@@ -146,8 +160,9 @@ __device__ __forceinline__ void sget(const T (&r)[S][V], const ChainParams& p, T
 // W packs per thread (pack indices j[0..W)): W independent dependency chains per lane-pair for the FP64 pipe
 template <int W> struct PackIdx { size_t j[W]; int nvalid[W]; };
 
-template <class TP, int PC, int END, typename T, int V, int W>
-__device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, const PackIdx<W>& ix, int nvalid, bool& bad) {
+template <class TP, int PC, int END, typename T, int V, int W, bool EXACT>
+__device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, const PackIdx<W>& ix, int nvalid, bool& bad,
+                                            unsigned& susp) {
   constexpr int PV = V / W;
   if constexpr (PC < END) {
     constexpr SIns I = TP::ins[PC];
@@ -177,11 +192,11 @@ __device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, 
       sget<I.a, T, V>(r, p, x);
       if constexpr (I.op >= MCM_TAPE_BINARY && I.op < MCM_TAPE_LOAD) sget<I.b, T, V>(r, p, y);
       if constexpr (I.op >= MCM_TAPE_TERNARY && I.op < MCM_TAPE_LOAD) sget<I.c, T, V>(r, p, z);
-      apply_op<I.op, T, V>(x, y, z, (int)(signed char)I.b, nvalid, bad);
+      apply_op<I.op, T, V, EXACT>(x, y, z, (int)(signed char)I.b, nvalid, bad, susp);
 #pragma unroll
       for (int v = 0; v < V; ++v) r[I.dst][v] = x[v];
     }
-    exec_static<TP, PC + 1, END, T, V, W>(r, p, ix, nvalid, bad);
+    exec_static<TP, PC + 1, END, T, V, W, EXACT>(r, p, ix, nvalid, bad, susp);
   }
 }
 
@@ -189,7 +204,7 @@ __device__ __forceinline__ void exec_static(T (&r)[S][V], const ChainParams& p, 
 #define MCM_CHAIN_W 1   // packs per thread in the registered-chain kernel
 #endif
 #ifndef MCM_CHAIN_PREFETCH
-#define MCM_CHAIN_PREFETCH 1   // 0 none, 1 prefetch.global.L1, 2 prefetch.global.L2 of the next iteration's inputs
+#define MCM_CHAIN_PREFETCH 0   // 0 none (default: measured no effect), 1 prefetch.global.L1, 2 prefetch.global.L2 of the next inputs
 #endif
 
 // The register budget (64 at 4 CTAs/SM) leaves no room to hold the next iteration's inputs, and the pc samples put
@@ -210,6 +225,34 @@ __device__ __forceinline__ void prefetch_static(const ChainParams& p, size_t jn)
   }
 }
 
+// Cold path of the domain check: the same pack once more with the per-lane test (stores repeat the same values).
+template <class TP, typename T, int V, int W>
+__device__ __noinline__ bool replay_exact(const ChainParams& p, size_t j, size_t stride) {
+  constexpr int PV = V / W;
+  const size_t n = p.n, nvec = (n + PV - 1) / PV;
+  PackIdx<W> ix;
+  int nvalid = 0;
+  bool bad = false;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    ix.j[w] = j + (size_t)w * stride;
+    ix.nvalid[w] = ix.j[w] >= nvec ? 0 : ((ix.j[w] + 1) * PV <= n ? PV : (int)(n - ix.j[w] * PV));
+    nvalid += ix.nvalid[w];
+  }
+  T r[S][V];
+#pragma unroll
+  for (int k = 0; k < S; ++k)
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[k][v] = T(0);
+  unsigned unused = 0;
+  exec_static<TP, 0, TP::loop_begin, T, V, W, true>(r, p, ix, nvalid, bad, unused);
+  if constexpr (TP::loop_end > TP::loop_begin) {
+    for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V, W, true>(r, p, ix, nvalid, bad, unused);
+  }
+  exec_static<TP, TP::loop_end, TP::n, T, V, W, true>(r, p, ix, nvalid, bad, unused);
+  return bad;
+}
+
 template <class TP, typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads, MCM_CHAIN_MIN_CTAS)
 k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
@@ -221,15 +264,22 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
   const size_t nvec = (n + PV - 1) / PV;
   const size_t stride = (size_t)gridDim.x * kThreads;
   bool bad = false;
+  const int ragged_n = (int)(n % PV);
+  const size_t ragged_pack = ragged_n ? nvec - 1 : ~(size_t)0;
   MomStream acc = ms_empty();
   for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < nvec; j += W * stride) {
     PackIdx<W> ix;
     int nvalid = 0;   // valid lanes form a prefix of the V lanes of this thread only when W == 1; used for the domain flag
+    if constexpr (W == 1) {
+      ix.j[0] = j;                                       // only the very last pack can be ragged
+      ix.nvalid[0] = nvalid = (j == ragged_pack) ? ragged_n : PV;
+    } else {
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-      ix.j[w] = j + (size_t)w * stride;
-      ix.nvalid[w] = ix.j[w] >= nvec ? 0 : ((ix.j[w] + 1) * PV <= n ? PV : (int)(n - ix.j[w] * PV));
-      nvalid += ix.nvalid[w];
+      for (int w = 0; w < W; ++w) {
+        ix.j[w] = j + (size_t)w * stride;
+        ix.nvalid[w] = ix.j[w] >= nvec ? 0 : ((ix.j[w] + 1) * PV <= n ? PV : (int)(n - ix.j[w] * PV));
+        nvalid += ix.nvalid[w];
+      }
     }
 #if MCM_CHAIN_PREFETCH
     if (j + W * stride < nvec) {
@@ -243,11 +293,13 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
     for (int k = 0; k < S; ++k)
 #pragma unroll
       for (int v = 0; v < V; ++v) r[k][v] = T(0);
-    exec_static<TP, 0, TP::loop_begin, T, V, W>(r, p, ix, nvalid, bad);
+    unsigned susp = 0;
+    exec_static<TP, 0, TP::loop_begin, T, V, W, false>(r, p, ix, nvalid, bad, susp);
     if constexpr (TP::loop_end > TP::loop_begin) {
-      for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V, W>(r, p, ix, nvalid, bad);
+      for (int rep = 0; rep < p.reps; ++rep) exec_static<TP, TP::loop_begin, TP::loop_end, T, V, W, false>(r, p, ix, nvalid, bad, susp);
     }
-    exec_static<TP, TP::loop_end, TP::n, T, V, W>(r, p, ix, nvalid, bad);
+    exec_static<TP, TP::loop_end, TP::n, T, V, W, false>(r, p, ix, nvalid, bad, susp);
+    if (nan_key_hit<T>(susp)) bad |= replay_exact<TP, T, V, W>(p, j, stride);   // rare: a checked primitive returned NaN
     if constexpr (STATS) {
       T x[V];
       // stats slot is a runtime choice among 8 registers: resolved by a uniform switch once per vector
@@ -369,6 +421,7 @@ __device__ __forceinline__ void iput(Pack<T>* sm, int idx, const T (&x)[V]) {
 template <typename T, int V>
 __device__ __forceinline__ void exec_range(Pack<T>* sm, const ChainParams& p, int pc0, int pc1, size_t j,
                                            int nvalid, bool& bad) {
+  unsigned unused_susp = 0;
   for (int pc = pc0; pc < pc1; ++pc) {
     const mcm_tape_ins ins = p.tape[pc];
     const int op = ins.op;
@@ -387,7 +440,7 @@ __device__ __forceinline__ void exec_range(Pack<T>* sm, const ChainParams& p, in
     if (op >= MCM_TAPE_TERNARY && op < MCM_TAPE_LOAD) iget<T, V>(sm, p, ins.c, z);
     const int imm = (int)(signed char)ins.b;
 #define MCM_OPC(OPC) \
-  case OPC: apply_op<OPC, T, V>(x, y, z, imm, nvalid, bad); break;
+  case OPC: apply_op<OPC, T, V, true>(x, y, z, imm, nvalid, bad, unused_susp); break;
 #define MCM_U(OP) MCM_OPC(MCM_TAPE_UNARY + OP)
 #define MCM_B(OP) MCM_OPC(MCM_TAPE_BINARY + OP)
 #define MCM_T(OP) MCM_OPC(MCM_TAPE_TERNARY + OP)

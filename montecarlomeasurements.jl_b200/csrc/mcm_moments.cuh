@@ -144,8 +144,8 @@ __device__ __forceinline__ void ms_push(MomStream& a, const double (&v)[C]) {
     a.s1 += d;
     a.s2 = fma(d, d, a.s2);
     a.sum += v[i];
-    a.mn = fmin(a.mn, v[i]);
-    a.mx = fmax(a.mx, v[i]);
+    a.mn = v[i] < a.mn ? v[i] : a.mn;              // a NaN compares false and leaves the extrema alone, like fmin/fmax
+    a.mx = v[i] > a.mx ? v[i] : a.mx;
     a.nanw = max(a.nanw, (unsigned)__double2hiint(v[i]) << 1);
   }
   a.c += C;
