@@ -16,11 +16,79 @@
 namespace mcm {
 
 constexpr int DN_NB = 64;   // panel width
+static int g_dense_v2 = 1;   // mcm_dense_use_v2: 1 = register-tiled diagonal block, right-looking solve, chol(S) on a side stream
 constexpr int DN_T = 256;
 
 // ---- diagonal block: unblocked Cholesky of an nb x nb block held in shared memory (one CTA) -----------------
 __global__ void __launch_bounds__(DN_T)
 k_potrf_diag(double* __restrict__ A, int ld, int nb, int* __restrict__ info, int col0) {
+  // thread (ty, tx) = (t / 16, t % 16) keeps elements (ty + 16 a, tx + 16 b), a, b < 4, in registers; per column k:
+  // pivot -> barrier -> owners scale and publish column k -> barrier -> everyone updates its own 16 elements.
+  // (first version: block in shared memory, trailing update indexed through a runtime division: 63 us per block)
+  __shared__ double colk[DN_NB];
+  __shared__ double s_diag;
+  __shared__ int s_bad;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double r[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, j = tx + 16 * b;
+      r[a][b] = (i < nb && j <= i) ? A[(size_t)i * ld + j] : 0.0;
+    }
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  for (int k = 0; k < nb; ++k) {
+    const int kq = k >> 4, kr = k & 15;
+    if (ty == kr && tx == kr) {
+      double akk = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a == kq) akk = r[a][a];
+      if (!(akk > 0.0)) {    // not positive definite (or NaN): report the 1-based column like LAPACK
+        atomicCAS(info, 0, col0 + k + 1);
+        s_bad = 1;
+      } else {
+        s_diag = sqrt(akk);
+      }
+    }
+    __syncthreads();
+    if (s_bad) return;
+    const double d = s_diag;
+    if (tx == kr) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (b == kq) {
+            const int i = ty + 16 * a;
+            if (i == k) r[a][b] = d;
+            else if (i > k) r[a][b] /= d;
+            if (i >= k) colk[i] = r[a][b];
+          }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = ty + 16 * a, j = tx + 16 * b;
+        if (j > k && j <= i) r[a][b] -= colk[i] * colk[j];
+      }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = ty + 16 * a, j = tx + 16 * b;
+      if (i < nb && j < nb) A[(size_t)i * ld + j] = j <= i ? r[a][b] : 0.0;   // upper part of the block: zeros
+    }
+}
+
+// first version (kept behind mcm_dense_use_v2(0)): block in shared memory, trailing update through a runtime division
+__global__ void __launch_bounds__(DN_T)
+k_potrf_diag_v1(double* __restrict__ A, int ld, int nb, int* __restrict__ info, int col0) {
   __shared__ double s[DN_NB][DN_NB + 1];
   for (int e = threadIdx.x; e < nb * nb; e += DN_T) {
     const int i = e / nb, j = e % nb;
@@ -169,16 +237,19 @@ __global__ void k_diag_sqrt(const double* __restrict__ Cm, int M, double* __rest
 }
 
 // in-place lower Cholesky on the library stream; *info_host = 0 or the 1-based column of the first non-positive pivot
-int potrf_lower_device(double* A, int M, int* info_host) {
+// enqueue only (no host synchronisation): *d_info_out receives the device flag to read once the stream has drained
+static int potrf_lower_enqueue(double* A, int M, int** d_info_out) {
   Ctx& c = ctx();
   if (int rc = dn_set_attrs()) return rc;
   int* d_info = nullptr;
   MCM_CUDA(cudaMallocAsync((void**)&d_info, sizeof(int), c.stream));
   MCM_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int), c.stream));
+  *d_info_out = d_info;
   for (int j0 = 0; j0 < M; j0 += DN_NB) {
     const int nb = std::min(DN_NB, M - j0);
     double* A11 = A + (size_t)j0 * M + j0;
-    k_potrf_diag<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
+    if (g_dense_v2) k_potrf_diag<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
+    else k_potrf_diag_v1<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
     MCM_CHECK_LAUNCH();
     const int rest = M - j0 - nb;
     if (rest > 0) {
@@ -193,10 +264,19 @@ int potrf_lower_device(double* A, int M, int* info_host) {
   }
   k_zero_upper<<<(unsigned)(((size_t)M * M + 255) / 256), 256, 0, c.stream>>>(A, M, M);
   MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+static int potrf_lower_finish(int* d_info, int* info_host) {
+  Ctx& c = ctx();
   MCM_CUDA(cudaMemcpyAsync(info_host, d_info, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaStreamSynchronize(c.stream));
   MCM_CUDA(cudaFreeAsync(d_info, c.stream));
   return MCM_OK;
+}
+int potrf_lower_device(double* A, int M, int* info_host) {
+  int* d_info = nullptr;
+  if (int rc = potrf_lower_enqueue(A, M, &d_info)) return rc;
+  return potrf_lower_finish(d_info, info_host);
 }
 
 // X L = B, in place in B (nrows x M), L lower triangular M x M
@@ -206,14 +286,23 @@ int trsm_right_lower_device(const double* L, double* B, int M, int nrows) {
   const int np = (M + DN_NB - 1) / DN_NB;
   for (int p = np - 1; p >= 0; --p) {
     const int j0 = p * DN_NB, nb = std::min(DN_NB, M - j0);
-    const int right = M - j0 - nb;
-    if (right > 0) {   // B[:, panel] -= X[:, right] * L[right, panel]
-      k_dgemm_sub<false, false><<<dim3((nb + 63) / 64, (nrows + 63) / 64), DN_T, 0, c.stream>>>(
-          B + j0, M, B + j0 + nb, M, L + (size_t)(j0 + nb) * M + j0, M, nrows, nb, right);
-      MCM_CHECK_LAUNCH();
+    if (!g_dense_v2) {   // first version, left-looking: B[:, panel] -= X[:, right] * L[right, panel] before the panel solve
+      const int right = M - j0 - nb;
+      if (right > 0) {
+        k_dgemm_sub<false, false><<<dim3((nb + 63) / 64, (nrows + 63) / 64), DN_T, 0, c.stream>>>(
+            B + j0, M, B + j0 + nb, M, L + (size_t)(j0 + nb) * M + j0, M, nrows, nb, right);
+        MCM_CHECK_LAUNCH();
+      }
     }
     k_trsm_right_rows<<<(nrows + DN_NB - 1) / DN_NB, DN_T, DN_TRSM_SMEM, c.stream>>>(L + (size_t)j0 * M + j0, B + j0, M, M, nb, nrows);
     MCM_CHECK_LAUNCH();
+    // right-looking: the solved panel updates every column to its left at once, B[:, 0:j0] -= X[:, panel] * L[panel, 0:j0]
+    // ((j0/64) x (nrows/64) CTAs with K = 64; the left-looking form ran 16 CTAs over K up to 960: 2.8 ms of 3.6)
+    if (g_dense_v2 && j0 > 0) {
+      k_dgemm_sub<false, false><<<dim3((j0 + 63) / 64, (nrows + 63) / 64), DN_T, 0, c.stream>>>(
+          B, M, B + j0, M, L + (size_t)j0 * M, M, nrows, j0, nb);
+      MCM_CHECK_LAUNCH();
+    }
   }
   return MCM_OK;
 }
@@ -221,6 +310,10 @@ int trsm_right_lower_device(const double* L, double* B, int M, int nrows) {
 }  // namespace mcm
 
 using namespace mcm;
+
+/* A/B switch for the dense M x M steps: 1 (default) = register-tiled diagonal block, right-looking triangular solve and
+ * chol(S) overlapped with the Gram on a side stream; 0 = the first versions.  Same results to rounding. */
+extern "C" int mcm_dense_use_v2(int on) { g_dense_v2 = on; return MCM_OK; }
 
 extern "C" int mcm_potrf(double* a_dev, int M, int* info_host) {
   MCM_NEED_INIT();
@@ -250,14 +343,51 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
   double* d = nullptr;   // [C | LS | means]
   MCM_CUDA(cudaMallocAsync((void**)&d, (2 * mm + (size_t)M) * sizeof(double), c.stream));
   double *dC = d, *dLS = d + mm, *dmu = d + 2 * mm;
-  auto release = [&]() { cudaFreeAsync(d, c.stream); };
+  static cudaStream_t side = nullptr;
+  static cudaEvent_t ev_fork = nullptr;
+  auto release = [&]() {
+    if (side) cudaStreamSynchronize(side);          // the side stream may still be factorising inside this block
+    cudaFreeAsync(d, c.stream);
+  };
   MCM_CUDA(cudaMemcpyAsync(dLS, S_host, mm * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  // chol(S) does not depend on the particles: its ~100 small launches go to a side stream and run under the Gram's
+  // HBM-bound prepass instead of after the Gram (the library stream is swapped for the enqueue only)
+  if (!side) {
+    MCM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    MCM_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+  }
+  MCM_CUDA(cudaEventRecord(ev_fork, c.stream));
+  MCM_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  int* d_info_S = nullptr;
+  const bool overlap = g_dense_v2 != 0;
+  if (overlap) {
+    const cudaStream_t main_stream = c.stream;
+    c.stream = side;
+    const int rcS = potrf_lower_enqueue(dLS, M, &d_info_S);
+    c.stream = main_stream;
+    if (rcS) { cudaStreamSynchronize(side); release(); return rcS; }
+  }
+  StatsHandoff& ho = stats_handoff();
+  ho = StatsHandoff{};
+  ho.armed = true;
+  auto drop_stats = [&]() {
+    if (ho.valid) { cudaFreeAsync(ho.d_ex, c.stream); cudaFreeAsync(ho.d_ratio, c.stream); }
+    ho = StatsHandoff{};
+  };
   int rc = mcm_gram(dtype, xs, M, n, 1, nullptr, dC, dmu);
-  if (rc) { release(); return rc; }
+  ho.armed = false;
+  if (rc) { drop_stats(); release(); return rc; }
   int info = 0;
-  rc = potrf_lower_device(dLS, M, &info);
-  if (rc) { release(); return rc; }
-  if (info) { release(); return fail(MCM_ERR_INVALID, "mcm_transform_moments: the target covariance is not positive definite (pivot %d)", info); }
+  if (overlap) {
+    const cudaStream_t main_stream = c.stream;
+    c.stream = side;
+    rc = potrf_lower_finish(d_info_S, &info);      // synchronises the side stream: dLS = chol(S).L from here on
+    c.stream = main_stream;
+  } else {
+    rc = potrf_lower_device(dLS, M, &info);
+  }
+  if (rc) { drop_stats(); release(); return rc; }
+  if (info) { drop_stats(); release(); return fail(MCM_ERR_INVALID, "mcm_transform_moments: the target covariance is not positive definite (pivot %d)", info); }
   if (preserve_latin) {
     double* dD = nullptr;
     MCM_CUDA(cudaMallocAsync((void**)&dD, mm * sizeof(double), c.stream));
@@ -267,11 +397,11 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
     MCM_CUDA(cudaFreeAsync(dD, c.stream));
   } else {
     rc = potrf_lower_device(dC, M, &info);
-    if (rc) { release(); return rc; }
-    if (info) { release(); return fail(MCM_ERR_INVALID, "mcm_transform_moments: the sample covariance is not positive definite (pivot %d): fewer particles than variables, or dependent columns", info); }
+    if (rc) { drop_stats(); release(); return rc; }
+    if (info) { drop_stats(); release(); return fail(MCM_ERR_INVALID, "mcm_transform_moments: the sample covariance is not positive definite (pivot %d): fewer particles than variables, or dependent columns", info); }
   }
   rc = trsm_right_lower_device(dC, dLS, M, M);   // dLS <- chol(S).L / xl
-  if (rc) { release(); return rc; }
+  if (rc) { drop_stats(); release(); return rc; }
   std::vector<double> A(mm), mu(M);
   MCM_CUDA(cudaMemcpyAsync(A.data(), dLS, mm * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaMemcpyAsync(mu.data(), dmu, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -281,5 +411,7 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
   // already; this keeps the early-exit of the application kernels independent of that)
   for (int i = 0; i < M; ++i)
     for (int j = i + 1; j < M; ++j) A[(size_t)i * M + j] = 0.0;
-  return mcm_pgemm(dtype, A.data(), M, M, xs, mu.data(), m_host, outs, n);
+  rc = mcm_pgemm(dtype, A.data(), M, M, xs, mu.data(), m_host, outs, n);
+  drop_stats();
+  return rc;
 }

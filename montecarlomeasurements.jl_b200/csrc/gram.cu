@@ -293,6 +293,7 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
                      const int* pre_ex, const double* pre_ratio);
 template <typename T>
 int varstats_device(const T* const* d_vars, int M, size_t n, double* d_means, int* d_ex, double* d_ratio);
+StatsHandoff& stats_handoff() { static StatsHandoff h; return h; }
 static int g_use_tensor = 1;  // mcm_gram_use_tensor: 0 = FP64 DMMA kernel only, 1 = Ozaki int8 on tcgen05 for large problems
 static int g_last_engine = 0; // 0 = DMMA, 1 = tcgen05
 
@@ -327,7 +328,14 @@ static int gram_impl(const void* const* vars_host, int M, size_t n, double scale
   g_last_engine = 0;
   if (tensor_ok) {
     int rc = gram_tensor_impl<T>(d_vars, d_means, M, n, scale, cov_out_dev, d_ex, d_ratio);
-    if (d_ex) { MCM_CUDA(cudaFreeAsync(d_ex, c.stream)); MCM_CUDA(cudaFreeAsync(d_ratio, c.stream)); }
+    if (d_ex) {
+      StatsHandoff& h = stats_handoff();
+      if (h.armed && !h.valid && rc >= 0) {     // mcm_transform_moments: the application reuses them (and frees them)
+        h.valid = true; h.M = M; h.n = n; h.first_var = vars_host[0]; h.d_ex = d_ex; h.d_ratio = d_ratio;
+      } else {
+        MCM_CUDA(cudaFreeAsync(d_ex, c.stream)); MCM_CUDA(cudaFreeAsync(d_ratio, c.stream));
+      }
+    }
     if (rc >= 0) {  // -1: declined by the accuracy guard (heavy-tailed rows) -> DMMA below
       g_last_engine = 1;
       MCM_CUDA(cudaFreeAsync(d_vars, c.stream));

@@ -63,18 +63,35 @@ k_varstats(const T* const* __restrict__ vars, size_t n, size_t slice, Mom* __res
   const size_t b = (size_t)blockIdx.y * slice;          // slice is a multiple of V and vars are 16-byte aligned
   size_t e = b + slice;
   if (e > n) e = n;
-  Mom m = mom_empty();
+  // shifted power sums folded every 16 values (MomStream) instead of a pairwise merge per pack, four packs in flight
+  MomStream acc = ms_empty();
   const size_t nvec = (e - b) / V;
   const P* px = reinterpret_cast<const P*>(x + b);
-  for (size_t i = threadIdx.x; i < nvec; i += kThreads) {
+  size_t i = threadIdx.x;
+  for (; i + 3 * (size_t)kThreads < nvec; i += 4 * (size_t)kThreads) {
+    P t[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) t[u] = ld_stream(px + i + (size_t)u * kThreads);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double d[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) d[v] = (double)t[u].v[v];
+      ms_push<V>(acc, d);
+    }
+  }
+  for (; i < nvec; i += kThreads) {
     const P t = ld_stream(px + i);
     double d[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) d[v] = (double)t.v[v];
-    mom_push_chunk<V>(m, d);
+    ms_push<V>(acc, d);
   }
-  for (size_t i = b + nvec * V + threadIdx.x; i < e; i += kThreads) mom_push_one(m, (double)x[i]);
-  m = mom_block_reduce(m);
+  for (size_t q = b + nvec * V + threadIdx.x; q < e; q += kThreads) {
+    const double d[1] = {(double)x[q]};
+    ms_push<1>(acc, d);
+  }
+  Mom m = mom_block_reduce(ms_finish(acc));
   if (threadIdx.x == 0) partial[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = m;
 }
 __global__ void k_varstats_finish(const Mom* __restrict__ partial, int M, int nsplit, double* __restrict__ means,

@@ -57,6 +57,20 @@ inline int stream_grid(size_t work, int items_per_thread, int ctas_per_sm) {
 
 #define MCM_CHECK_LAUNCH() MCM_CUDA(cudaGetLastError())
 
+namespace mcm {
+// Row statistics (digit-split exponents and max/sigma ratios about the column means) handed from the Gram to the
+// application inside mcm_transform_moments, so that the 8 GB particle matrix is not read a third time for them.
+struct StatsHandoff {
+  bool armed = false, valid = false;
+  int M = 0;
+  size_t n = 0;
+  const void* first_var = nullptr;
+  int* d_ex = nullptr;
+  double* d_ratio = nullptr;
+};
+StatsHandoff& stats_handoff();
+}  // namespace mcm
+
 #ifdef __CUDACC__
 namespace mcm {
 

@@ -87,6 +87,31 @@ int main() {
   uint32_t bits = 0;
   CK(mcm_check_flags(&bits, 1));
   EXPECT(bits & MCM_FLAG_DOMAIN);
+  // decision layer: nearest particle to pi is the median of the sorted sample; with_nominal moves it to index 0
+  uint64_t nearest = 0;
+  CK(mcm_argmin_absdiff(MCM_F64, a, N, 3.14159265358979323846, &nearest));
+  EXPECT(nearest == N / 2 - 1 || nearest == N / 2);
+  CK(mcm_shuffle_insert(MCM_F64, a, N, nearest, 3.0, t1));
+  double first = 0.0;
+  CK(mcm_download(&first, t1, 8));
+  EXPECT(first == 3.0);
+  // per-particle 2 x 2 matrices [[a, 1], [0, a]]: determinant a^2, inverse (0,0) entry 1/a
+  CK(mcm_fill(MCM_F64, t1, N, 1.0));
+  CK(mcm_fill(MCM_F64, t2, N, 0.0));
+  const void* Am[4] = {a, t1, t2, a};
+  void* det = nullptr;
+  CK(mcm_alloc(&det, N * 8));
+  void* outs1[1] = {det};
+  CK(mcm_batched_linalg(MCM_LA_DET, MCM_F64, 2, 0, Am, nullptr, outs1, nullptr, N));
+  CK(mcm_binary(MCM_B_MUL, MCM_F64, a, 0.0, a, 0.0, yf, N));
+  CK(mcm_binary(MCM_B_SUB, MCM_F64, det, 0.0, yf, 0.0, det, N));
+  CK(mcm_moments(MCM_F64, det, N, m));
+  EXPECT(std::fabs(m[3]) < 1e-14 && std::fabs(m[4]) < 1e-14);
+  // Complex{Particles}: (a + i)(a - i) = a^2 + 1 exactly in the real part, 0 in the imaginary part
+  CK(mcm_complex_op(MCM_C_MUL, MCM_F64, a, nullptr, 0.0, 1.0, a, nullptr, 0.0, -1.0, det, t2, N));
+  CK(mcm_moments(MCM_F64, t2, N, m));
+  EXPECT(m[3] == 0.0 && m[4] == 0.0);
+  CK(mcm_free(det));
   // bad arguments are rejected on the host with a message
   EXPECT(mcm_unary(9999, MCM_F64, a, t1, N) != MCM_OK && std::strlen(mcm_last_error()) > 0);
   CK(mcm_free(a)); CK(mcm_free(t1)); CK(mcm_free(t2)); CK(mcm_free(y)); CK(mcm_free(yf)); CK(mcm_free(dC));

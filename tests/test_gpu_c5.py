@@ -285,8 +285,16 @@ def test_quantile_batch_errors(mcm):
 
 
 # ---- M x M dense steps (dense.cu) ------------------------------------------------------------------------
+@pytest.fixture(params=[1, 0], ids=["dense-v2", "dense-v1"])
+def dense_mode(request, mcm):
+    """Both generations of the dense kernels (mcm_dense_use_v2): the default and the first versions."""
+    mcm._lib.lib().mcm_dense_use_v2(request.param)
+    yield request.param
+    mcm._lib.lib().mcm_dense_use_v2(1)
+
+
 @pytest.mark.parametrize("M", [1, 5, 64, 65, 200, 517])
-def test_device_cholesky_and_triangular_solve(mcm, M):
+def test_device_cholesky_and_triangular_solve(mcm, M, dense_mode):
     """cholesky(C).L and B / L on device against LAPACK (numpy): same factor up to rounding."""
     rng = np.random.default_rng(M)
     Q = rng.normal(size=(M, M + 3))
@@ -330,3 +338,40 @@ def test_transform_moments_device_matches_host_linear_algebra(mcm):
         mcm.transform_moments(cols, m, -S)
     with pytest.raises(mcm.ArgumentError):
         mcm.transform_moments(cols, m, S[:5, :5])
+
+
+def test_transform_moments_tensor_path_with_shared_statistics(mcm):
+    """d = 256 variables: the Gram runs on tcgen05 and hands its row statistics to the tcgen05 application (no third
+    pass over the particles); the target Cholesky runs on a side stream.  Y must have exactly the requested moments
+    and agree with the same transform assembled from separate calls (pcov -> host factorisations -> pgemm)."""
+    d, n = 256, 20_000
+    rng = np.random.default_rng(3)
+    cols = mcm.systematic_batch(n, d, permute=True, seed=5)
+    Aq = rng.normal(size=(d, d))
+    S = Aq @ Aq.T / d + np.eye(d)
+    m = np.linspace(-2, 2, d)
+    Y = mcm.transform_moments(cols, m, S)
+    L = mcm._lib
+    assert L.lib().mcm_gram_last_engine() == 1 and L.lib().mcm_pgemm_last_engine() == 1
+    assert np.max(np.abs(np.array(mcm.pmean(Y)) - m)) < 1e-13
+    assert np.max(np.abs(mcm.pcov(Y) - S)) < 1e-11
+    # the same transform from separate calls
+    cov = mcm.pcov(cols)
+    mu = np.array(mcm.pmean(cols))
+    xl = np.linalg.cholesky(cov)
+    A = np.tril(np.linalg.solve(xl.T, np.linalg.cholesky(S).T).T)
+    Y2 = mcm.pgemm(A, cols, shift=mu, bias=m)
+    for j in (0, 1, d // 2, d - 1):
+        a, b = Y[j].to_numpy(), Y2[j].to_numpy()
+        assert np.max(np.abs(a - b)) < 1e-10 * max(1.0, np.max(np.abs(b)))
+    # twice in a row: the side stream, the cached statistics and the pool are reusable
+    Y3 = mcm.transform_moments(cols, m, S)
+    assert np.array_equal(Y3[7].to_numpy(), Y[7].to_numpy())
+    # first-generation dense steps (no side stream, left-looking solve): the same transform to rounding
+    L.lib().mcm_dense_use_v2(0)
+    try:
+        Y4 = mcm.transform_moments(cols, m, S)
+    finally:
+        L.lib().mcm_dense_use_v2(1)
+    a, b = Y4[d - 1].to_numpy(), Y[d - 1].to_numpy()
+    assert np.max(np.abs(a - b)) < 1e-10 * max(1.0, np.max(np.abs(b)))
