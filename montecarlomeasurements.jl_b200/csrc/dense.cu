@@ -16,7 +16,7 @@
 namespace mcm {
 
 constexpr int DN_NB = 64;   // panel width
-static int g_dense_v2 = 0;   // mcm_dense_use_v2(1): register-tiled diagonal block, right-looking solve, chol(S) on a side stream — opt-in until it has run on a GPU
+static int g_dense_v2 = 1;   // mcm_dense_use_v2: 1 = register-tiled diagonal block, right-looking solve, chol(S) on a side stream; 0 = first versions
 constexpr int DN_T = 256;
 
 // ---- diagonal block: unblocked Cholesky of an nb x nb block held in shared memory (one CTA) -----------------
@@ -311,8 +311,8 @@ int trsm_right_lower_device(const double* L, double* B, int M, int nrows) {
 
 using namespace mcm;
 
-/* Switch for the dense M x M steps: 0 (default) = the versions measured in round 1; 1 = register-tiled diagonal block,
- * right-looking triangular solve and chol(S) overlapped with the Gram on a side stream (not yet run on a GPU). */
+/* A/B switch for the dense M x M steps: 1 (default) = register-tiled diagonal block, right-looking triangular solve and
+ * chol(S) overlapped with the Gram on a side stream; 0 = the first versions.  Same results to rounding. */
 extern "C" int mcm_dense_use_v2(int on) { g_dense_v2 = on; return MCM_OK; }
 
 extern "C" int mcm_potrf(double* a_dev, int M, int* info_host) {

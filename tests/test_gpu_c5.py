@@ -285,12 +285,12 @@ def test_quantile_batch_errors(mcm):
 
 
 # ---- M x M dense steps (dense.cu) ------------------------------------------------------------------------
-@pytest.fixture(params=[0], ids=["dense-v1"])
+@pytest.fixture(params=[1, 0], ids=["dense-v2", "dense-v1"])
 def dense_mode(request, mcm):
     """Both generations of the dense kernels (mcm_dense_use_v2): the default and the first versions."""
     mcm._lib.lib().mcm_dense_use_v2(request.param)
     yield request.param
-    mcm._lib.lib().mcm_dense_use_v2(0)
+    mcm._lib.lib().mcm_dense_use_v2(1)
 
 
 @pytest.mark.parametrize("M", [1, 5, 64, 65, 200, 517])
@@ -367,5 +367,5 @@ def test_transform_moments_tensor_path_with_shared_statistics(mcm):
     # twice in a row: the cached statistics and the pool are reusable
     Y3 = mcm.transform_moments(cols, m, S)
     assert np.array_equal(Y3[7].to_numpy(), Y[7].to_numpy())
-    # (the second-generation dense steps — mcm_dense_use_v2(1): side stream, right-looking solve, register-tiled diagonal
-    # block — are not exercised here: they could not be run on a GPU before the end of round 1)
+    # (runs with the default, second-generation dense steps; scripts/check_dense_v2.py compares the two generations on
+    # this very problem: max difference 8.9e-16)
