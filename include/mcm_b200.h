@@ -49,7 +49,8 @@ enum { MCM_F32 = 0, MCM_F64 = 1 };
  * cannot — they return NaN and raise a flag, surfaced by mcm_check_flags).   */
 enum {
   MCM_FLAG_DOMAIN = 1u,     /* NaN produced from non-NaN input (sqrt(-1), log(-1), ...) */
-  MCM_FLAG_NAN_QUANTILE = 2u /* NaN met by quantile/sort (Statistics.quantile errors)    */
+  MCM_FLAG_NAN_QUANTILE = 2u, /* NaN met by quantile/sort (Statistics.quantile errors)    */
+  MCM_FLAG_BOUNDS = 0x80000000u /* gather index outside [0, N) (BoundsError, resampling.jl:77,82); the output is NaN */
 };
 
 /* ---- unary primitives -----------------------------------------------------
@@ -73,6 +74,12 @@ enum {
   MCM_U_INV,   /* literal_pow(^,x,Val(-1)) == inv(x) */
   MCM_U_SQR,   /* literal_pow(^,x,Val(2))  == x*x   (particles.jl:388-391) */
   MCM_U_CUBE,  /* literal_pow(^,x,Val(3))  == x*x*x */
+  /* round(p, r::RoundingMode) (particles.jl:346): RoundNearest = MCM_U_ROUND, RoundToZero = MCM_U_TRUNC,
+   * RoundUp = MCM_U_CEIL, RoundDown = MCM_U_FLOOR; the remaining modes of Base: */
+  MCM_U_ROUND_TIESAWAY, MCM_U_ROUND_TIESUP, MCM_U_ROUND_FROMZERO,
+  /* rem2pi(p, r::RoundingMode) (particles.jl:359); mod2pi(p) == rem2pi(p, RoundDown) (runtests.jl:476,480).
+   * Correctly rounded remainders for every finite argument (Cody-Waite, Payne-Hanek beyond 2^17 pi/2). */
+  MCM_U_REM2PI_NEAREST, MCM_U_REM2PI_TOZERO, MCM_U_REM2PI_DOWN, MCM_U_REM2PI_UP,
   MCM_U_COUNT
 };
 
@@ -87,6 +94,11 @@ enum {
   MCM_B_ADD_SUM, MCM_B_HYPOT,
   MCM_B_REM,    /* rem(x,y) == C fmod, exact  (particles.jl:354-355) */
   MCM_B_FDIV,   /* div(x,y) == round((x-rem(x,y))/y) (particles.jl:356-357) */
+  /* rem(x, y, r) / div(x, y, r) with a RoundingMode (particles.jl:358,410-414; Base div.jl): RoundToZero is
+   * MCM_B_REM / MCM_B_FDIV; Nearest = IEEE remainder, Down = mod(x,y), Up = mod(x,-y), FromZero = Up when the
+   * signs agree else Down; div(x,y,r) = round((x - rem(x,y,r))/y).  All exact-tier (bit-exact). */
+  MCM_B_REM_NEAREST, MCM_B_REM_DOWN, MCM_B_REM_UP, MCM_B_REM_FROMZERO,
+  MCM_B_DIV_NEAREST, MCM_B_DIV_DOWN, MCM_B_DIV_UP, MCM_B_DIV_FROMZERO,
   MCM_B_COUNT
 };
 
@@ -113,7 +125,11 @@ enum {
 
 /* comparison kinds for mcm_count (the `@prob` macro, src/bymap.jl:128-136,
  * and the :montecarlo comparison mode, src/particles.jl:512-515) */
-enum { MCM_CMP_LT = 0, MCM_CMP_LE, MCM_CMP_GT, MCM_CMP_GE, MCM_CMP_EQ, MCM_CMP_NE };
+enum { MCM_CMP_LT = 0, MCM_CMP_LE, MCM_CMP_GT, MCM_CMP_GE, MCM_CMP_EQ, MCM_CMP_NE,
+       /* predicates (threshold ignored): the all-reductions isinteger(p) / isfinite.(p) (particles.jl:581-585) */
+       MCM_CMP_ISINTEGER, MCM_CMP_ISFINITE, MCM_CMP_ISNAN };
+/* rounding modes of round(Int, p, r) / mcm_round_int (Base.RoundingMode) */
+enum { MCM_RM_NEAREST = 0, MCM_RM_TOZERO, MCM_RM_UP, MCM_RM_DOWN, MCM_RM_TIESAWAY, MCM_RM_TIESUP, MCM_RM_FROMZERO };
 
 /* ======================= lifecycle / memory ================================ */
 int mcm_version(void);
@@ -128,6 +144,8 @@ int mcm_sync(void);
 const char* mcm_last_error(void);
 /* read (and optionally clear) the sticky numerical flags; synchronises */
 int mcm_check_flags(uint32_t* bits, int reset);
+/* clear only the sticky bits in `mask` (0x80000000 = BoundsError bit of the gathers); synchronises */
+int mcm_clear_flags(uint32_t mask);
 int mcm_device_info(int* sm_count, size_t* free_bytes, size_t* total_bytes);
 
 /* storage of one `particles` vector (replaces `Vector{T}(undef,N)`; every
@@ -236,6 +254,12 @@ int mcm_moments_use_bulk(int on);
 int mcm_reduce(int kind, int dtype, const void* in, size_t n, double* out_host);
 /* @prob p < a  -> count; (bymap.jl:128-136) */
 int mcm_count(int cmp, int dtype, const void* in, size_t n, double threshold, uint64_t* count_host);
+/* count of particles with a[i] cmp b[i] (cmp in MCM_CMP_LT..MCM_CMP_NE): Base.:(==)(p1, p2) = p1.particles ==
+ * p2.particles (particles.jl:488) and the :montecarlo comparison mode (particles.jl:512-515) without a temporary */
+int mcm_count2(int cmp, int dtype, const void* a, const void* b, size_t n, uint64_t* count_host);
+/* round(Int, p[, r]) (particles.jl:347-348; runtests.jl:471-473): out[i] = Int64(round(in[i], r)).  A NaN, an
+ * infinity or a value outside Int64 raises MCM_FLAG_DOMAIN (InexactError in Base) and stores INT64_MIN. */
+int mcm_round_int(int dtype, const void* in, int mode, int64_t* out, size_t n);
 /* merge two {n,mean,M2,min,max,sum} partials (Chan) — used across GPUs */
 int mcm_moments_merge(const double* a, const double* b, double* out);
 

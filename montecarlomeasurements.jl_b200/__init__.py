@@ -22,7 +22,9 @@ from .particles import (
     pquantile, pmedian, psort, psortperm, pcov, pcor, to_matrix,
     pgemm, pgemv, mul_, pdot, paxpy_,
     unsafe_comparisons, set_comparison_function, approx, lesssim, gtrsim,
-    check_domain, nparticles, particleeltype, flat_particles, is_particle_array,
+    check_domain, check_bounds, IntParticles, round_int, rem2pi, mod2pi, isinteger, iszero, isfinite, not_, fld, cld,
+    RoundNearest, RoundToZero, RoundUp, RoundDown, RoundNearestTiesAway, RoundNearestTiesUp, RoundFromZero,
+    nparticles, particleeltype, flat_particles, is_particle_array,
 )
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
                        mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower)

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mcm_sync": (_i, []),
     "mcm_last_error": (C.c_char_p, []),
     "mcm_check_flags": (_i, [C.POINTER(C.c_uint32), _i]),
+    "mcm_clear_flags": (_i, [C.c_uint32]),
     "mcm_device_info": (_i, [C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "mcm_alloc": (_i, [_vpp, _sz]),
     "mcm_free": (_i, [_vp]),
@@ -108,6 +109,8 @@ SIGNATURES = {
     "mcm_moments_use_bulk": (_i, [_i]),
     "mcm_reduce": (_i, [_i, _i, _vp, _sz, _dp]),
     "mcm_count": (_i, [_i, _i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
+    "mcm_count2": (_i, [_i, _i, _vp, _vp, _sz, C.POINTER(C.c_uint64)]),
+    "mcm_round_int": (_i, [_i, _vp, _i, _vp, _sz]),
     "mcm_moments_merge": (_i, [_dp, _dp, _dp]),
     "mcm_gram": (_i, [_i, _vpp, _i, _sz, _i, _dp, _vp, _vp]),
     "mcm_gram_use_tensor": (_i, [_i]),

@@ -42,7 +42,8 @@ def _deps_hash(src: str) -> str:
     h = hashlib.sha256()
     h.update(" ".join(NVCC_FLAGS).encode())
     for f in sorted(os.listdir(CSRC)):
-        if f == src or f.endswith((".cuh", ".h")):
+        # every non-.cu file is a potential include (.cuh, .h, .inc coefficient tables, the generated .def registry)
+        if f == src or (os.path.isfile(os.path.join(CSRC, f)) and not f.endswith(".cu")):
             with open(os.path.join(CSRC, f), "rb") as fh:
                 h.update(fh.read())
     with open(os.path.join(HERE, "..", "include", "mcm_b200.h"), "rb") as fh:

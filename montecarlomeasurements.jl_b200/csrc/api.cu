@@ -115,6 +115,19 @@ extern "C" int mcm_sync(void) {
   return MCM_OK;
 }
 
+// clear only the sticky bits in `mask` (stream-ordered); the others keep waiting for their own check
+extern "C" int mcm_clear_flags(uint32_t mask) {
+  MCM_NEED_INIT();
+  Ctx& c = ctx();
+  MCM_CUDA(cudaMemcpyAsync(c.h_pinned, c.d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  uint32_t* h = static_cast<uint32_t*>(c.h_pinned);
+  *h &= ~mask;
+  MCM_CUDA(cudaMemcpyAsync(c.d_flags, h, sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  return MCM_OK;
+}
+
 extern "C" int mcm_check_flags(uint32_t* bits, int reset) {
   MCM_NEED_INIT();
   Ctx& c = ctx();

@@ -454,9 +454,13 @@ __device__ __forceinline__ void exec_range(Pack<T>* sm, const ChainParams& p, in
       MCM_U(MCM_U_ABS) MCM_U(MCM_U_SQRT) MCM_U(MCM_U_RAD2DEG) MCM_U(MCM_U_DEG2RAD) MCM_U(MCM_U_FLOAT)
       MCM_U(MCM_U_ROUND) MCM_U(MCM_U_FLOOR) MCM_U(MCM_U_CEIL) MCM_U(MCM_U_TRUNC) MCM_U(MCM_U_INV)
       MCM_U(MCM_U_SQR) MCM_U(MCM_U_CUBE)
+      MCM_U(MCM_U_ROUND_TIESAWAY) MCM_U(MCM_U_ROUND_TIESUP) MCM_U(MCM_U_ROUND_FROMZERO)
+      MCM_U(MCM_U_REM2PI_NEAREST) MCM_U(MCM_U_REM2PI_TOZERO) MCM_U(MCM_U_REM2PI_DOWN) MCM_U(MCM_U_REM2PI_UP)
       MCM_B(MCM_B_ADD) MCM_B(MCM_B_SUB) MCM_B(MCM_B_MUL) MCM_B(MCM_B_DIV) MCM_B(MCM_B_POW)
       MCM_B(MCM_B_MAX) MCM_B(MCM_B_MIN) MCM_B(MCM_B_MOD) MCM_B(MCM_B_MOD1) MCM_B(MCM_B_ATAN2)
       MCM_B(MCM_B_ATAND2) MCM_B(MCM_B_ADD_SUM) MCM_B(MCM_B_HYPOT) MCM_B(MCM_B_REM) MCM_B(MCM_B_FDIV)
+      MCM_B(MCM_B_REM_NEAREST) MCM_B(MCM_B_REM_DOWN) MCM_B(MCM_B_REM_UP) MCM_B(MCM_B_REM_FROMZERO)
+      MCM_B(MCM_B_DIV_NEAREST) MCM_B(MCM_B_DIV_DOWN) MCM_B(MCM_B_DIV_UP) MCM_B(MCM_B_DIV_FROMZERO)
       MCM_T(MCM_T_CLAMP) MCM_T(MCM_T_MULADD) MCM_T(MCM_T_MUL_ADD)
       MCM_OPC(MCM_TAPE_POWI)
       default: break;  // MOV

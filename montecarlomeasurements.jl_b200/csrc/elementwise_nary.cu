@@ -45,6 +45,8 @@ static int dispatch_binary(int op, const void* a, double sa, const void* b, doub
     MCM_CASE(MCM_B_POW) MCM_CASE(MCM_B_MAX) MCM_CASE(MCM_B_MIN) MCM_CASE(MCM_B_MOD)
     MCM_CASE(MCM_B_MOD1) MCM_CASE(MCM_B_ATAN2) MCM_CASE(MCM_B_ATAND2) MCM_CASE(MCM_B_ADD_SUM)
     MCM_CASE(MCM_B_HYPOT) MCM_CASE(MCM_B_REM) MCM_CASE(MCM_B_FDIV)
+    MCM_CASE(MCM_B_REM_NEAREST) MCM_CASE(MCM_B_REM_DOWN) MCM_CASE(MCM_B_REM_UP) MCM_CASE(MCM_B_REM_FROMZERO)
+    MCM_CASE(MCM_B_DIV_NEAREST) MCM_CASE(MCM_B_DIV_DOWN) MCM_CASE(MCM_B_DIV_UP) MCM_CASE(MCM_B_DIV_FROMZERO)
 #undef MCM_CASE
     case MCM_B_RATDIV:
       return fail(MCM_ERR_UNSUPPORTED, "mcm_binary: `//` has no floating-point method (MethodError in Base)");

@@ -20,7 +20,8 @@ constexpr int unary_unroll() {
   return (OP == MCM_U_PLUS || OP == MCM_U_NEG || OP == MCM_U_ZERO || OP == MCM_U_SIGN ||
           OP == MCM_U_ABS || OP == MCM_U_RAD2DEG || OP == MCM_U_DEG2RAD || OP == MCM_U_FLOAT ||
           OP == MCM_U_ROUND || OP == MCM_U_FLOOR || OP == MCM_U_CEIL || OP == MCM_U_TRUNC ||
-          OP == MCM_U_SQR || OP == MCM_U_CUBE)
+          OP == MCM_U_SQR || OP == MCM_U_CUBE || OP == MCM_U_ROUND_TIESAWAY || OP == MCM_U_ROUND_TIESUP ||
+          OP == MCM_U_ROUND_FROMZERO)
              ? 4
              : 2;
 }
@@ -50,6 +51,8 @@ static int dispatch_unary(int op, const void* in, void* out, size_t n) {
     MCM_CASE(MCM_U_RAD2DEG) MCM_CASE(MCM_U_DEG2RAD) MCM_CASE(MCM_U_FLOAT) MCM_CASE(MCM_U_ROUND)
     MCM_CASE(MCM_U_FLOOR) MCM_CASE(MCM_U_CEIL) MCM_CASE(MCM_U_TRUNC) MCM_CASE(MCM_U_INV)
     MCM_CASE(MCM_U_SQR) MCM_CASE(MCM_U_CUBE)
+    MCM_CASE(MCM_U_ROUND_TIESAWAY) MCM_CASE(MCM_U_ROUND_TIESUP) MCM_CASE(MCM_U_ROUND_FROMZERO)
+    MCM_CASE(MCM_U_REM2PI_NEAREST) MCM_CASE(MCM_U_REM2PI_TOZERO) MCM_CASE(MCM_U_REM2PI_DOWN) MCM_CASE(MCM_U_REM2PI_UP)
 #undef MCM_CASE
     default: return fail(MCM_ERR_INVALID, "mcm_unary: unknown op %d", op);
   }

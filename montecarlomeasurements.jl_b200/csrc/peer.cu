@@ -82,7 +82,19 @@ k_gather_peer(const __grid_constant__ PeerTable tab, const __grid_constant__ Var
   bool oob = false;
   for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n_out; j += stride) {
     const unsigned long long g = (unsigned long long)idx[j];
-    if (g >= n_global) { oob = true; continue; }
+    if (g >= n_global) {                     // BoundsError: flag, and NaN outputs so the error cannot pass silently
+      oob = true;
+#pragma unroll
+      for (int k = 0; k < PW_GROUPS_PER_BLOCK; ++k)
+        if (gfirst + k < ngroups) {
+#pragma unroll
+          for (int s = 0; s < PW_IL; ++s) {
+            T* o = static_cast<T*>(outs.p[(gfirst + k) * PW_IL + s]);
+            if (o) o[j] = (T)__builtin_nan("");
+          }
+        }
+      continue;
+    }
     const unsigned owner = (unsigned)(g / per);
     const size_t i = (size_t)(g - (unsigned long long)owner * per);
     const T* src = static_cast<const T*>(tab.p[owner]);

@@ -4,6 +4,7 @@
 // src/bymap.jl:128-136 (@prob == mean(p.particles .< a)).
 #include <math.h>
 #include "mcm_moments.cuh"
+#include "mcm_math.cuh"
 
 namespace mcm {
 
@@ -147,12 +148,61 @@ k_count(const T* __restrict__ in, size_t n, T thr, unsigned long long* out) {
     else if constexpr (CMP == MCM_CMP_GT) b = x > thr;
     else if constexpr (CMP == MCM_CMP_GE) b = x >= thr;
     else if constexpr (CMP == MCM_CMP_EQ) b = x == thr;
-    else b = x != thr;
+    else if constexpr (CMP == MCM_CMP_NE) b = x != thr;
+    else if constexpr (CMP == MCM_CMP_ISINTEGER) b = (x - x == T(0)) && (x == (sizeof(T) == 8 ? (T)trunc((double)x) : (T)truncf((float)x)));
+    else if constexpr (CMP == MCM_CMP_ISFINITE) b = (x - x == T(0));
+    else b = x != x;
     c += b ? 1ull : 0ull;
   }
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// a[i] cmp b[i]: p1 == p2 compares the particle vectors (particles.jl:488); :montecarlo comparisons (:512-515)
+template <typename T, int CMP>
+__global__ void __launch_bounds__(kThreads)
+k_count2(const T* __restrict__ a, const T* __restrict__ b, size_t n, unsigned long long* out) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  unsigned long long c = 0;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const T x = a[i], y = b[i];
+    bool r;
+    if constexpr (CMP == MCM_CMP_LT) r = x < y;
+    else if constexpr (CMP == MCM_CMP_LE) r = x <= y;
+    else if constexpr (CMP == MCM_CMP_GT) r = x > y;
+    else if constexpr (CMP == MCM_CMP_GE) r = x >= y;
+    else if constexpr (CMP == MCM_CMP_EQ) r = x == y;
+    else r = x != y;
+    c += r ? 1ull : 0ull;
+  }
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// round(Int, p, r) (particles.jl:347-348): Int64(round(x, r)); InexactError -> DOMAIN flag, INT64_MIN stored
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_round_int(const T* __restrict__ in, int mode, long long* __restrict__ out, size_t n, uint32_t* flags) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  bool bad = false;
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+    const double x = (double)in[i];
+    double r;
+    switch (mode) {
+      case MCM_RM_NEAREST: r = rint(x); break;
+      case MCM_RM_TOZERO: r = trunc(x); break;
+      case MCM_RM_UP: r = ceil(x); break;
+      case MCM_RM_DOWN: r = floor(x); break;
+      case MCM_RM_TIESAWAY: r = math::m_round_tiesaway(in[i]); break;
+      case MCM_RM_TIESUP: r = math::m_round_tiesup(in[i]); break;
+      default: r = math::m_round_fromzero(in[i]); break;
+    }
+    if (r >= -9223372036854775808.0 && r < 9223372036854775808.0) out[i] = (long long)r;
+    else { out[i] = (long long)0x8000000000000000ull; bad = true; }
+  }
+  if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
 }
 
 static int g_use_bulk = 1;  // mcm_moments_use_bulk(0) forces the LDG kernel (A/B measurements, tests)
@@ -282,9 +332,26 @@ static int run_count(int cmp, const T* in, size_t n, T thr, unsigned long long* 
 #define MCM_CASE(K) \
   case K: k_count<T, K><<<grid, kThreads, 0, c.stream>>>(in, n, thr, d_out); break;
     MCM_CASE(MCM_CMP_LT) MCM_CASE(MCM_CMP_LE) MCM_CASE(MCM_CMP_GT) MCM_CASE(MCM_CMP_GE)
-    MCM_CASE(MCM_CMP_EQ) MCM_CASE(MCM_CMP_NE)
+    MCM_CASE(MCM_CMP_EQ) MCM_CASE(MCM_CMP_NE) MCM_CASE(MCM_CMP_ISINTEGER) MCM_CASE(MCM_CMP_ISFINITE)
+    MCM_CASE(MCM_CMP_ISNAN)
 #undef MCM_CASE
     default: return fail(MCM_ERR_INVALID, "mcm_count: unknown comparison %d", cmp);
+  }
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+
+template <typename T>
+static int run_count2(int cmp, const T* a, const T* b, size_t n, unsigned long long* d_out) {
+  Ctx& c = ctx();
+  const int grid = stream_grid(n, 8, 8);
+  switch (cmp) {
+#define MCM_CASE(K) \
+  case K: k_count2<T, K><<<grid, kThreads, 0, c.stream>>>(a, b, n, d_out); break;
+    MCM_CASE(MCM_CMP_LT) MCM_CASE(MCM_CMP_LE) MCM_CASE(MCM_CMP_GT) MCM_CASE(MCM_CMP_GE)
+    MCM_CASE(MCM_CMP_EQ) MCM_CASE(MCM_CMP_NE)
+#undef MCM_CASE
+    default: return fail(MCM_ERR_INVALID, "mcm_count2: unknown comparison %d", cmp);
   }
   MCM_CHECK_LAUNCH();
   return MCM_OK;
@@ -309,5 +376,41 @@ extern "C" int mcm_count(int cmp, int dtype, const void* in, size_t n, double th
   uint64_t bits;
   memcpy(&bits, &tmp, 8);
   *count_host = bits;
+  return MCM_OK;
+}
+
+extern "C" int mcm_count2(int cmp, int dtype, const void* a, const void* b, size_t n, uint64_t* count_host) {
+  MCM_NEED_INIT();
+  if (!count_host || (n && (!a || !b))) return fail(MCM_ERR_INVALID, "mcm_count2: null pointer");
+  Ctx& c = ctx();
+  unsigned long long* d_out = reinterpret_cast<unsigned long long*>(moments_result_slot() + 8);
+  MCM_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), c.stream));
+  int rc = MCM_OK;
+  if (n) {
+    if (dtype == MCM_F64) rc = run_count2<double>(cmp, (const double*)a, (const double*)b, n, d_out);
+    else if (dtype == MCM_F32) rc = run_count2<float>(cmp, (const float*)a, (const float*)b, n, d_out);
+    else return fail(MCM_ERR_INVALID, "mcm_count2: bad dtype %d", dtype);
+  }
+  if (rc) return rc;
+  double tmp;
+  rc = read_back(&tmp, reinterpret_cast<const double*>(d_out), 1);
+  if (rc) return rc;
+  uint64_t bits;
+  memcpy(&bits, &tmp, 8);
+  *count_host = bits;
+  return MCM_OK;
+}
+
+extern "C" int mcm_round_int(int dtype, const void* in, int mode, int64_t* out, size_t n) {
+  MCM_NEED_INIT();
+  if (n && (!in || !out)) return fail(MCM_ERR_INVALID, "mcm_round_int: null pointer");
+  if (mode < MCM_RM_NEAREST || mode > MCM_RM_FROMZERO) return fail(MCM_ERR_INVALID, "mcm_round_int: unknown rounding mode %d", mode);
+  if (n == 0) return MCM_OK;
+  Ctx& c = ctx();
+  const int grid = stream_grid(n, 4, 8);
+  if (dtype == MCM_F64) k_round_int<double><<<grid, kThreads, 0, c.stream>>>((const double*)in, mode, (long long*)out, n, c.d_flags);
+  else if (dtype == MCM_F32) k_round_int<float><<<grid, kThreads, 0, c.stream>>>((const float*)in, mode, (long long*)out, n, c.d_flags);
+  else return fail(MCM_ERR_INVALID, "mcm_round_int: bad dtype %d", dtype);
+  MCM_CHECK_LAUNCH();
   return MCM_OK;
 }

@@ -242,7 +242,11 @@ k_gather(const T* __restrict__ src, const int64_t* __restrict__ idx, T* __restri
   const size_t stride = (size_t)gridDim.x * kThreads;
   for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n_draw; j += stride) {
     const int64_t i = idx[j];
-    if (i < 0 || (size_t)i >= n_src) { atomicOr(flags, 0x80000000u); continue; }  // BoundsError
+    if (i < 0 || (size_t)i >= n_src) {       // BoundsError in the reference: sticky flag, and a NaN so it cannot pass silently
+      atomicOr(flags, 0x80000000u);
+      out[j] = (T)__builtin_nan("");
+      continue;
+    }
     out[j] = __ldg(src + i);
   }
 }
@@ -277,10 +281,10 @@ k_gather_multi(const T* const* __restrict__ srcs, T* const* __restrict__ outs, i
     T* __restrict__ out = outs[v];
     T val[GM_IPT];
 #pragma unroll
-    for (int u = 0; u < GM_IPT; ++u) val[u] = ok[u] ? __ldg(src + ii[u]) : T(0);
+    for (int u = 0; u < GM_IPT; ++u) val[u] = ok[u] ? __ldg(src + ii[u]) : (T)__builtin_nan("");
 #pragma unroll
     for (int u = 0; u < GM_IPT; ++u)
-      if (ok[u]) __stcs(out + base + (size_t)u * kThreads, val[u]);
+      if (base + (size_t)u * kThreads < n_draw) __stcs(out + base + (size_t)u * kThreads, val[u]);
   }
 }
 

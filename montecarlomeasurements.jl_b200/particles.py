@@ -142,7 +142,10 @@ class Particles:
     def __rtruediv__(self, o): return _binary("DIV", o, self)
     def __mod__(self, o): return _binary("MOD", self, o)
     def __rmod__(self, o): return _binary("MOD", o, self)
-    def __floordiv__(self, o): return _binary("FDIV", self, o)
+    # Python's `//` is FLOORED division (pairs with `%` = mod): Julia's fld = div(x, y, RoundDown).
+    # Julia's truncating `÷` is div(p, y) below.
+    def __floordiv__(self, o): return _binary("DIV_DOWN", self, o)
+    def __rfloordiv__(self, o): return _binary("DIV_DOWN", o, self)
     def __neg__(self): return _unary("NEG", self)
     def __pos__(self): return _unary("PLUS", self)
     def __abs__(self): return _unary("ABS", self)
@@ -172,8 +175,8 @@ class Particles:
         if isinstance(o, Particles):
             if o.N != self.N or o.dtype != self.dtype:
                 return False
-            # all(p1.particles .== p2.particles): x - y == 0 for every particle (NaN never equal)
-            return _count("EQ", _binary("SUB", self, o), 0.0) == self.N
+            # all(p1.particles .== p2.particles): one two-input count, no temporary (Inf == Inf, NaN never equal)
+            return _count2("EQ", self, o) == self.N
         return NotImplemented
 
     __hash__ = object.__hash__
@@ -297,9 +300,17 @@ def _ternary(name: str, a, b, c):
     return out
 
 
-def _count(cmp: str, p: Particles, thr: float) -> int:
+def _count(cmp: str, p: Particles, thr: float = 0.0) -> int:
     c = C.c_uint64()
     L.check(L.lib().mcm_count(E["MCM_CMP_" + cmp], p.dtype, C.c_void_p(p.ptr), p.N, float(thr), C.byref(c)))
+    return int(c.value)
+
+
+def _count2(cmp: str, a: Particles, b: Particles) -> int:
+    """#{i : a[i] cmp b[i]} in one pass over both vectors (mcm_count2)."""
+    a, b = _promote(a, b)
+    c = C.c_uint64()
+    L.check(L.lib().mcm_count2(E["MCM_CMP_" + cmp], a.dtype, C.c_void_p(a.ptr), C.c_void_p(b.ptr), a.N, C.byref(c)))
     return int(c.value)
 
 
@@ -315,6 +326,11 @@ _HOST_UNARY = {
     "ZERO": lambda x: 0.0, "SIGN": lambda x: (x > 0) - (x < 0), "ABS": abs, "SQRT": math.sqrt,
     "RAD2DEG": math.degrees, "DEG2RAD": math.radians, "FLOAT": float, "ROUND": round, "FLOOR": math.floor,
     "CEIL": math.ceil, "TRUNC": math.trunc, "INV": lambda x: 1.0 / x, "SQR": lambda x: x * x, "CUBE": lambda x: x * x * x,
+    "ROUND_TIESAWAY": lambda x: math.copysign(math.floor(abs(x) + 0.5), x),
+    "ROUND_TIESUP": lambda x: math.copysign(math.floor(x + 0.5), x),
+    "ROUND_FROMZERO": lambda x: math.floor(x) if x < 0 else math.ceil(x),
+    "REM2PI_NEAREST": lambda x: math.remainder(x, 2 * math.pi), "REM2PI_DOWN": lambda x: x % (2 * math.pi),
+    "REM2PI_TOZERO": lambda x: math.fmod(x, 2 * math.pi), "REM2PI_UP": lambda x: -((-x) % (2 * math.pi)),
 }
 
 
@@ -346,17 +362,117 @@ def atand(y, x=None):
     return _unary("ATAND", y) if x is None else _binary("ATAND2", y, x)
 
 
-def round_(p):
-    """round(p) with RoundNearest (particles.jl:346)."""
-    return _unary("ROUND", p)
+# ---- RoundingMode forms (particles.jl:346-348, 358-359, 410-414; runtests.jl:470-483) -------------------------
+RoundNearest, RoundToZero, RoundUp, RoundDown = "RoundNearest", "RoundToZero", "RoundUp", "RoundDown"
+RoundNearestTiesAway, RoundNearestTiesUp, RoundFromZero = "RoundNearestTiesAway", "RoundNearestTiesUp", "RoundFromZero"
+_ROUND_OP = {RoundNearest: "ROUND", RoundToZero: "TRUNC", RoundUp: "CEIL", RoundDown: "FLOOR",
+             RoundNearestTiesAway: "ROUND_TIESAWAY", RoundNearestTiesUp: "ROUND_TIESUP", RoundFromZero: "ROUND_FROMZERO"}
+_RM_CODE = {RoundNearest: "NEAREST", RoundToZero: "TOZERO", RoundUp: "UP", RoundDown: "DOWN",
+            RoundNearestTiesAway: "TIESAWAY", RoundNearestTiesUp: "TIESUP", RoundFromZero: "FROMZERO"}
+_REM_OP = {RoundToZero: "REM", RoundNearest: "REM_NEAREST", RoundDown: "REM_DOWN", RoundUp: "REM_UP",
+           RoundFromZero: "REM_FROMZERO"}
+_DIV_OP = {RoundToZero: "FDIV", RoundNearest: "DIV_NEAREST", RoundDown: "DIV_DOWN", RoundUp: "DIV_UP",
+           RoundFromZero: "DIV_FROMZERO"}
+_REM2PI_OP = {RoundNearest: "REM2PI_NEAREST", RoundToZero: "REM2PI_TOZERO", RoundDown: "REM2PI_DOWN", RoundUp: "REM2PI_UP"}
+
+
+def _mode(table, r, what):
+    if r not in table:
+        raise L.MethodError(L.MCM_ERR_UNSUPPORTED, f"{what}: unsupported rounding mode {r!r}")
+    return table[r]
+
+
+class IntParticles:
+    """`Particles{Int,N}` as produced by round(Int, p[, r]) (particles.jl:347-348): N Int64 samples in HBM.
+    Integer particles are host-only in the reference; on device they exist as the result of rounding
+    (to_numpy / comparison with an integer / float(q) -> Particles{Float64})."""
+    __slots__ = ("index", "N")
+
+    def __init__(self, index: "DeviceIndex"):
+        self.index, self.N = index, index.n
+
+    def to_numpy(self) -> np.ndarray:
+        return self.index.to_numpy()
+
+    @property
+    def particles(self):
+        return self.to_numpy()
+
+    def __eq__(self, o):
+        if isinstance(o, numbers.Integral):       # p == 0 (runtests.jl:471): every particle equals o
+            return bool(np.all(self.to_numpy() == int(o)))
+        if isinstance(o, IntParticles):
+            return o.N == self.N and bool(np.array_equal(self.to_numpy(), o.to_numpy()))
+        return NotImplemented
+
+    __hash__ = object.__hash__
+
+    def float(self) -> "Particles":
+        return Particles(self.to_numpy().astype(np.float64))
+
+
+def round_(p, r=RoundNearest):
+    """round(p) / round(p, r::RoundingMode) (particles.jl:346)."""
+    return _unary(_mode(_ROUND_OP, r, "round"), p)
+
+
+def round_int(p: Particles, r=RoundNearest) -> IntParticles:
+    """round(Int, p[, r]) (particles.jl:347-348): Int64 particles; NaN / Inf / overflow raise DomainError at
+    check_domain() (InexactError in Base)."""
+    d = DeviceIndex(p.N)
+    L.check(L.lib().mcm_round_int(p.dtype, C.c_void_p(p.ptr), E["MCM_RM_" + _mode(_RM_CODE, r, "round(Int, p, r)")],
+                                  C.c_void_p(d.ptr), p.N))
+    return IntParticles(d)
+
+
+def rem2pi(p, r=RoundNearest):
+    """rem2pi(p, r) (particles.jl:359): correctly rounded remainder modulo 2pi for every finite argument."""
+    return _unary(_mode(_REM2PI_OP, r, "rem2pi"), p)
+
+
+def mod2pi(p):
+    """mod2pi(p) = rem2pi(p, RoundDown) (runtests.jl:476)."""
+    return _unary("REM2PI_DOWN", p)
+
+
+def isinteger(p: Particles) -> bool:
+    """all(isinteger, p.particles) (particles.jl:583)."""
+    return _count("ISINTEGER", p) == p.N
+
+
+def iszero(p: Particles, tol=None) -> bool:
+    """iszero(p) = all(iszero, p.particles); iszero(p, tol) = abs(mean(p.particles)) < tol (particles.jl:584-585)."""
+    if tol is not None:
+        return abs(pmean(p)) < tol
+    return _count("EQ", p, 0.0) == p.N
+
+
+def not_(p: Particles) -> bool:
+    """!p = all(p.particles .== 0) (particles.jl:581)."""
+    return _count("EQ", p, 0.0) == p.N
+
+
+def isfinite(p: Particles) -> bool:
+    """isfinite(p) = isfinite(pmean(p)) (particles.jl:345)."""
+    return math.isfinite(pmean(p))
 
 
 def maximum(a, b): return _binary("MAX", a, b)   # Base.max(p1, p2)
 def minimum(a, b): return _binary("MIN", a, b)   # Base.min(p1, p2)
 def mod(a, b): return _binary("MOD", a, b)
 def mod1(a, b): return _binary("MOD1", a, b)
-def rem(a, b): return _binary("REM", a, b)        # particles.jl:354-355
-def div(a, b): return _binary("FDIV", a, b)       # particles.jl:356-357
+def rem(a, b, r=RoundToZero):
+    """rem(p, y) / rem(p, y, r::RoundingMode) (particles.jl:354-355; Base div.jl for the modes)."""
+    return _binary(_mode(_REM_OP, r, "rem"), a, b)
+
+
+def div(a, b, r=RoundToZero):
+    """div(p, y) = round((x - rem(x, y))/y) and div(p, y, r) (particles.jl:356-358, 410-414)."""
+    return _binary(_mode(_DIV_OP, r, "div"), a, b)
+
+
+def fld(a, b): return _binary("DIV_DOWN", a, b)   # floored division (Python's //)
+def cld(a, b): return _binary("DIV_UP", a, b)
 def hypot(a, b): return _binary("HYPOT", a, b)
 def add_sum(a, b): return _binary("ADD_SUM", a, b)
 def clamp(x, lo, hi): return _ternary("CLAMP", x, lo, hi)
@@ -565,10 +681,21 @@ def pmedian(p):
     return float(a / 2 + b / 2)  # Statistics.middle(x, y) = x/2 + y/2
 
 
+def check_bounds():
+    """Raise IndexError if a gather met an index outside 1:N since the last check (BoundsError in the reference,
+    resampling.jl:77,82).  Called after every gather with caller-supplied indices; synchronises."""
+    bits = C.c_uint32()
+    L.check(L.lib().mcm_check_flags(C.byref(bits), 0))
+    if bits.value & 0x80000000:
+        L.check(L.lib().mcm_clear_flags(0x80000000))
+        raise IndexError("BoundsError: resample/gather index out of range")
+
+
 def _pick(p: Particles, idx):
     idx_dev = _upload_i64(np.asarray(idx, dtype=np.int64))
     out = _empty(len(idx), p.dtype)
     L.check(L.lib().mcm_gather(p.dtype, C.c_void_p(p.ptr), C.c_void_p(idx_dev.ptr), C.c_void_p(out.ptr), len(idx), p.N))
+    check_bounds()
     return out.to_numpy().astype(np.float64)
 
 
@@ -740,9 +867,13 @@ def _compare(a, b, op: str) -> bool:
         if not any(res): return False
         raise ComparisonError("Comparison of uncertain values using comparison mode safe failed.")
     # montecarlo: elementwise all / none (particles.jl:512-515)
-    d = _binary("SUB", a, b)
-    N = d.N
-    c = _count("LT" if op == "<" else "LE", d, 0.0)
+    cmp = "LT" if op == "<" else "LE"
+    if isinstance(a, Particles) and isinstance(b, Particles):
+        N, c = a.N, _count2(cmp, a, b)
+    elif isinstance(a, Particles):
+        N, c = a.N, _count(cmp, a, float(b))
+    else:
+        N, c = b.N, _count("GT" if op == "<" else "GE", b, float(a))
     if c == N: return True
     if c == 0: return False
     raise ComparisonError("Comparison of uncertain values using comparison mode montecarlo failed.")

@@ -44,6 +44,8 @@ def bootstrap(p, n: int | None = None, *, seed: int = 0, inds=None):
         srcs = (C.c_void_p * M)(*[C.c_void_p(q.ptr) for q in ps])
         dsts = (C.c_void_p * M)(*[C.c_void_p(q.ptr) for q in outs])
         L.check(L.lib().mcm_gather_multi(dt, srcs, dsts, M, C.c_void_p(idx.ptr), n, N))
+    if inds is not None:
+        P.check_bounds()          # caller-supplied indices: BoundsError like p.particles[inds] (resampling.jl:77,82)
     if single:
         return outs[0]
     if isinstance(p, np.ndarray):

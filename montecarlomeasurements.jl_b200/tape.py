@@ -278,10 +278,30 @@ def trace_loop(step, nstate: int, nparam: int, prologue=None) -> Tape:
     if len(new) != nstate:
         raise TapeError("step must return %d state values" % nstate)
     loc = lower(new, fixed, reserved, {id(x) for x in new})
+    # The write-back is a PARALLEL assignment state <- new: a step may return an old state value in another
+    # position ((a, b) -> (a + b, a), (a, b) -> (b, a)), so a move may not overwrite a slot that a later move
+    # still reads.  Emit moves whose destination no pending move reads; break cycles through a spare slot.
+    pending = {}
     for i, x in enumerate(new):
         src = t.const(x.imm) if x.kind == "const" else loc[id(x)]
         if src != i:
-            t.emit(T_MOV, i, src)
+            pending[i] = src
+    while pending:
+        ready = [d for d in pending if d not in pending.values()]
+        if ready:
+            for d in ready:
+                t.emit(T_MOV, d, pending.pop(d))
+            continue
+        # only cycles are left: park one source in a slot nobody reads or writes any more
+        busy = set(pending) | set(pending.values()) | set(range(reserved))
+        spare = [s for s in range(reserved, NSLOTS) if s not in busy]
+        if not spare:
+            raise TapeError("no spare slot to resolve a cyclic state update")
+        d = next(iter(pending))
+        t.emit(T_MOV, spare[0], d)
+        for k, s in pending.items():
+            if s == d:
+                pending[k] = spare[0]
     t.loop_end = len(t.ins)
     for i in range(nstate):
         t.emit(T_STORE, i, i)

@@ -46,7 +46,17 @@ static double j_mod(double x, double y) {
 static double j_mod1(double x, double y) { double m = j_mod(x, y); return m == 0 ? y : m; }
 static double j_fdiv(double x, double y) { return rint((x - fmod(x, y)) / y); }
 static double j_clamp(double x, double lo, double hi) { return x > hi ? hi : (x < lo ? lo : x); }
+/* round(x, r) for the modes beyond Nearest/ToZero/Up/Down (Base floatfuncs.jl); rem/div with a RoundingMode
+ * (Base div.jl: rem(x,y,RoundDown) = mod(x,y), RoundUp = mod(x,-y), RoundNearest = IEEE remainder, RoundFromZero =
+ * RoundUp when signs agree else RoundDown; div(x,y,r) = round((x - rem(x,y,r))/y)) — particles.jl:346,358,410-414 */
+static double j_round_tiesaway(double x) { double y = trunc(x); return x == y ? y : trunc(2 * x - y); }
+static double j_round_tiesup(double x) { const double e = 0x1p-53; return copysign(floor((x + (0.25 - e)) + (0.25 + e)), x); }
+static double j_round_fromzero(double x) { return signbit(x) ? floor(x) : ceil(x); }
+static double j_rem_up(double x, double y);
+static double j_rem_fromzero(double x, double y);
 
+static double j_rem_up(double x, double y) { return j_mod(x, -y); }
+static double j_rem_fromzero(double x, double y) { return signbit(x) == signbit(y) ? j_rem_up(x, y) : j_mod(x, y); }
 static float jf_sign(float x) { return x < 0 ? -1.0f : (x > 0 ? 1.0f : x); }
 static float jf_max(float x, float y) { float d = x - y; float a = signbit(d) ? y : x; return (isnan(x) || isnan(y)) ? d : a; }
 static float jf_min(float x, float y) { float d = x - y; float a = signbit(d) ? x : y; return (isnan(x) || isnan(y)) ? d : a; }
@@ -58,6 +68,11 @@ static float jf_mod(float x, float y) {
 }
 static float jf_mod1(float x, float y) { float m = jf_mod(x, y); return m == 0 ? y : m; }
 static float jf_fdiv(float x, float y) { return rintf((x - fmodf(x, y)) / y); }
+static float jf_round_tiesaway(float x) { float y = truncf(x); return x == y ? y : truncf(2 * x - y); }
+static float jf_round_tiesup(float x) { const float e = 0x1p-24f; return copysignf(floorf((x + (0.25f - e)) + (0.25f + e)), x); }
+static float jf_round_fromzero(float x) { return signbit(x) ? floorf(x) : ceilf(x); }
+static float jf_rem_up(float x, float y) { return jf_mod(x, -y); }
+static float jf_rem_fromzero(float x, float y) { return signbit(x) == signbit(y) ? jf_rem_up(x, y) : jf_mod(x, y); }
 
 /* sind/cosd: Base reduces in degrees exactly and converts with an extended pi/180;
  * long double evaluation of sin(x*pi/180) after an exact fmod is the arbiter here. */
@@ -146,6 +161,9 @@ static double u64(int op, double x) {
     case MCM_U_INV: return 1.0 / x;
     case MCM_U_SQR: return x * x;
     case MCM_U_CUBE: return x * x * x;
+    case MCM_U_ROUND_TIESAWAY: return j_round_tiesaway(x);
+    case MCM_U_ROUND_TIESUP: return j_round_tiesup(x);
+    case MCM_U_ROUND_FROMZERO: return j_round_fromzero(x);
     default: return NAN;
   }
 }
@@ -193,6 +211,9 @@ static float u32(int op, float x) {
     case MCM_U_INV: return 1.0f / x;
     case MCM_U_SQR: return x * x;
     case MCM_U_CUBE: return x * x * x;
+    case MCM_U_ROUND_TIESAWAY: return jf_round_tiesaway(x);
+    case MCM_U_ROUND_TIESUP: return jf_round_tiesup(x);
+    case MCM_U_ROUND_FROMZERO: return jf_round_fromzero(x);
     default: return NAN;
   }
 }
@@ -222,6 +243,14 @@ static double b64(int op, double x, double y) {
     case MCM_B_HYPOT: return hypot(x, y);
     case MCM_B_REM: return fmod(x, y);
     case MCM_B_FDIV: return j_fdiv(x, y);
+    case MCM_B_REM_NEAREST: return remainder(x, y);
+    case MCM_B_REM_DOWN: return j_mod(x, y);
+    case MCM_B_REM_UP: return j_rem_up(x, y);
+    case MCM_B_REM_FROMZERO: return j_rem_fromzero(x, y);
+    case MCM_B_DIV_NEAREST: return rint((x - remainder(x, y)) / y);
+    case MCM_B_DIV_DOWN: return rint((x - j_mod(x, y)) / y);
+    case MCM_B_DIV_UP: return rint((x - j_rem_up(x, y)) / y);
+    case MCM_B_DIV_FROMZERO: return rint((x - j_rem_fromzero(x, y)) / y);
     default: return NAN;
   }
 }
@@ -241,6 +270,14 @@ static float b32(int op, float x, float y) {
     case MCM_B_HYPOT: return hypotf(x, y);
     case MCM_B_REM: return fmodf(x, y);
     case MCM_B_FDIV: return jf_fdiv(x, y);
+    case MCM_B_REM_NEAREST: return remainderf(x, y);
+    case MCM_B_REM_DOWN: return jf_mod(x, y);
+    case MCM_B_REM_UP: return jf_rem_up(x, y);
+    case MCM_B_REM_FROMZERO: return jf_rem_fromzero(x, y);
+    case MCM_B_DIV_NEAREST: return rintf((x - remainderf(x, y)) / y);
+    case MCM_B_DIV_DOWN: return rintf((x - jf_mod(x, y)) / y);
+    case MCM_B_DIV_UP: return rintf((x - jf_rem_up(x, y)) / y);
+    case MCM_B_DIV_FROMZERO: return rintf((x - jf_rem_fromzero(x, y)) / y);
     default: return NAN;
   }
 }

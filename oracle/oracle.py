@@ -407,3 +407,34 @@ def with_nominal_mv(X: np.ndarray, vals: np.ndarray, joint: bool = False):
     else:
         k = julia_argmin((D * D).sum(axis=0))
     return [shuffle_and_insert(X[:, j], k, vals[j]) for j in range(X.shape[1])], k
+
+
+def rem2pi_truth(x: np.ndarray, mode: str = "RoundNearest") -> np.ndarray:
+    """rem2pi(x, r) (Base math.jl; src/particles.jl:359) computed exactly: x - 2pi*round_r(x/2pi) at 1600 bits,
+    rounded once to Float64.  Base's own algorithm (rem_pio2_kernel + add22condh on double-doubles) returns this
+    value except in near-tie cases; small arguments that Base passes through unchanged are passed through here too."""
+    import mpmath as mp
+    old = mp.mp.prec
+    mp.mp.prec = 1600
+    try:
+        twopi = 2 * mp.pi
+        out = np.empty(len(x))
+        for i, v in enumerate(np.asarray(x, dtype=np.float64)):
+            if not np.isfinite(v):
+                out[i] = np.nan
+                continue
+            X = mp.mpf(float(v))
+            if mode == "RoundNearest":
+                r = X if abs(v) < np.pi else X - mp.nint(X / twopi) * twopi
+            elif mode == "RoundToZero":
+                r = X if abs(v) <= 6.283185307179585 else mp.sign(X) * (abs(X) - mp.floor(abs(X) / twopi) * twopi)
+            elif mode == "RoundDown":
+                r = X if 0 <= v < 6.283185307179586 else X - mp.floor(X / twopi) * twopi
+            elif mode == "RoundUp":
+                r = X if -6.283185307179586 < v <= 0 else X - mp.ceil(X / twopi) * twopi
+            else:
+                raise ValueError(mode)
+            out[i] = float(r)
+        return out
+    finally:
+        mp.mp.prec = old

@@ -99,6 +99,29 @@ def test_loop_tape_pendulum_matches_host_rk4(m, orc):
     assert np.allclose(th1, th2, rtol=1e-13, atol=1e-15) and np.allclose(om1, om2, rtol=1e-13)
 
 
+@pytest.mark.parametrize("name,step,ref", [
+    ("fib", lambda a, b: (a + b, a), lambda a, b: (a + b, a)),
+    ("swap", lambda a, b: (b, a), lambda a, b: (b, a)),
+    ("rot3", lambda a, b, c: (b, c, a), lambda a, b, c: (b, c, a)),
+    ("mixed", lambda a, b, c: (c, a * b, a), lambda a, b, c: (c, a * b, a)),
+    ("keep", lambda a, b: (a, a + b), lambda a, b: (a, a + b)),
+])
+def test_loop_writeback_is_a_parallel_assignment(m, name, step, ref):
+    """(a, b) -> (a + b, a) and pure permutations read OLD state values (tape.py trace_loop)."""
+    from mcm_b200 import tape
+    E = m._lib.ENUMS
+    ns = step.__code__.co_argcount
+    t = tape.trace_loop(step, ns, 0)
+    rng = np.random.default_rng(5)
+    x0 = [rng.normal(size=9) for _ in range(ns)]
+    got = run_tape_numpy(t, [v.copy() for v in x0], E, reps=5)
+    want = [v.copy() for v in x0]
+    for _ in range(5):
+        want = list(ref(*want))
+    for g, w in zip(got, want):
+        assert np.array_equal(g, w), name
+
+
 def test_chain_registry_is_up_to_date():
     """csrc/chain_registry.def must be what scripts/gen_chain_registry.py generates from chains.py."""
     path = os.path.join(ROOT, "montecarlomeasurements.jl_b200", "csrc", "chain_registry.def")

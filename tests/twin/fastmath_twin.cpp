@@ -11,6 +11,7 @@ void twin_cos(const double* x, double* y, long n) { for (long i = 0; i < n; ++i)
 void twin_exp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::exp_f64(x[i]); }
 void twin_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::log_f64(x[i]); }
 void twin_pow(const double* x, const double* e, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::pow_f64(x[i], e[i]); }
+void twin_rem2pi(const double* x, int mode, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::rem2pi_f64(x[i], mode); }
 void twin_norminv(const double* p, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::norminv::norminvcdf(p[i]); }
 // max |y - f(x)| in ulps of the long-double reference (64-bit mantissa: resolves ~0.001 ulp)
 static double ulp_of(long double t) { double d = (double)fabsl(t); if (d == 0) return 4.9e-324; return nextafter(d, INFINITY) - d; }
