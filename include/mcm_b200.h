@@ -50,6 +50,7 @@ enum { MCM_F32 = 0, MCM_F64 = 1 };
 enum {
   MCM_FLAG_DOMAIN = 1u,     /* NaN produced from non-NaN input (sqrt(-1), log(-1), ...) */
   MCM_FLAG_NAN_QUANTILE = 2u, /* NaN met by quantile/sort (Statistics.quantile errors)    */
+  MCM_FLAG_COMM = 4u,         /* a rank never arrived in an in-kernel cross-rank merge (20 s)  */
   MCM_FLAG_BOUNDS = 0x80000000u /* gather index outside [0, N) (BoundsError, resampling.jl:77,82); the output is NaN */
 };
 
@@ -224,8 +225,21 @@ int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, in
               size_t n, int stats_slot, double* stats_out_host);
 
 /* Statistics of the most recent mcm_chain call made with stats_slot >= 0 and
- * stats_out_host == NULL (the launch is then fully asynchronous); synchronises. */
+ * stats_out_host == NULL (the launch is then fully asynchronous); waits for that launch only. */
 int mcm_chain_stats_fetch(double* stats_out_host);
+/* Deferred collection: mcm_chain_ticket() names the most recent statistics-producing launch; mcm_chain_stats_wait
+ * collects the statistics of any of the last 8 tickets, waiting only for that launch (the kernel's last CTA writes
+ * them into mapped pinned host memory, there is no copy to wait for) — step k's readback overlaps kernel k+1. */
+uint64_t mcm_chain_ticket(void);
+int mcm_chain_stats_wait(uint64_t ticket, double* stats_out_host);
+/* mcm_chain on a particle-SHARDED variable (one process per GPU): same arguments; the statistics are
+ * those of the GLOBAL particle set.  The last CTA stores this rank's partial into every rank's peer window (P2P
+ * stores over NVLink) and merges all partials in rank order: no NCCL launch, no host round trip, bit-identical
+ * results on all ranks.  COLLECTIVE when stats_slot >= 0 (same call order on every rank; needs mcm_comm_init). */
+int mcm_chain_sharded(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                      int reps, const double* consts, int nconst,
+                      const void* const* inputs, int nin, void* const* outputs, int nout,
+                      size_t n, int stats_slot, double* stats_out_host);
 
 /* Same as mcm_chain but inputs/outputs are HOST arrays (the `particles::Vector{T}` of an
  * ordinary reference Particles, types.jl:18): chunks are copied host->device, computed and
@@ -472,7 +486,7 @@ int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_h
 /* merge host-resident per-rank moments (e.g. mcm_chain's fused statistics) across ranks, in place */
 int mcm_moments_allmerge(double* inout_host6);
 /* sharded pquantile (particles.jl:316-323 over a particle index spread across GPUs): every rank passes its
- * shard (balanced to 1 %, >= 8192 particles, power-of-two rank count); all ranks return the quantiles of the
+ * shard (balanced to 1 %, >= 8192 particles, <= 64 ranks); all ranks return the quantiles of the
  * GLOBAL particle set, out_host[m*nq + i].  Sampled pivots (all-gather of 8192 sample keys per variable),
  * local streaming count/collect, radix select on all-reduced histograms; only the <= 2048 finalists per rank
  * group ever leave a GPU.  With a single rank this is mcm_quantile_batch. */

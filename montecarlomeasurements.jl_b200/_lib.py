@@ -102,6 +102,9 @@ SIGNATURES = {
     "mcm_lincomb": (_i, [_i, _i, _vpp, _dp, _vp, _sz]),
     "mcm_chain": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
     "mcm_chain_stats_fetch": (_i, [_dp]),
+    "mcm_chain_ticket": (C.c_uint64, []),
+    "mcm_chain_stats_wait": (_i, [C.c_uint64, _dp]),
+    "mcm_chain_sharded": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
     "mcm_chain_host": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
     "mcm_chain_last_engine": (_i, []),
     "mcm_chain_force_interpreter": (_i, [_i]),

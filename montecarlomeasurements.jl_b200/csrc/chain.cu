@@ -256,7 +256,7 @@ __device__ __noinline__ bool replay_exact(const ChainParams& p, size_t j, size_t
 template <class TP, typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads, MCM_CHAIN_MIN_CTAS)
 k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
-               uint32_t* flags) {
+               uint32_t* flags, const __grid_constant__ MomExchange px) {
   constexpr int W = MCM_CHAIN_W;
   constexpr int PV = Pack<T>::N;
   constexpr int V = W * PV;
@@ -321,7 +321,7 @@ k_chain_static(const __grid_constant__ ChainParams p, Mom* partials, unsigned in
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
   if constexpr (STATS) {
     Mom m = mom_block_reduce(ms_finish(acc));
-    mom_grid_finish(m, partials, ticket, stats_out);
+    mom_grid_finish(m, partials, ticket, stats_out, &px);
   }
 }
 
@@ -359,8 +359,9 @@ static bool tape_matches(const ChainParams& p) {
   return true;
 }
 
+MomExchange mom_exchange_none();
 template <class TP, typename T>
-static int launch_static(const ChainParams& p, bool stats, double* stats_dev) {
+static int launch_static(const ChainParams& p, bool stats, double* stats_dev, const MomExchange& px) {
   Ctx& c = ctx();
   constexpr int V = Pack<T>::N;
   static int occ[2] = {0, 0};
@@ -376,18 +377,18 @@ static int launch_static(const ChainParams& p, bool stats, double* stats_dev) {
   if ((size_t)grid > max_grid) grid = (int)max_grid;
   Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
   if (stats)
-    k_chain_static<TP, T, true><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain_static<TP, T, true><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags, px);
   else
-    k_chain_static<TP, T, false><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain_static<TP, T, false><<<grid, kThreads, 0, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags, px);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
 
 // returns -1 if no registered chain matches
 template <typename T>
-static int try_registered(const ChainParams& p, bool stats, double* stats_dev) {
+static int try_registered(const ChainParams& p, bool stats, double* stats_dev, const MomExchange& px) {
 #define MCM_CHAIN_USE(NAME) \
-  if (tape_matches<NAME>(p)) return launch_static<NAME, T>(p, stats, stats_dev);
+  if (tape_matches<NAME>(p)) return launch_static<NAME, T>(p, stats, stats_dev, px);
   MCM_REGISTERED_CHAINS(MCM_CHAIN_USE)
 #undef MCM_CHAIN_USE
   return -1;
@@ -476,7 +477,7 @@ __device__ __forceinline__ void exec_range(Pack<T>* sm, const ChainParams& p, in
 template <typename T, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 k_chain(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* ticket, double* stats_out,
-        uint32_t* flags) {
+        uint32_t* flags, const __grid_constant__ MomExchange px) {
   constexpr int V = Pack<T>::N;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Pack<T>* sm = reinterpret_cast<Pack<T>*>(smem_raw);
@@ -506,11 +507,18 @@ k_chain(const __grid_constant__ ChainParams p, Mom* partials, unsigned int* tick
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
   if constexpr (STATS) {
     m = mom_block_reduce(m);
-    mom_grid_finish(m, partials, ticket, stats_out);
+    mom_grid_finish(m, partials, ticket, stats_out, &px);
   }
 }
 
 double* moments_result_slot();
+MomExchange mom_exchange_none();
+int mom_exchange_next(MomExchange* px);
+int ring_acquire(double** dev_slot, unsigned long long* ticket);
+int ring_publish(unsigned long long ticket);
+int ring_wait(unsigned long long ticket, double* out6);
+unsigned long long ring_last_ticket();
+double* ring_host_slot(unsigned long long ticket);
 int read_back(double* host_dst, const double* dev_src, size_t count);
 
 static int validate(const ChainParams& p, int nconst, int nin, int nout) {
@@ -541,8 +549,8 @@ static int validate(const ChainParams& p, int nconst, int nin, int nout) {
 static int g_last_engine = 0;  // 1 = registered/static, 2 = interpreter (introspection for tests)
 
 template <typename T>
-static int run_chain(const ChainParams& p, bool stats, double* stats_dev, bool allow_registered) {
-  int rc = allow_registered ? try_registered<T>(p, stats, stats_dev) : -1;
+static int run_chain(const ChainParams& p, bool stats, double* stats_dev, bool allow_registered, const MomExchange& px) {
+  int rc = allow_registered ? try_registered<T>(p, stats, stats_dev, px) : -1;
   if (rc >= 0) { g_last_engine = 1; return rc; }
   g_last_engine = 2;
   Ctx& c = ctx();
@@ -563,9 +571,9 @@ static int run_chain(const ChainParams& p, bool stats, double* stats_dev, bool a
   if ((size_t)grid > max_grid) grid = (int)max_grid;
   Mom* partials = reinterpret_cast<Mom*>(c.d_scratch);
   if (stats)
-    k_chain<T, true><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain<T, true><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags, px);
   else
-    k_chain<T, false><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags);
+    k_chain<T, false><<<grid, kThreads, kSmem, c.stream>>>(p, partials, c.d_tickets, stats_dev, c.d_flags, px);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
@@ -583,7 +591,8 @@ extern "C" int mcm_chain_force_interpreter(int on) { g_force_interpreter = on; r
 // Validate + launch; statistics (if stats_slot >= 0) land in the 6 doubles at stats_dev.  No sync.
 static int chain_launch(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
                         int reps, const double* consts, int nconst, const void* const* inputs, int nin,
-                        void* const* outputs, int nout, size_t n, int stats_slot, double* stats_dev) {
+                        void* const* outputs, int nout, size_t n, int stats_slot, double* stats_dev,
+                        bool sharded = false) {
   if (!tape && ntape) return fail(MCM_ERR_INVALID, "mcm_chain: null tape");
   if (nconst < 0 || nconst > MCM_TAPE_MAX_CONST || nin < 0 || nin > MCM_TAPE_MAX_IN || nout < 0 ||
       nout > MCM_TAPE_MAX_OUT)
@@ -608,36 +617,82 @@ static int chain_launch(int dtype, const mcm_tape_ins* tape, int ntape, int loop
   p.stats_slot = stats_slot < 0 ? 0 : stats_slot;
   int rc = validate(p, nconst, nin, nout);
   if (rc) return rc;
-  if (n == 0) return MCM_OK;
-  const bool allow = !g_force_interpreter;
   const bool stats = stats_slot >= 0;
-  return (dtype == MCM_F64) ? run_chain<double>(p, stats, stats_dev, allow) : run_chain<float>(p, stats, stats_dev, allow);
+  MomExchange px = mom_exchange_none();
+  if (sharded && stats) {             // collective: every rank takes the next epoch, an empty shard included
+    rc = mom_exchange_next(&px);
+    if (rc) return rc;
+  }
+  if (n == 0 && !(sharded && stats && px.world > 1)) return MCM_OK;
+  const bool allow = !g_force_interpreter;
+  return (dtype == MCM_F64) ? run_chain<double>(p, stats, stats_dev, allow, px) : run_chain<float>(p, stats, stats_dev, allow, px);
 }
 
+extern "C" int mcm_comm_info(int* nranks, int* rank);
 static void empty_stats(double* s) {
   s[0] = 0; s[1] = NAN; s[2] = 0; s[3] = INFINITY; s[4] = -INFINITY; s[5] = 0;
+}
+
+// Statistics travel through the result ring (reduce.cu): the last CTA writes them into mapped pinned host memory;
+// with stats_out_host == NULL the call returns at once and the caller collects them later by ticket.
+static int chain_entry(bool sharded, int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                       int reps, const double* consts, int nconst, const void* const* inputs, int nin,
+                       void* const* outputs, int nout, size_t n, int stats_slot, double* stats_out_host) {
+  if (stats_slot < 0)
+    return chain_launch(dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
+                        stats_slot, nullptr, false);
+  double* slot = nullptr;
+  unsigned long long ticket = 0;
+  int rc = ring_acquire(&slot, &ticket);
+  if (rc) return rc;
+  int world = 1, rank = 0;
+  if (sharded) mcm_comm_info(&world, &rank);
+  if (n == 0 && world == 1) {
+    empty_stats(ring_host_slot(ticket));
+  } else {
+    rc = chain_launch(dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
+                      stats_slot, slot, sharded);
+    if (rc) return rc;
+  }
+  rc = ring_publish(ticket);
+  if (rc) return rc;
+  if (stats_out_host) return ring_wait(ticket, stats_out_host);
+  return MCM_OK;
 }
 
 extern "C" int mcm_chain(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
                          int reps, const double* consts, int nconst, const void* const* inputs, int nin,
                          void* const* outputs, int nout, size_t n, int stats_slot, double* stats_out_host) {
   MCM_NEED_INIT();
-  double* slot = moments_result_slot();
-  int rc = chain_launch(dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
-                        stats_slot, slot);
-  if (rc) return rc;
-  if (stats_slot >= 0 && stats_out_host) {
-    if (n == 0) { empty_stats(stats_out_host); return MCM_OK; }
-    return read_back(stats_out_host, slot, 6);
-  }
-  return MCM_OK;  // stats_out_host == NULL: statistics stay on device until mcm_chain_stats_fetch
+  return chain_entry(false, dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
+                     stats_slot, stats_out_host);
 }
 
-// Fetch the statistics of the most recent mcm_chain launched with stats_out_host == NULL (synchronises).
+// The same chain on a particle-sharded variable (one process per GPU): the statistics are those of the GLOBAL
+// particle set, merged across ranks inside the kernel's epilogue over peer memory (mcm_moments.cuh: mom_exchange).
+// Collective when stats_slot >= 0: every rank of the communicator must call it, in the same order.
+extern "C" int mcm_chain_sharded(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                                 int reps, const double* consts, int nconst, const void* const* inputs, int nin,
+                                 void* const* outputs, int nout, size_t n, int stats_slot, double* stats_out_host) {
+  MCM_NEED_INIT();
+  return chain_entry(true, dtype, tape, ntape, loop_begin, loop_end, reps, consts, nconst, inputs, nin, outputs, nout, n,
+                     stats_slot, stats_out_host);
+}
+
+// Fetch the statistics of the most recent mcm_chain launched with stats_out_host == NULL (waits for that launch only).
 extern "C" int mcm_chain_stats_fetch(double* stats_out_host) {
   MCM_NEED_INIT();
   if (!stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain_stats_fetch: null pointer");
-  return read_back(stats_out_host, moments_result_slot(), 6);
+  return ring_wait(ring_last_ticket(), stats_out_host);
+}
+
+// Ticket of the most recent statistics-producing mcm_chain / mcm_chain_sharded call, and a wait for a given ticket
+// (one of the last 8): launch k+1 can be queued before the statistics of launch k are collected.
+extern "C" uint64_t mcm_chain_ticket(void) { return ring_last_ticket(); }
+extern "C" int mcm_chain_stats_wait(uint64_t ticket, double* stats_out_host) {
+  MCM_NEED_INIT();
+  if (!stats_out_host) return fail(MCM_ERR_INVALID, "mcm_chain_stats_wait: null pointer");
+  return ring_wait(ticket, stats_out_host);
 }
 
 // Host-buffer entry point: the whole chain with inputs/outputs in HOST memory (what a Julia caller holding

@@ -11,6 +11,7 @@
 #include <string.h>
 #include <vector>
 #include "mcm_common.cuh"
+#include "mcm_moments.cuh"
 
 namespace mcm {
 
@@ -63,7 +64,9 @@ static int nccl_load() {
   } while (0)
 
 struct Mom6 { double v[6]; };
-int moments_device(int dtype, const void* in, size_t n, double* d_out6);
+int moments_device(int dtype, const void* in, size_t n, double* d_out6, const MomExchange* pxp);
+int window_lookup(int id, void** peers16, int* world, int* rank, size_t* bytes);
+int window_drop(int id);
 double* moments_result_slot();
 int read_back(double* host_dst, const double* dev_src, size_t count);
 int gram_dispatch(int dtype, const void* const* vars, int M, size_t n, double scale, const double* center_host,
@@ -92,6 +95,45 @@ int comm_allgather_bytes(const void* send, void* recv, size_t bytes_per_rank) {
     return MCM_OK;
   }
   MCM_NCCL(g_nccl.AllGather(send, recv, bytes_per_rank, 1, g_nccl.comm, ctx().stream));
+  return MCM_OK;
+}
+
+// ---- the in-kernel moment exchange (mcm_moments.cuh: mom_exchange) ------------------------------------------------
+// One 4 KiB peer window per rank, created on first use (COLLECTIVE, like every sharded entry point) and zeroed
+// before any rank can store into it.  Every sharded reduction takes the next epoch; all ranks must issue their
+// sharded reductions in the same order (the usual collective contract).
+static int g_mx_window = -1;
+static void* g_mx_peers[16] = {};
+static unsigned long long g_mx_epoch = 0;
+extern "C" int mcm_window_create(size_t bytes, int* id_out, void** local_out);
+extern "C" int mcm_comm_fence(void);
+
+int mom_exchange_next(MomExchange* px) {
+  memset(px, 0, sizeof(*px));
+  px->world = 1;
+  px->flags = ctx().d_flags;
+  if (!g_nccl.comm || g_nccl.nranks == 1) return MCM_OK;
+  if (g_nccl.nranks > MX_MAXRANKS) return fail(MCM_ERR_UNSUPPORTED, "in-kernel moment exchange: at most %d ranks", MX_MAXRANKS);
+  if (g_mx_window < 0) {
+    const size_t bytes = (size_t)MX_SLOTS * MX_MAXRANKS * MX_REC * sizeof(double);
+    void* local = nullptr;
+    int id = -1;
+    int rc = mcm_window_create(bytes, &id, &local);
+    if (rc) return rc;
+    MCM_CUDA(cudaMemsetAsync(local, 0, bytes, ctx().stream));
+    rc = mcm_comm_fence();                      // nobody stores into a window that is still being zeroed
+    if (rc) return rc;
+    MCM_CUDA(cudaStreamSynchronize(ctx().stream));
+    int world, rank; size_t b;
+    rc = window_lookup(id, g_mx_peers, &world, &rank, &b);
+    if (rc) return rc;
+    g_mx_window = id;
+    g_mx_epoch = 0;
+  }
+  for (int r = 0; r < g_nccl.nranks; ++r) px->peer[r] = static_cast<double*>(g_mx_peers[r]);
+  px->world = g_nccl.nranks;
+  px->rank = g_nccl.rank;
+  px->epoch = ++g_mx_epoch;
   return MCM_OK;
 }
 
@@ -132,6 +174,7 @@ extern "C" int mcm_comm_init(const void* id128, int nranks, int rank) {
 }
 
 extern "C" int mcm_comm_destroy(void) {
+  if (g_mx_window >= 0) { window_drop(g_mx_window); g_mx_window = -1; }
   if (g_nccl.comm) {
     g_nccl.CommDestroy(g_nccl.comm);
     g_nccl.comm = nullptr;
@@ -157,36 +200,24 @@ extern "C" int mcm_comm_allreduce_sum_f64(double* dptr, size_t count) {
   return MCM_OK;
 }
 
-// All ranks: local six moments -> all-gather (6 doubles per rank) -> every rank merges the
-// partials in rank order with the Chan update, so all ranks return bit-identical results.
+// All ranks: one pass over the local shard; the last CTA stores the rank's partial into every rank's peer window
+// and merges all partials in rank order (mom_exchange) — every rank returns bit-identical results after ONE
+// device->host read.  (First version: all-gather of 6 doubles per rank + host merge.)
 extern "C" int mcm_moments_sharded(int dtype, const void* in, size_t n_local, double* out_host) {
   MCM_NEED_INIT();
   if (!out_host) return fail(MCM_ERR_INVALID, "mcm_moments_sharded: null output");
   Ctx& c = ctx();
-  const int g = g_nccl.comm ? g_nccl.nranks : 1;
-  double* slot = moments_result_slot();      // 6 doubles (local)
-  double* gathered = c.d_scratch + (c.scratch_doubles - 16 - 6 * 64);  // up to 64 ranks
-  if (g > 64) return fail(MCM_ERR_UNSUPPORTED, "mcm_moments_sharded: at most 64 ranks");
-  if (n_local) {
-    int rc = moments_device(dtype, in, n_local, slot);
-    if (rc) return rc;
-  } else {
-    const double e[6] = {0.0, 0.0, 0.0, __builtin_huge_val(), -__builtin_huge_val(), 0.0};
-    MCM_CUDA(cudaMemcpyAsync(slot, e, sizeof(e), cudaMemcpyHostToDevice, c.stream));
-  }
-  if (g == 1) return read_back(out_host, slot, 6);
-  MCM_NCCL(g_nccl.AllGather(slot, gathered, 6, ncclFloat64, g_nccl.comm, c.stream));
-  std::vector<double> h(6 * (size_t)g);
-  int rc = read_back(h.data(), gathered, 6 * (size_t)g);
+  double* slot = moments_result_slot();      // 6 doubles
+  MomExchange px;
+  int rc = mom_exchange_next(&px);
   if (rc) return rc;
-  double acc[6] = {h[0], h[1], h[2], h[3], h[4], h[5]};
-  for (int r = 1; r < g; ++r) {
-    double t[6];
-    mcm_moments_merge(acc, &h[6 * r], t);
-    memcpy(acc, t, sizeof(t));
-  }
-  memcpy(out_host, acc, sizeof(acc));
-  return MCM_OK;
+  // an empty shard still takes part in the exchange: reduce a zero-length range (the kernel handles n == 0)
+  static double* d_dummy = nullptr;
+  if (!d_dummy) MCM_CUDA(cudaMalloc((void**)&d_dummy, 16));
+  rc = moments_device(dtype, n_local ? in : d_dummy, n_local, slot, &px);
+  if (rc) return rc;
+  (void)c;
+  return read_back(out_host, slot, 6);
 }
 
 // Merge per-rank moments that already sit on the host (e.g. the fused statistics of mcm_chain):

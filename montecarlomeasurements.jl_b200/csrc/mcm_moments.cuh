@@ -183,11 +183,73 @@ __device__ __forceinline__ Mom mom_block_reduce(Mom m) {
   return m;
 }
 
+// ---- cross-rank merge inside the kernel (only the reduction partials cross NVLink) -------------
+// Every rank owns a small peer-visible window (CUDA IPC, csrc/comm.cu): MX_SLOTS x MX_MAXRANKS records of 8 doubles
+// {n, K, dm, m2, min, max, sum, epoch}.  The last CTA of a reducing kernel stores its rank's partial straight into
+// the window of EVERY rank (P2P stores over NVLink / NVSwitch), then waits until the records of all ranks for this
+// epoch have arrived in its own window and merges them in rank order — all ranks get bit-identical results with no
+// host round trip, no separate collective launch and no data-path synchronisation with the CPU.  (First version:
+// kernel -> D2H -> H2D -> ncclAllGather(48 B) -> D2H -> host merge: 0.8 ms per step at 8 ranks for a 48-byte exchange.)
+// Slots are indexed by epoch % MX_SLOTS: a rank can run at most one exchange ahead of the slowest peer, because its
+// own merge needs that peer's record of the same epoch.
+constexpr int MX_MAXRANKS = 16;
+constexpr int MX_SLOTS = 4;
+constexpr int MX_REC = 8;
+struct MomExchange {
+  double* peer[MX_MAXRANKS];     // window base on every rank (peer[rank] is the local one)
+  int world, rank;
+  unsigned long long epoch;      // sequence number of this exchange (>= 1, the same on all ranks)
+  uint32_t* flags;               // sticky flags (a peer that never arrives raises MCM_FLAG_COMM)
+};
+__device__ __forceinline__ unsigned long long mx_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// called by all threads of ONE CTA; m valid in thread 0; returns the merged moments in thread 0
+__device__ __forceinline__ Mom mom_exchange(Mom m, const MomExchange& px) {
+  __shared__ double s_rec[MX_REC];
+  if (threadIdx.x == 0) {
+    s_rec[0] = m.n; s_rec[1] = m.K; s_rec[2] = m.dm; s_rec[3] = m.m2; s_rec[4] = m.mn; s_rec[5] = m.mx; s_rec[6] = m.sum;
+  }
+  __syncthreads();
+  const size_t slot = (size_t)(px.epoch % MX_SLOTS) * MX_MAXRANKS * MX_REC;
+  if ((int)threadIdx.x < px.world) {
+    // my record into the window of rank t
+    volatile double* dst = px.peer[threadIdx.x] + slot + (size_t)px.rank * MX_REC;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) dst[k] = s_rec[k];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(dst + 7) = px.epoch;
+    // the record of rank t in my window
+    const volatile double* src = px.peer[px.rank] + slot + (size_t)threadIdx.x * MX_REC;
+    const volatile unsigned long long* flag = reinterpret_cast<const volatile unsigned long long*>(src + 7);
+    const unsigned long long t0 = mx_timer_ns();
+    while (*flag != px.epoch) {
+      if (mx_timer_ns() - t0 > 20000000000ull) { atomicOr(px.flags, 4u); break; }   // 20 s: a rank is missing (MCM_FLAG_COMM)
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  Mom r = mom_empty();
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < px.world; ++t) {
+      const volatile double* src = px.peer[px.rank] + slot + (size_t)t * MX_REC;
+      Mom b;
+      b.n = src[0]; b.K = src[1]; b.dm = src[2]; b.m2 = src[3]; b.mn = src[4]; b.mx = src[5]; b.sum = src[6];
+      r = mom_merge(r, b);
+    }
+  }
+  return r;
+}
+
 // Grid-level finish: every CTA deposits its partial; the last CTA to arrive
 // merges all partials in index order and writes out[0..5].  `ticket` must be 0
 // on entry and is reset to 0 on exit (so launches can be queued back to back).
+// px (optional): merge with the other ranks' results before writing (mom_exchange).
 __device__ __forceinline__ void mom_grid_finish(Mom block_m, Mom* partials, unsigned int* ticket,
-                                                double* out) {
+                                                double* out, const MomExchange* px = nullptr) {
   __shared__ bool s_last;
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = block_m;
@@ -206,8 +268,10 @@ __device__ __forceinline__ void mom_grid_finish(Mom block_m, Mom* partials, unsi
     m = mom_merge(m, b);
   }
   m = mom_block_reduce(m);
+  if (px != nullptr && px->world > 1) m = mom_exchange(m, *px);
   if (threadIdx.x == 0) {
     out[0] = m.n; out[1] = m.K + m.dm; out[2] = m.m2; out[3] = m.mn; out[4] = m.mx; out[5] = m.sum;
+    __threadfence_system();     // `out` may be mapped host memory (result ring)
     *ticket = 0u;
   }
 }

@@ -115,6 +115,17 @@ k_gather_peer(const __grid_constant__ PeerTable tab, const __grid_constant__ Var
   if (oob) atomicOr(flags, 0x80000000u);     // BoundsError bit, as mcm_gather
 }
 
+// non-collective teardown (process exit): close the peer mappings and free the local buffer without fences
+int window_drop(int id) {
+  if (id < 0 || id >= (int)g_windows.size() || !g_windows[id].live) return MCM_OK;
+  Window& w = g_windows[id];
+  for (int r = 0; r < w.world; ++r)
+    if (r != w.rank && w.peers[r]) cudaIpcCloseMemHandle(w.peers[r]);
+  cudaFree(w.local);
+  w.live = false;
+  return MCM_OK;
+}
+
 // for other translation units (sampling.cu: sharded resampling writes into index windows)
 int window_lookup(int id, void** peers16, int* world, int* rank, size_t* bytes) {
   if (id < 0 || id >= (int)g_windows.size() || !g_windows[id].live) return fail(MCM_ERR_INVALID, "bad window %d", id);

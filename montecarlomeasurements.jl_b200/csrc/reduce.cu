@@ -3,6 +3,7 @@
 // :316-323 (pmean, pextrema, pminimum, pmaximum forwarded to Statistics/Base),
 // src/bymap.jl:128-136 (@prob == mean(p.particles .< a)).
 #include <math.h>
+#include <string.h>
 #include "mcm_moments.cuh"
 #include "mcm_math.cuh"
 
@@ -10,7 +11,8 @@ namespace mcm {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out) {
+k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out,
+          const __grid_constant__ MomExchange px) {
   using P = Pack<T>;
   constexpr int V = P::N;
   constexpr int UNROLL = 4;
@@ -45,7 +47,7 @@ k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticke
   for (size_t i = nvec * V + tid; i < n; i += stride) mom_push_one(m, (double)in[i]);
 
   m = mom_block_reduce(m);
-  mom_grid_finish(m, partials, ticket, out);
+  mom_grid_finish(m, partials, ticket, out, &px);
 }
 
 // ---- TMA (bulk async copy) variant for large inputs ---------------------------------------
@@ -83,7 +85,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_moments_bulk(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out) {
+k_moments_bulk(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticket, double* out,
+               const __grid_constant__ MomExchange px) {
   using P = Pack<T>;
   constexpr int V = P::N;
   constexpr int EPT = MB_TILE_BYTES / (int)sizeof(T);           // elements per tile
@@ -132,7 +135,7 @@ k_moments_bulk(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* 
   const size_t stride = (size_t)gridDim.x * kThreads;
   for (size_t j = ntiles * EPT + (size_t)blockIdx.x * kThreads + tid; j < n; j += stride) mom_push_one(m, (double)in[j]);
   m = mom_block_reduce(m);
-  mom_grid_finish(m, partials, ticket, out);
+  mom_grid_finish(m, partials, ticket, out, &px);
 }
 
 template <typename T, int CMP>
@@ -207,8 +210,18 @@ k_round_int(const T* __restrict__ in, int mode, long long* __restrict__ out, siz
 
 static int g_use_bulk = 1;  // mcm_moments_use_bulk(0) forces the LDG kernel (A/B measurements, tests)
 
-int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
+MomExchange mom_exchange_none() {
+  MomExchange px;
+  memset(&px, 0, sizeof(px));
+  px.world = 1;
+  px.flags = ctx().d_flags;
+  return px;
+}
+
+// px == nullptr: this rank only; else the partial is merged with every other rank's inside the kernel (comm.cu)
+int moments_device(int dtype, const void* in, size_t n, double* d_out6, const MomExchange* pxp) {
   Ctx& c = ctx();
+  const MomExchange px = pxp ? *pxp : mom_exchange_none();
   static int occ64 = 0, occ32 = 0;
   if (occ64 == 0) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ64, k_moments<double>, kThreads, 0);
@@ -235,20 +248,20 @@ int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
     const size_t ntiles = n * esz / MB_TILE_BYTES;
     if ((size_t)grid > ntiles) grid = (int)(ntiles ? ntiles : 1);
     if (dtype == MCM_F64)
-      k_moments_bulk<double><<<grid, kThreads, kSmem, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6);
+      k_moments_bulk<double><<<grid, kThreads, kSmem, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6, px);
     else
-      k_moments_bulk<float><<<grid, kThreads, kSmem, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6);
+      k_moments_bulk<float><<<grid, kThreads, kSmem, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6, px);
     MCM_CHECK_LAUNCH();
     return MCM_OK;
   }
   if (dtype == MCM_F64) {
     int grid = stream_grid((n + 1) / 2, 4, occ64 > 4 ? 4 : occ64);
     if ((size_t)grid > max_grid) grid = (int)max_grid;
-    k_moments<double><<<grid, kThreads, 0, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6);
+    k_moments<double><<<grid, kThreads, 0, c.stream>>>((const double*)in, n, partials, c.d_tickets, d_out6, px);
   } else if (dtype == MCM_F32) {
     int grid = stream_grid((n + 3) / 4, 4, occ32 > 4 ? 4 : occ32);
     if ((size_t)grid > max_grid) grid = (int)max_grid;
-    k_moments<float><<<grid, kThreads, 0, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6);
+    k_moments<float><<<grid, kThreads, 0, c.stream>>>((const float*)in, n, partials, c.d_tickets, d_out6, px);
   } else {
     return fail(MCM_ERR_INVALID, "moments: bad dtype %d", dtype);
   }
@@ -256,8 +269,47 @@ int moments_device(int dtype, const void* in, size_t n, double* d_out6) {
   return MCM_OK;
 }
 
+int moments_device(int dtype, const void* in, size_t n, double* d_out6) { return moments_device(dtype, in, n, d_out6, nullptr); }
+
 // device result slot (6 doubles) lives at the end of the scratch buffer
 double* moments_result_slot() { return ctx().d_scratch + (ctx().scratch_doubles - 16); }
+
+// ---- result ring -----------------------------------------------------------------------------------------------
+// Statistics that go back to the caller are written by the kernel's last CTA straight into MAPPED PINNED host
+// memory (no cudaMemcpy), eight slots used round-robin, one event per slot: an asynchronous launch returns a
+// ticket, and waiting for ticket k (cudaEventSynchronize) does not wait for launches queued after it — step k's
+// readback overlaps kernel k+1.
+struct ResultRing {
+  double* h = nullptr;              // 8 x 8 doubles, cudaHostAllocMapped (same pointer on the device: UVA)
+  cudaEvent_t ev[8];
+  unsigned long long seq = 0;       // tickets handed out so far
+};
+static ResultRing g_ring;
+int ring_acquire(double** dev_slot, unsigned long long* ticket) {
+  ResultRing& r = g_ring;
+  if (!r.h) {
+    MCM_CUDA(cudaHostAlloc((void**)&r.h, 8 * 8 * sizeof(double), cudaHostAllocMapped | cudaHostAllocPortable));
+    for (int i = 0; i < 8; ++i) MCM_CUDA(cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming));
+  }
+  *ticket = r.seq++;
+  *dev_slot = r.h + 8 * (*ticket % 8);
+  return MCM_OK;
+}
+int ring_publish(unsigned long long ticket) {
+  MCM_CUDA(cudaEventRecord(g_ring.ev[ticket % 8], ctx().stream));
+  return MCM_OK;
+}
+int ring_wait(unsigned long long ticket, double* out6) {
+  ResultRing& r = g_ring;
+  if (!r.h || ticket >= r.seq || r.seq - ticket > 8)
+    return fail(MCM_ERR_INVALID, "statistics ticket %llu is not among the last 8 launches", ticket);
+  MCM_CUDA(cudaEventSynchronize(r.ev[ticket % 8]));
+  const volatile double* src = r.h + 8 * (ticket % 8);
+  for (int i = 0; i < 6; ++i) out6[i] = src[i];
+  return MCM_OK;
+}
+unsigned long long ring_last_ticket() { return g_ring.seq ? g_ring.seq - 1 : 0; }
+double* ring_host_slot(unsigned long long ticket) { return g_ring.h + 8 * (ticket % 8); }
 
 int read_back(double* host_dst, const double* dev_src, size_t count) {
   Ctx& c = ctx();

@@ -455,7 +455,11 @@ k_bq_pivots(const unsigned long long* __restrict__ uni, int world, int M, BqPara
   extern __shared__ unsigned long long sk[];
   const int m = blockIdx.x;
   const int per = BQ_SAMPLE / world;
-  for (int e = threadIdx.x; e < BQ_SAMPLE; e += 1024) sk[e] = uni[((size_t)(e / per) * M + m) * per + e % per];
+  // world need not divide BQ_SAMPLE: the < world missing keys are padded with the largest key, which moves every
+  // sample position by < world places — far inside the 4.5 sigma bracket margins (exactness never depends on pivots)
+  const int real = per * world;
+  for (int e = threadIdx.x; e < BQ_SAMPLE; e += 1024)
+    sk[e] = e < real ? uni[((size_t)(e / per) * M + m) * per + e % per] : (key64 ? ~0ull : 0xffffffffull);
   __syncthreads();
   for (int k = 2; k <= BQ_SAMPLE; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -1047,7 +1051,7 @@ extern "C" int mcm_quantile_sharded(int dtype, const void* const* vars, int M, s
   if (!vars || !q_host || !out_host || nq < 1 || M < 1) return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: bad arguments");
   if (M > 16383) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: at most 16383 variables per call");
   if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_quantile_sharded: bad dtype %d", dtype);
-  if (world > 64 || (world & (world - 1))) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: the number of ranks must be a power of two <= 64");
+  if (world > 64) return fail(MCM_ERR_UNSUPPORTED, "mcm_quantile_sharded: at most 64 ranks");
   const size_t esz = dtype == MCM_F64 ? 8 : 4;
   for (int m = 0; m < M; ++m)
     if (!vars[m] || (reinterpret_cast<uintptr_t>(vars[m]) % esz) != 0)

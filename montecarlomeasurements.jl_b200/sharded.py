@@ -100,6 +100,25 @@ def allmerge(local: P.Moments) -> P.Moments:
     return P.Moments(*m)
 
 
+def fused_stats(fn, *ps_local, materialize: bool = True):
+    """`fused(fn)(p1, p2, ...; stats=True)` on particle-sharded variables: every rank evaluates the chain on its own
+    slice (no communication) and receives the statistics of the GLOBAL result — the ranks' partials are exchanged and
+    merged inside the kernel's epilogue over peer memory (mcm_chain_sharded).  Returns (local result or None, Moments).
+    Collective."""
+    from . import tape as _tape
+    f = fn if isinstance(fn, P.fused) else P.fused(fn)
+    ps = list(ps_local)
+    N = ps[0].N
+    dt = L.F64 if any(p.dtype == L.F64 for p in ps) else L.F32
+    ps = [p.astype(P._NP[dt]) for p in ps]
+    t = f.tape(len(ps))
+    outs = [P._empty(N, dt) for _ in range(t.nout)] if materialize else []
+    st = _tape.run_tape(t, [p.ptr for p in ps], N, dt, [o.ptr for o in outs] if materialize else None,
+                        stats_output=0, sharded=True)
+    res = (outs[0] if t.nout == 1 else tuple(outs)) if materialize else None
+    return res, P.Moments(*st)
+
+
 def pmean(p_local): return pmoments(p_local).mean
 def pstd(p_local, corrected=True): return pmoments(p_local).std(corrected)
 def pvar(p_local, corrected=True): return pmoments(p_local).var(corrected)

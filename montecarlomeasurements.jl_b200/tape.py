@@ -309,9 +309,12 @@ def trace_loop(step, nstate: int, nparam: int, prologue=None) -> Tape:
     return t
 
 
-def run_tape(t: Tape, inputs, n: int, dtype: int, outputs=None, stats_output: int | None = None, reps: int = 0):
-    """Launch mcm_chain.  inputs/outputs: device pointers (ints / c_void_p).  Returns the six
-    moments {n, mean, M2, min, max, sum} of output `stats_output` if requested, else None."""
+def run_tape(t: Tape, inputs, n: int, dtype: int, outputs=None, stats_output: int | None = None, reps: int = 0,
+             sharded: bool = False, wait: bool = True):
+    """Launch mcm_chain (or mcm_chain_sharded: statistics of the GLOBAL particle set, merged across ranks inside the
+    kernel).  inputs/outputs: device pointers (ints / c_void_p).  Returns the six moments {n, mean, M2, min, max,
+    sum} of output `stats_output` if requested, else None.  wait=False returns the launch's TICKET instead and does
+    not synchronise: collect with stats_wait(ticket) (any of the last 8 launches)."""
     lib = L.lib()
     if len(inputs) != t.nin:
         raise TapeError(f"tape expects {t.nin} inputs, got {len(inputs)}")
@@ -322,7 +325,17 @@ def run_tape(t: Tape, inputs, n: int, dtype: int, outputs=None, stats_output: in
     lb, le = t.bounds
     stats = np.zeros(6)
     slot = -1 if stats_output is None else t.out_slots[stats_output]
-    L.check(lib.mcm_chain(dtype, t.as_ctypes(), len(t.ins), lb, le, int(reps), consts.ctypes.data_as(L._dp),
-                          len(t.consts), ins, t.nin, outs, t.nout, int(n), slot,
-                          stats.ctypes.data_as(L._dp) if slot >= 0 else None))
-    return stats if slot >= 0 else None
+    fn = lib.mcm_chain_sharded if sharded else lib.mcm_chain
+    L.check(fn(dtype, t.as_ctypes(), len(t.ins), lb, le, int(reps), consts.ctypes.data_as(L._dp),
+               len(t.consts), ins, t.nin, outs, t.nout, int(n), slot,
+               stats.ctypes.data_as(L._dp) if (slot >= 0 and wait) else None))
+    if slot < 0:
+        return None
+    return stats if wait else int(lib.mcm_chain_ticket())
+
+
+def stats_wait(ticket: int) -> np.ndarray:
+    """Statistics of the launch with this ticket (run_tape(..., wait=False)); waits for that launch only."""
+    stats = np.zeros(6)
+    L.check(L.lib().mcm_chain_stats_wait(int(ticket), stats.ctypes.data_as(L._dp)))
+    return stats

@@ -118,36 +118,39 @@ static float jf_powi(float x, int k) {
 
 /* ---------- f(p): register_primitive_single, src/register_primitive.jl:94-97;
  *            list at src/particles.jl:185-190; SLEEF overrides src/sleefpirates.jl:2-36 */
+/* Ulp-tier functions: the reference's own implementations (SLEEFPirates / Base, < 1 ulp class) are not vendored
+ * (SURVEY.md H4), so the oracle returns the CORRECTLY ROUNDED value: x87 long double evaluation (64-bit mantissa)
+ * rounded once to Float64; Float32 through Float64.  Device results are compared with these at <= 2 ulp. */
 static double u64(int op, double x) {
   switch (op) {
     case MCM_U_PLUS: case MCM_U_FLOAT: return x;
     case MCM_U_NEG: return -x;
-    case MCM_U_EXP: return exp(x);
-    case MCM_U_EXP2: return exp2(x);
-    case MCM_U_EXP10: return exp10(x);
-    case MCM_U_EXPM1: return expm1(x);
-    case MCM_U_LOG: return log(x);
-    case MCM_U_LOG10: return log10(x);
-    case MCM_U_LOG2: return log2(x);
-    case MCM_U_LOG1P: return log1p(x);
-    case MCM_U_SIN: return sin(x);
-    case MCM_U_COS: return cos(x);
-    case MCM_U_TAN: return tan(x);
+    case MCM_U_EXP: return (double)expl((long double)x);
+    case MCM_U_EXP2: return (double)exp2l((long double)x);
+    case MCM_U_EXP10: return (double)exp10l((long double)x);
+    case MCM_U_EXPM1: return (double)expm1l((long double)x);
+    case MCM_U_LOG: return (double)logl((long double)x);
+    case MCM_U_LOG10: return (double)log10l((long double)x);
+    case MCM_U_LOG2: return (double)log2l((long double)x);
+    case MCM_U_LOG1P: return (double)log1pl((long double)x);
+    case MCM_U_SIN: return (double)sinl((long double)x);
+    case MCM_U_COS: return (double)cosl((long double)x);
+    case MCM_U_TAN: return (double)tanl((long double)x);
     case MCM_U_SIND: return j_sind(x);
     case MCM_U_COSD: return j_cosd(x);
     case MCM_U_TAND: return j_sind(x) / j_cosd(x);
-    case MCM_U_SINH: return sinh(x);
-    case MCM_U_COSH: return cosh(x);
-    case MCM_U_TANH: return tanh(x);
-    case MCM_U_ASIN: return asin(x);
-    case MCM_U_ACOS: return acos(x);
-    case MCM_U_ATAN: return atan(x);
-    case MCM_U_ASIND: return asin(x) * (180.0 / M_PI); /* rad2deg(asin(x)) */
-    case MCM_U_ACOSD: return acos(x) * (180.0 / M_PI);
-    case MCM_U_ATAND: return atan(x) * (180.0 / M_PI);
-    case MCM_U_ASINH: return asinh(x);
-    case MCM_U_ACOSH: return acosh(x);
-    case MCM_U_ATANH: return atanh(x);
+    case MCM_U_SINH: return (double)sinhl((long double)x);
+    case MCM_U_COSH: return (double)coshl((long double)x);
+    case MCM_U_TANH: return (double)tanhl((long double)x);
+    case MCM_U_ASIN: return (double)asinl((long double)x);
+    case MCM_U_ACOS: return (double)acosl((long double)x);
+    case MCM_U_ATAN: return (double)atanl((long double)x);
+    case MCM_U_ASIND: return (double)asinl((long double)x) * (180.0 / M_PI); /* rad2deg(asin(x)) */
+    case MCM_U_ACOSD: return (double)acosl((long double)x) * (180.0 / M_PI);
+    case MCM_U_ATAND: return (double)atanl((long double)x) * (180.0 / M_PI);
+    case MCM_U_ASINH: return (double)asinhl((long double)x);
+    case MCM_U_ACOSH: return (double)acoshl((long double)x);
+    case MCM_U_ATANH: return (double)atanhl((long double)x);
     case MCM_U_ZERO: return 0.0;
     case MCM_U_SIGN: return j_sign(x);
     case MCM_U_ABS: return fabs(x);
@@ -172,32 +175,32 @@ static float u32(int op, float x) {
   switch (op) {
     case MCM_U_PLUS: case MCM_U_FLOAT: return x;
     case MCM_U_NEG: return -x;
-    case MCM_U_EXP: return expf(x);
-    case MCM_U_EXP2: return exp2f(x);
-    case MCM_U_EXP10: return exp10f(x);
-    case MCM_U_EXPM1: return expm1f(x);
-    case MCM_U_LOG: return logf(x);
-    case MCM_U_LOG10: return log10f(x);
-    case MCM_U_LOG2: return log2f(x);
-    case MCM_U_LOG1P: return log1pf(x);
-    case MCM_U_SIN: return sinf(x);
-    case MCM_U_COS: return cosf(x);
-    case MCM_U_TAN: return tanf(x);
+    case MCM_U_EXP: return (float)exp((double)x);
+    case MCM_U_EXP2: return (float)exp2((double)x);
+    case MCM_U_EXP10: return (float)exp10((double)x);
+    case MCM_U_EXPM1: return (float)expm1((double)x);
+    case MCM_U_LOG: return (float)log((double)x);
+    case MCM_U_LOG10: return (float)log10((double)x);
+    case MCM_U_LOG2: return (float)log2((double)x);
+    case MCM_U_LOG1P: return (float)log1p((double)x);
+    case MCM_U_SIN: return (float)sin((double)x);
+    case MCM_U_COS: return (float)cos((double)x);
+    case MCM_U_TAN: return (float)tan((double)x);
     case MCM_U_SIND: return (float)j_sind((double)x);
     case MCM_U_COSD: return (float)j_cosd((double)x);
     case MCM_U_TAND: return (float)(j_sind((double)x) / j_cosd((double)x));
-    case MCM_U_SINH: return sinhf(x);
-    case MCM_U_COSH: return coshf(x);
-    case MCM_U_TANH: return tanhf(x);
-    case MCM_U_ASIN: return asinf(x);
-    case MCM_U_ACOS: return acosf(x);
-    case MCM_U_ATAN: return atanf(x);
-    case MCM_U_ASIND: return asinf(x) * (180.0f / PI_F);
-    case MCM_U_ACOSD: return acosf(x) * (180.0f / PI_F);
-    case MCM_U_ATAND: return atanf(x) * (180.0f / PI_F);
-    case MCM_U_ASINH: return asinhf(x);
-    case MCM_U_ACOSH: return acoshf(x);
-    case MCM_U_ATANH: return atanhf(x);
+    case MCM_U_SINH: return (float)sinh((double)x);
+    case MCM_U_COSH: return (float)cosh((double)x);
+    case MCM_U_TANH: return (float)tanh((double)x);
+    case MCM_U_ASIN: return (float)asin((double)x);
+    case MCM_U_ACOS: return (float)acos((double)x);
+    case MCM_U_ATAN: return (float)atan((double)x);
+    case MCM_U_ASIND: return (float)asin((double)x) * (180.0f / PI_F);
+    case MCM_U_ACOSD: return (float)acos((double)x) * (180.0f / PI_F);
+    case MCM_U_ATAND: return (float)atan((double)x) * (180.0f / PI_F);
+    case MCM_U_ASINH: return (float)asinh((double)x);
+    case MCM_U_ACOSH: return (float)acosh((double)x);
+    case MCM_U_ATANH: return (float)atanh((double)x);
     case MCM_U_ZERO: return 0.0f;
     case MCM_U_SIGN: return jf_sign(x);
     case MCM_U_ABS: return fabsf(x);
@@ -233,14 +236,14 @@ static double b64(int op, double x, double y) {
     case MCM_B_SUB: return x - y;
     case MCM_B_MUL: return x * y;
     case MCM_B_DIV: return x / y;
-    case MCM_B_POW: return pow(x, y);
+    case MCM_B_POW: return (double)powl((long double)x, (long double)y);
     case MCM_B_MAX: return j_max(x, y);
     case MCM_B_MIN: return j_min(x, y);
     case MCM_B_MOD: return j_mod(x, y);
     case MCM_B_MOD1: return j_mod1(x, y);
-    case MCM_B_ATAN2: return atan2(x, y);
-    case MCM_B_ATAND2: return atan2(x, y) * (180.0 / M_PI);
-    case MCM_B_HYPOT: return hypot(x, y);
+    case MCM_B_ATAN2: return (double)atan2l((long double)x, (long double)y);
+    case MCM_B_ATAND2: return (double)atan2l((long double)x, (long double)y) * (180.0 / M_PI);
+    case MCM_B_HYPOT: return (double)hypotl((long double)x, (long double)y);
     case MCM_B_REM: return fmod(x, y);
     case MCM_B_FDIV: return j_fdiv(x, y);
     case MCM_B_REM_NEAREST: return remainder(x, y);
@@ -260,14 +263,14 @@ static float b32(int op, float x, float y) {
     case MCM_B_SUB: return x - y;
     case MCM_B_MUL: return x * y;
     case MCM_B_DIV: return x / y;
-    case MCM_B_POW: return powf(x, y);
+    case MCM_B_POW: return (float)pow((double)x, (double)y);
     case MCM_B_MAX: return jf_max(x, y);
     case MCM_B_MIN: return jf_min(x, y);
     case MCM_B_MOD: return jf_mod(x, y);
     case MCM_B_MOD1: return jf_mod1(x, y);
-    case MCM_B_ATAN2: return atan2f(x, y);
+    case MCM_B_ATAN2: return (float)atan2((double)x, (double)y);
     case MCM_B_ATAND2: return atan2f(x, y) * (180.0f / 3.14159274f);
-    case MCM_B_HYPOT: return hypotf(x, y);
+    case MCM_B_HYPOT: return (float)hypot((double)x, (double)y);
     case MCM_B_REM: return fmodf(x, y);
     case MCM_B_FDIV: return jf_fdiv(x, y);
     case MCM_B_REM_NEAREST: return remainderf(x, y);

@@ -343,16 +343,25 @@ def refcpu():
     return _ref
 
 
+_ref_bufs = {}
+
+
 def ref_chain10(a: np.ndarray, threads: int = 1):
-    """Run the SLEEF loop-per-primitive baseline once; returns (y, mean, std, seconds)."""
+    """Run the SLEEF loop-per-primitive baseline once; returns (y, mean, std, seconds).  The result and work vectors
+    are allocated (and their pages touched) once per size and reused: the reference pays allocation and page faults
+    on fresh vectors for every primitive, this baseline does not charge them."""
     import time
     r = refcpu()
     vl = r.ref_vector_width()
     n = (a.size // vl) * vl
     a = np.ascontiguousarray(a[:n])
-    y = np.empty(n); w1 = np.empty(n); w2 = np.empty(n); w3 = np.empty(n)
-    for buf in (y, w1, w2, w3):
-        buf.fill(0.0)  # touch pages before timing (the reference pays page faults on fresh vectors; we do not charge them)
+    if n not in _ref_bufs:
+        _ref_bufs.clear()
+        bufs = [np.empty(n) for _ in range(4)]
+        for buf in bufs:
+            buf.fill(0.0)
+        _ref_bufs[n] = bufs
+    y, w1, w2, w3 = _ref_bufs[n]
     m = C.c_double(); s = C.c_double()
     t0 = time.perf_counter()
     r.ref_chain10(_p(a), _p(y), _p(w1), _p(w2), _p(w3), C.c_long(n), C.c_int(threads), C.byref(m), C.byref(s))

@@ -49,18 +49,69 @@ static inline vd vneg(vd x) { return _mm256_sub_pd(_mm256_setzero_pd(), x); }
 static inline vd vabs(vd x) { return _mm256_andnot_pd(_mm256_set1_pd(-0.0), x); }
 #endif
 
-// static partition of [0, n) over `threads` std::threads (libgomp's spec file is not in this image)
+// Static partition of [0, n) over a PERSISTENT pool of worker threads (libgomp's spec file is not in this image).
+// The first version spawned and joined `threads` std::threads per pass — 13 passes per chain10 evaluation; the pool
+// keeps the workers parked on a condition variable between passes, so a pass costs two notifications.
+#include <condition_variable>
+#include <mutex>
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n) {
+    for (int t = 1; t < n_; ++t) workers_.emplace_back([this, t] { loop(t); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return n_; }
+  void run(const std::function<void(int)>& job) {      // job(t) for t in [0, n); the caller is worker 0
+    { std::lock_guard<std::mutex> lk(mu_); job_ = &job; pending_ = n_ - 1; ++gen_; }
+    cv_.notify_all();
+    job(0);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+ private:
+  void loop(int t) {
+    unsigned long seen = 0;
+    for (;;) {
+      const std::function<void(int)>* job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        job = job_;
+      }
+      (*job)(t);
+      { std::lock_guard<std::mutex> lk(mu_); if (--pending_ == 0) done_.notify_one(); }
+    }
+  }
+  int n_;
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* job_ = nullptr;
+  int pending_ = 0;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+};
+static Pool* g_pool = nullptr;
+static Pool& pool(int threads) {
+  if (!g_pool || g_pool->size() != threads) { delete g_pool; g_pool = new Pool(threads); }
+  return *g_pool;
+}
+
 template <class F>
 static void parallel_for(long n, int threads, F&& body) {
   if (threads <= 1) { body(0, n, 0); return; }
-  std::vector<std::thread> pool;
   const long chunk = (n + threads - 1) / threads;
-  for (int t = 0; t < threads; ++t) {
+  const std::function<void(int)> job = [&](int t) {
     const long b = t * chunk, e = b + chunk < n ? b + chunk : n;
-    if (b >= e) break;
-    pool.emplace_back([&body, b, e, t] { body(b, e, t); });
-  }
-  for (auto& th : pool) th.join();
+    if (b < e) body(b, e, t);
+  };
+  pool(threads).run(job);
 }
 
 #define PASS1(dst, src, expr)                                      \

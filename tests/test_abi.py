@@ -52,8 +52,10 @@ def test_built_for_sm100a_only(L):
 
 def test_enums_match_header(L):
     E = L.ENUMS
-    assert E["MCM_U_PLUS"] == 0 and E["MCM_U_FLOAT"] == 34 and E["MCM_U_COUNT"] == 42   # 35 registered + 7 extra
-    assert E["MCM_B_COUNT"] == 16 and E["MCM_T_COUNT"] == 3
+    assert E["MCM_U_PLUS"] == 0 and E["MCM_U_FLOAT"] == 34 and E["MCM_U_CUBE"] == 41     # 35 registered + 7 extra
+    assert E["MCM_U_COUNT"] == 49 and E["MCM_U_COUNT"] <= 0x40                            # + 3 round modes + 4 rem2pi; tape opcode space
+    assert E["MCM_B_FDIV"] == 15 and E["MCM_B_COUNT"] == 24 and E["MCM_B_COUNT"] <= 0x20 and E["MCM_T_COUNT"] == 3
+    assert E["MCM_FLAG_BOUNDS"] == 0x80000000 and E["MCM_CMP_ISNAN"] == 8 and E["MCM_RM_FROMZERO"] == 6
     assert E["MCM_TAPE_CONST"] == 0x40 and E["MCM_TAPE_SLOTS"] == 16
     assert C.sizeof(L.TapeIns) == 8
 

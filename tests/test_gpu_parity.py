@@ -25,16 +25,18 @@ def rand_inputs(dt, seed=0):
 
 EXACT_UNARY = ["PLUS", "NEG", "ZERO", "SIGN", "ABS", "FLOAT", "ROUND", "FLOOR", "CEIL", "TRUNC", "SQR", "CUBE",
                "RAD2DEG", "DEG2RAD"]
-ULP_UNARY = {  # name -> (domain map, ulp limit vs oracle)
+ULP_UNARY = {  # name -> (domain map, ulp limit vs the oracle = the correctly rounded value, oracle/mcm_oracle.c u64/u32)
+    # north_star: transcendentals within 2 ulp.  Measured on a B200 over 2e5 points (scripts/probe_ulps.py,
+    # profiles/r2_ulps.txt): every Float64 function <= 2 from the truth, hand-written sin/cos/exp <= 1.
     "EXP": (lambda x: x, 2), "EXP2": (lambda x: x, 2), "EXP10": (lambda x: x, 2), "EXPM1": (lambda x: x, 2),
     "LOG": (lambda x: np.abs(x) + 0.01, 2), "LOG10": (lambda x: np.abs(x) + 0.01, 2),
     "LOG2": (lambda x: np.abs(x) + 0.01, 2), "LOG1P": (lambda x: np.abs(x), 2),
-    "SIN": (lambda x: x * 3, 2), "COS": (lambda x: x * 3, 2), "TAN": (lambda x: x, 3),
-    "SINH": (lambda x: x * 2, 3), "COSH": (lambda x: x * 2, 3), "TANH": (lambda x: x, 3),
+    "SIN": (lambda x: x * 3, 2), "COS": (lambda x: x * 3, 2), "TAN": (lambda x: x, 2),
+    "SINH": (lambda x: x * 2, 2), "COSH": (lambda x: x * 2, 2), "TANH": (lambda x: x, 2),
     "ASIN": (lambda x: np.clip(x, -0.99, 0.99), 2), "ACOS": (lambda x: np.clip(x, -0.99, 0.99), 2),
-    "ATAN": (lambda x: x * 5, 2), "ASIND": (lambda x: np.clip(x, -0.99, 0.99), 3),
-    "ACOSD": (lambda x: np.clip(x, -0.99, 0.99), 3), "ATAND": (lambda x: x * 5, 3),
-    "ASINH": (lambda x: x * 5, 3), "ACOSH": (lambda x: np.abs(x) + 1.01, 3), "ATANH": (lambda x: np.clip(x, -0.99, 0.99), 3),
+    "ATAN": (lambda x: x * 5, 2), "ASIND": (lambda x: np.clip(x, -0.99, 0.99), 2),
+    "ACOSD": (lambda x: np.clip(x, -0.99, 0.99), 2), "ATAND": (lambda x: x * 5, 2),
+    "ASINH": (lambda x: x * 5, 2), "ACOSH": (lambda x: np.abs(x) + 1.01, 2), "ATANH": (lambda x: np.clip(x, -0.99, 0.99), 2),
 }
 
 
@@ -114,7 +116,7 @@ def test_binary_forms_and_exactness(mcm, orc, dt):
     assert bits_equal(mcm.clamp(px, -0.5, 0.7).to_numpy(), orc.ternary("CLAMP", x, -0.5, 0.7))
     assert bits_equal(mcm.muladd(px, py, 0.25).to_numpy(), orc.ternary("MULADD", x, y, 0.25))
     for name, got in (("ATAN2", mcm.atan(px, py)), ("ATAND2", mcm.atand(px, py)), ("HYPOT", mcm.hypot(px, py))):
-        assert ulp_err(got.to_numpy(), orc.binary(name, x, y)).max() <= 3, name
+        assert ulp_err(got.to_numpy(), orc.binary(name, x, y)).max() <= 2, name
     xp = np.abs(x) + dt(0.01)
     got = (mcm.Particles(xp) ** py).to_numpy()
     assert ulp_err(got, orc.binary("POW", xp, y)).max() <= 2
