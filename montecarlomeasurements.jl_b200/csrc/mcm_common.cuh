@@ -1,10 +1,23 @@
 // mcm_common.cuh — shared host/device plumbing for libmcm_b200.so (sm_100a only).
 #pragma once
+// Under NVRTC (runtime-specialised chain kernels, chain_jit.cu) only the device half of this header is compiled;
+// <stdint.h> / <stddef.h> / mcm_b200.h are then the small stand-ins chain_jit.cu hands to the compiler.
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stddef.h>
+#ifdef __CUDACC_RTC__
+#include "mcm_b200.h"
+#else
 #include "../../include/mcm_b200.h"
+#endif
 
+namespace mcm {
+static constexpr int kThreads = 256;          // CTA size for streaming kernels
+}
+
+#ifndef __CUDACC_RTC__
 namespace mcm {
 
 // One context per process (one process per GPU).
@@ -25,7 +38,6 @@ struct Ctx {
 Ctx& ctx();
 int fail(int code, const char* fmt, ...);
 
-static constexpr int kThreads = 256;          // CTA size for streaming kernels
 static constexpr size_t kScratchDoubles = 1u << 17;  // 1 MiB of doubles
 static constexpr size_t kPinnedBytes = 1u << 20;
 static constexpr int kMaxTickets = 64;
@@ -70,6 +82,7 @@ struct StatsHandoff {
 };
 StatsHandoff& stats_handoff();
 }  // namespace mcm
+#endif  // !__CUDACC_RTC__
 
 #ifdef __CUDACC__
 namespace mcm {

@@ -9,7 +9,11 @@
 // DESIGN.md §accuracy for the measured bounds against the oracle.
 #pragma once
 #include <math.h>
+#ifdef __CUDACC_RTC__
+#include "mcm_b200.h"
+#else
 #include "../../include/mcm_b200.h"
+#endif
 #include "mcm_fastmath.cuh"
 
 namespace mcm {
