@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--no-c3", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chain-engine", type=int, default=0, help="mcm_chain_force_engine: 0 automatic, 1 registered (ahead of time), 2 interpreter, 3 generated")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -285,6 +286,7 @@ def main():
     lib = L.lib()
     stream = torch.cuda.Stream()
     L.check(lib.mcm_set_stream(C.c_void_p(stream.cuda_stream)))
+    L.check(lib.mcm_chain_force_engine(args.chain_engine))
 
     def barrier():
         if world > 1:

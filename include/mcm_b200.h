@@ -257,6 +257,23 @@ int mcm_chain_host(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begi
  * registered tapes run on the interpreter too (parity tests compare the two). */
 int mcm_chain_last_engine(void);
 int mcm_chain_force_interpreter(int on);
+/* Engine 3 — kernels GENERATED from the tape at run time (csrc/chain_jit.cu): the tape becomes straight-line CUDA
+ * C++ (structural constants folded: `a^1.5` is the x*sqrt(x) kernel, integer powers unroll; branch-free fast paths
+ * with a per-pack replay for out-of-range arguments), compiled for sm_100a with NVRTC and cached by tape — what
+ * register_primitive's `eval` does for ANY function (register_primitive.jl:19-82), so user chains run as fast as the
+ * built-in ones.  mcm_chain_last_engine() == 3 when it ran.  Results are bit-identical to the other engines.
+ * mcm_chain_jit_mode: 0 = off, 1 (default) = generate when particles x instructions x reps >= 2^22 (compilation
+ * costs ~1 s once per tape), 2 = always.  mcm_chain_force_engine: 0 = automatic, 1 = registered + interpreter only,
+ * 2 = interpreter only, 3 = always generate.  mcm_chain_jit_compiles(): kernels compiled so far. */
+int mcm_chain_jit_mode(int mode);
+int mcm_chain_force_engine(int engine);
+int mcm_chain_jit_compiles(void);
+/* Generate (do_compile = 0) or generate + compile the kernel of a tape WITHOUT launching it; needs no GPU.  src_out
+ * (capacity src_cap) receives the generated source; *cubin_bytes the size of the sm_100a cubin; cubin_path, if not
+ * NULL, a file to write it to (for cuobjdump -sass). */
+int mcm_chain_jit_source(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
+                         const double* consts, int nconst, int stats_slot, int do_compile, char* src_out,
+                         size_t src_cap, size_t* cubin_bytes, const char* cubin_path);
 
 /* ======================= statistics ======================================== */
 /* one pass: out_host[0..5] = {n, mean, M2 = sum (x-mean)^2, min, max, sum} */

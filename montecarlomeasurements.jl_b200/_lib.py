@@ -108,6 +108,10 @@ SIGNATURES = {
     "mcm_chain_host": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _i, _dp, _i, _vpp, _i, _vpp, _i, _sz, _i, _dp]),
     "mcm_chain_last_engine": (_i, []),
     "mcm_chain_force_interpreter": (_i, [_i]),
+    "mcm_chain_jit_mode": (_i, [_i]),
+    "mcm_chain_force_engine": (_i, [_i]),
+    "mcm_chain_jit_compiles": (_i, []),
+    "mcm_chain_jit_source": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _dp, _i, _i, _i, C.c_char_p, _sz, C.POINTER(_sz), C.c_char_p]),
     "mcm_moments": (_i, [_i, _vp, _sz, _dp]),
     "mcm_moments_use_bulk": (_i, [_i]),
     "mcm_reduce": (_i, [_i, _i, _vp, _sz, _dp]),

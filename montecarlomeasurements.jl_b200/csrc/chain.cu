@@ -404,7 +404,7 @@ unsigned long long ring_last_ticket();
 double* ring_host_slot(unsigned long long ticket);
 int read_back(double* host_dst, const double* dev_src, size_t count);
 
-static int validate(const ChainParams& p, int nconst, int nin, int nout) {
+int chain_validate(const ChainParams& p, int nconst, int nin, int nout) {
   if (p.ntape < 0 || p.ntape > MCM_TAPE_MAX_INS) return fail(MCM_ERR_INVALID, "mcm_chain: ntape %d out of range", p.ntape);
   if (p.loop_begin < 0 || p.loop_end < p.loop_begin || p.loop_end > p.ntape)
     return fail(MCM_ERR_INVALID, "mcm_chain: bad loop section [%d,%d) of %d", p.loop_begin, p.loop_end, p.ntape);
@@ -429,11 +429,20 @@ static int validate(const ChainParams& p, int nconst, int nin, int nout) {
   return MCM_OK;
 }
 
-static int g_last_engine = 0;  // 1 = registered/static, 2 = interpreter (introspection for tests)
+static int g_last_engine = 0;  // 1 = registered/static, 2 = interpreter, 3 = generated at run time (introspection for tests)
+static int g_force_engine = 0; // 0 = automatic, 1 = registered (no generation), 2 = interpreter, 3 = always generate
+int jit_try_launch(const ChainParams& p, int nconst, bool f64, bool stats, double* stats_dev, const MomExchange& px,
+                   bool force);
 
 template <typename T>
 static int run_chain(const ChainParams& p, bool stats, double* stats_dev, bool allow_registered, const MomExchange& px) {
-  int rc = allow_registered ? try_registered<T>(p, stats, stats_dev, px) : -1;
+  if (allow_registered && g_force_engine != 1 && g_force_engine != 2) {
+    // engine 3: a kernel generated from this tape (chain_jit.cu) — cached, or compiled now if the launch is large
+    const int j = jit_try_launch(p, p.nconst, sizeof(T) == 8, stats, stats_dev, px, g_force_engine == 3);
+    if (j > 0) { g_last_engine = 3; return MCM_OK; }
+    if (j < 0) return -j;
+  }
+  int rc = (allow_registered && g_force_engine != 2) ? try_registered<T>(p, stats, stats_dev, px) : -1;
   if (rc >= 0) { g_last_engine = 1; return rc; }
   g_last_engine = 2;
   Ctx& c = ctx();
@@ -470,6 +479,13 @@ extern "C" int mcm_chain_last_engine(void) { return g_last_engine; }
 
 static int g_force_interpreter = 0;
 extern "C" int mcm_chain_force_interpreter(int on) { g_force_interpreter = on; return MCM_OK; }
+// 0 = automatic (generated kernel if cached or the launch is large, else registered, else interpreter), 1 = registered
+// chains + interpreter only, 2 = interpreter only, 3 = always generate (compiles on first use whatever the size)
+extern "C" int mcm_chain_force_engine(int engine) {
+  if (engine < 0 || engine > 3) return fail(MCM_ERR_INVALID, "mcm_chain_force_engine: 0..3");
+  g_force_engine = engine;
+  return MCM_OK;
+}
 
 // Validate + launch; statistics (if stats_slot >= 0) land in the 6 doubles at stats_dev.  No sync.
 static int chain_launch(int dtype, const mcm_tape_ins* tape, int ntape, int loop_begin, int loop_end,
@@ -498,7 +514,8 @@ static int chain_launch(int dtype, const mcm_tape_ins* tape, int ntape, int loop
   }
   p.n = n; p.ntape = ntape; p.loop_begin = loop_begin; p.loop_end = loop_end; p.reps = reps;
   p.stats_slot = stats_slot < 0 ? 0 : stats_slot;
-  int rc = validate(p, nconst, nin, nout);
+  p.nconst = nconst;
+  int rc = chain_validate(p, nconst, nin, nout);
   if (rc) return rc;
   const bool stats = stats_slot >= 0;
   MomExchange px = mom_exchange_none();

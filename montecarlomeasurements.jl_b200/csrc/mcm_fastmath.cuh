@@ -77,6 +77,7 @@ MCM_FM_CONST double kTrig[20] = {
 #define kTrigFastMax kTrig[16]
 
 struct Reduced { double r, rl; int q; };
+MCM_FM_HD bool is_zero_bits(double x) { return (d2bits(x) << 1) == 0; }
 
 MCM_FM_HD Reduced trig_reduce(double x) {
   Reduced o;
@@ -124,7 +125,7 @@ MCM_FM_HD double sin_f64(double x) {
   const Reduced a = trig_reduce(x);
   const double s = (a.q & 1) ? cos_kernel(a.r, a.rl) : sin_kernel(a.r, a.rl);
   const double y = (a.q & 2) ? -s : s;
-  return (x == 0.0) ? x : y;                           // keep -0.0
+  return is_zero_bits(x) ? x : y;                      // keep -0.0 (integer test: the FP64 pipe is the scarce one)
 }
 MCM_FM_HD double cos_f64(double x) {
   if (!(fabs(x) <= kTrigFastMax)) return lib_cos(x);

@@ -109,15 +109,17 @@ __device__ __forceinline__ void mom_push_one(Mom& m, double x) {
 // (d = v - K; s1 += d; s2 += d*d), folded into running (n, mean, m2) every MS_FOLD values by the same merge formula;
 // at every fold the shift K moves onto the running mean, so from the second fold on the in-chunk cancellation
 // s2 - s1^2/c loses log2(1 + (mean_chunk - K)^2 / var_chunk) bits of at most MS_FOLD values.
-constexpr int MS_FOLD = 16;
+constexpr int MS_FOLD = 64;
 struct MomStream {
-  double n, K, m2, mn, mx, sum, s1, s2;
+  double n, K, m2, mn, mx, s1, s2;
   int c;             // values in the open chunk; -1 until the first value fixed K
   unsigned nanw;     // max over values of (high word << 1): > 0xffe00000 iff a NaN was pushed
 };
+// The running sum is not accumulated separately (one FP64 add per value on a pipe-bound loop): after the last fold
+// K is the mean of everything pushed, so sum = n * K to 1 ulp.
 __device__ __forceinline__ MomStream ms_empty() {
   MomStream a;
-  a.n = 0.0; a.K = 0.0; a.m2 = 0.0; a.mn = __builtin_huge_val(); a.mx = -__builtin_huge_val(); a.sum = 0.0;
+  a.n = 0.0; a.K = 0.0; a.m2 = 0.0; a.mn = __builtin_huge_val(); a.mx = -__builtin_huge_val();
   a.s1 = 0.0; a.s2 = 0.0; a.c = -1; a.nanw = 0u;
   return a;
 }
@@ -132,18 +134,17 @@ __device__ __forceinline__ void ms_fold(MomStream& a) {
   a.K += cm * f;                               // K is the running mean from here on
   a.n = nn; a.s1 = 0.0; a.s2 = 0.0; a.c = 0;
 }
+// the first value a thread sees fixes its shift; kept out of line so that the steady-state loop carries one
+// predictable branch instead of a compare and four selects per pack
+static __device__ __noinline__ double ms_first_shift(double v0) { return (fabs(v0) <= 1.7976931348623157e308) ? v0 : 0.0; }
 template <int C>
 __device__ __forceinline__ void ms_push(MomStream& a, const double (&v)[C]) {
-  if (a.c < 0) {
-    a.K = (fabs(v[0]) <= 1.7976931348623157e308) ? v[0] : 0.0;
-    a.c = 0;
-  }
+  if (a.c < 0) { a.K = ms_first_shift(v[0]); a.c = 0; }
 #pragma unroll
   for (int i = 0; i < C; ++i) {
     const double d = v[i] - a.K;
     a.s1 += d;
     a.s2 = fma(d, d, a.s2);
-    a.sum += v[i];
     a.mn = v[i] < a.mn ? v[i] : a.mn;              // a NaN compares false and leaves the extrema alone, like fmin/fmax
     a.mx = v[i] > a.mx ? v[i] : a.mx;
     a.nanw = max(a.nanw, (unsigned)__double2hiint(v[i]) << 1);
@@ -154,8 +155,8 @@ __device__ __forceinline__ void ms_push(MomStream& a, const double (&v)[C]) {
 __device__ __forceinline__ Mom ms_finish(MomStream& a) {
   if (a.c > 0) ms_fold(a);
   Mom m;
-  m.n = a.n; m.K = a.K; m.dm = 0.0; m.m2 = a.m2; m.mn = a.mn; m.mx = a.mx; m.sum = a.sum;
-  if (a.nanw > 0xffe00000u) m.mn = m.mx = a.sum;   // a NaN was pushed: sum is NaN
+  m.n = a.n; m.K = a.K; m.dm = 0.0; m.m2 = a.m2; m.mn = a.mn; m.mx = a.mx; m.sum = a.n * a.K;
+  if (a.nanw > 0xffe00000u) m.mn = m.mx = m.sum = __builtin_nan("");   // a NaN was pushed
   return m;
 }
 

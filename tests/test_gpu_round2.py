@@ -176,3 +176,105 @@ def test_loop_tape_parallel_writeback_on_device(mcm, dt):
         for _ in range(7):
             wa, wb = ref(wa, wb)
         assert bits_equal(oa.to_numpy(), wa) and bits_equal(ob.to_numpy(), wb)
+
+
+# ---- engine 3: kernels generated from the tape at run time (csrc/chain_jit.cu) ----------------------------------
+def _run(mcm, t, arrays, n, dt_code, engine, reps=0, stats=True):
+    from mcm_b200 import tape
+    L = mcm._lib
+    L.check(L.lib().mcm_chain_force_engine(engine))
+    try:
+        ins = [mcm.Particles(a) for a in arrays]
+        outs = [mcm.particles._empty(n, dt_code) for _ in range(t.nout)]
+        st = tape.run_tape(t, [p.ptr for p in ins], n, dt_code, [o.ptr for o in outs], stats_output=0 if stats else None, reps=reps)
+        eng = L.lib().mcm_chain_last_engine()
+        return [o.to_numpy() for o in outs], st, eng
+    finally:
+        L.check(L.lib().mcm_chain_force_engine(0))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("n", [1, 3, 1001, 262144 + 5])
+def test_generated_kernels_are_bit_identical_to_the_interpreter(mcm, dt, n):
+    from mcm_b200 import chains, tape
+    L = mcm._lib
+    code = L.F64 if dt == np.float64 else L.F32
+    rng = np.random.default_rng(n)
+    a = (np.pi + 0.1 * rng.normal(size=n)).astype(dt)
+    b = rng.normal(0.5, 1.0, n).astype(dt)
+    cases = [
+        (tape.trace(chains.chain10, 1), [a], 0),
+        (tape.trace(chains.readme_expr, 1), [a], 0),
+        # constant-exponent powers of several kinds, integer powers, two outputs, ternary ops, a user-style chain
+        (tape.trace(lambda x, y: (mcm.sqrt(abs(x)) ** 2.5 + abs(y) ** 0.5 - (abs(x) + 1.0) ** -1.5 + x ** 5 + y ** -3,
+                                  mcm.clamp(mcm.muladd(x, y, 0.25), -2.0, 2.0) / (abs(y) ** 1.7 + 1.0)), 2), [a, b], 0),
+        (tape.trace(lambda x, y: mcm.log(abs(x * y) + 0.1) + mcm.cos(x - y) * mcm.atan(y, x) + mcm.mod2pi(x * 7.0), 2), [a, b], 0),
+        (tape.trace_loop(lambda u, v: (u + 0.01 * v, v - 0.01 * mcm.sin(u)), 2, 0), [a, b], 37),
+    ]
+    for t, arrs, reps in cases:
+        o3, s3, e3 = _run(mcm, t, arrs, n, code, 3, reps)
+        o2, s2, e2 = _run(mcm, t, arrs, n, code, 2, reps)
+        assert e3 == 3 and e2 == 2
+        for x3, x2 in zip(o3, o2):
+            assert bits_equal(x3, x2)
+        assert s3[0] == s2[0] == n and s3[3] == s2[3] and s3[4] == s2[4]                    # n, min, max exact
+        assert abs(s3[1] - s2[1]) <= 1e-13 * max(abs(s2[1]), 1e-300) + 1e-300
+        assert abs(s3[2] - s2[2]) <= 1e-12 * s2[2] + 1e-300
+    mcm.check_domain()
+
+
+def test_generated_kernel_replays_out_of_range_packs_exactly(mcm):
+    """Arguments outside the branch-free fast paths (|x| >= 708 for exp, >= 2^17 pi/2 for sin, bases outside
+    (1e-280, 1e280) or negative for x^1.5, NaN, Inf) make the pack replay through the exact instantiation."""
+    from mcm_b200 import tape
+    L = mcm._lib
+    x = np.array([0.5, 800.0, -750.0, 3e5, -1e300, 1e-300, 1e290, 0.0, -0.0, np.inf, -np.inf, np.nan, 2.0, 708.0, 205887.0, 1e-285,
+                  709.5, -708.0000001, 1.0, 4.0], dtype=np.float64)
+    x = np.concatenate([x, np.random.default_rng(0).normal(3.0, 0.5, 4096 - len(x))])
+    for f in (lambda p: mcm.exp(p) + mcm.sin(p), lambda p: p ** 1.5, lambda p: mcm.exp(-p) * mcm.cos(p) + abs(p) ** 2.5,
+              lambda p: mcm.sqrt(p) + mcm.log(p)):
+        t = tape.trace(f, 1)
+        o3, s3, e3 = _run(mcm, t, [x], len(x), L.F64, 3)
+        o2, s2, e2 = _run(mcm, t, [x], len(x), L.F64, 2)
+        assert e3 == 3 and bits_equal(o3[0], o2[0])
+        b3 = C.c_uint32(); L.check(L.lib().mcm_check_flags(C.byref(b3), 1))
+    # the DomainError flag survives the fast path: sqrt(-1) inside a generated kernel
+    t = tape.trace(lambda p: mcm.sqrt(p - 10.0), 1)
+    _run(mcm, t, [x], len(x), L.F64, 3)
+    with pytest.raises(mcm.DomainError):
+        mcm.check_domain()
+
+
+def test_generation_policy_and_cache(mcm):
+    from mcm_b200 import tape
+    L = mcm._lib
+    lib = L.lib()
+    f = lambda p: mcm.tanh(p) * 1.25 + mcm.sqrt(abs(p)) ** 3.5
+    t = tape.trace(f, 1)
+    small = np.linspace(-1, 1, 2000)
+    before = lib.mcm_chain_jit_compiles()
+    _, _, e = _run(mcm, t, [small], len(small), L.F64, 0)
+    assert e == 2 and lib.mcm_chain_jit_compiles() == before          # small launch: the interpreter, nothing compiled
+    big = np.linspace(-1, 1, 1 << 20)
+    o_big, _, e = _run(mcm, t, [big], len(big), L.F64, 0)
+    assert e == 3 and lib.mcm_chain_jit_compiles() == before + 1      # large launch: generated once ...
+    _, _, e = _run(mcm, t, [big], len(big), L.F64, 0)
+    assert e == 3 and lib.mcm_chain_jit_compiles() == before + 1      # ... and cached
+    _, _, e = _run(mcm, t, [small], len(small), L.F64, 0)
+    assert e == 3                                                      # a cached kernel serves small launches too
+    # a different run-time constant reuses the kernel; a different pow exponent is a different kernel
+    t2 = tape.trace(lambda p: mcm.tanh(p) * 7.5 + mcm.sqrt(abs(p)) ** 3.5, 1)
+    _, _, e = _run(mcm, t2, [big], len(big), L.F64, 0)
+    assert e == 3 and lib.mcm_chain_jit_compiles() == before + 1
+    t3 = tape.trace(lambda p: mcm.tanh(p) * 1.25 + mcm.sqrt(abs(p)) ** 2.5, 1)
+    _, _, e = _run(mcm, t3, [big], len(big), L.F64, 0)
+    assert e == 3 and lib.mcm_chain_jit_compiles() == before + 2
+    L.check(lib.mcm_chain_jit_mode(0))
+    try:
+        t4 = tape.trace(lambda p: mcm.tanh(p) * 1.25 - 3.0, 1)
+        _, _, e = _run(mcm, t4, [big], len(big), L.F64, 0)
+        assert e == 2
+    finally:
+        L.check(lib.mcm_chain_jit_mode(1))
+    ref = np.tanh(big) * 1.25 + np.sqrt(np.abs(big)) ** 3.5
+    assert np.allclose(o_big[0], ref, rtol=1e-14, atol=1e-15)

@@ -157,3 +157,36 @@ def test_distribution_promotion_rules(m):
 def test_error_classes(m):
     assert issubclass(m.ArgumentError, ValueError) and issubclass(m.MethodError, TypeError)
     assert issubclass(m.ArgumentError, m.MCMError)
+
+
+def test_chain_kernel_generation_and_nvrtc_compile_without_a_gpu(m, tmp_path):
+    """csrc/chain_jit.cu: the tape -> CUDA C++ generator and its NVRTC compilation need no device."""
+    import ctypes as C
+    import subprocess
+    from mcm_b200 import chains, tape
+    L = m._lib
+    lib = L.load()
+    for name, t, f64 in (("chain10", tape.trace(chains.chain10, 1), True), ("rk4", chains.pendulum_rk4_tape(0.01), True),
+                         ("chain10_f32", tape.trace(chains.chain10, 1), False)):
+        src = C.create_string_buffer(1 << 18)
+        nb = C.c_size_t(0)
+        consts = np.asarray(t.consts if t.consts else [0.0])
+        lb, le = t.bounds
+        cub = str(tmp_path / (name + ".cubin"))
+        rc = lib.mcm_chain_jit_source(L.F64 if f64 else L.F32, t.as_ctypes(), len(t.ins), lb, le, consts.ctypes.data_as(L._dp),
+                                      len(t.consts), t.out_slots[0], 1, src, len(src), C.byref(nb), cub.encode())
+        assert rc == 0, lib.mcm_last_error()
+        text = src.value.decode()
+        assert "mcm_jit_kernel" in text and nb.value > 10000
+        if name == "chain10":
+            assert "pow_three_halves" in text and "sin_fast" in text and "exp_fast" in text   # structural constant folded
+        if name == "chain10_f32":
+            assert "pow_three_halves" not in text                                              # Float32 keeps the library pow
+        if name == "rk4":
+            assert "for (int rep = 0; rep < p.reps; ++rep)" in text
+        out = subprocess.run(["cuobjdump", "--list-elf", cub], capture_output=True, text=True).stdout
+        assert "sm_100a" in out
+    # an invalid tape is rejected by the same validator as mcm_chain
+    bad = (L.TapeIns * 1)()
+    bad[0].op = 0x7f
+    assert lib.mcm_chain_jit_source(L.F64, bad, 1, 1, 1, None, 0, -1, 0, None, 0, None, None) != 0
