@@ -268,6 +268,9 @@ int mcm_chain_force_interpreter(int on);
 int mcm_chain_jit_mode(int mode);
 int mcm_chain_force_engine(int engine);
 int mcm_chain_jit_compiles(void);
+/* generation tunables for A/B measurements (part of the cache key): which = 0: resident CTAs per SM asked of the
+ * compiler (default 3), which = 1: request the next pack's inputs one iteration ahead (default 1) */
+int mcm_chain_jit_option(int which, int value);
 /* Generate (do_compile = 0) or generate + compile the kernel of a tape WITHOUT launching it; needs no GPU.  src_out
  * (capacity src_cap) receives the generated source; *cubin_bytes the size of the sm_100a cubin; cubin_path, if not
  * NULL, a file to write it to (for cuobjdump -sass). */

@@ -176,7 +176,7 @@ def test_chain10_fused_vs_oracle_and_engines_agree(mcm, orc, dt):
     pa = mcm.Particles(a)
     f = mcm.fused(chains.chain10)
     y, st = f(pa, stats=True)
-    assert L.lib().mcm_chain_last_engine() == 1                     # registered, ahead-of-time kernel
+    assert L.lib().mcm_chain_last_engine() in (1, 3)                # a straight-line kernel: registered or generated
     got = y.to_numpy()
     ref = orc.chain10(a)
     assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= orc.chain10_bound(a))
@@ -196,6 +196,16 @@ def test_chain10_fused_vs_oracle_and_engines_agree(mcm, orc, dt):
     finally:
         L.lib().mcm_chain_force_interpreter(0)
     assert bits_equal(y2.to_numpy(), got)
+    # so do the registered (ahead-of-time) kernel and the kernel generated from the tape at run time
+    for eng in (1, 3):
+        L.check(L.lib().mcm_chain_force_engine(eng))
+        try:
+            ye, ste = f(pa, stats=True)
+            assert L.lib().mcm_chain_last_engine() == eng
+        finally:
+            L.check(L.lib().mcm_chain_force_engine(0))
+        assert bits_equal(ye.to_numpy(), got)
+        assert ste.n == N and abs(ste.mean - st.mean) <= 1e-13 * abs(st.mean) and abs(ste.m2 - st.m2) <= 1e-12 * st.m2
     # unfused evaluation (one launch per primitive, like the reference) is bit-identical too
     y3 = mcm.sqrt(abs(mcm.sin(pa) * pa ** 2 + mcm.exp(-pa))) / pa ** 1.5
     assert bits_equal(y3.to_numpy(), got)
@@ -236,7 +246,18 @@ def test_pendulum_rk4_in_register_loop(mcm, orc, dt):
     ins = [mcm.Particles(v) for v in (th, om, g, Lp, c)]
     o1, o2 = mcm.particles._empty(n, ins[0].dtype), mcm.particles._empty(n, ins[0].dtype)
     tape.run_tape(t, [p.ptr for p in ins], n, ins[0].dtype, [o1.ptr, o2.ptr], reps=steps)
-    assert mcm._lib.lib().mcm_chain_last_engine() == 1
+    assert mcm._lib.lib().mcm_chain_last_engine() in (1, 3)
+    # the three engines agree bit for bit on the loop tape
+    ref_bits = (o1.to_numpy(), o2.to_numpy())
+    for eng in (1, 2, 3):
+        mcm._lib.check(mcm._lib.lib().mcm_chain_force_engine(eng))
+        try:
+            q1, q2 = mcm.particles._empty(n, ins[0].dtype), mcm.particles._empty(n, ins[0].dtype)
+            tape.run_tape(t, [p.ptr for p in ins], n, ins[0].dtype, [q1.ptr, q2.ptr], reps=steps)
+            assert mcm._lib.lib().mcm_chain_last_engine() == eng
+        finally:
+            mcm._lib.check(mcm._lib.lib().mcm_chain_force_engine(0))
+        assert bits_equal(q1.to_numpy(), ref_bits[0]) and bits_equal(q2.to_numpy(), ref_bits[1]), eng
     rth, rom = orc.pendulum_rk4(th.astype(np.float64), om.astype(np.float64), g.astype(np.float64),
                                 Lp.astype(np.float64), c.astype(np.float64), 0.01, steps)
     tol = 1e-11 if dt == np.float64 else 2e-4
