@@ -269,7 +269,8 @@ int mcm_chain_jit_mode(int mode);
 int mcm_chain_force_engine(int engine);
 int mcm_chain_jit_compiles(void);
 /* generation tunables for A/B measurements (part of the cache key): which = 0: resident CTAs per SM asked of the
- * compiler (default 3), which = 1: request the next pack's inputs one iteration ahead (default 1) */
+ * compiler (default 3); which = 1: request the next pack's inputs one iteration ahead (default 0: measured no gain);
+ * which = 2: 128-bit packs per thread, 1 / 2 / 4 or 0 = automatic (2 for short straight-line tapes, else 1) */
 int mcm_chain_jit_option(int which, int value);
 /* Generate (do_compile = 0) or generate + compile the kernel of a tape WITHOUT launching it; needs no GPU.  src_out
  * (capacity src_cap) receives the generated source; *cubin_bytes the size of the sm_100a cubin; cubin_path, if not
@@ -384,6 +385,28 @@ int mcm_systematic_normal(int dtype, void* out, size_t n, double mu, double sigm
 /* a..b  Uniform systematic sample: out = a + (b-a)*(2i+1)/(2 n_total) */
 int mcm_systematic_uniform(int dtype, void* out, size_t n, double a, double b,
                            const int64_t* perm_dev, uint64_t i0, uint64_t n_total);
+/* ---- any continuous univariate Distribution (sampling.jl:10 `quantile.((d,), y)`; types.jl:67-90; `a ⊠ d`, `a ⊞ d`
+ * particles.jl:42,50).  Families and parameters (a, b, c) follow Distributions.jl:
+ *   NORMAL(mu, sigma) UNIFORM(a, b) EXPONENTIAL(theta) LOGNORMAL(mu, sigma) CAUCHY(mu, sigma) LAPLACE(mu, theta)
+ *   LOGISTIC(mu, theta) RAYLEIGH(sigma) WEIBULL(alpha, theta) PARETO(alpha, theta) GUMBEL(mu, theta)
+ *   TRIANGULAR(a, b, c) FRECHET(alpha, theta) KUMARASWAMY(a, b) GAMMA(alpha, theta) CHISQ(nu) INVERSEGAMMA(alpha, theta)
+ *   BETA(alpha, beta) TDIST(nu) FDIST(nu1, nu2)
+ * Closed forms where they exist; Halley iterations on the regularised incomplete gamma / beta functions otherwise
+ * (csrc/mcm_dist.cuh), solved on the smaller of p and 1 - p: <= 1e-12 relative in both tails (tolerance tier).
+ * Anything else goes through a host-supplied quantile table (host mirror: GenericDistribution). */
+enum mcm_dist_kind {
+  MCM_D_NORMAL = 0, MCM_D_UNIFORM, MCM_D_EXPONENTIAL, MCM_D_LOGNORMAL, MCM_D_CAUCHY, MCM_D_LAPLACE, MCM_D_LOGISTIC,
+  MCM_D_RAYLEIGH, MCM_D_WEIBULL, MCM_D_PARETO, MCM_D_GUMBEL, MCM_D_TRIANGULAR, MCM_D_FRECHET, MCM_D_KUMARASWAMY,
+  MCM_D_GAMMA, MCM_D_CHISQ, MCM_D_INVERSEGAMMA, MCM_D_BETA, MCM_D_TDIST, MCM_D_FDIST, MCM_D_COUNT
+};
+/* systematic_sample(N, d; permute): out[j] = quantile(d, (2i+1)/(2 n_total)), i = i0 + j or perm[j] */
+int mcm_systematic_dist(int dtype, int kind, double a, double b, double c, void* out, size_t n,
+                        const int64_t* perm_dev, uint64_t i0, uint64_t n_total);
+/* iid draws by inversion: out[j] = quantile(d, u_j), u_j the Philox uniform of mcm_rand_real — the device stand-in
+ * for rand(rng, d, N) (types.jl:71,79, systematic = false) */
+int mcm_rand_dist(int dtype, int kind, double a, double b, double c, void* out, size_t n, uint64_t seed, uint64_t offset);
+/* quantile.(d, p) for a device vector of probabilities */
+int mcm_quantile_dist(int dtype, int kind, double a, double b, double c, const void* p_in, void* out, size_t n);
 /* randperm(rng, N) stand-in: device permutation from a counter-based generator
  * (Philox-4x32-10 keys + stable radix sort).  Stream differs from Julia's RNG (H5). */
 int mcm_randperm(int64_t* perm_out, size_t n, uint64_t seed);

@@ -26,6 +26,9 @@ from .particles import (
     RoundNearest, RoundToZero, RoundUp, RoundDown, RoundNearestTiesAway, RoundNearestTiesUp, RoundFromZero,
     nparticles, particleeltype, flat_particles, is_particle_array,
 )
+from .sampling import (Exponential, LogNormal, Cauchy, Laplace, Logistic, Rayleigh, Weibull, Pareto, Gumbel, TriangularDist,
+                       Frechet, Kumaraswamy, Gamma, Erlang, Chisq, InverseGamma, Beta, TDist, FDist, GenericDistribution,
+                       UnivariateDistribution, boxtimes, boxplus, outer_product, otimes, rand_particles_dist, quantile_dist)
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
                        mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower)
 from .resampling import bootstrap, resample, resample_indices, rand_indices

@@ -131,6 +131,9 @@ SIGNATURES = {
     "mcm_norminvcdf": (_i, [_i, _vp, _vp, _sz]),
     "mcm_systematic_normal": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_systematic_uniform": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
+    "mcm_systematic_dist": (_i, [_i, _i, _d, _d, _d, _vp, _sz, _vp, C.c_uint64, C.c_uint64]),
+    "mcm_rand_dist": (_i, [_i, _i, _d, _d, _d, _vp, _sz, C.c_uint64, C.c_uint64]),
+    "mcm_quantile_dist": (_i, [_i, _i, _d, _d, _d, _vp, _vp, _sz]),
     "mcm_randperm": (_i, [_vp, _sz, C.c_uint64]),
     "mcm_resample_use_search": (_i, [_i]),
     "mcm_rand_real": (_i, [_i, _i, _vp, _sz, _d, _d, C.c_uint64, C.c_uint64]),

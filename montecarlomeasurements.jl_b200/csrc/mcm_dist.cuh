@@ -21,8 +21,10 @@
 
 #ifdef MCM_HOST_TWIN
 #define MCM_DS_HD inline
+#define MCM_DS_COLD inline
 #else
 #define MCM_DS_HD __device__ __forceinline__
+#define MCM_DS_COLD static __device__ __noinline__     // the iterative inverses: one copy each, out of the switch
 #endif
 
 namespace mcm {
@@ -78,7 +80,7 @@ MCM_DS_HD void gamma_pq(double a, double x, double& P, double& Q) {
 }
 
 // x with P(a, x) = p (q = 1 - p given separately)
-MCM_DS_HD double gamma_inv(double a, double p, double q) {
+MCM_DS_COLD double gamma_inv(double a, double p, double q) {
   if (!(a > 0.0) || !(p >= 0.0) || !(q >= 0.0)) return __builtin_nan("");
   if (p == 0.0) return 0.0;
   if (q == 0.0) return __builtin_huge_val();
@@ -164,7 +166,7 @@ MCM_DS_HD void beta_pq(double a, double b, double x, double y, double& P, double
   }
 }
 // x with I_x(a,b) = p; also returns y = 1 - x with full relative accuracy
-MCM_DS_HD double beta_inv(double a, double b, double p, double q, double* y_out) {
+MCM_DS_COLD double beta_inv(double a, double b, double p, double q, double* y_out) {
   if (!(a > 0.0) || !(b > 0.0) || !(p >= 0.0) || !(q >= 0.0)) { if (y_out) *y_out = __builtin_nan(""); return __builtin_nan(""); }
   if (p == 0.0) { if (y_out) *y_out = 1.0; return 0.0; }
   if (q == 0.0) { if (y_out) *y_out = 0.0; return 1.0; }
@@ -224,10 +226,10 @@ MCM_DS_HD double quantile(int kind, const Params& d, double p, double q) {
   const double lq = (q > 0.5) ? log1p(-p) : log(q);      // log(1 - p)
   const double lp = (p > 0.5) ? log1p(-q) : log(p);      // log(p)
   switch (kind) {
-    case NORMAL: return d.a + d.b * norminv::norminvcdf(p);                              // mu + sigma Phi^-1(p)
+    case NORMAL: return d.a + d.b * (p <= q ? norminv::norminvcdf(p) : -norminv::norminvcdf(q));   // mu + sigma Phi^-1(p)
     case UNIFORM: return d.a + (d.b - d.a) * p;
     case EXPONENTIAL: return -d.a * lq;                                                   // theta: scale
-    case LOGNORMAL: return exp(d.a + d.b * norminv::norminvcdf(p));
+    case LOGNORMAL: return exp(d.a + d.b * (p <= q ? norminv::norminvcdf(p) : -norminv::norminvcdf(q)));
     case CAUCHY: {                                                                          // mu + sigma tan(pi (p - 1/2))
       if (p == 0.0) return -__builtin_huge_val();
       if (q == 0.0) return __builtin_huge_val();

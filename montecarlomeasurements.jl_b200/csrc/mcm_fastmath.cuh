@@ -79,7 +79,7 @@ MCM_FM_CONST double kTrig[20] = {
 struct Reduced { double r, rl; int q; };
 MCM_FM_HD bool is_zero_bits(double x) { return (d2bits(x) << 1) == 0; }
 
-MCM_FM_HD Reduced trig_reduce(double x) {
+MCM_FM_HD Reduced trig_reduce_full(double x) {
   Reduced o;
   const double n = rint(x * kTwoOverPi);
   const double r0 = fma(-n, kPio2_1, x);          // exact
@@ -92,6 +92,29 @@ MCM_FM_HD Reduced trig_reduce(double x) {
   o.q = (int)n;
   return o;
 }
+// Four FP64 instructions cheaper: r = RN(r0 - n P2) by one FMA and its rounding error by a second one.  The second
+// FMA is exact only while r0 - r is representable, i.e. while r has not cancelled against n P2 (|n P2| <= 2^-16):
+// for |r| >= 2^-11 the two are within a factor of two (Sterbenz).  Arguments that close to a multiple of pi/2 —
+// one in ~3000 of uniformly spread ones — take trig_reduce_full (`ok` = false).
+MCM_FM_HD Reduced trig_reduce_cheap(double x, bool& ok) {
+  Reduced o;
+  const double n = rint(x * kTwoOverPi);
+  const double r0 = fma(-n, kPio2_1, x);          // exact
+  const double r = fma(-n, kPio2_2, r0);
+  const double e = fma(-n, kPio2_2, r0 - r);      // rounding error of r (exact when ok)
+  o.r = r;
+  o.rl = fma(-n, kPio2_3, e);
+  o.q = (int)n;
+  ok = (d2bits(r) & 0x7fffffffffffffffLL) >= 0x3f40000000000000LL || is_zero_bits(x);   // |r| >= 2^-11
+  return o;
+}
+MCM_FM_HD Reduced trig_reduce(double x) {
+  bool ok;
+  const Reduced a = trig_reduce_cheap(x, ok);
+  return ok ? a : trig_reduce_full(x);
+}
+// (-1)^(q>>1) applied on the integer pipe
+MCM_FM_HD double flip_sign_if(double v, int bit2) { return bits2d(d2bits(v) ^ ((int64_t)(bit2 & 2) << 62)); }
 
 // minimax kernels on |r| <= pi/4 (coefficients of the classic fdlibm __kernel_sin/__kernel_cos)
 MCM_FM_HD double sin_kernel(double r, double rl) {
@@ -124,14 +147,14 @@ MCM_FM_HD double sin_f64(double x) {
   if (!(fabs(x) <= kTrigFastMax)) return lib_sin(x);  // huge, Inf, NaN: library (Payne-Hanek)
   const Reduced a = trig_reduce(x);
   const double s = (a.q & 1) ? cos_kernel(a.r, a.rl) : sin_kernel(a.r, a.rl);
-  const double y = (a.q & 2) ? -s : s;
+  const double y = flip_sign_if(s, a.q);
   return is_zero_bits(x) ? x : y;                      // keep -0.0 (integer test: the FP64 pipe is the scarce one)
 }
 MCM_FM_HD double cos_f64(double x) {
   if (!(fabs(x) <= kTrigFastMax)) return lib_cos(x);
   const Reduced a = trig_reduce(x);
   const double c = (a.q & 1) ? sin_kernel(a.r, a.rl) : cos_kernel(a.r, a.rl);
-  return ((a.q + 1) & 2) ? -c : c;
+  return flip_sign_if(c, a.q + 1);
 }
 
 // ---------------------------------------------------------------------------------

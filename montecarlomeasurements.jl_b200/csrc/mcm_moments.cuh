@@ -145,9 +145,20 @@ __device__ __forceinline__ void ms_push(MomStream& a, const double (&v)[C]) {
     const double d = v[i] - a.K;
     a.s1 += d;
     a.s2 = fma(d, d, a.s2);
-    a.mn = v[i] < a.mn ? v[i] : a.mn;              // a NaN compares false and leaves the extrema alone, like fmin/fmax
-    a.mx = v[i] > a.mx ? v[i] : a.mx;
     a.nanw = max(a.nanw, (unsigned)__double2hiint(v[i]) << 1);
+  }
+  // extrema: one compare orders a pair, then one compare each against the running minimum / maximum (3 FP64
+  // compares per pair instead of 4).  A NaN compares false and is caught by nanw, like fmin/fmax would skip it.
+#pragma unroll
+  for (int i = 0; i + 1 < C; i += 2) {
+    const bool lt = v[i] < v[i + 1];
+    const double lo = lt ? v[i] : v[i + 1], hi = lt ? v[i + 1] : v[i];
+    a.mn = lo < a.mn ? lo : a.mn;
+    a.mx = hi > a.mx ? hi : a.mx;
+  }
+  if constexpr (C & 1) {
+    a.mn = v[C - 1] < a.mn ? v[C - 1] : a.mn;
+    a.mx = v[C - 1] > a.mx ? v[C - 1] : a.mx;
   }
   a.c += C;
   if (a.c >= MS_FOLD) ms_fold(a);

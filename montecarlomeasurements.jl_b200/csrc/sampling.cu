@@ -7,6 +7,7 @@
 #include <vector>
 #include "mcm_common.cuh"
 #include "mcm_norminv.cuh"
+#include "mcm_dist.cuh"
 
 namespace mcm {
 
@@ -232,6 +233,41 @@ k_systematic_batch_scatter(T* const* __restrict__ outs, size_t n, const double* 
       out[j] = (T)val;
     }
   }
+}
+
+// ---- any univariate distribution (mcm_dist.cuh) ----------------------------------------------------------------
+// MODE 0: systematic grid (src/sampling.jl:8-10): p_i = (2i+1)/(2N) and q_i = 1 - p_i = (2(N-1-i)+1)/(2N), both
+//         correctly rounded quotients of exact integers, so the upper tail is as accurate as the lower one;
+// MODE 1: iid draws through the inverse CDF of a Philox uniform (types.jl:71,79 with systematic = false);
+// MODE 2: quantile.(d, p) on a caller-supplied probability vector.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_dist(T* __restrict__ out, size_t n, int kind, dist::Params dp, const int64_t* __restrict__ perm, const T* __restrict__ pin,
+       unsigned long long i0, unsigned long long n_total, unsigned long long seed, unsigned long long offset, uint32_t* flags) {
+  const size_t stride = (size_t)gridDim.x * kThreads;
+  const double two_n = 2.0 * (double)n_total;
+  bool bad = false;
+  for (size_t j = (size_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += stride) {
+    double p, q;
+    if constexpr (MODE == 0) {
+      const unsigned long long i = perm ? (unsigned long long)perm[j] : i0 + j;
+      p = (double)(2ull * i + 1ull) / two_n;
+      q = (double)(2ull * (n_total - 1ull - i) + 1ull) / two_n;
+    } else if constexpr (MODE == 1) {
+      uint32_t r[4];
+      philox4x32(offset + j, seed, r);
+      const unsigned long long k = ((((unsigned long long)r[1] << 32) | r[0]) >> 11);
+      p = ((double)k + 0.5) * 0x1p-53;
+      q = ((double)(9007199254740991ull - k) + 0.5) * 0x1p-53;          // 1 - p, exactly
+    } else {
+      p = (double)pin[j];
+      q = 1.0 - p;
+    }
+    const double v = dist::quantile(kind, dp, p, q);
+    bad |= (v != v) && (p == p);
+    out[j] = (T)v;
+  }
+  if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
 }
 
 // ---- gather ----------------------------------------------------------------------
@@ -786,4 +822,44 @@ extern "C" int mcm_resample_systematic_sharded(const double* w_local, size_t n_l
     MCM_CUDA(cudaFreeAsync(W, c.stream));
   }
   return MCM_OK;
+}
+
+// ---- any univariate distribution ---------------------------------------------------------------------------------
+static int dist_check(const char* who, int dtype, int kind, const void* out, size_t n) {
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "%s: bad dtype %d", who, dtype);
+  if (kind < 0 || kind >= mcm::dist::KIND_COUNT) return fail(MCM_ERR_INVALID, "%s: unknown distribution %d", who, kind);
+  if (n && !out) return fail(MCM_ERR_INVALID, "%s: null output", who);
+  return MCM_OK;
+}
+template <int MODE>
+static int dist_launch(int dtype, int kind, double a, double b, double c3, void* out, size_t n, const int64_t* perm, const void* pin,
+                       uint64_t i0, uint64_t n_total, uint64_t seed, uint64_t offset) {
+  if (n == 0) return MCM_OK;
+  Ctx& c = ctx();
+  const mcm::dist::Params dp{a, b, c3};
+  const int grid = stream_grid(n, 1, 8);
+  if (dtype == MCM_F64)
+    k_dist<double, MODE><<<grid, kThreads, 0, c.stream>>>((double*)out, n, kind, dp, perm, (const double*)pin, i0, n_total, seed, offset, c.d_flags);
+  else
+    k_dist<float, MODE><<<grid, kThreads, 0, c.stream>>>((float*)out, n, kind, dp, perm, (const float*)pin, i0, n_total, seed, offset, c.d_flags);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+extern "C" int mcm_systematic_dist(int dtype, int kind, double a, double b, double c3, void* out, size_t n,
+                                   const int64_t* perm_dev, uint64_t i0, uint64_t n_total) {
+  MCM_NEED_INIT();
+  if (int rc = dist_check("mcm_systematic_dist", dtype, kind, out, n)) return rc;
+  if (n_total == 0 || (!perm_dev && i0 + n > n_total)) return fail(MCM_ERR_INVALID, "mcm_systematic_dist: grid range out of bounds");
+  return dist_launch<0>(dtype, kind, a, b, c3, out, n, perm_dev, nullptr, i0, n_total, 0, 0);
+}
+extern "C" int mcm_rand_dist(int dtype, int kind, double a, double b, double c3, void* out, size_t n, uint64_t seed, uint64_t offset) {
+  MCM_NEED_INIT();
+  if (int rc = dist_check("mcm_rand_dist", dtype, kind, out, n)) return rc;
+  return dist_launch<1>(dtype, kind, a, b, c3, out, n, nullptr, nullptr, 0, 1, seed, offset);
+}
+extern "C" int mcm_quantile_dist(int dtype, int kind, double a, double b, double c3, const void* p_in, void* out, size_t n) {
+  MCM_NEED_INIT();
+  if (int rc = dist_check("mcm_quantile_dist", dtype, kind, out, n)) return rc;
+  if (n && !p_in) return fail(MCM_ERR_INVALID, "mcm_quantile_dist: null input");
+  return dist_launch<2>(dtype, kind, a, b, c3, out, n, nullptr, p_in, 0, 1, 0, 0);
 }

@@ -53,8 +53,84 @@ class MvNormal:
             self.S = np.diag(S) if S.ndim == 1 else S
 
 
+# ---- the other continuous univariate families (Distributions.jl parameterisation; csrc/mcm_dist.cuh) ----------
+class UnivariateDistribution:
+    """A continuous univariate Distribution whose quantile function runs on device (mcm_systematic_dist)."""
+    kind = None          # MCM_D_* name
+
+    def __init__(self, *params):
+        self._params = tuple(params)
+
+    @property
+    def params(self):
+        p = [float(x) for x in self._params] + [0.0, 0.0, 0.0]
+        return p[0], p[1], p[2]
+
+    @property
+    def eltype(self):
+        return np.float32 if self._params and all(isinstance(x, np.float32) for x in self._params) else np.float64
+
+    def __repr__(self):
+        return f"{type(self).__name__}{self._params}"
+
+
+def _family(name, kind, defaults, check=None):
+    def __init__(self, *args):
+        vals = list(args) + list(defaults[len(args):])
+        if len(args) > len(defaults):
+            raise L.MethodError(L.MCM_ERR_UNSUPPORTED, f"{name} takes at most {len(defaults)} parameters")
+        if check is not None and not check(*[float(v) for v in vals]):
+            raise L.ArgumentError(L.MCM_ERR_INVALID, f"{name}{tuple(vals)}: parameters outside the distribution's domain")
+        UnivariateDistribution.__init__(self, *vals)
+    return type(name, (UnivariateDistribution,), {"kind": kind, "__init__": __init__,
+                                                  "__doc__": f"{name}{tuple(defaults)} as in Distributions.jl; quantile on device (MCM_D_{kind})."})
+
+
+Exponential = _family("Exponential", "EXPONENTIAL", (1.0,), lambda t: t > 0)
+LogNormal = _family("LogNormal", "LOGNORMAL", (0.0, 1.0), lambda m, s: s >= 0)
+Cauchy = _family("Cauchy", "CAUCHY", (0.0, 1.0), lambda m, s: s > 0)
+Laplace = _family("Laplace", "LAPLACE", (0.0, 1.0), lambda m, t: t > 0)
+Logistic = _family("Logistic", "LOGISTIC", (0.0, 1.0), lambda m, t: t > 0)
+Rayleigh = _family("Rayleigh", "RAYLEIGH", (1.0,), lambda s: s > 0)
+Weibull = _family("Weibull", "WEIBULL", (1.0, 1.0), lambda a, t: a > 0 and t > 0)
+Pareto = _family("Pareto", "PARETO", (1.0, 1.0), lambda a, t: a > 0 and t > 0)
+Gumbel = _family("Gumbel", "GUMBEL", (0.0, 1.0), lambda m, t: t > 0)
+TriangularDist = _family("TriangularDist", "TRIANGULAR", (0.0, 1.0, 0.5), lambda a, b, c: a <= c <= b and a < b)
+Frechet = _family("Frechet", "FRECHET", (1.0, 1.0), lambda a, t: a > 0 and t > 0)
+Kumaraswamy = _family("Kumaraswamy", "KUMARASWAMY", (1.0, 1.0), lambda a, b: a > 0 and b > 0)
+Gamma = _family("Gamma", "GAMMA", (1.0, 1.0), lambda a, t: a > 0 and t > 0)
+Erlang = _family("Erlang", "GAMMA", (1.0, 1.0), lambda a, t: a > 0 and t > 0 and float(a).is_integer())
+Chisq = _family("Chisq", "CHISQ", (1.0,), lambda n: n > 0)
+InverseGamma = _family("InverseGamma", "INVERSEGAMMA", (1.0, 1.0), lambda a, t: a > 0 and t > 0)
+Beta = _family("Beta", "BETA", (1.0, 1.0), lambda a, b: a > 0 and b > 0)
+TDist = _family("TDist", "TDIST", (1.0,), lambda n: n > 0)
+FDist = _family("FDist", "FDIST", (1.0, 1.0), lambda a, b: a > 0 and b > 0)
+
+
+class GenericDistribution:
+    """Any other univariate distribution, through a HOST-SUPPLIED QUANTILE TABLE: `quantile` maps a numpy vector of
+    probabilities to values (a scipy.stats frozen distribution's `.ppf` works as is).  The systematic grid is
+    evaluated on the host once, uploaded, and permuted on device.  `rvs(n, rng)` (optional) draws iid samples for
+    systematic=False / discrete distributions (types.jl:67-82 with VS != Continuous)."""
+
+    def __init__(self, quantile=None, rvs=None, continuous: bool = True, eltype=np.float64):
+        if quantile is not None and hasattr(quantile, "ppf"):          # a scipy.stats frozen distribution
+            frozen = quantile
+            quantile = frozen.ppf
+            rvs = rvs or (lambda n, rng: frozen.rvs(size=n, random_state=rng))
+            continuous = hasattr(frozen.dist, "pdf")
+        self.quantile, self.rvs, self.continuous, self.eltype = quantile, rvs, continuous, eltype
+
+
 def is_distribution(x) -> bool:
-    return isinstance(x, (Normal, Uniform, MvNormal))
+    return isinstance(x, (Normal, Uniform, MvNormal, UnivariateDistribution, GenericDistribution)) or \
+        (hasattr(x, "ppf") and hasattr(x, "rvs"))
+
+
+def _as_distribution(d):
+    if hasattr(d, "ppf") and hasattr(d, "rvs") and not isinstance(d, GenericDistribution):
+        return GenericDistribution(d)
+    return d
 
 
 # ---- systematic_sample -------------------------------------------------------------------------
@@ -67,11 +143,13 @@ def systematic_sample(N: int, d=None, *, permute=True, seed: int | None = None, 
     DeviceIndex) supplies an explicit permutation instead — the way to reproduce a Julia `randperm`.
     i0 / n_total / n_local: generate only grid points [i0, i0+n_local) of an n_total-point grid (sharding).
     """
-    d = Normal() if d is None else d
+    d = _as_distribution(Normal() if d is None else d)
     N = int(N)
     n_total = N if n_total is None else int(n_total)
     n_loc = N if n_local is None else int(n_local)
     code = P._dtype_code(d.eltype)
+    if isinstance(d, GenericDistribution):
+        return _systematic_generic(d, N, n_total, n_loc, i0, permute, seed, perm, as_particles)
     out = P._empty(n_loc, code)
     perm_dev = None
     if perm is not None:
@@ -90,13 +168,81 @@ def systematic_sample(N: int, d=None, *, permute=True, seed: int | None = None, 
     elif isinstance(d, Uniform):
         L.check(L.lib().mcm_systematic_uniform(code, C.c_void_p(out.ptr), n_loc, float(d.a), float(d.b), pp,
                                                int(i0), n_total))
+    elif isinstance(d, UnivariateDistribution):
+        a, b, c = d.params
+        L.check(L.lib().mcm_systematic_dist(code, L.ENUMS["MCM_D_" + d.kind], a, b, c, C.c_void_p(out.ptr), n_loc, pp,
+                                            int(i0), n_total))
     else:
-        raise L.MethodError(L.MCM_ERR_UNSUPPORTED,
-                            f"systematic_sample on device supports Normal and Uniform, got {type(d).__name__}")
+        raise L.MethodError(L.MCM_ERR_UNSUPPORTED, f"systematic_sample: {type(d).__name__} is not a univariate distribution")
     return out if as_particles else out.to_numpy()
 
 
-def particles_from_distribution(N=None, d=None, *, permute=True, systematic=True, seed=None, perm=None):
+def _systematic_generic(d, N, n_total, n_loc, i0, permute, seed, perm, as_particles):
+    """Host-supplied quantile table: grid values from d.quantile on the host, permutation on device."""
+    if d.quantile is None:
+        raise L.MethodError(L.MCM_ERR_UNSUPPORTED, "GenericDistribution without a quantile function cannot be sampled systematically")
+    i = np.arange(int(i0), int(i0) + n_loc, dtype=np.float64)
+    vals = np.asarray(d.quantile((2.0 * i + 1.0) / (2.0 * n_total)), dtype=d.eltype)
+    out = P.Particles(np.ascontiguousarray(vals))
+    if perm is not None or permute:
+        if perm is None:
+            if n_loc != n_total:
+                raise L.ArgumentError(L.MCM_ERR_INVALID, "sharded generation needs an explicit perm or permute=False")
+            pd = P.DeviceIndex(n_loc)
+            L.check(L.lib().mcm_randperm(C.c_void_p(pd.ptr), n_loc, int(0 if seed is None else seed)))
+        else:
+            pd = perm if isinstance(perm, P.DeviceIndex) else P._upload_i64(np.asarray(perm))
+        res = P._empty(n_loc, out.dtype)
+        L.check(L.lib().mcm_gather(out.dtype, C.c_void_p(out.ptr), C.c_void_p(pd.ptr), C.c_void_p(res.ptr), n_loc, n_loc))
+        P.check_bounds()
+        out = res
+    return out if as_particles else out.to_numpy()
+
+
+def rand_particles_dist(N: int, d, seed: int = 0, offset: int = 0):
+    """iid draws Particles(N, d; systematic=false) (types.jl:71,79): inversion of device Philox uniforms for the
+    device families; `rvs` on the host for a GenericDistribution (Julia's RNG stream is not reproducible, H5)."""
+    d = _as_distribution(d)
+    N = int(N)
+    if isinstance(d, GenericDistribution):
+        rng = np.random.default_rng(seed)
+        if d.rvs is not None:
+            v = np.asarray(d.rvs(N, rng))
+        elif d.quantile is not None:
+            v = np.asarray(d.quantile(rng.random(N)))
+        else:
+            raise L.MethodError(L.MCM_ERR_UNSUPPORTED, "GenericDistribution needs rvs or quantile")
+        return P.Particles(np.ascontiguousarray(v.astype(np.float64) if v.dtype.kind in "iub" else v))
+    code = P._dtype_code(d.eltype)
+    out = P._empty(N, code)
+    if isinstance(d, Normal):
+        kind, (a, b, c) = "NORMAL", (float(d.mu), float(d.sigma), 0.0)
+    elif isinstance(d, Uniform):
+        kind, (a, b, c) = "UNIFORM", (float(d.a), float(d.b), 0.0)
+    else:
+        kind, (a, b, c) = d.kind, d.params
+    L.check(L.lib().mcm_rand_dist(code, L.ENUMS["MCM_D_" + kind], a, b, c, C.c_void_p(out.ptr), N, int(seed), int(offset)))
+    return out
+
+
+def quantile_dist(d, p):
+    """quantile.(d, p) for a Particles / array of probabilities, on device."""
+    d = _as_distribution(d)
+    pp = p if isinstance(p, P.Particles) else P.Particles(np.asarray(p, dtype=np.float64))
+    if isinstance(d, Normal):
+        kind, (a, b, c) = "NORMAL", (float(d.mu), float(d.sigma), 0.0)
+    elif isinstance(d, Uniform):
+        kind, (a, b, c) = "UNIFORM", (float(d.a), float(d.b), 0.0)
+    elif isinstance(d, UnivariateDistribution):
+        kind, (a, b, c) = d.kind, d.params
+    else:
+        return P.Particles(np.asarray(d.quantile(pp.to_numpy())))
+    out = P._empty_like(pp)
+    L.check(L.lib().mcm_quantile_dist(pp.dtype, L.ENUMS["MCM_D_" + kind], a, b, c, C.c_void_p(pp.ptr), C.c_void_p(out.ptr), pp.N))
+    return out
+
+
+def particles_from_distribution(N=None, d=None, *, permute=True, systematic=None, seed=None, perm=None):
     """Particles([rng,] N, d; permute, systematic) (types.jl:67-82) and the multivariate form (types.jl:92-100)."""
     if P_is_dist(N):
         N, d = None, N
@@ -104,9 +250,11 @@ def particles_from_distribution(N=None, d=None, *, permute=True, systematic=True
     d = Normal() if d is None else d
     if isinstance(d, MvNormal):
         return mvnormal_particles(N, d, seed=seed)
+    d = _as_distribution(d)
+    if systematic is None:                       # systematic = (VS == Continuous) by default (types.jl:67)
+        systematic = getattr(d, "continuous", True)
     if not systematic:
-        raise L.MethodError(L.MCM_ERR_UNSUPPORTED, "iid sampling (systematic=false) uses the host RNG: "
-                            "draw with numpy and pass the vector to Particles(v)")
+        return rand_particles_dist(N, d, seed=0 if seed is None else int(seed))
     return systematic_sample(N, d, permute=permute, seed=seed, perm=perm, as_particles=True)
 
 
@@ -130,6 +278,32 @@ def pm(mu, sigma=None, N: int = P.DEFAULT_NUM_PARTICLES, seed: int | None = None
 def mp(mu, sigma=None, seed: int | None = None, perm=None):
     """μ ∓ σ (particles.jl:23-25): the StaticParticles flavour, N = 100 (storage is the same on device)."""
     return pm(mu, sigma, N=P.DEFAULT_STATIC_NUM_PARTICLES, seed=seed, perm=perm)
+
+
+def boxtimes(a, d, seed: int | None = None):
+    """a ⊠ d = a * Particles(d) (particles.jl:42): e.g. boxtimes(2.0, Gamma(1))."""
+    return a * particles_from_distribution(P.DEFAULT_NUM_PARTICLES, d, seed=seed)
+
+
+def boxplus(a, d, seed: int | None = None):
+    """a ⊞ d = a + Particles(d) (particles.jl:50): e.g. boxplus(1, GenericDistribution(scipy.stats.binom(3, 0.5)))."""
+    return a + particles_from_distribution(P.DEFAULT_NUM_PARTICLES, d, seed=seed)
+
+
+def outer_product(dists, N: int = 100_000, seed: int = 0):
+    """outer_product(dists, N) / μ ⊗ σ (particles.jl:60-75): Nd = floor(N^(1/d)) permuted systematic samples per
+    dimension, combined as the full Cartesian product (Iterators.product: first dimension fastest)."""
+    dists = list(dists)
+    dim = len(dists)
+    Nd = max(int(np.floor(N ** (1.0 / dim) + 1e-9)), 1)
+    cols = [systematic_sample(Nd, d, permute=True, seed=seed + k) for k, d in enumerate(dists)]
+    grids = np.meshgrid(*cols, indexing="ij")
+    return [P.Particles(np.ascontiguousarray(g.reshape(-1, order="F"))) for g in grids]
+
+
+def otimes(mu, sigma, N: int = 100_000):
+    """⊗(μ, σ) = outer_product(Normal.(μ, σ)) (particles.jl:58)."""
+    return outer_product([Normal(m, s) for m, s in zip(np.atleast_1d(mu), np.atleast_1d(sigma))], N)
 
 
 def dotdot(a, b, N: int = P.DEFAULT_NUM_PARTICLES, seed: int | None = None):

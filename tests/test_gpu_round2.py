@@ -223,6 +223,30 @@ def test_generated_kernels_are_bit_identical_to_the_interpreter(mcm, dt, n):
     mcm.check_domain()
 
 
+@pytest.mark.parametrize("opts", [(2, 1, 2), (2, 0, 4), (4, 0, 1)])
+def test_generation_options_do_not_change_results(mcm, opts):
+    """packs per thread / prefetch / occupancy are tunables of the generator: same bits, any size (leftover packs)."""
+    from mcm_b200 import chains, tape
+    L = mcm._lib
+    lib = L.lib()
+    t = tape.trace(chains.chain10, 1)
+    t2 = tape.trace_loop(lambda u, v: (u + 0.01 * v, v - 0.01 * mcm.sin(u)), 2, 0)
+    try:
+        for n in (1, 2, 5, 7, 9, 4099, 100003):
+            rng = np.random.default_rng(n)
+            a = np.pi + 0.1 * rng.normal(size=n); b = rng.normal(size=n)
+            L.check(lib.mcm_chain_jit_option(0, 3)); L.check(lib.mcm_chain_jit_option(1, 1)); L.check(lib.mcm_chain_jit_option(2, 1))
+            o_ref, s_ref, _ = _run(mcm, t, [a], n, L.F64, 3)
+            l_ref, _, _ = _run(mcm, t2, [a, b], n, L.F64, 3, reps=11)
+            L.check(lib.mcm_chain_jit_option(0, opts[0])); L.check(lib.mcm_chain_jit_option(1, opts[1])); L.check(lib.mcm_chain_jit_option(2, opts[2]))
+            o, s, e = _run(mcm, t, [a], n, L.F64, 3)
+            l, _, _ = _run(mcm, t2, [a, b], n, L.F64, 3, reps=11)
+            assert e == 3 and bits_equal(o[0], o_ref[0]) and bits_equal(l[0], l_ref[0]) and bits_equal(l[1], l_ref[1])
+            assert s[0] == n and s[3] == s_ref[3] and s[4] == s_ref[4] and abs(s[1] - s_ref[1]) <= 1e-13 * abs(s_ref[1])
+    finally:
+        L.check(lib.mcm_chain_jit_option(0, 3)); L.check(lib.mcm_chain_jit_option(1, 0)); L.check(lib.mcm_chain_jit_option(2, 0))
+
+
 def test_generated_kernel_replays_out_of_range_packs_exactly(mcm):
     """Arguments outside the branch-free fast paths (|x| >= 708 for exp, >= 2^17 pi/2 for sin, bases outside
     (1e-280, 1e280) or negative for x^1.5, NaN, Inf) make the pack replay through the exact instantiation."""
@@ -278,3 +302,128 @@ def test_generation_policy_and_cache(mcm):
         L.check(lib.mcm_chain_jit_mode(1))
     ref = np.tanh(big) * 1.25 + np.sqrt(np.abs(big)) ** 3.5
     assert np.allclose(o_big[0], ref, rtol=1e-14, atol=1e-15)
+
+
+# ---- any univariate Distribution on device (src/sampling.jl:10, src/types.jl:67-90, src/particles.jl:42,50) -------------
+def _dist_cases(mcm):
+    return [("NORMAL", mcm.Normal(0.5, 2.0), (0.5, 2.0)), ("UNIFORM", mcm.Uniform(-1.0, 3.0), (-1.0, 3.0)),
+            ("EXPONENTIAL", mcm.Exponential(2.5), (2.5,)), ("LOGNORMAL", mcm.LogNormal(0.3, 0.7), (0.3, 0.7)),
+            ("CAUCHY", mcm.Cauchy(1.0, 2.0), (1.0, 2.0)), ("LAPLACE", mcm.Laplace(1.0, 2.0), (1.0, 2.0)),
+            ("LOGISTIC", mcm.Logistic(1.0, 2.0), (1.0, 2.0)), ("RAYLEIGH", mcm.Rayleigh(1.5), (1.5,)),
+            ("WEIBULL", mcm.Weibull(1.7, 2.0), (1.7, 2.0)), ("PARETO", mcm.Pareto(3.0, 2.0), (3.0, 2.0)),
+            ("GUMBEL", mcm.Gumbel(1.0, 2.0), (1.0, 2.0)), ("TRIANGULAR", mcm.TriangularDist(1.0, 4.0, 2.0), (1.0, 4.0, 2.0)),
+            ("FRECHET", mcm.Frechet(2.5, 1.5), (2.5, 1.5)), ("KUMARASWAMY", mcm.Kumaraswamy(2.0, 3.0), (2.0, 3.0)),
+            ("GAMMA", mcm.Gamma(0.05, 1.5), (0.05, 1.5)), ("GAMMA", mcm.Gamma(7.3, 1.5), (7.3, 1.5)),
+            ("GAMMA", mcm.Gamma(5000.0, 1.0), (5000.0, 1.0)), ("CHISQ", mcm.Chisq(3.0), (3.0,)),
+            ("INVERSEGAMMA", mcm.InverseGamma(3.0, 2.0), (3.0, 2.0)), ("BETA", mcm.Beta(0.5, 0.5), (0.5, 0.5)),
+            ("BETA", mcm.Beta(30.0, 2.0), (30.0, 2.0)), ("BETA", mcm.Beta(200.0, 300.0), (200.0, 300.0)),
+            ("TDIST", mcm.TDist(1.0), (1.0,)), ("TDIST", mcm.TDist(2.5), (2.5,)), ("TDIST", mcm.TDist(200.0), (200.0,)),
+            ("FDIST", mcm.FDist(3.0, 7.0), (3.0, 7.0)), ("FDIST", mcm.FDist(10.0, 4.0), (10.0, 4.0))]
+
+
+def test_device_quantiles_match_the_host_twin_on_the_systematic_grid(mcm):
+    """systematic_sample(N, d; permute=false) = quantile.(d, (2i-1)/(2N)) for every device family: the device runs the
+    same source as the host twin, which tests/test_dist_twin.py pins to scipy / mpmath at 1e-12; the two differ only by
+    libm vs libdevice log/exp/pow/lgamma (tolerance tier, 1e-12 relative to max(|x|, IQR/1000))."""
+    from test_dist_twin import build_dist_twin, grid, twin_quantile
+    twin = build_dist_twin()
+    for N in (2000, 100003):
+        p, q = grid(N)
+        for kind, d, params in _dist_cases(mcm):
+            got = mcm.systematic_sample(N, d, permute=False)
+            ref = twin_quantile(twin, kind, params, p, q)
+            iqr = abs(ref[(3 * N) // 4] - ref[N // 4])
+            err = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3 * iqr)
+            assert got.shape == (N,) and not np.isnan(got).any() and err.max() <= 1e-12, (kind, params, N, err.max(), int(np.argmax(err)))
+            assert np.all(np.diff(got) >= 0), (kind, params)
+    mcm.check_domain()
+
+
+def test_systematic_sample_of_other_families_like_the_reference_tests(mcm):
+    """test/runtests.jl:24-28: moment fits of systematic samples; a permuted sample is a permutation of the grid;
+    Float32 eltype comes from the parameters (types.jl:85-90)."""
+    x = mcm.systematic_sample(10000, mcm.Normal(1, 1))
+    assert abs(x.mean() - 1) < 0.1 and abs(x.std() - 1) < 0.1
+    g = mcm.systematic_sample(10000, mcm.Gamma(1, 1))
+    assert abs(g.mean() - 1) < 0.02 and g.min() > 0
+    t = mcm.systematic_sample(10000, mcm.TDist(1))
+    assert np.isfinite(t).all() and abs(np.median(t)) < 1e-3
+    b = mcm.systematic_sample(10000, mcm.Beta(1, 1))                     # Beta(1,1) = Uniform(0,1): fit gives (1,1)
+    m, v = b.mean(), b.var()
+    k = m * (1 - m) / v - 1
+    assert abs(m * k - 1) < 0.1 and abs((1 - m) * k - 1) < 0.1
+    s0 = mcm.systematic_sample(5000, mcm.Gamma(2.0, 3.0), permute=False)
+    s1 = mcm.systematic_sample(5000, mcm.Gamma(2.0, 3.0), permute=True, seed=3)
+    assert not np.array_equal(s0, s1) and np.array_equal(np.sort(s1), s0)
+    f = mcm.systematic_sample(1000, mcm.Exponential(np.float32(2.0)), permute=False, as_particles=True)
+    assert f.to_numpy().dtype == np.float32
+    with pytest.raises(mcm.ArgumentError):
+        mcm.Gamma(-1.0, 1.0)
+
+
+def test_boxplus_boxtimes_outer_product(mcm):
+    """runtests.jl:43-44 (`-50 ⊞ Normal(0,1) ≈ -50 ± 1`, `10 ⊠ Normal(0,1) ≈ 10*Particles(Normal(0,1))`) and
+    runtests.jl:610-632 (outer_product: d variables, <= N particles, identity covariance, reproducible by seed)."""
+    a = mcm.boxplus(-50, mcm.Normal(0, 1), seed=1)
+    assert abs(mcm.pmean(a) + 50) < 1e-9 and abs(mcm.pstd(a) - 1) < 2e-3
+    assert mcm.approx(a, mcm.pm(-50, 1))
+    b = mcm.boxtimes(10, mcm.Normal(0, 1), seed=1)
+    assert abs(mcm.pmean(b)) < 1e-9 and abs(mcm.pstd(b) - 10) < 2e-2
+    g = mcm.boxtimes(2.0, mcm.Gamma(3.0, 1.0))
+    assert abs(mcm.pmean(g) - 6.0) < 1e-2 and abs(mcm.pvar(g) - 12.0) < 0.2
+    p = mcm.otimes([0.0, 0.0], [1.0, 1.0])
+    assert len(p) == 2 and p[0].N <= 100_000 and p[0].N == 316 ** 2
+    assert np.allclose(mcm.pcov(p), np.eye(2), atol=1e-1)
+    p1 = mcm.outer_product([mcm.Normal(0, 1), mcm.Gamma(2.0, 1.0), mcm.Uniform(0, 1)], 1000, seed=38)
+    p2 = mcm.outer_product([mcm.Normal(0, 1), mcm.Gamma(2.0, 1.0), mcm.Uniform(0, 1)], 1000, seed=38)
+    assert len(p1) == 3 and p1[0].N == 1000 and all(x == y for x, y in zip(p1, p2))
+    c = mcm.pcov(p1)
+    assert abs(c[0, 1]) < 1e-12 and abs(c[0, 2]) < 1e-12 and abs(c[1, 2]) < 1e-12      # a full product grid is uncorrelated
+
+
+def test_iid_construction_and_quantile_vector_on_device(mcm):
+    """Particles(N, d; systematic=false) (types.jl:71,79): inversion of Philox uniforms on device; reproducible by
+    seed, right law (Kolmogorov distance), upper tail not truncated.  quantile.(d, p) on a probability vector
+    equals the systematic grid when p is the grid."""
+    import scipy.stats as st
+    n = 200000
+    for d, ref in ((mcm.Normal(1.0, 2.0), st.norm(1.0, 2.0)), (mcm.Gamma(2.5, 1.5), st.gamma(2.5, scale=1.5)),
+                   (mcm.Exponential(0.5), st.expon(scale=0.5)), (mcm.Beta(2.0, 5.0), st.beta(2.0, 5.0)),
+                   (mcm.TDist(4.0), st.t(4.0))):
+        p1 = mcm.Particles(n, d, systematic=False, seed=7)
+        p2 = mcm.Particles(n, d, systematic=False, seed=7)
+        p3 = mcm.Particles(n, d, systematic=False, seed=8)
+        x = p1.to_numpy()
+        assert np.array_equal(x, p2.to_numpy()) and not np.array_equal(x, p3.to_numpy())
+        assert st.kstest(x, ref.cdf).statistic < 1.63 / np.sqrt(n) * 1.5, type(d).__name__
+    N = 4001
+    pg = (2 * np.arange(N) + 1) / (2.0 * N)
+    for d in (mcm.Gamma(2.5, 1.5), mcm.LogNormal(0.0, 0.5), mcm.Normal(0.0, 1.0)):
+        qv = mcm.quantile_dist(d, pg).to_numpy()
+        sv = mcm.systematic_sample(N, d, permute=False)
+        lo = pg < 0.9                                    # 1 - p is rounded once in the vector form: compare off the far tail
+        assert np.allclose(qv[lo], sv[lo], rtol=1e-12, atol=0) and np.allclose(qv, sv, rtol=1e-9)
+    edge = mcm.quantile_dist(mcm.Exponential(1.0), np.array([0.0, 1.0, -0.5, 2.0])).to_numpy()
+    assert edge[0] == 0.0 and edge[1] == np.inf and np.isnan(edge[2:]).all()
+    with pytest.raises(mcm.DomainError):                 # p outside [0,1]: NaN + the sticky flag (Distributions throws)
+        mcm.check_domain()
+
+
+def test_host_supplied_quantile_table_and_discrete_distributions(mcm):
+    """Any other Distribution goes through a host-supplied quantile table (GenericDistribution; a scipy frozen
+    distribution works as is).  Discrete ones are sampled iid by default (systematic = VS == Continuous, types.jl:67;
+    runtests.jl:274-277: Particles(Poisson(50)))."""
+    import scipy.stats as st
+    d = st.skewnorm(4.0, loc=1.0, scale=2.0)
+    s = mcm.systematic_sample(3000, d, permute=False)
+    N = 3000
+    assert np.array_equal(s, d.ppf((2.0 * np.arange(N) + 1.0) / (2.0 * N)))
+    sp = mcm.systematic_sample(3000, d, permute=True, seed=5)
+    assert np.array_equal(np.sort(sp), s) and not np.array_equal(sp, s)
+    p = mcm.Particles(2000, st.poisson(50))
+    x = p.to_numpy()
+    assert np.all(x == np.round(x)) and abs(x.mean() - 50) < 1.0 and abs(x.var() - 50) < 8.0
+    y = (p * p - 1.0).to_numpy()
+    assert np.all(y == np.round(y))
+    c = mcm.boxplus(1, st.binom(3, 0.5))
+    assert set(np.unique(c.to_numpy())) <= {1.0, 2.0, 3.0, 4.0}
