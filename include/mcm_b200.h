@@ -270,7 +270,8 @@ int mcm_chain_force_engine(int engine);
 int mcm_chain_jit_compiles(void);
 /* generation tunables for A/B measurements (part of the cache key): which = 0: resident CTAs per SM asked of the
  * compiler (default 3); which = 1: request the next pack's inputs one iteration ahead (default 0: measured no gain);
- * which = 2: 128-bit packs per thread, 1 / 2 / 4 or 0 = automatic (2 for short straight-line tapes, else 1) */
+ * which = 2: 128-bit packs per thread, 1 / 2 / 4 or 0 = automatic (2 for short straight-line tapes, else 1);
+ * which = 3: sqrt / division / inv as inline branch-free sequences guarded by the window predicate (default 1) */
 int mcm_chain_jit_option(int which, int value);
 /* Generate (do_compile = 0) or generate + compile the kernel of a tape WITHOUT launching it; needs no GPU.  src_out
  * (capacity src_cap) receives the generated source; *cubin_bytes the size of the sm_100a cubin; cubin_path, if not

@@ -69,7 +69,8 @@ MCM_FM_CONST double kTrig[20] = {
     -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
     2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
     205887.0,                      // [16] fast-path limit 2^17 * pi/2
-    0.0, 0.0, 0.0};
+    -1.66666666666666324348e-01,   // [17] S1 with its sign (sincos_kernel)
+    0.0, 0.0};
 #define kTwoOverPi kTrig[0]
 #define kPio2_1 kTrig[1]
 #define kPio2_2 kTrig[2]
@@ -94,8 +95,9 @@ MCM_FM_HD Reduced trig_reduce_full(double x) {
 }
 // Four FP64 instructions cheaper: r = RN(r0 - n P2) by one FMA and its rounding error by a second one.  The second
 // FMA is exact only while r0 - r is representable, i.e. while r has not cancelled against n P2 (|n P2| <= 2^-16):
-// for |r| >= 2^-11 the two are within a factor of two (Sterbenz).  Arguments that close to a multiple of pi/2 —
-// one in ~3000 of uniformly spread ones — take trig_reduce_full (`ok` = false).
+// for |r| >= 2^-11 the two are within a factor of two (Sterbenz).  Arguments that close to a NONZERO multiple of pi/2
+// — one in ~3000 of uniformly spread ones — take trig_reduce_full (`ok` = false).  n == 0 (|x| < pi/4: small angles,
+// the common case of a pendulum near rest) never cancels: r = x exactly, whatever its size.
 MCM_FM_HD Reduced trig_reduce_cheap(double x, bool& ok) {
   Reduced o;
   const double n = rint(x * kTwoOverPi);
@@ -105,7 +107,7 @@ MCM_FM_HD Reduced trig_reduce_cheap(double x, bool& ok) {
   o.r = r;
   o.rl = fma(-n, kPio2_3, e);
   o.q = (int)n;
-  ok = (d2bits(r) & 0x7fffffffffffffffLL) >= 0x3f40000000000000LL || is_zero_bits(x);   // |r| >= 2^-11
+  ok = (d2bits(r) & 0x7fffffffffffffffLL) >= 0x3f40000000000000LL || o.q == 0;   // |r| >= 2^-11, or no multiple removed
   return o;
 }
 MCM_FM_HD Reduced trig_reduce(double x) {
@@ -143,18 +145,62 @@ MCM_FM_HD double cos_kernel(double r, double rl) {
   return w + (((1.0 - w) - hz) + fma(z * z, p, -r * rl));
 }
 
+// sin(r + rl) (C == false) or cos(r + rl) (C == true) in ONE common form: both kernels above are
+//   A + (v P(z) + B),  sin: A = r, v = z r, P = S1..S6, B = rl - (z/2) rl;  cos: A = w = 1 - z/2, v = z z, P = C1..C6,
+//   B = ((1 - w) - z/2) - r rl
+// (11 resp. 14 FP64 instructions, the leading terms r resp. 1 - z/2 exact or compensated: <= 0.80 ulp over the tested
+// ranges).  sincos_kernel_t<C> fixes the parity at compile time; sincos_kernel selects the operands by the parity at
+// run time — the SAME arithmetic on the selected operands, so all three return the same bits.  A warp whose lanes
+// all need the same kernel (the usual case: an uncertain angle is narrow compared with pi/2) runs the fixed form;
+// a warp with mixed parities runs the selecting form once (14 FP64 instructions + operand selects) instead of
+// both kernels under divergence (25).
+template <bool C>
+MCM_FM_HD double sincos_kernel_t(double r, double rl) {
+  const double z = r * r;
+  const double hz = 0.5 * z;
+  double p = C ? kTrig[10] : kTrig[4];
+  p = fma(p, z, C ? kTrig[11] : kTrig[5]);
+  p = fma(p, z, C ? kTrig[12] : kTrig[6]);
+  p = fma(p, z, C ? kTrig[13] : kTrig[7]);
+  p = fma(p, z, C ? kTrig[14] : kTrig[8]);
+  p = fma(p, z, C ? kTrig[15] : kTrig[17]);
+  if (C) {
+    const double w = 1.0 - hz;
+    const double e = (1.0 - w) - hz;
+    return w + fma(z * z, p, fma(-r, rl, e));
+  }
+  return r + fma(z * r, p, fma(-hz, rl, rl));
+}
+MCM_FM_HD double sincos_kernel(double r, double rl, int odd) {
+  const bool c = (odd & 1) != 0;
+  const double z = r * r;
+  const double hz = 0.5 * z;
+  const double w = 1.0 - hz;
+  const double e = (1.0 - w) - hz;
+  double p = c ? kTrig[10] : kTrig[4];
+  p = fma(p, z, c ? kTrig[11] : kTrig[5]);
+  p = fma(p, z, c ? kTrig[12] : kTrig[6]);
+  p = fma(p, z, c ? kTrig[13] : kTrig[7]);
+  p = fma(p, z, c ? kTrig[14] : kTrig[8]);
+  p = fma(p, z, c ? kTrig[15] : kTrig[17]);
+  const double v = z * (c ? z : r);
+  const double b = fma(-(c ? r : hz), rl, c ? e : rl);
+  return (c ? w : r) + fma(v, p, b);
+}
+MCM_FM_HD double sincos_branch(double r, double rl, int odd) {   // per-lane form of the exact paths
+  return (odd & 1) ? sincos_kernel_t<true>(r, rl) : sincos_kernel_t<false>(r, rl);
+}
+
 MCM_FM_HD double sin_f64(double x) {
   if (!(fabs(x) <= kTrigFastMax)) return lib_sin(x);  // huge, Inf, NaN: library (Payne-Hanek)
   const Reduced a = trig_reduce(x);
-  const double s = (a.q & 1) ? cos_kernel(a.r, a.rl) : sin_kernel(a.r, a.rl);
-  const double y = flip_sign_if(s, a.q);
+  const double y = flip_sign_if(sincos_branch(a.r, a.rl, a.q), a.q);
   return is_zero_bits(x) ? x : y;                      // keep -0.0 (integer test: the FP64 pipe is the scarce one)
 }
 MCM_FM_HD double cos_f64(double x) {
   if (!(fabs(x) <= kTrigFastMax)) return lib_cos(x);
   const Reduced a = trig_reduce(x);
-  const double c = (a.q & 1) ? sin_kernel(a.r, a.rl) : cos_kernel(a.r, a.rl);
-  return flip_sign_if(c, a.q + 1);
+  return flip_sign_if(sincos_branch(a.r, a.rl, a.q + 1), a.q + 1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -220,7 +266,7 @@ MCM_FM_HD void powi_dd(double x, int m, double& hi, double& lo) {  // m >= 0
   hi = yh; lo = yl;
 }
 
-MCM_FM_HD double pow_half_int(double x, int k) {  // k odd, exponent k/2; 1e-280 < x < 1e280
+MCM_FM_HD double pow_half_int(double x, int k) {  // k odd, exponent k/2; pow_half_window(x, k)
   const double s = sqrt(x);
   const double res = fma(-s, s, x);                 // exact
   const double rs = res * (0.5 / s);                // sqrt(x) = s + rs
@@ -250,13 +296,24 @@ MCM_FM_HD double pow_three_halves(double x) {
   return p + fma(0.5 * res, s, pe);
 }
 
+// x > 0, normal, and neither x^(k/2) nor an intermediate power (x^((|k|+1)/2)) leaves the normal range:
+// (|exponent(x)| + 1) (|k| + 1) < 2000.  Zero, denormals, Inf and NaN fail (|exponent| >= 1023).  Outside the
+// window the compensated products overflow to Inf - Inf = NaN where the true power is Inf (or lose bits to
+// denormals), so those arguments go to the library.
+MCM_FM_HD bool pow_half_window(double x, int k) {
+  const int e = (int)((d2bits(x) >> 52) & 0x7ff) - 1023;
+  const int ae = e < 0 ? -e : e, ak = k < 0 ? -k : k;
+  return x > 0.0 && (ae + 1) * (ak + 1) < 2000;
+}
 MCM_FM_HD double pow_f64(double x, double y) {
   const double t = y + y;
-  if (fabs(t) <= 17.0 && t == rint(t) && x > 1e-280 && x < 1e280) {
-    if (t == 3.0) return pow_three_halves(x);
-    if (t == 1.0) return sqrt(x);
+  if (fabs(t) <= 17.0 && t == rint(t)) {
     const int k = (int)t;
-    if (k & 1) return pow_half_int(x, k);
+    if ((k & 1) && pow_half_window(x, k)) {
+      if (k == 3) return pow_three_halves(x);
+      if (k == 1) return sqrt(x);
+      return pow_half_int(x, k);
+    }
   }
   return lib_pow(x, y);
 }

@@ -42,21 +42,21 @@ nxt = k.find("Function :", 10)
 k = k[:nxt] if nxt > 0 else k
 ins = re.findall(r"^\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", k, flags=re.M)
 print("kernel instructions (static):", len(ins))
-# the hot loop = the largest backward branch region
-best = None
+# every loop (backward branch region) of more than 60 instructions: the fast body's loop comes first, the exact
+# replay's copy (library fallbacks, CALLs) later
+loops = []
 for addr, text in ins:
     m = re.search(r"BRA\S*\s+(?:\S+,\s*)?0x([0-9a-f]+)", text)
-    if m and int(m.group(1), 16) < int(addr, 16):
-        span = (int(m.group(1), 16), int(addr, 16))
-        if best is None or span[1] - span[0] > best[1] - best[0]:
-            best = span
-print("hot loop: 0x%x .. 0x%x = %d instructions (static)" % (best[0], best[1], (best[1] - best[0]) // 16 + 1))
-hist = {}
-for addr, text in ins:
-    a = int(addr, 16)
-    if best[0] <= a <= best[1]:
-        op = re.sub(r"^@!?U?P\w+\s+", "", text.strip()).split()[0].split(".")[0]
-        hist[op] = hist.get(op, 0) + 1
-fp64 = sum(v for k_, v in hist.items() if k_ in ("DFMA", "DADD", "DMUL", "DSETP"))
-print("FP64 in loop:", fp64, " other:", sum(hist.values()) - fp64)
-print(sorted(hist.items(), key=lambda kv: -kv[1]))
+    if m and int(m.group(1), 16) < int(addr, 16) and (int(addr, 16) - int(m.group(1), 16)) // 16 > 60:
+        loops.append((int(m.group(1), 16), int(addr, 16)))
+for best in loops:
+    print("loop: 0x%x .. 0x%x = %d instructions (static)" % (best[0], best[1], (best[1] - best[0]) // 16 + 1))
+    hist = {}
+    for addr, text in ins:
+        a = int(addr, 16)
+        if best[0] <= a <= best[1]:
+            op = re.sub(r"^@!?U?P\w+\s+", "", text.strip()).split()[0].split(".")[0]
+            hist[op] = hist.get(op, 0) + 1
+    fp64 = sum(v for k_, v in hist.items() if k_ in ("DFMA", "DADD", "DMUL", "DSETP"))
+    print("  FP64 in loop:", fp64, " other:", sum(hist.values()) - fp64)
+    print("  ", sorted(hist.items(), key=lambda kv: -kv[1]))

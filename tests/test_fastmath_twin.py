@@ -46,6 +46,17 @@ def maxulp(lib, fn, x, e=None):
     return lib.twin_maxulp(fn, x.ctypes.data_as(C.c_void_p), ep, C.c_long(x.size), C.byref(wx)), wx.value
 
 
+def test_sincos_kernel_forms_return_the_same_bits(twin):
+    """Generated kernels pick the sin / cos kernel per warp (fixed parity or selected operands): the result of a lane
+    must not depend on its neighbours, so all forms must agree bit for bit."""
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    r = rng.uniform(-0.7854, 0.7854, n); r[:1000] = rng.normal(0, 1e-9, 1000); r[1000] = 0.0; r[1001] = -0.0
+    rl = r * rng.uniform(-1, 1, n) * 2.0 ** -53
+    twin.twin_sincos_forms_differ.restype = C.c_long
+    assert twin.twin_sincos_forms_differ(r.ctypes.data_as(C.c_void_p), rl.ctypes.data_as(C.c_void_p), C.c_long(n)) == 0
+
+
 def test_sin_cos_fast_range(twin):
     rng = np.random.default_rng(0)
     n = 1_000_000

@@ -427,3 +427,59 @@ def test_host_supplied_quantile_table_and_discrete_distributions(mcm):
     assert np.all(y == np.round(y))
     c = mcm.boxplus(1, st.binom(3, 0.5))
     assert set(np.unique(c.to_numpy())) <= {1.0, 2.0, 3.0, 4.0}
+
+
+def _wide_doubles(n, seed):
+    """Doubles with random sign, exponents over the whole range (denormals, zeros, Inf, NaN included) and random
+    mantissas, with a dense share around 1 and values hugging the window edges of the inline sqrt / division."""
+    rng = np.random.default_rng(seed)
+    bits = rng.integers(0, 1 << 63, n, dtype=np.int64) | (rng.integers(0, 2, n, dtype=np.int64) << 63)
+    x = bits.view(np.float64).copy()
+    k = n // 4
+    x[:k] = rng.normal(0.0, 3.0, k)                                   # ordinary data
+    x[k:2 * k] = np.exp2(rng.uniform(-60, 60, k)) * rng.choice([-1.0, 1.0], k)
+    edge = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 1.0, -1.0,
+                     2.0 ** -400, 2.0 ** 400, 2.0 ** -401, 2.0 ** 401, 2.0 ** -900, 2.0 ** 900, 2.0 ** 901, 2.0 ** -901,
+                     np.nextafter(2.0 ** 400, np.inf), np.nextafter(2.0 ** -400, 0.0), 2.0 ** 498, 2.0 ** 499, 2.0 ** -498, 2.0 ** -499,
+                     1e205, 1e250, 1e-250, 4.0, 9.0, 1e10, 1e16, 8.2e5, 8.4e5, 3e9, -1e10, 205886.9, 205887.1, 1e22])
+    x[2 * k:2 * k + len(edge)] = edge
+    return x
+
+
+def test_inline_sqrt_and_division_are_the_ieee_results(mcm):
+    """Generated kernels expand sqrt, /, inv and x^(k/2) inline (compiler's fast-path sequences restated, no slow-path
+    call); values outside the windows replay through the real operators.  Every result must be the correctly rounded
+    one: bit-equal to numpy's sqrt and / on the host, for operands over the whole double range."""
+    from mcm_b200 import tape
+    L = mcm._lib
+    n = 1 << 20
+    x, y = _wide_doubles(n, 1), _wide_doubles(n, 2)
+    with np.errstate(all="ignore"):
+        want = {"sqrt": np.sqrt(x), "div": x / y, "inv": 1.0 / x, "cdiv": 3.0 / y, "divc": x / 7.0}
+    got = {}
+    got["sqrt"], _, e1 = _run(mcm, tape.trace(lambda p: mcm.sqrt(p), 1), [x], n, L.F64, 3, stats=False)
+    got["div"], _, e2 = _run(mcm, tape.trace(lambda p, q: p / q, 2), [x, y], n, L.F64, 3, stats=False)
+    got["inv"], _, e3 = _run(mcm, tape.trace(lambda p: p ** -1, 1), [x], n, L.F64, 3, stats=False)
+    got["cdiv"], _, e4 = _run(mcm, tape.trace(lambda q: 3.0 / q, 1), [y], n, L.F64, 3, stats=False)
+    got["divc"], _, e5 = _run(mcm, tape.trace(lambda p: p / 7.0, 1), [x], n, L.F64, 3, stats=False)
+    assert (e1, e2, e3, e4, e5) == (3, 3, 3, 3, 3)
+    for k_, w in want.items():
+        g = got[k_][0]
+        bad = ~((g == w) | (np.isnan(g) & np.isnan(w))) | (np.signbit(g) != np.signbit(w)) & ~np.isnan(w)
+        assert not bad.any(), (k_, int(bad.sum()), x[bad][:4], y[bad][:4], g[bad][:4], w[bad][:4])
+    # half-integer powers and sin / cos / exp over the whole range: the generated kernel equals the interpreter bit for bit
+    ax = np.abs(x)
+    for f in (lambda p: p ** 1.5, lambda p: p ** 2.5, lambda p: p ** -1.5, lambda p: p ** 0.5, lambda p: p ** 8.5,
+              lambda p: mcm.sin(p) + mcm.cos(p), lambda p: mcm.exp(p)):
+        t = tape.trace(f, 1)
+        for arr in (ax, x):
+            o3, _, e3 = _run(mcm, t, [arr], n, L.F64, 3, stats=False)
+            o2, _, e2 = _run(mcm, t, [arr], n, L.F64, 2, stats=False)
+            assert e3 == 3 and e2 == 2 and bits_equal(o3[0], o2[0])
+    b = C.c_uint32(); L.check(L.lib().mcm_check_flags(C.byref(b), 1))
+    # powers whose true value overflows are Inf, not NaN (the compensated product must not be used there)
+    big = mcm.Particles(np.array([1e205, 1e250, 1e300, 1e-300, 1e100]))
+    r = (big ** 1.5).to_numpy()
+    assert r[0] > 1e307 and np.isinf(r[1]) and np.isinf(r[2]) and r[3] == 0.0 and abs(r[4] / 1e150 - 1) < 1e-15
+    assert np.isinf((big ** 3.5).to_numpy()[4])
+    L.check(L.lib().mcm_check_flags(C.byref(b), 1))

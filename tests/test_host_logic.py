@@ -179,7 +179,8 @@ def test_chain_kernel_generation_and_nvrtc_compile_without_a_gpu(m, tmp_path):
         text = src.value.decode()
         assert "mcm_jit_kernel" in text and nb.value > 10000
         if name == "chain10":
-            assert "pow_three_halves" in text and "sin_fast" in text and "exp_fast" in text   # structural constant folded
+            assert "pow_three_halves_fast" in text and "sincos_fast_v" in text and "exp_fast" in text   # structural constant folded
+            assert "sqrt_fast" in text and "div_fast" in text and "ok = ok &&" in text   # inline sqrt / division, window predicate
         if name == "chain10_f32":
             assert "pow_three_halves" not in text                                              # Float32 keeps the library pow
         if name == "rk4":

@@ -7,6 +7,18 @@
 #include <cmath>
 extern "C" {
 void twin_sin(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::sin_f64(x[i]); }
+// the three forms of the sin / cos kernel (fixed parity, selected operands, per-lane branch) on the same reduced arguments
+long twin_sincos_forms_differ(const double* r, const double* rl, long n) {
+  long bad = 0;
+  for (long i = 0; i < n; ++i)
+    for (int odd = 0; odd < 2; ++odd) {
+      const double a = odd ? mcm::fast::sincos_kernel_t<true>(r[i], rl[i]) : mcm::fast::sincos_kernel_t<false>(r[i], rl[i]);
+      const double b = mcm::fast::sincos_kernel(r[i], rl[i], odd);
+      const double c = mcm::fast::sincos_branch(r[i], rl[i], odd + 2);
+      bad += (memcmp(&a, &b, 8) != 0) + (memcmp(&a, &c, 8) != 0);
+    }
+  return bad;
+}
 void twin_cos(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::cos_f64(x[i]); }
 void twin_exp(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::exp_f64(x[i]); }
 void twin_log(const double* x, double* y, long n) { for (long i = 0; i < n; ++i) y[i] = mcm::fast::log_f64(x[i]); }
