@@ -5,6 +5,7 @@
 #include <math.h>
 #include <string.h>
 #include "mcm_moments.cuh"
+#include "mcm_bulk.cuh"
 #include "mcm_math.cuh"
 
 namespace mcm {
@@ -57,31 +58,6 @@ k_moments(const T* __restrict__ in, size_t n, Mom* partials, unsigned int* ticke
 // occupancy: 3 resident CTAs x 4 stages x 16 KiB.  Same per-thread chunk statistics as k_moments.
 constexpr int MB_STAGES = 4;
 constexpr int MB_TILE_BYTES = 16384;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "MBAR_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MBAR_DONE_%=;\n"
-      "bra MBAR_WAIT_%=;\n"
-      "MBAR_DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)

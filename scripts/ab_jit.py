@@ -56,12 +56,12 @@ print("chain10  registered (ahead of time)            %.4f ms engine %d" % (ms, 
 ms, e = time_chain(trk, ins3, o3, n3, 100, 0, k=3)
 print("rk4x100  registered (ahead of time)            %.3f ms engine %d" % (ms, e))
 L.check(lib.mcm_chain_force_engine(0))
-for ctas, pf, packs, inl in ((3, 0, 2, 0), (3, 0, 1, 1), (3, 1, 1, 1), (4, 0, 1, 1), (2, 0, 2, 1), (2, 1, 2, 1), (3, 0, 2, 1), (3, 1, 2, 1),
-                            (4, 0, 2, 1), (2, 0, 4, 1), (1, 0, 4, 1), (2, 1, 4, 1)):
+for ctas, pf, packs, inl, bulk in ((3, 0, 2, 0, 0), (3, 0, 2, 1, 0), (3, 0, 1, 1, 0), (2, 0, 2, 1, 0), (3, 0, 2, 1, 1), (3, 0, 1, 1, 1), (4, 0, 1, 1, 1),
+                                  (2, 0, 2, 1, 1), (4, 0, 2, 1, 1), (2, 0, 4, 1, 1), (5, 0, 1, 1, 1)):
     L.check(lib.mcm_chain_jit_option(0, ctas)); L.check(lib.mcm_chain_jit_option(1, pf)); L.check(lib.mcm_chain_jit_option(2, packs))
-    L.check(lib.mcm_chain_jit_option(3, inl))
+    L.check(lib.mcm_chain_jit_option(3, inl)); L.check(lib.mcm_chain_jit_option(4, bulk))
     ms, e = time_chain(t10, [a], [y], N, 0, t10.out_slots[0])
     ms2, e2 = time_chain(t10, [a], [y], N, 0, -1)
     ms3, e3 = time_chain(trk, ins3, o3, n3, 100, 0, k=3)
-    print("generated min_ctas=%d prefetch=%d packs=%d inline_divsqrt=%d : chain10+stats %.4f ms  chain10 no stats %.4f ms  rk4x100 %.3f ms  (engines %d %d %d)"
-          % (ctas, pf, packs, inl, ms, ms2, ms3, e, e2, e3), flush=True)
+    print("generated min_ctas=%d prefetch=%d packs=%d inline_divsqrt=%d bulk=%d : chain10+stats %.4f ms  chain10 no stats %.4f ms  rk4x100 %.3f ms  (engines %d %d %d)"
+          % (ctas, pf, packs, inl, bulk, ms, ms2, ms3, e, e2, e3), flush=True)

@@ -15,7 +15,11 @@ from mcm_b200 import chains, tape as tp
 
 L = mcm._lib
 lib = L.load()
-name = sys.argv[1] if len(sys.argv) > 1 else "chain10"
+for a_ in sys.argv[1:]:
+    if a_.startswith("opt"):
+        w_, v_ = a_[3:].split("=")
+        L.check(lib.mcm_chain_jit_option(int(w_), int(v_)))
+name = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("opt") else "chain10"
 f64 = "f32" not in sys.argv
 stats = "nostats" not in sys.argv
 t = {"chain10": lambda: tp.trace(chains.chain10, 1), "readme": lambda: tp.trace(chains.readme_expr, 1),

@@ -223,28 +223,40 @@ def test_generated_kernels_are_bit_identical_to_the_interpreter(mcm, dt, n):
     mcm.check_domain()
 
 
-@pytest.mark.parametrize("opts", [(2, 1, 2), (2, 0, 4), (4, 0, 1)])
+@pytest.mark.parametrize("opts", [(2, 1, 2, 0), (2, 0, 4, 0), (4, 0, 1, 0), (3, 0, 2, 1), (2, 0, 4, 1), (4, 0, 1, 1), (0, 0, 0, 2)])
 def test_generation_options_do_not_change_results(mcm, opts):
-    """packs per thread / prefetch / occupancy are tunables of the generator: same bits, any size (leftover packs)."""
+    """CTAs per SM / prefetch / packs per thread / input staging through shared memory (bulk async copies) are tunables
+    of the generator: same bits, any size (tiles, leftover packs, ragged last pack), one and two inputs."""
     from mcm_b200 import chains, tape
     L = mcm._lib
     lib = L.lib()
     t = tape.trace(chains.chain10, 1)
     t2 = tape.trace_loop(lambda u, v: (u + 0.01 * v, v - 0.01 * mcm.sin(u)), 2, 0)
+    t3 = tape.trace(lambda u, v: (mcm.sqrt(abs(u)) / (v * v + 1.0), u - v), 2)
+
+    def setopts(o):
+        for which, val in zip((0, 1, 2, 4), o):
+            L.check(lib.mcm_chain_jit_option(which, val))
     try:
-        for n in (1, 2, 5, 7, 9, 4099, 100003):
+        for n in (1, 2, 5, 7, 9, 4099, 100003, 1 << 20):
             rng = np.random.default_rng(n)
             a = np.pi + 0.1 * rng.normal(size=n); b = rng.normal(size=n)
-            L.check(lib.mcm_chain_jit_option(0, 3)); L.check(lib.mcm_chain_jit_option(1, 1)); L.check(lib.mcm_chain_jit_option(2, 1))
+            setopts((3, 0, 1, 0))
             o_ref, s_ref, _ = _run(mcm, t, [a], n, L.F64, 3)
             l_ref, _, _ = _run(mcm, t2, [a, b], n, L.F64, 3, reps=11)
-            L.check(lib.mcm_chain_jit_option(0, opts[0])); L.check(lib.mcm_chain_jit_option(1, opts[1])); L.check(lib.mcm_chain_jit_option(2, opts[2]))
+            m_ref, _, _ = _run(mcm, t3, [a, b], n, L.F64, 3)
+            f_ref, _, _ = _run(mcm, t3, [a.astype(np.float32), b.astype(np.float32)], n, L.F32, 3)
+            setopts(opts)
             o, s, e = _run(mcm, t, [a], n, L.F64, 3)
             l, _, _ = _run(mcm, t2, [a, b], n, L.F64, 3, reps=11)
+            m, _, _ = _run(mcm, t3, [a, b], n, L.F64, 3)
+            f, _, _ = _run(mcm, t3, [a.astype(np.float32), b.astype(np.float32)], n, L.F32, 3)
             assert e == 3 and bits_equal(o[0], o_ref[0]) and bits_equal(l[0], l_ref[0]) and bits_equal(l[1], l_ref[1])
+            assert bits_equal(m[0], m_ref[0]) and bits_equal(m[1], m_ref[1]) and bits_equal(f[0], f_ref[0]) and bits_equal(f[1], f_ref[1])
             assert s[0] == n and s[3] == s_ref[3] and s[4] == s_ref[4] and abs(s[1] - s_ref[1]) <= 1e-13 * abs(s_ref[1])
+            assert abs(s[2] - s_ref[2]) <= 1e-12 * s_ref[2] + 1e-300
     finally:
-        L.check(lib.mcm_chain_jit_option(0, 3)); L.check(lib.mcm_chain_jit_option(1, 0)); L.check(lib.mcm_chain_jit_option(2, 0))
+        setopts((0, 0, 0, 2))
 
 
 def test_generated_kernel_replays_out_of_range_packs_exactly(mcm):
@@ -483,3 +495,28 @@ def test_inline_sqrt_and_division_are_the_ieee_results(mcm):
     assert r[0] > 1e307 and np.isinf(r[1]) and np.isinf(r[2]) and r[3] == 0.0 and abs(r[4] / 1e150 - 1) < 1e-15
     assert np.isinf((big ** 3.5).to_numpy()[4])
     L.check(L.lib().mcm_check_flags(C.byref(b), 1))
+
+
+def test_elementwise_fast_forms_equal_the_exact_functions(mcm):
+    """mcm_unary runs sin / cos / exp / sqrt / inv of Float64 vectors through branch-free fast forms with an exact
+    redo outside their windows (csrc/elementwise_unary.cu k_map_fast): same bits as the per-value functions the
+    interpreter uses, over the whole double range, for any length / alignment, and DomainError still raised."""
+    from mcm_b200 import tape
+    L = mcm._lib
+    x = _wide_doubles(1 << 18, 5)
+    with np.errstate(all="ignore"):
+        want_sqrt, want_inv = np.sqrt(x), 1.0 / x
+    for n in (len(x), 4097, 4099):
+        xs = x[:n]
+        p = mcm.Particles(xs)
+        for f in (mcm.sin, mcm.cos, mcm.exp, mcm.sqrt, lambda q: q ** -1):
+            got = f(p).to_numpy()
+            ref, _, e2 = _run(mcm, tape.trace(f, 1), [xs], n, L.F64, 2, stats=False)
+            assert e2 == 2 and bits_equal(got, ref[0])
+        assert bits_equal(mcm.sqrt(p).to_numpy(), want_sqrt[:n]) and bits_equal((p ** -1).to_numpy(), want_inv[:n])
+    b = C.c_uint32(); L.check(L.lib().mcm_check_flags(C.byref(b), 1))
+    mcm.sqrt(mcm.Particles(np.concatenate([np.full(8192, 2.0), [-1.0]])))
+    with pytest.raises(mcm.DomainError):
+        mcm.check_domain()
+    mcm.sin(mcm.Particles(np.full(8192, 1e300)))           # huge but finite: library path, no DomainError
+    mcm.check_domain()
