@@ -503,6 +503,24 @@ def pcov_bench(mcm, L, lib, stream, rank, world):
             out[name] = {"ms": ms, "TFLOP/s": 2.0 * M * M * n * world / (ms * 1e-3) / 1e12,
                          "engine_used": "tcgen05" if lib.mcm_gram_last_engine() == 1 else "dmma"}
         lib.mcm_gram_use_tensor(1)
+        if world == 1:
+            # heavy-tailed rows (the outputs of nonlinear chains: exp of a Gaussian) stay on the tensor cores with 7 / 8 digits
+            vh = [mcm.exp(1.5 * p) for p in v[:64]]
+            vh = [mcm.lincomb([1.0 + 0.001 * j, 0.5], [vh[j % 64], vh[(j * 7 + 3) % 64]]) for j in range(M)]
+            ph = (C.c_void_p * M)(*[C.c_void_p(p.ptr) for p in vh])
+            L.check(lib.mcm_gram(L.F64, ph, M, n, 1, None, C.c_void_p(dC), None)); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                L.check(lib.mcm_gram(L.F64, ph, M, n, 1, None, C.c_void_p(dC), None))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out["heavy_tailed_rows"] = {"data": "lognormal rows exp(1.5 z) (max/sigma ~ 50-100)", "ms": ms,
+                                        "TFLOP/s": 2.0 * M * M * n / (ms * 1e-3) / 1e12,
+                                        "engine_used": "tcgen05" if lib.mcm_gram_last_engine() == 1 else "dmma",
+                                        "digits": int(lib.mcm_gram_last_digits())}
+            del vh
         if world > 1:
             # parity of the sharded pcov: the leading Ms x Ms block against a single-rank Gram of the concatenated slices
             import torch.distributed as dist

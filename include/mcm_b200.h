@@ -315,6 +315,9 @@ int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale,
  * mcm_gram_last_engine: 0 = DMMA, 1 = tcgen05 for the most recent mcm_gram call. */
 int mcm_gram_use_tensor(int on);
 int mcm_gram_last_engine(void);
+/* digits per value (6, 7 or 8 signed 8-bit digits) the last tcgen05 Gram split its rows into: chosen from the
+ * heaviest row's max/sigma so that heavy-tailed data (lognormal, t, exp(p)) stays on the tensor cores at 1e-12 */
+int mcm_gram_last_digits(void);
 /* column means of M variables into means_out_host[M] */
 int mcm_colmeans(int dtype, const void* const* vars, int M, size_t n, double* means_out_host);
 

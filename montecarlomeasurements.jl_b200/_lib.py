@@ -123,6 +123,7 @@ SIGNATURES = {
     "mcm_gram": (_i, [_i, _vpp, _i, _sz, _i, _dp, _vp, _vp]),
     "mcm_gram_use_tensor": (_i, [_i]),
     "mcm_gram_last_engine": (_i, []),
+    "mcm_gram_last_digits": (_i, []),
     "mcm_colmeans": (_i, [_i, _vpp, _i, _sz, _dp]),
     "mcm_sort": (_i, [_i, _vp, _vp, _sz]),
     "mcm_sortperm": (_i, [_i, _vp, _vp, _vp, _sz]),

@@ -389,9 +389,10 @@ int gram_dispatch(int dtype, const void* const* vars, int M, size_t n, double sc
 
 using namespace mcm;
 
-namespace mcm { extern int g_a_in_tmem; }
+namespace mcm { extern int g_a_in_tmem; extern int g_oz_last_digits; }
 extern "C" int mcm_gram_use_tensor(int on) { g_use_tensor = on; mcm::g_a_in_tmem = (on == 2); return MCM_OK; }
 extern "C" int mcm_gram_last_engine(void) { return g_last_engine; }
+extern "C" int mcm_gram_last_digits(void) { return mcm::g_oz_last_digits; }
 
 extern "C" int mcm_gram(int dtype, const void* const* vars, int M, size_t n, int scale_mode,
                         const double* center_host, double* cov_out_dev, double* means_out_dev) {

@@ -35,7 +35,11 @@
 
 namespace mcm {
 
-constexpr int OZ_S = 6;              // digits per value
+// Digits per value: 6 by default; 7 or 8 for heavy-tailed rows (the truncation error is (max/sigma)^2 2^(2 - 8 S)
+// relative to sigma_i sigma_j N in the worst case: 6 digits hold 1e-12 up to max/sigma = 10, 7 up to 160, 8 up to 2560 —
+// and max/sigma <= sqrt(N) always, so 8 digits cover every row up to N = 6.5e6 particles).  More digits = more MMAs
+// per k-block (21 / 28 / 36 digit pairs), still far ahead of the FP64 DMMA kernel (C4: 12.7 / ~17 / ~22 ms against 69).
+constexpr int OZ_S_MIN = 6, OZ_S_MAX = 8;
 constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 32;   // tile rows, tile cols, k per block (== UMMA K for i8)
 #ifndef MCM_OZ_STAGES
 #define MCM_OZ_STAGES 4
@@ -44,10 +48,11 @@ constexpr int OZ_STAGES = MCM_OZ_STAGES;
 constexpr int OZ_THREADS = 256;
 constexpr int OZ_A_SLICE = OZ_TM * OZ_KB;            // 4096 B
 constexpr int OZ_B_SLICE = OZ_TN * OZ_KB;            // 2048 B
-constexpr int OZ_STAGE_BYTES = OZ_S * (OZ_A_SLICE + OZ_B_SLICE);  // 43008 B
-constexpr int OZ_CHUNK_KB = 16384 / OZ_KB;           // k-blocks between flushes
+template <int S> constexpr int oz_stage_bytes() { return S * (OZ_A_SLICE + OZ_B_SLICE); }   // 36864 / 43008 / 49152 B
+// k-blocks between flushes: int32 headroom S pairs x 128 x 128 x K < 2^31 -> K <= 16384 for S <= 7, 8192 for S = 8
+template <int S> constexpr int oz_chunk_kb() { return (S <= 7 ? 16384 : 8192) / OZ_KB; }
 constexpr int OZ_DBITS = 8;                          // bits per digit
-constexpr double OZ_MAX_RATIO = 10.0;                // max/sigma above which the caller must use DMMA
+constexpr double OZ_MAX_RATIO = 10.0;                // max/sigma that 6 digits hold at 1e-12; x16 per extra digit
 constexpr int OZ_TMEM_COLS = 512;
 
 // ---- one-pass row statistics ----------------------------------------------------------------------------
@@ -143,7 +148,7 @@ template int varstats_device<float>(const float* const*, int, size_t, double*, i
 // contiguous, so the 128 (or 64) rows of one k-block of one digit plane are ONE contiguous 4096 (2048) byte
 // run that a single cp.async.bulk drops into shared memory already in MMA layout.
 // One thread = 16 consecutive k of one row (reads 128 contiguous bytes of Float64, writes 16 bytes per digit).
-template <typename T>
+template <typename T, int OZ_S>
 __global__ void __launch_bounds__(256)
 k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, const int* __restrict__ ex, int M,
         size_t n, size_t kpad, size_t mpad, int8_t* __restrict__ slices) {
@@ -213,6 +218,7 @@ __device__ __forceinline__ void oz_tile_decode(int t, int mb, int nbk, int& bi, 
 // Warp-specialised: warp 0 lane 0 = TMA producer (14 bulk copies per k-block), warp 1 lane 0 = MMA issuer
 // (28 tcgen05.mma per k-block), all 8 warps = TMEM flush + epilogue.  K range [kb_begin, kb_end) of this CTA
 // (split-K when there are fewer tiles than SMs); `out` is C (ksplit == 1) or the split workspace.
+template <int OZ_S>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
 k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, size_t mpad, size_t kpad,
           int ksplit, int kb_per_split, double scale, double* __restrict__ C, double* __restrict__ ws, int a_in_tmem) {
@@ -222,6 +228,8 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
   __shared__ __align__(8) unsigned long long bar_acc;
   __shared__ uint32_t tmem_base_sh;
 
+  constexpr int OZ_STAGE_BYTES = oz_stage_bytes<OZ_S>();
+  constexpr int OZ_CHUNK_KB = oz_chunk_kb<OZ_S>();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mb = (int)(mpad / OZ_TM), nbk = (int)(mpad / OZ_TN);
   int bi, bj;
@@ -353,14 +361,27 @@ k_gram_i8(const int8_t* __restrict__ slices, const int* __restrict__ ex, int M, 
             if (a_in_tmem) umma_i8_ts(dcol, abuf + s * 8, db, idn, s == 0 ? acc0 : 1u);
             else umma_i8(dcol, dA0 + (uint64_t)((s * OZ_A_SLICE) >> 4), db, idn, s == 0 ? acc0 : 1u);
           };
-          static_assert(OZ_S == 6 && OZ_TN == 64, "issue schedule is written for 6 digits and 64-column accumulators");
-          issue(0, 0, 256); issue(0, 256, 128);     // diagonals 0..3, 4..5
-          issue(5, 0, 64);                          // 5
-          issue(4, 0, 128);                         // 4..5
-          issue(3, 0, 192);                         // 3..5
-          issue(1, 256, 64);                        // plane 1 x plane 4 -> diagonal 5
-          issue(2, 0, 256);                         // 2..5
-          issue(1, 0, 256);                         // 1..4
+          static_assert(OZ_TN == 64, "accumulators are 64 columns wide");
+          if constexpr (OZ_S == 6) {
+            issue(0, 0, 256); issue(0, 256, 128);     // diagonals 0..3, 4..5
+            issue(5, 0, 64);                          // 5
+            issue(4, 0, 128);                         // 4..5
+            issue(3, 0, 192);                         // 3..5
+            issue(1, 256, 64);                        // plane 1 x plane 4 -> diagonal 5
+            issue(2, 0, 256);                         // 2..5
+            issue(1, 0, 256);                         // 1..4
+          } else {
+            // plane s meets B planes 0 .. S-1-s: 64 (S - s) accumulator columns starting at diagonal s, cut at 256 per
+            // MMA; plane 0 first (it alone may overwrite), then the short ones, the long ones last
+#pragma unroll
+            for (int c0n = 0; c0n < 64 * OZ_S; c0n += 256) issue(0, c0n, (64 * OZ_S - c0n) < 256 ? (64 * OZ_S - c0n) : 256);
+#pragma unroll
+            for (int sp = OZ_S - 1; sp >= 1; --sp) {
+#pragma unroll
+              for (int c0n = (64 * (OZ_S - sp) - 1) / 256 * 256; c0n >= 0; c0n -= 256)
+                issue(sp, c0n, (64 * (OZ_S - sp) - c0n) < 256 ? (64 * (OZ_S - sp) - c0n) : 256);
+            }
+          }
 #ifdef MCM_EXP_NO_MC
           umma_commit(&bar_free[st]);
 #else
@@ -442,49 +463,23 @@ k_gram_i8_reduce(const double* __restrict__ ws, const int* __restrict__ ex, int 
 
 int g_a_in_tmem = 0;   // 0 (default): A planes read from shared memory by wide-N MMAs; mcm_gram_use_tensor(2): staged in TMEM (A/B runs)
 
-// pre_ex / pre_ratio: row statistics already on device (varstats_device), or nullptr to compute them here about
-// the given means (k_rowstats: the centre was supplied by the caller, e.g. the global means of a sharded pcov)
-template <typename T>
-int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C,
-                     const int* pre_ex, const double* pre_ratio) {
+int g_oz_last_digits = 0;   // digits per value of the last tensor-core Gram (introspection for tests / bench)
+
+// slicing + MMA kernel + split-K reduction for S digits per value; ex = per-row exponents (device, mpad entries)
+template <typename T, int OZ_S>
+static int gram_tensor_run(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C, const int* ex) {
   Ctx& c = ctx();
+  constexpr int OZ_STAGE_BYTES = oz_stage_bytes<OZ_S>();
   const size_t mpad = ((size_t)M + OZ_TM - 1) / OZ_TM * OZ_TM;
   const size_t kpad = (n + OZ_KB - 1) / OZ_KB * OZ_KB;
   int8_t* slices = nullptr;
-  int* ex = nullptr;
-  const size_t sbytes = (size_t)OZ_S * mpad * kpad;
-  MCM_CUDA(cudaMallocAsync((void**)&slices, sbytes, c.stream));
-  MCM_CUDA(cudaMallocAsync((void**)&ex, mpad * sizeof(int), c.stream));
-  if (mpad > (size_t)M) MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
-  double* d_ratio = nullptr;
-  MCM_CUDA(cudaMallocAsync((void**)&d_ratio, (size_t)M * sizeof(double), c.stream));
-  if (pre_ex) {
-    MCM_CUDA(cudaMemcpyAsync(ex, pre_ex, (size_t)M * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
-    MCM_CUDA(cudaMemcpyAsync(d_ratio, pre_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
-  } else {
-    k_rowstats<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex, d_ratio);
-    MCM_CHECK_LAUNCH();
-  }
-  {
-    // accuracy guard: (max/sigma)^2 * 2^-46 must stay below 1e-12
-    std::vector<double> h_ratio(M);
-    MCM_CUDA(cudaMemcpyAsync(h_ratio.data(), d_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    MCM_CUDA(cudaStreamSynchronize(c.stream));
-    MCM_CUDA(cudaFreeAsync(d_ratio, c.stream));
-    double worst = 0.0;
-    for (int i = 0; i < M; ++i) worst = std::max(worst, h_ratio[i]);
-    if (!(worst <= OZ_MAX_RATIO)) {
-      MCM_CUDA(cudaFreeAsync(slices, c.stream));
-      MCM_CUDA(cudaFreeAsync(ex, c.stream));
-      return -1;  // decline: heavy-tailed rows, the caller runs the DMMA kernel
-    }
-  }
+  MCM_CUDA(cudaMallocAsync((void**)&slices, (size_t)OZ_S * mpad * kpad, c.stream));
   {
     const size_t total = (kpad / OZ_KB) * (mpad / 8) * 16;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)c.sm_count * 16;
     if (blocks > cap) blocks = cap;
-    k_slice<T><<<(unsigned)blocks, 256, 0, c.stream>>>(d_vars, d_means, ex, M, n, kpad, mpad, slices);
+    k_slice<T, OZ_S><<<(unsigned)blocks, 256, 0, c.stream>>>(d_vars, d_means, ex, M, n, kpad, mpad, slices);
     MCM_CHECK_LAUNCH();
   }
   const int mb = (int)(mpad / OZ_TM), nbk = (int)(mpad / OZ_TN);
@@ -493,7 +488,7 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   constexpr size_t kSmem = (size_t)OZ_STAGES * OZ_STAGE_BYTES;
   static bool attr = false;
   if (!attr) {
-    MCM_CUDA(cudaFuncSetAttribute(k_gram_i8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    MCM_CUDA(cudaFuncSetAttribute(k_gram_i8<OZ_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     attr = true;
   }
   // split-K when the tiles alone cannot fill the GPU
@@ -518,7 +513,8 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
   ksplit = (nkb_total + kb_per_split - 1) / kb_per_split;
   double* ws = nullptr;
   if (ksplit > 1) MCM_CUDA(cudaMallocAsync((void**)&ws, (size_t)ksplit * ntiles * OZ_TM * OZ_TN * sizeof(double), c.stream));
-  k_gram_i8<<<dim3(ntiles, ksplit), OZ_THREADS, kSmem, c.stream>>>(slices, ex, M, mpad, kpad, ksplit, kb_per_split, scale, C, ws, g_a_in_tmem);
+  k_gram_i8<OZ_S><<<dim3(ntiles, ksplit), OZ_THREADS, kSmem, c.stream>>>(slices, ex, M, mpad, kpad, ksplit, kb_per_split, scale, C, ws,
+                                                                        OZ_S == 6 ? g_a_in_tmem : 0);
   MCM_CHECK_LAUNCH();
   if (ksplit > 1) {
     k_gram_i8_reduce<<<ntiles, 256, 0, c.stream>>>(ws, ex, M, mb, nbk, ntiles, ksplit, scale, C);
@@ -526,8 +522,43 @@ int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_
     MCM_CUDA(cudaFreeAsync(ws, c.stream));
   }
   MCM_CUDA(cudaFreeAsync(slices, c.stream));
-  MCM_CUDA(cudaFreeAsync(ex, c.stream));
+  g_oz_last_digits = OZ_S;
   return MCM_OK;
+}
+
+// pre_ex / pre_ratio: row statistics already on device (varstats_device), or nullptr to compute them here about
+// the given means (k_rowstats: the centre was supplied by the caller, e.g. the global means of a sharded pcov)
+template <typename T>
+int gram_tensor_impl(const T* const* d_vars, const double* d_means, int M, size_t n, double scale, double* C,
+                     const int* pre_ex, const double* pre_ratio) {
+  Ctx& c = ctx();
+  const size_t mpad = ((size_t)M + OZ_TM - 1) / OZ_TM * OZ_TM;
+  int* ex = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&ex, mpad * sizeof(int), c.stream));
+  if (mpad > (size_t)M) MCM_CUDA(cudaMemsetAsync(ex + M, 0, (mpad - M) * sizeof(int), c.stream));
+  double* d_ratio = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_ratio, (size_t)M * sizeof(double), c.stream));
+  if (pre_ex) {
+    MCM_CUDA(cudaMemcpyAsync(ex, pre_ex, (size_t)M * sizeof(int), cudaMemcpyDeviceToDevice, c.stream));
+    MCM_CUDA(cudaMemcpyAsync(d_ratio, pre_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+  } else {
+    k_rowstats<T><<<M, 256, 0, c.stream>>>(d_vars, d_means, n, ex, d_ratio);
+    MCM_CHECK_LAUNCH();
+  }
+  // accuracy guard: (max/sigma)^2 2^(2 - 8 S) must stay below ~1e-12 -> the digit count follows the heaviest row
+  std::vector<double> h_ratio(M);
+  MCM_CUDA(cudaMemcpyAsync(h_ratio.data(), d_ratio, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));
+  MCM_CUDA(cudaFreeAsync(d_ratio, c.stream));
+  double worst = 0.0;
+  for (int i = 0; i < M; ++i) worst = std::max(worst, h_ratio[i]);
+  int rc;
+  if (worst <= OZ_MAX_RATIO) rc = gram_tensor_run<T, 6>(d_vars, d_means, M, n, scale, C, ex);
+  else if (worst <= 16.0 * OZ_MAX_RATIO) rc = gram_tensor_run<T, 7>(d_vars, d_means, M, n, scale, C, ex);
+  else if (worst <= 256.0 * OZ_MAX_RATIO) rc = gram_tensor_run<T, 8>(d_vars, d_means, M, n, scale, C, ex);
+  else rc = -1;      // Inf / NaN rows or max/sigma > 2560 (needs N > 6.5e6 and one dominant outlier): the caller runs the DMMA kernel
+  MCM_CUDA(cudaFreeAsync(ex, c.stream));
+  return rc;
 }
 
 template int gram_tensor_impl<double>(const double* const*, const double*, int, size_t, double, double*, const int*, const double*);

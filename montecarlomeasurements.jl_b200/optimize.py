@@ -43,13 +43,16 @@ def perturb(p, Cp, seed: int = 0):
 
 
 def optimize(f, p, tau: float = 1.0, *, tau_i: float = 1.005, iters: int = 10000, tol: float = 1e-8, seed: int = 0,
-             resampling: str = "systematic", info=None):
+             resampling: str = "systematic", info=None, trace=None):
     """res = optimize([rng,] f, p, τ=1; τi=1.005, iters=10000, tol=1e-8) (optimize.jl:14-30): simulated-annealing
     style minimisation of f over a particle cloud.  Per iteration: y = -f(p); we = exp.(τ y); j = weighted sample of
     N ancestors (ordered); every variable gathered with the SAME j; Cp = pcov(p); stop when tr(Cp) < tol; else
     re-perturb around the mean and raise τ.  `resampling`: "systematic" (exact integer prefix scan, one uniform
     offset per iteration) stands in for StatsBase.sample(…, ProbabilityWeights, ordered=true).
-    Returns the final list of Particles (a new list; the input is not modified, like the reference's deepcopy)."""
+    Returns the final list of Particles (a new list; the input is not modified, like the reference's deepcopy).
+    `trace` (a list, tests only): every iteration appends the host copies of its intermediates (weights, the uniform
+    offset, ancestors, gathered cloud, Cp, the perturbation seed, the new cloud, τ) so that each step can be replayed
+    against the oracle with the same Philox stream."""
     p = [x for x in P._check_mv(p)]
     N = p[0].N
     rng = np.random.default_rng(seed)
@@ -59,15 +62,22 @@ def optimize(f, p, tau: float = 1.0, *, tau_i: float = 1.005, iters: int = 10000
         if not isinstance(y, P.Particles):
             raise L.ArgumentError(L.MCM_ERR_INVALID, "optimize: f must return a Particles")
         we = P.exp(tau * y)
-        j = R.resample_indices(we, u=float(rng.random()))
+        u = float(rng.random())
+        j = R.resample_indices(we, u=u)
         p = R.bootstrap(p, N, inds=j)
         Cp = P.pcov(p)
+        if trace is not None:
+            trace.append({"tau": tau, "y": y.to_numpy(), "we": we.to_numpy(), "u": u, "j": j.to_numpy(),
+                          "gathered": [x.to_numpy() for x in p], "Cp": np.array(Cp)})
         if np.trace(Cp) < tol:
             if info is not None:
                 info["iterations"] = it + 1
                 info["converged"] = True
             return p
-        p = perturb(p, Cp, seed=int(rng.integers(0, 2**62)))
+        pseed = int(rng.integers(0, 2**62))
+        p = perturb(p, Cp, seed=pseed)
+        if trace is not None:
+            trace[-1].update(seed=pseed, perturbed=[x.to_numpy() for x in p])
         tau *= tau_i
     if info is not None:
         info["iterations"] = int(iters)

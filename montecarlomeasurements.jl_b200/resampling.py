@@ -36,7 +36,7 @@ def bootstrap(p, n: int | None = None, *, seed: int = 0, inds=None):
     idx = _as_index(inds) if inds is not None else rand_indices(n, N, seed)
     if idx.n != n:
         raise L.ArgumentError(L.MCM_ERR_INVALID, "index vector length must equal n")
-    outs = [P._empty(n, dt) for _ in ps]
+    outs = P._empty_many(len(ps), n, dt)
     if len(ps) == 1:
         L.check(L.lib().mcm_gather(dt, C.c_void_p(ps[0].ptr), C.c_void_p(idx.ptr), C.c_void_p(outs[0].ptr), n, N))
     else:

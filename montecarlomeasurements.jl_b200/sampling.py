@@ -323,7 +323,7 @@ def transform_moments(X, m, S, preserve_latin: bool = False):
     S = np.ascontiguousarray(np.asarray(S, dtype=np.float64))
     if S.shape != (M, M):
         raise L.ArgumentError(L.MCM_ERR_INVALID, f"DimensionMismatch: Σ must be {M} x {M}")
-    outs = [P._empty_like(X[0]) for _ in range(M)]
+    outs = P._empty_many(M, X[0].N, X[0].dtype)
     pin = (C.c_void_p * M)(*[C.c_void_p(x.ptr) for x in X])
     pout = (C.c_void_p * M)(*[C.c_void_p(y.ptr) for y in outs])
     L.check(L.lib().mcm_transform_moments(X[0].dtype, pin, M, X[0].N, m.ctypes.data_as(L._dp), S.ctypes.data_as(L._dp),
@@ -392,7 +392,7 @@ def systematic_batch(N: int, dists, *, permute=True, seed: int = 0, i0: int = 0,
     n_total = int(N if n_total is None else n_total)
     n_loc = int(N if n_local is None else n_local)
     code = P._dtype_code(dtype)
-    outs = [P._empty(n_loc, code) for _ in range(M)]
+    outs = P._empty_many(M, n_loc, code)
     ptrs = (C.c_void_p * M)(*[C.c_void_p(o.ptr) for o in outs])
     L.check(L.lib().mcm_systematic_batch(code, kind, ptrs, M, n_loc,
                                          None if a is None else a.ctypes.data_as(L._dp),

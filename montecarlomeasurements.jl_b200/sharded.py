@@ -226,7 +226,7 @@ def _gather_global(ps, idx, N_global: int, n_out_local: int):
     es = P._NP[dt].itemsize
     chunk = max(4, min(-(-len(ps) // 4) * 4, ((8 << 30) // max(per * es, 1)) // 4 * 4))    # variables per fill (<= 8 GB)
     wid, _ = _window(lib.mcm_window_bytes(chunk, per, dt))
-    outs = [P._empty(n_out_local, dt) for _ in ps]
+    outs = P._empty_many(len(ps), n_out_local, dt)
     for v0 in range(0, len(ps), chunk):
         grp = ps[v0:v0 + chunk]
         sptr = (C.c_void_p * len(grp))(*[C.c_void_p(q.ptr) for q in grp])

@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from conftest import bits_equal
+from conftest import bits_equal, ulp_err
 
 pytestmark = pytest.mark.gpu
 
@@ -128,3 +128,46 @@ def test_sharded_bootstrap_single_rank_equals_bootstrap(mcm):
     lib = mcm._lib.lib()
     assert lib.mcm_window_free(12345) == mcm._lib.MCM_ERR_INVALID
     assert lib.mcm_comm_fence() == 0
+
+
+def test_optimize_trajectory_step_by_step_against_the_oracle(mcm, orc):
+    """optimize.jl:14-30 replayed on the host with the SAME Philox streams: every iteration's weights, ancestors
+    (bit-exact integer scan), gathered cloud (bit-exact), Cp (1e-12) and re-perturbed cloud
+    (mu + chol(1.1 Cp + 1e-12 I) z, z = Phi^-1 of the Philox uniforms keyed by (seed, j N)) are checked against the
+    oracle from that iteration's own inputs, and the loop wiring (tau schedule, one uniform offset and one seed per
+    iteration from the host generator) against a host restatement of the loop."""
+    def rosenbrock2d(x):
+        return (1.0 - x[0]) ** 2 + 100.0 * (x[1] - x[0] ** 2) ** 2
+    N, iters, seed0 = 500, 12, 321
+    p0 = [-1.0 + 2.0 * mcm.Particles(N, mcm.Normal(), seed=j) for j in range(2)]
+    trace = []
+    mcm.optimize(rosenbrock2d, p0, tau=1.0, tau_i=1.005, iters=iters, tol=0.0, seed=seed0, trace=trace)
+    assert len(trace) == iters
+    rng = np.random.default_rng(seed0)
+    cloud = [x.to_numpy() for x in p0]
+    tau = 1.0
+    for it, tr in enumerate(trace):
+        assert tr["tau"] == tau
+        y = -((1.0 - cloud[0]) * (1.0 - cloud[0]) + 100.0 * ((cloud[1] - cloud[0] * cloud[0]) * (cloud[1] - cloud[0] * cloud[0])))
+        assert bits_equal(tr["y"], y), it                                   # + - * and literal powers are bit-exact
+        assert ulp_err(tr["we"], orc.unary("EXP", tau * y)).max() <= 2
+        u = float(rng.random())
+        assert tr["u"] == u
+        j = orc.resample_systematic(tr["we"], u)                           # from the device's own weights
+        assert np.array_equal(tr["j"], j), it
+        for k in range(2):
+            assert bits_equal(tr["gathered"][k], cloud[k][j])
+        G = np.stack(tr["gathered"])
+        Co = orc.cov(np.ascontiguousarray(G))
+        assert np.max(np.abs(tr["Cp"] - Co)) <= 1e-12 * np.max(np.abs(Co)), it
+        pseed = int(rng.integers(0, 2 ** 62))
+        assert tr["seed"] == pseed
+        Lc = np.linalg.cholesky(1.1 * tr["Cp"] + 1e-12 * np.eye(2))
+        z = np.stack([orc.norminvcdf(orc.rand_uniform(N, pseed, k * N)) for k in range(2)])
+        mu = np.array([orc.moments(G[k])[1] for k in range(2)])
+        want = mu[:, None] + Lc @ z
+        got = np.stack(tr["perturbed"])
+        scale = np.abs(Lc).max() * np.abs(z).max() + np.abs(mu).max()
+        assert np.max(np.abs(got - want)) <= 1e-11 * scale, (it, np.max(np.abs(got - want)))
+        cloud = [got[0], got[1]]                                           # continue from the device's cloud
+        tau *= 1.005

@@ -513,9 +513,36 @@ def test_pcov_tcgen05_engine_vs_oracle_and_dmma(mcm, orc, dt):
         sub = [0, 1, 2, 7, M // 2, M - 1]
         Cr = orc.cov(X[sub])
         assert np.max(np.abs(Ct[np.ix_(sub, sub)] - Cr)) <= tol * np.max(np.abs(Cr))
-    Xh = rng.standard_t(3, size=(256, 20000))                      # heavy tails: max/sigma >> 10 -> guard -> DMMA
-    mcm.pcov([mcm.Particles(r) for r in Xh])
-    assert lib.mcm_gram_last_engine() == 0
+    if dt == np.float64:
+        # heavy tails stay on the tensor cores: the digit count follows the heaviest row (7 digits up to max/sigma = 160,
+        # 8 up to 2560), 1e-12 against the oracle and the DMMA kernel
+        cases = {"t(3)": (rng.standard_t(3, size=(256, 20000)), (7, 8)), "lognormal": (np.exp(rng.normal(0.0, 1.5, size=(256, 40001))), (7, 8)),
+                 "exp(p) with one wild row": (np.exp(rng.normal(0.0, 0.3, size=(300, 30000))), (7, 8)),
+                 "cauchy": (rng.standard_cauchy(size=(256, 16384)), (7, 8))}
+        cases["exp(p) with one wild row"][0][17] = rng.standard_t(2, size=30000) * 1e3
+        for name, (Xh, digits) in cases.items():
+            vh = [mcm.Particles(r) for r in Xh]
+            Ct = mcm.pcov(vh)
+            if lib.mcm_gram_last_engine() != 1:               # a Cauchy row beyond max/sigma = 2560 may still decline
+                assert name == "cauchy"
+                continue
+            assert lib.mcm_gram_last_digits() in digits, (name, lib.mcm_gram_last_digits())
+            lib.mcm_gram_use_tensor(0)
+            try:
+                Cd = mcm.pcov(vh)
+            finally:
+                lib.mcm_gram_use_tensor(1)
+            d = np.sqrt(np.diag(Cd))
+            assert np.max(np.abs(Ct - Cd) / np.outer(d, d)) <= 1e-12, (name, np.max(np.abs(Ct - Cd) / np.outer(d, d)))
+            sub = [0, 1, 17, 100, 255]
+            Cr = orc.cov(np.ascontiguousarray(Xh[sub]))
+            dr = np.sqrt(np.diag(Cr))
+            assert np.max(np.abs(Ct[np.ix_(sub, sub)] - Cr) / np.outer(dr, dr)) <= 1e-12, name
+        Xi = rng.normal(size=(256, 8192)); Xi[3, 5] = np.inf        # a non-finite row: the guard declines, DMMA propagates it
+        mcm.pcov([mcm.Particles(r) for r in Xi])
+        assert lib.mcm_gram_last_engine() == 0
+    mcm.pcov([mcm.Particles(r) for r in rng.normal(size=(256, 8192)).astype(dt)])
+    assert lib.mcm_gram_last_engine() == 1 and lib.mcm_gram_last_digits() == 6
     Xc = rng.normal(size=(256, 8192)); Xc[5] = 1.25                # a constant (zero-variance) row
     Cc = mcm.pcov([mcm.Particles(r) for r in Xc])
     assert np.all(Cc[5] == 0) and np.all(Cc[:, 5] == 0) and abs(Cc[0, 0] - Xc[0].var(ddof=1)) <= 1e-12
