@@ -491,6 +491,16 @@ enum mcm_la_op {
 };
 int mcm_batched_linalg(int op, int dtype, int nmat, int m, const void* const* A, const void* const* B,
                        void* const* out, void* const* out_im, size_t n);
+/* The same for matrices with Complex{Particles} entries (complex.jl:104-181: exp, exp!, log through ℂⁿ2ℂⁿ_function; det
+ * through ℂⁿ2ℂ_function; eigvals; svdvals) and for log of a REAL uncertain matrix, whose result is complex
+ * (particles.jl:603, Base.log(::Matrix{<:AbstractParticles}) = ℝⁿ2ℂⁿ_function(log, p)): A_im == NULL.  Tables are
+ * row-major nmat x nmat (inputs; EXP / LOG outputs), one entry (DET) or nmat entries (EIGVALS ordered by (re, im);
+ * SVDVALS descending, real: out_im unused).  Algorithms: csrc/mcm_small_linalg_c.cuh (LU, Higham expm, complex Schur +
+ * inverse scaling and squaring log, one-sided Jacobi).  A singular matrix under LOG or a QR iteration that does not
+ * converge stores NaN and raises MCM_FLAG_DOMAIN. */
+enum mcm_lac_opcode { MCM_LAC_EXP = 0, MCM_LAC_LOG, MCM_LAC_DET, MCM_LAC_EIGVALS, MCM_LAC_SVDVALS, MCM_LAC_COUNT };
+int mcm_batched_linalg_complex(int op, int dtype, int nmat, const void* const* A_re, const void* const* A_im,
+                               void* const* out_re, void* const* out_im, size_t n);
 /* ---- Complex{Particles} (src/complex.jl:1-93) ----------------------------------------------------------------
  * A complex uncertain number is two device vectors (re, im).  One streaming kernel per operation replaces the host
  * loop of C2C_function (complex.jl:30-67).  Operand components: a null pointer selects the constant beside it, so

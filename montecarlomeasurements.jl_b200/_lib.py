@@ -149,6 +149,7 @@ SIGNATURES = {
     "mcm_complex_op": (_i, [_i, _i, _vp, _vp, _d, _d, _vp, _vp, _d, _d, _vp, _vp, _sz]),
     "mcm_dense_use_v2": (_i, [_i]),
     "mcm_batched_linalg": (_i, [_i, _i, _i, _i, _vpp, _vpp, _vpp, _vpp, _sz]),
+    "mcm_batched_linalg_complex": (_i, [_i, _i, _i, _vpp, _vpp, _vpp, _vpp, _sz]),
     "mcm_argmin_absdiff": (_i, [_i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),
     "mcm_argmin_sqdist": (_i, [_i, _vpp, _i, _sz, _dp, C.POINTER(C.c_uint64)]),
     "mcm_shuffle_insert": (_i, [_i, _vp, _sz, C.c_uint64, _d, _vp]),

@@ -8,6 +8,7 @@
 // FP64 pipe beyond.
 #include "mcm_common.cuh"
 #include "mcm_small_linalg.cuh"
+#include "mcm_small_linalg_c.cuh"
 
 namespace mcm {
 
@@ -130,6 +131,79 @@ static int la_by_op(int op, int nmat, const LaArgs& g, int m, size_t n) {
   }
 }
 
+
+// ---- matrices with Complex{Particles} entries, and log of a real uncertain matrix ---------------------------------
+// complex.jl:104-181 (ℂⁿ2ℂⁿ_function: exp, exp!, log; ℂⁿ2ℂ_function: det; eigvals; svdvals) and particles.jl:603
+// (Base.log(::Matrix{<:AbstractParticles}) = ℝⁿ2ℂⁿ_function(log, p)): entry (r, c) is a pair of length-N vectors.
+struct LacArgs {
+  const void* Are[LA_MAXPTR];
+  const void* Aim[LA_MAXPTR];     // all null: a real matrix
+  void* ore[LA_MAXPTR];
+  void* oim[LA_MAXPTR];
+};
+template <int OP, int N, typename T>
+__global__ void __launch_bounds__(128)
+k_batched_lac(const __grid_constant__ LacArgs g, int real_input, size_t n_particles, uint32_t* flags) {
+  using namespace sla;
+  const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n_particles) return;
+  CMat<N> a;
+  for (int e = 0; e < N * N; ++e) a.a[e] = cmk(la_ld<T>(g.Are[e], i), real_input ? 0.0 : la_ld<T>(g.Aim[e], i));
+  bool bad = false;
+  if constexpr (OP == MCM_LAC_EXP || OP == MCM_LAC_LOG) {
+    if constexpr (OP == MCM_LAC_EXP) bad = !cexpm(a); else bad = !clogm(a);
+    for (int e = 0; e < N * N; ++e) { la_st<T>(g.ore[e], i, a.a[e].re); la_st<T>(g.oim[e], i, a.a[e].im); }
+  } else if constexpr (OP == MCM_LAC_DET) {
+    int piv[N];
+    const int s = clu_factor(a, piv);
+    const cx d = s == 0 ? cmk(0.0, 0.0) : cdet_from_lu(a, s);
+    la_st<T>(g.ore[0], i, d.re); la_st<T>(g.oim[0], i, d.im);
+  } else if constexpr (OP == MCM_LAC_EIGVALS) {
+    cx w[N];
+    bad = !ceigvals(a, w);
+    for (int e = 0; e < N; ++e) { la_st<T>(g.ore[e], i, w[e].re); la_st<T>(g.oim[e], i, w[e].im); }
+  } else if constexpr (OP == MCM_LAC_SVDVALS) {
+    double sv[N];
+    csvdvals(a, sv);
+    for (int e = 0; e < N; ++e) la_st<T>(g.ore[e], i, sv[e]);
+  }
+  if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
+}
+template <int OP, int N, typename T>
+static int lac_launch(const LacArgs& g, int real_input, size_t n) {
+  Ctx& c = ctx();
+  const size_t grid = (n + 127) / 128;
+  if (grid > 0x7fffffffull) return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg_complex: too many particles");
+  k_batched_lac<OP, N, T><<<(unsigned)grid, 128, 0, c.stream>>>(g, real_input, n, c.d_flags);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+template <int OP, typename T>
+static int lac_by_n(int nmat, const LacArgs& g, int real_input, size_t n) {
+  switch (nmat) {
+    case 1: return lac_launch<OP, 1, T>(g, real_input, n);
+    case 2: return lac_launch<OP, 2, T>(g, real_input, n);
+    case 3: return lac_launch<OP, 3, T>(g, real_input, n);
+    case 4: return lac_launch<OP, 4, T>(g, real_input, n);
+    case 5: return lac_launch<OP, 5, T>(g, real_input, n);
+    case 6: return lac_launch<OP, 6, T>(g, real_input, n);
+    case 7: return lac_launch<OP, 7, T>(g, real_input, n);
+    case 8: return lac_launch<OP, 8, T>(g, real_input, n);
+    default: return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg_complex: matrix size %d not supported", nmat);
+  }
+}
+template <typename T>
+static int lac_by_op(int op, int nmat, const LacArgs& g, int real_input, size_t n) {
+  switch (op) {
+    case MCM_LAC_EXP: return lac_by_n<MCM_LAC_EXP, T>(nmat, g, real_input, n);
+    case MCM_LAC_LOG: return lac_by_n<MCM_LAC_LOG, T>(nmat, g, real_input, n);
+    case MCM_LAC_DET: return lac_by_n<MCM_LAC_DET, T>(nmat, g, real_input, n);
+    case MCM_LAC_EIGVALS: return lac_by_n<MCM_LAC_EIGVALS, T>(nmat, g, real_input, n);
+    case MCM_LAC_SVDVALS: return lac_by_n<MCM_LAC_SVDVALS, T>(nmat, g, real_input, n);
+    default: return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: unknown operation %d", op);
+  }
+}
+
 }  // namespace mcm
 
 using namespace mcm;
@@ -173,4 +247,33 @@ extern "C" int mcm_batched_linalg(int op, int dtype, int nmat, int m, const void
     }
   if (n == 0) return MCM_OK;
   return dtype == MCM_F64 ? la_by_op<double>(op, nmat, g, m, n) : la_by_op<float>(op, nmat, g, m, n);
+}
+
+extern "C" int mcm_batched_linalg_complex(int op, int dtype, int nmat, const void* const* A_re, const void* const* A_im,
+                                          void* const* out_re, void* const* out_im, size_t n) {
+  MCM_NEED_INIT();
+  if (dtype != MCM_F64 && dtype != MCM_F32) return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: bad dtype %d", dtype);
+  if (nmat < 1 || nmat > LA_MAXN) return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg_complex: matrix size must be 1..%d", LA_MAXN);
+  if (!A_re || !out_re) return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: null table");
+  int nout = 0;
+  switch (op) {
+    case MCM_LAC_EXP: case MCM_LAC_LOG: nout = nmat * nmat; break;
+    case MCM_LAC_DET: nout = 1; break;
+    case MCM_LAC_EIGVALS: case MCM_LAC_SVDVALS: nout = nmat; break;
+    default: return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: unknown operation %d", op);
+  }
+  if (op != MCM_LAC_SVDVALS && !out_im) return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: this operation needs out_im");
+  LacArgs g{};
+  for (int e = 0; e < nmat * nmat; ++e) {
+    if (!A_re[e] || (A_im && !A_im[e])) return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: A[%d] is null", e);
+    g.Are[e] = A_re[e];
+    g.Aim[e] = A_im ? A_im[e] : nullptr;
+  }
+  for (int e = 0; e < nout; ++e) {
+    if (!out_re[e] || (op != MCM_LAC_SVDVALS && !out_im[e])) return fail(MCM_ERR_INVALID, "mcm_batched_linalg_complex: out[%d] is null", e);
+    g.ore[e] = out_re[e];
+    g.oim[e] = op != MCM_LAC_SVDVALS ? out_im[e] : nullptr;
+  }
+  if (n == 0) return MCM_OK;
+  return dtype == MCM_F64 ? lac_by_op<double>(op, nmat, g, A_im ? 0 : 1, n) : lac_by_op<float>(op, nmat, g, A_im ? 0 : 1, n);
 }

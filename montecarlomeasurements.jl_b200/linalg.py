@@ -124,3 +124,95 @@ def lyap(A, Cm):
 
 def svdvals(A):
     return _call("SVDVALS", A, None, lambda n, m: n, who="svdvals")[2]
+
+
+# ---- matrices with Complex{Particles} entries; log of a real uncertain matrix (complex.jl:104-181, particles.jl:603) ----
+def _as_complex_table(M, who: str):
+    """-> (n, re entries, im entries or None, N, dtype).  Entries: ComplexParticles, Particles, complex or real numbers."""
+    from .complexp import ComplexParticles
+    if isinstance(M, np.ndarray):
+        arr = M.astype(object)
+    else:                        # element by element: np.array() would download Particles through __array__
+        rows = [list(r) if isinstance(r, (list, tuple, np.ndarray)) else [r] for r in M]
+        if len({len(r) for r in rows}) != 1:
+            raise L.ArgumentError(L.MCM_ERR_INVALID, f"{who}: ragged matrix")
+        arr = np.empty((len(rows), len(rows[0])), dtype=object)
+        for i, r in enumerate(rows):
+            for j, v in enumerate(r):
+                arr[i, j] = v
+    if arr.ndim != 2 or arr.shape[0] != arr.shape[1]:
+        raise L.ArgumentError(L.MCM_ERR_INVALID, f"{who}: matrix must be square (DimensionMismatch in the reference)")
+    n = arr.shape[0]
+    if n > MAX_N:
+        raise L.MethodError(L.MCM_ERR_UNSUPPORTED, f"{who}: device path handles n <= {MAX_N}; use bymap for larger matrices")
+    ref = None
+    for v in arr.ravel():
+        if isinstance(v, ComplexParticles):
+            ref = v.re
+        elif isinstance(v, P.Particles):
+            ref = v
+        if ref is not None:
+            break
+    if ref is None:
+        raise L.MethodError(L.MCM_ERR_INVALID, f"{who}: no Particles among the entries (use numpy for plain matrices)")
+    N, dt = ref.N, ref.dtype
+    any_complex = any(isinstance(v, (ComplexParticles, complex)) and not isinstance(v, numbers.Real) for v in arr.ravel())
+    re, im = [], []
+    for v in arr.ravel():
+        if isinstance(v, ComplexParticles):
+            a, b = v.re, v.im
+        elif isinstance(v, P.Particles):
+            a, b = v, None
+        elif isinstance(v, numbers.Real):
+            a, b = P.fill(float(v), N, P._NP[dt]), None
+        elif isinstance(v, numbers.Complex):
+            a, b = P.fill(float(v.real), N, P._NP[dt]), P.fill(float(v.imag), N, P._NP[dt])
+        else:
+            raise L.MethodError(L.MCM_ERR_INVALID, f"{who}: unsupported entry type {type(v).__name__}")
+        if a.N != N or a.dtype != dt or (b is not None and (b.N != N or b.dtype != dt)):
+            raise L.MethodError(L.MCM_ERR_INVALID, f"{who}: all entries need the same number of particles and element type")
+        re.append(a)
+        im.append(b if b is not None else (P.fill(0.0, N, P._NP[dt]) if any_complex else None))
+    return n, re, (im if any_complex else None), N, dt
+
+
+def _ccall(op: str, A, nout, who: str, real_out: bool = False):
+    from .complexp import ComplexParticles
+    n, re, im, N, dt = _as_complex_table(A, who)
+    k = nout(n)
+    ore = P._empty_many(k, N, dt)
+    oim = None if real_out else P._empty_many(k, N, dt)
+    L.check(L.lib().mcm_batched_linalg_complex(E["MCM_LAC_" + op], dt, n, _ptrs(re), _ptrs(im) if im is not None else None,
+                                               _ptrs(ore), _ptrs(oim) if oim is not None else None, N))
+    if real_out:
+        return n, ore
+    return n, [ComplexParticles(a, b) for a, b in zip(ore, oim)]
+
+
+def cexpm(A):
+    """`exp(A)` / `exp!(A)` for a Matrix{Complex{Particles}} (complex.jl:129-130): n x n nested list of ComplexParticles."""
+    n, out = _ccall("EXP", A, lambda n: n * n, "exp")
+    return _grid(out, n, n)
+
+
+def logm(A):
+    """`log(A)` for a real uncertain matrix (particles.jl:603, complex-valued like the reference's ℝⁿ2ℂⁿ_function) or a
+    Matrix{Complex{Particles}} (complex.jl:131): principal matrix logarithm per particle."""
+    n, out = _ccall("LOG", A, lambda n: n * n, "log")
+    return _grid(out, n, n)
+
+
+def cdet(A):
+    """`det(A)` for a Matrix{Complex{Particles}} (complex.jl:145): one ComplexParticles."""
+    return _ccall("DET", A, lambda n: 1, "det")[1][0]
+
+
+def ceigvals(A):
+    """`eigvals(A)` for a Matrix{Complex{Particles}} (complex.jl:147-163): list of ComplexParticles, each particle's
+    spectrum ordered by (real, imaginary part)."""
+    return _ccall("EIGVALS", A, lambda n: n, "eigvals")[1]
+
+
+def csvdvals(A):
+    """`svdvals(A)` for a Matrix{Complex{Particles}} (complex.jl:165-181): list of Particles, descending."""
+    return _ccall("SVDVALS", A, lambda n: n, "svdvals", real_out=True)[1]

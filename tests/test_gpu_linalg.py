@@ -138,3 +138,81 @@ def test_full_size_properties(mcm):
     assert max(abs(m.min), abs(m.max)) < 1e-12
     m = mcm.moments(im[0] + im[1] + im[2])
     assert max(abs(m.min), abs(m.max)) == 0.0
+
+
+# ---- matrices with Complex{Particles} entries; log of a real uncertain matrix (complex.jl:104-181, particles.jl:603) -------
+def ctable(mcm, Z):
+    return [[mcm.ComplexParticles(mcm.Particles(np.ascontiguousarray(Z[:, i, j].real)), mcm.Particles(np.ascontiguousarray(Z[:, i, j].imag)))
+             for j in range(Z.shape[2])] for i in range(Z.shape[1])]
+
+
+def cgather(grid):
+    return np.stack([np.stack([z.re.to_numpy() + 1j * z.im.to_numpy() for z in row], axis=1) for row in grid], axis=1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 8])
+def test_complex_matrix_functions_equal_the_twin(mcm, n):
+    """Device == host twin bit for bit (tests/test_small_linalg_c_twin.py pins the twin against LAPACK / scipy)."""
+    import test_small_linalg_c_twin as tw
+    twin = tw.build_twin()
+    la = mcm.linalg
+    rng = np.random.default_rng(300 + n)
+    N = 2000
+    Z = rng.normal(size=(N, n, n)) + 1j * rng.normal(size=(N, n, n))
+    Zt = ctable(mcm, Z)
+    assert np.array_equal(cgather(la.cexpm(ctable(mcm, 0.7 * Z))), tw.twin_run(twin, "exp", 0.7 * Z))
+    d = la.cdet(Zt)
+    assert np.array_equal(d.re.to_numpy() + 1j * d.im.to_numpy(), tw.twin_run(twin, "det", Z))
+    w = la.ceigvals(Zt)
+    assert np.array_equal(np.stack([z.re.to_numpy() + 1j * z.im.to_numpy() for z in w], 1), tw.twin_run(twin, "eigvals", Z))
+    sv = la.csvdvals(Zt)
+    assert np.array_equal(np.stack([p.to_numpy() for p in sv], 1), tw.twin_run(twin, "svdvals", Z))
+    import scipy.linalg as sl
+    B = np.array([sl.expm(0.5 * z) for z in Z[:500]])
+    assert np.array_equal(cgather(la.logm(ctable(mcm, B))), tw.twin_run(twin, "log", B))
+    R = rng.normal(size=(500, n, n))                                   # real input: A_im == NULL
+    Lr = cgather(la.logm(table(mcm, R)))
+    assert np.array_equal(Lr, tw.twin_run(twin, "log", R))
+    mcm.check_domain()
+
+
+def test_complex_matrix_reference_style_assertions(mcm):
+    """B = A .± 0 behaves like A (the pattern of runtests.jl:490-523 and :572-575 for complex entries); exp(log(A)) == A;
+    log of a positive definite uncertain matrix is real; a singular matrix raises the DomainError flag."""
+    import scipy.linalg as sl
+    la = mcm.linalg
+    rng = np.random.default_rng(5)
+    A = rng.normal(size=(3, 3)) + 1j * rng.normal(size=(3, 3))
+    N = 64
+    Zt = [[mcm.ComplexParticles(mcm.Particles(np.full(N, A[i, j].real)), mcm.Particles(np.full(N, A[i, j].imag))) for j in range(3)] for i in range(3)]
+    E = cgather(la.cexpm(Zt))
+    assert np.max(np.abs(E - sl.expm(A)[None])) < 1e-12 * np.abs(sl.expm(A)).max()
+    Lg = cgather(la.logm(Zt))
+    assert np.max(np.abs(Lg - sl.logm(A)[None])) < 1e-11 * np.linalg.cond(A)
+    assert abs(complex(la.cdet(Zt).re.to_numpy()[0], la.cdet(Zt).im.to_numpy()[0]) - np.linalg.det(A)) < 1e-12 * abs(np.linalg.det(A))
+    sv = np.array([p.to_numpy()[0] for p in la.csvdvals(Zt)])
+    assert np.max(np.abs(sv - np.linalg.svd(A, compute_uv=False))) < 1e-13 * sv[0]
+    w = np.array([complex(z.re.to_numpy()[0], z.im.to_numpy()[0]) for z in la.ceigvals(Zt)])
+    wr = np.linalg.eigvals(A)
+    assert np.max(np.min(np.abs(w[:, None] - wr[None, :]), axis=1)) < 1e-12 * np.abs(wr).max()
+    # mixed entries: plain numbers, Particles and ComplexParticles promote like the reference's `promote`
+    p = mcm.pm(1.0, 0.1, seed=1)
+    M = [[p, 2.0 + 1.0j], [0.5, mcm.ComplexParticles(p, p)]]
+    ph = p.to_numpy()
+    Zs = np.zeros((p.N, 2, 2), dtype=complex)
+    Zs[:, 0, 0] = ph; Zs[:, 0, 1] = 2 + 1j; Zs[:, 1, 0] = 0.5; Zs[:, 1, 1] = ph + 1j * ph
+    dd = la.cdet(M)
+    assert np.max(np.abs(dd.re.to_numpy() + 1j * dd.im.to_numpy() - np.linalg.det(Zs))) < 1e-13
+    # exp(log(A)) == A on uncertain real matrices, and real logs for positive definite ones
+    R = rng.normal(size=(4000, 3, 3))
+    S = R @ R.transpose(0, 2, 1) + 0.5 * np.eye(3)
+    Ls = cgather(la.logm(table(mcm, S)))
+    assert np.max(np.abs(Ls.imag)) < 1e-12
+    back = cgather(la.cexpm(ctable(mcm, Ls)))
+    assert np.max(np.abs(back - S) / np.abs(S).max(axis=(1, 2), keepdims=True)) < 1e-11
+    mcm.check_domain()
+    la.logm([[mcm.Particles(np.zeros(8)), 0.0], [0.0, mcm.Particles(np.ones(8))]])
+    with pytest.raises(mcm.DomainError):
+        mcm.check_domain()
+    with pytest.raises(mcm.MethodError):
+        la.logm(np.zeros((2, 2)))
