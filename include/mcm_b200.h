@@ -153,6 +153,8 @@ int mcm_device_info(int* sm_count, size_t* free_bytes, size_t* total_bytes);
  * reference primitive allocates its result, register_primitive.jl:45,49,53,95) */
 int mcm_alloc(void** dptr, size_t bytes);   /* stream-ordered (cudaMallocAsync pool) */
 int mcm_free(void* dptr);                   /* stream-ordered; safe from a GC finalizer thread */
+/* M vectors of bytes_each bytes in one call (the result of an operation on a vector of M uncertain variables) */
+int mcm_alloc_many(void** dptrs, int M, size_t bytes_each);
 int mcm_host_alloc(void** hptr, size_t bytes); /* pinned host staging */
 int mcm_host_free(void* hptr);
 /* Particles(v::Vector) (types.jl:55)  /  Array(p), Vector(p) (particles.jl:458-459) */

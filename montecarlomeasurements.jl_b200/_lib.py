@@ -85,6 +85,7 @@ SIGNATURES = {
     "mcm_clear_flags": (_i, [C.c_uint32]),
     "mcm_device_info": (_i, [C.POINTER(_i), C.POINTER(_sz), C.POINTER(_sz)]),
     "mcm_alloc": (_i, [_vpp, _sz]),
+    "mcm_alloc_many": (_i, [_vpp, _i, _sz]),
     "mcm_free": (_i, [_vp]),
     "mcm_host_alloc": (_i, [_vpp, _sz]),
     "mcm_host_free": (_i, [_vp]),

@@ -206,35 +206,60 @@ MCM_FM_HD double cos_f64(double x) {
 // ---------------------------------------------------------------------------------
 // exp
 // ---------------------------------------------------------------------------------
-// x = n*ln2 + r, |r| <= ln2/2 (two-constant Cody-Waite, ln2_hi has 32 trailing zero bits);
-// exp(r) = 1 + (r + r^2 * Q(r)) with Q a degree-10 minimax polynomial (scripts/fit_fastmath.py);
-// 2^n by exponent arithmetic.  |x| > 708: library (overflow / gradual underflow).
-#include "mcm_fastmath_coeffs.inc"  // MCM_EXPQ_LIST: kExpQ0 .. kExpQ10
+// Table-driven (round 2): x = k (ln2/32) + r with k = rint(x 32/ln2), |r| <= ln2/64 (two-constant Cody-Waite, L1 holds 36
+// bits so k L1 is exact, the rounding error of the second step is recovered into rl); k = 32 m + j;
+//   exp(x) = 2^m * T_j * (1 + p),   T_j = 2^(j/32) = th + tl (mcm_exp_table.inc),   p = expm1(r + rl) = r + (r^2 q(r) + rl)
+// with q the degree-4 Taylor polynomial of (expm1(r) - r)/r^2 (truncation r^7/5040 < 2^-57 on this range); the result is
+// th + (tl + th p): <= 0.55 ulp measured on the host twin (0.83 before).  14 FP64 instructions against the 19 of the degree-10 polynomial on |r| <= ln2/2 it
+// replaces (the FP64 pipe is what bounds the fused chains), plus one 16-byte table load.  |x| > 708: library.
+#include "mcm_fastmath_coeffs.inc"  // MCM_EXPQ_LIST: kExpQ0 .. kExpQ10 (the former polynomial; kept for exp10 / tests)
+#include "mcm_exp_table.inc"
 MCM_FM_CONST double kExp[16] = {
-    1.44269504088896338700e+00,   // [0] log2(e)
-    6.93147180369123816490e-01,   // [1] ln2_hi
-    1.90821492927058770002e-10,   // [2] ln2_lo
+    MCM_EXP_INV_L,                // [0] 32 / ln2
+    MCM_EXP_L1,                   // [1] ln2/32, leading 36 bits
+    MCM_EXP_L2,                   // [2] ln2/32 - L1
     708.0,                        // [3] fast-path limit
-    MCM_EXPQ_LIST,                // [4..14] Q0..Q10
-    0.0};
-#define kLog2e kExp[0]
-#define kLn2Hi kExp[1]
-#define kLn2Lo kExp[2]
+    5.00000000000000000000e-01, 1.66666666666666657415e-01, 4.16666666666666643537e-02, 8.33333333333333321769e-03,
+    1.38888888888888894189e-03,   // [4..8] 1/2!, 1/3!, 1/4!, 1/5!, 1/6!
+    0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#define kExpInvL kExp[0]
+#define kExpL1 kExp[1]
+#define kExpL2 kExp[2]
+// The table is read with a per-lane index: __constant__ memory would serialise the 32 lanes of a warp, so on the device
+// it lives in global memory and is read through L1 (one 16-byte load per value, 512 bytes in all).
+#ifdef MCM_HOST_TWIN
+static const double kExpTab[64] = {MCM_EXP_TABLE};
+inline void exp_tab(int j, double& th, double& tl) { th = kExpTab[2 * j]; tl = kExpTab[2 * j + 1]; }
+#else
+static __device__ const double2 kExpTab[32] = {
+#define MCM_PAIR_(a, b) {a, b}
+    MCM_EXP_TABLE_PAIRS
+#undef MCM_PAIR_
+};
+__device__ __forceinline__ void exp_tab(int j, double& th, double& tl) {
+  const double2 t = __ldg(&kExpTab[j]);
+  th = t.x; tl = t.y;
+}
+#endif
 
+// the branch-free core, valid for |x| <= 708 (the callers test the range)
+MCM_FM_HD double exp_core(double x) {
+  const double k = rint(x * kExpInvL);
+  const double rh = fma(-k, kExpL1, x);            // exact (k L1 has <= 53 bits)
+  const double r = fma(-k, kExpL2, rh);
+  const double rl = fma(-k, kExpL2, rh - r);       // rounding error of the line above
+  const int ki = (int)k;
+  double th, tl;
+  exp_tab(ki & 31, th, tl);
+  double q = kExp[8];
+  q = fma(q, r, kExp[7]); q = fma(q, r, kExp[6]); q = fma(q, r, kExp[5]); q = fma(q, r, kExp[4]);
+  const double p = r + fma(r * r, q, rl);          // expm1(r + rl)
+  const double y = th + fma(th, p, tl);            // in (0.98, 2.02)
+  return bits2d(d2bits(y) + ((int64_t)(ki >> 5) << 52));   // |m| <= 1022 and 2^m y stays normal for |x| <= 708
+}
 MCM_FM_HD double exp_f64(double x) {
   if (!(fabs(x) <= kExp[3])) return lib_exp(x);
-  const double n = rint(x * kLog2e);
-  const double rh = fma(-n, kLn2Hi, x);            // exact (n*ln2_hi has <= 53 bits)
-  const double r = fma(-n, kLn2Lo, rh);
-  const double rl = fma(-n, kLn2Lo, rh - r);       // rounding error of the line above
-  double q = kExp[14];
-  q = fma(q, r, kExp[13]); q = fma(q, r, kExp[12]); q = fma(q, r, kExp[11]); q = fma(q, r, kExp[10]);
-  q = fma(q, r, kExp[9]); q = fma(q, r, kExp[8]); q = fma(q, r, kExp[7]); q = fma(q, r, kExp[6]);
-  q = fma(q, r, kExp[5]); q = fma(q, r, kExp[4]);
-  // exp(r + rl) = 1 + r + r^2 q + rl (to first order in rl)
-  const double t = fma(r * r, q, rl);
-  const double p = 1.0 + (r + t);
-  return bits2d(d2bits(p) + ((int64_t)n << 52));   // p in [0.70, 1.42], |n| <= 1022: stays normal
+  return exp_core(x);
 }
 
 // ---------------------------------------------------------------------------------

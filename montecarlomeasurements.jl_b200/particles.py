@@ -50,7 +50,7 @@ class Particles:
       Particles(m) with m 2-D       -> list of Particles, one per column; dim 1 is the particle dim (types.jl:35-52)
     """
 
-    __slots__ = ("ptr", "N", "dtype", "_own", "_slab", "__weakref__")
+    __slots__ = ("ptr", "N", "dtype", "_own", "__weakref__")
     __array_priority__ = 1000
 
     def __new__(cls, *args, **kw):
@@ -206,33 +206,20 @@ def _empty(N: int, dtype: int) -> Particles:
     return Particles(_ptr=ptr, _N=N, _dtype=dtype)
 
 
-class _Slab:
-    """One device allocation shared by many Particles (vectors of M uncertain variables produced by one call: 1024
-    separate allocations and frees cost more than the gather that fills them).  Freed when the last view is gone."""
-    __slots__ = ("ptr",)
-
-    def __init__(self, nbytes: int):
-        self.ptr = _alloc(nbytes)
-
-    def __del__(self):
-        try:
-            if self.ptr and L._lib is not None:
-                L._lib.mcm_free(C.c_void_p(self.ptr))
-        except Exception:
-            pass
-
-
 def _empty_many(M: int, N: int, dtype: int):
-    """M uninitialised Particles of length N in ONE allocation (each 256-byte aligned)."""
+    """M uninitialised Particles of length N: the allocations in ONE C call (mcm_alloc_many) and the handles built
+    without the keyword-argument constructor — 1024 separate `_empty` calls cost 4.8 ms of interpreter time, as much
+    as the gather that fills them (C5 bootstrap).  One big slab instead was measured too: the pool cannot reuse an
+    8 GB block reliably (9-18 ms per call, 150 ms when it has to grow)."""
     if M <= 4:
         return [_empty(N, dtype) for _ in range(M)]
-    stride = (N * _NP[dtype].itemsize + 255) & ~255
-    slab = _Slab(max(stride, 256) * M)
+    ptrs = (C.c_void_p * M)()
+    L.check(L.lib().mcm_alloc_many(ptrs, M, max(N * _NP[dtype].itemsize, 16)))
     out = []
+    new = object.__new__
     for j in range(M):
-        q = Particles(_ptr=slab.ptr + j * stride, _N=N, _dtype=dtype)
-        q._own = False
-        q._slab = slab
+        q = new(Particles)
+        q.ptr = ptrs[j]; q.N = N; q.dtype = dtype; q._own = True
         out.append(q)
     return out
 
