@@ -370,9 +370,10 @@ int mcm_potrf(double* a_dev, int M, int* info_host);
 /* X L = B solved in place in b_dev (nrows x M, row-major) for lower-triangular L (M x M): the `/` of
  * `cholesky(S).L / xl` (sigmapoints.jl:71). */
 int mcm_trsm_right_lower(const double* l_dev, double* b_dev, int M, int nrows);
-/* A/B switch for the dense M x M steps (mcm_potrf, mcm_trsm_right_lower, mcm_transform_moments): 1 (default) = register-
- * tiled diagonal block, right-looking solve, chol(S) on a side stream under the Gram; 0 = the first versions.  Same
- * results to rounding (scripts/check_dense_v2.py; both are run by tests/test_gpu_c5.py). */
+/* A/B switch for the dense M x M steps (mcm_potrf, mcm_trsm_right_lower, mcm_transform_moments): 2 (default) = as 1 with the
+ * diagonal block factored in panels of 16 columns (one warp, shuffles; bit-identical to 1); 1 = register-tiled diagonal
+ * block, right-looking solve, chol(S) on a side stream under the Gram; 0 = the first versions.  Same results to rounding
+ * (scripts/check_dense_v2.py; all are run by tests/test_gpu_c5.py). */
 int mcm_dense_use_v2(int on);
 /* transform_moments(X, m, S; preserve_latin) (sigmapoints.jl:63-72) entirely on device:
  * outs[j] = m[j] + sum_k A[j,k] (xs[k] - mean(xs[k])),  A = cholesky(S).L / xl,

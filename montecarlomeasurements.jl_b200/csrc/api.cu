@@ -163,6 +163,22 @@ extern "C" int mcm_alloc(void** dptr, size_t bytes) {
   return MCM_OK;
 }
 
+namespace mcm {
+void* pinned_scratch(int slot, size_t bytes) {
+  static void* buf[8] = {};
+  static size_t cap[8] = {};
+  if (slot < 0 || slot >= 8) return nullptr;
+  if (bytes > cap[slot]) {
+    if (buf[slot]) cudaFreeHost(buf[slot]);
+    buf[slot] = nullptr; cap[slot] = 0;
+    const size_t want = bytes + bytes / 4;
+    if (cudaHostAlloc(&buf[slot], want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); buf[slot] = nullptr; return nullptr; }
+    cap[slot] = want;
+  }
+  return buf[slot];
+}
+}  // namespace mcm
+
 // M result vectors of one call (a vector of uncertain variables): M pool allocations in one C call — through ctypes
 // each costs ~5 us of interpreter time, which at M = 1024 is as long as the gather that fills them
 extern "C" int mcm_alloc_many(void** dptrs, int M, size_t bytes_each) {

@@ -16,7 +16,7 @@
 namespace mcm {
 
 constexpr int DN_NB = 64;   // panel width
-static int g_dense_v2 = 1;   // mcm_dense_use_v2: 1 = register-tiled diagonal block, right-looking solve, chol(S) on a side stream; 0 = first versions
+static int g_dense_v2 = 2;   // mcm_dense_use_v2: 2 = as 1 with the panelled diagonal block (k_potrf_diag_v3); 1 = register-tiled diagonal block, right-looking solve, chol(S) on a side stream; 0 = first versions
 constexpr int DN_T = 256;
 
 // ---- diagonal block: unblocked Cholesky of an nb x nb block held in shared memory (one CTA) -----------------
@@ -84,6 +84,92 @@ k_potrf_diag(double* __restrict__ A, int ld, int nb, int* __restrict__ info, int
       const int i = ty + 16 * a, j = tx + 16 * b;
       if (i < nb && j < nb) A[(size_t)i * ld + j] = j <= i ? r[a][b] : 0.0;   // upper part of the block: zeros
     }
+}
+
+// third version (default, mcm_dense_use_v2(2)): the same arithmetic in the same order — every element sees its
+// updates a_ij -= l_ik l_jk with k ascending, every off-diagonal entry one division by the rounded pivot root — but
+// organised in panels of 16 columns so that the CTA meets at 3 barriers per panel instead of 2 per column:
+//   (1) the 16 x 16 diagonal block is factored by ONE warp, lane i holding row i in registers, pivots and multipliers
+//       exchanged by shuffles (no barrier, no shared-memory round trip inside the 16 columns);
+//   (2) the rows below solve against it, one thread per row (forward substitution along the row);
+//   (3) all threads apply the panel to the trailing lower triangle.
+// ncu showed the second version at 92 us per 64 x 64 block (2750 cycles per column between two CTA-wide barriers).
+__global__ void __launch_bounds__(DN_T)
+k_potrf_diag_v3(double* __restrict__ A, int ld, int nb, int* __restrict__ info, int col0) {
+  __shared__ double s[DN_NB][DN_NB + 1];
+  __shared__ int s_bad;
+  for (int e = threadIdx.x; e < DN_NB * DN_NB; e += DN_T) {
+    const int i = e / DN_NB, j = e % DN_NB;
+    s[i][j] = (i < nb && j <= i) ? A[(size_t)i * ld + j] : (i == j ? 1.0 : 0.0);    // identity padding beyond nb
+  }
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c0 = 0; c0 < nb; c0 += 16) {
+    if (warp == 0) {
+      const int li = lane & 15;                       // lanes 16..31 mirror lanes 0..15 (their results are not stored)
+      double a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) a[j] = j <= li ? s[c0 + li][c0 + j] : 0.0;
+      int bad_col = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const double akk = __shfl_sync(0xffffffffu, a[k], k);
+        if (!(akk > 0.0) && bad_col == 0) bad_col = col0 + c0 + k + 1;     // not positive definite (or NaN), 1-based like LAPACK
+        const double d = sqrt(akk);
+        if (li == k) a[k] = d;
+        else if (li > k) a[k] /= d;
+        const double lik = a[k];
+#pragma unroll
+        for (int j = k + 1; j < 16; ++j) {
+          const double ljk = __shfl_sync(0xffffffffu, lik, j);
+          if (li >= j) a[j] -= lik * ljk;
+        }
+      }
+      if (bad_col) {
+        if (lane == 0) { atomicCAS(info, 0, bad_col); s_bad = 1; }
+      } else if (lane < 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j <= li) s[c0 + li][c0 + j] = a[j];
+      }
+    }
+    __syncthreads();
+    if (s_bad) return;
+    // (2) rows below the diagonal block: x L11' = a, one thread per row
+    const int r = c0 + 16 + (int)threadIdx.x;
+    if (r < nb) {
+      double x[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double v = s[r][c0 + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) v -= x[k] * s[c0 + j][c0 + k];
+        x[j] = v / s[c0 + j][c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s[r][c0 + j] = x[j];
+    }
+    __syncthreads();
+    // (3) trailing lower triangle: a_ij -= l_ik l_jk, k ascending
+    const int t0 = c0 + 16, m = nb - t0;
+    if (m > 0) {
+      for (int e = threadIdx.x; e < m * m; e += DN_T) {
+        const int i = t0 + e / m, j = t0 + e % m;
+        if (j <= i) {
+          double v = s[i][j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v -= s[i][c0 + k] * s[j][c0 + k];
+          s[i][j] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nb * nb; e += DN_T) {
+    const int i = e / nb, j = e % nb;
+    A[(size_t)i * ld + j] = j <= i ? s[i][j] : 0.0;   // upper part of the block: zeros
+  }
 }
 
 // first version (kept behind mcm_dense_use_v2(0)): block in shared memory, trailing update through a runtime division
@@ -248,7 +334,8 @@ static int potrf_lower_enqueue(double* A, int M, int** d_info_out) {
   for (int j0 = 0; j0 < M; j0 += DN_NB) {
     const int nb = std::min(DN_NB, M - j0);
     double* A11 = A + (size_t)j0 * M + j0;
-    if (g_dense_v2) k_potrf_diag<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
+    if (g_dense_v2 == 2) k_potrf_diag_v3<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
+    else if (g_dense_v2) k_potrf_diag<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
     else k_potrf_diag_v1<<<1, DN_T, 0, c.stream>>>(A11, M, nb, d_info, j0);
     MCM_CHECK_LAUNCH();
     const int rest = M - j0 - nb;
@@ -402,8 +489,11 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
   }
   rc = trsm_right_lower_device(dC, dLS, M, M);   // dLS <- chol(S).L / xl
   if (rc) { drop_stats(); release(); return rc; }
-  std::vector<double> A(mm), mu(M);
-  MCM_CUDA(cudaMemcpyAsync(A.data(), dLS, mm * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  // A and the means go back through PINNED staging (a pageable 8 MB copy each way cost ~2 ms here)
+  std::vector<double> A_fallback, mu(M);
+  double* A = static_cast<double*>(pinned_scratch(0, mm * sizeof(double)));
+  if (!A) { A_fallback.resize(mm); A = A_fallback.data(); }
+  MCM_CUDA(cudaMemcpyAsync(A, dLS, mm * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaMemcpyAsync(mu.data(), dmu, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaStreamSynchronize(c.stream));
   release();
@@ -411,7 +501,7 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
   // already; this keeps the early-exit of the application kernels independent of that)
   for (int i = 0; i < M; ++i)
     for (int j = i + 1; j < M; ++j) A[(size_t)i * M + j] = 0.0;
-  rc = mcm_pgemm(dtype, A.data(), M, M, xs, mu.data(), m_host, outs, n);
+  rc = mcm_pgemm(dtype, A, M, M, xs, mu.data(), m_host, outs, n);
   drop_stats();
   return rc;
 }

@@ -37,6 +37,9 @@ struct Ctx {
 
 Ctx& ctx();
 int fail(int code, const char* fmt, ...);
+// grow-only pinned host staging buffers (slots 0..7), for host <-> device copies of MB-sized tables: pageable copies run
+// at a few GB/s on this class of VM and synchronise; returns nullptr if the allocation fails
+void* pinned_scratch(int slot, size_t bytes);
 
 static constexpr size_t kScratchDoubles = 1u << 17;  // 1 MiB of doubles
 static constexpr size_t kPinnedBytes = 1u << 20;

@@ -386,12 +386,16 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   const size_t o_xs = 0, o_outs = al((size_t)Mi * sizeof(void*)), o_shift = o_outs + al((size_t)Mo * sizeof(void*));
   const size_t o_bias = o_shift + kpad * sizeof(double), o_A = o_bias + mopad * sizeof(double);
   const size_t up_bytes = o_A + (size_t)Mo * Mi * sizeof(double);
-  std::vector<unsigned char> up(up_bytes, 0);
-  memcpy(up.data() + o_xs, xs_host, (size_t)Mi * sizeof(void*));
-  memcpy(up.data() + o_outs, outs_host, (size_t)Mo * sizeof(void*));
-  if (shift_host) memcpy(up.data() + o_shift, shift_host, (size_t)Mi * sizeof(double));
-  if (bias_host) memcpy(up.data() + o_bias, bias_host, (size_t)Mo * sizeof(double));
-  memcpy(up.data() + o_A, A_host, (size_t)Mo * Mi * sizeof(double));
+  // staged in pinned memory (slot 2; a pageable upload of the 8 MB of A at C5 cost ~2 ms and synchronised)
+  std::vector<unsigned char> up_fallback;
+  unsigned char* up = static_cast<unsigned char*>(pinned_scratch(2, up_bytes));
+  if (!up) { up_fallback.resize(up_bytes); up = up_fallback.data(); }
+  memset(up, 0, o_A);
+  memcpy(up + o_xs, xs_host, (size_t)Mi * sizeof(void*));
+  memcpy(up + o_outs, outs_host, (size_t)Mo * sizeof(void*));
+  if (shift_host) memcpy(up + o_shift, shift_host, (size_t)Mi * sizeof(double));
+  if (bias_host) memcpy(up + o_bias, bias_host, (size_t)Mo * sizeof(double));
+  memcpy(up + o_A, A_host, (size_t)Mo * Mi * sizeof(double));
   // ---- device workspace: ex, ratio, sc56, apow, rowscale, cscale, kend, flag, coefficient planes
   const size_t w_ex = 0, w_ratio = al((size_t)Mi * sizeof(int)), w_sc = w_ratio + al((size_t)Mi * sizeof(double));
   const size_t w_apow = w_sc + kpad * sizeof(double), w_rows = w_apow + kpad * sizeof(double);
@@ -401,7 +405,7 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   unsigned char *d_up = nullptr, *d_ws = nullptr;
   MCM_CUDA(cudaMallocAsync((void**)&d_up, up_bytes, c.stream));
   MCM_CUDA(cudaMallocAsync((void**)&d_ws, ws_bytes, c.stream));
-  MCM_CUDA(cudaMemcpyAsync(d_up, up.data(), up_bytes, cudaMemcpyHostToDevice, c.stream));
+  MCM_CUDA(cudaMemcpyAsync(d_up, up, up_bytes, cudaMemcpyHostToDevice, c.stream));
   MCM_CUDA(cudaMemsetAsync(d_ws + w_rows, 0, w_planes - w_rows, c.stream));   // rowscale, cscale, kend, flag
   const T* const* d_xs = reinterpret_cast<const T* const*>(d_up + o_xs);
   const double* d_shift = reinterpret_cast<const double*>(d_up + o_shift);

@@ -285,12 +285,13 @@ def test_quantile_batch_errors(mcm):
 
 
 # ---- M x M dense steps (dense.cu) ------------------------------------------------------------------------
-@pytest.fixture(params=[1, 0], ids=["dense-v2", "dense-v1"])
+@pytest.fixture(params=[2, 1, 0], ids=["dense-v3", "dense-v2", "dense-v1"])
 def dense_mode(request, mcm):
-    """Both generations of the dense kernels (mcm_dense_use_v2): the default and the first versions."""
+    """All generations of the dense kernels (mcm_dense_use_v2): the default (panelled diagonal block), the second and
+    the first versions."""
     mcm._lib.lib().mcm_dense_use_v2(request.param)
     yield request.param
-    mcm._lib.lib().mcm_dense_use_v2(1)
+    mcm._lib.lib().mcm_dense_use_v2(2)
 
 
 @pytest.mark.parametrize("M", [1, 5, 64, 65, 200, 517])
@@ -369,3 +370,26 @@ def test_transform_moments_tensor_path_with_shared_statistics(mcm):
     assert np.array_equal(Y3[7].to_numpy(), Y[7].to_numpy())
     # (runs with the default, second-generation dense steps; scripts/check_dense_v2.py compares the two generations on
     # this very problem: max difference 8.9e-16)
+
+
+def test_panelled_cholesky_block_is_bit_identical_to_the_column_version(mcm):
+    """k_potrf_diag_v3 applies the same updates in the same order as the per-column kernel: same bits, any size,
+    and the same 1-based pivot report for a matrix that is not positive definite."""
+    lib = mcm._lib.lib()
+    rng = np.random.default_rng(3)
+    try:
+        for M in (1, 7, 16, 17, 40, 64, 65, 130, 517, 1024):
+            Q = rng.normal(size=(M, M + 3))
+            A = Q @ Q.T + 0.1 * np.eye(M)
+            lib.mcm_dense_use_v2(2); L3 = mcm.cholesky_lower(A)
+            lib.mcm_dense_use_v2(1); L2 = mcm.cholesky_lower(A)
+            assert np.array_equal(L3, L2), M
+            assert np.max(np.abs(L3 @ L3.T - A)) <= 1e-12 * np.abs(A).max()
+        B = np.eye(70); B[50, 50] = -1.0
+        for mode in (2, 1):
+            lib.mcm_dense_use_v2(mode)
+            with pytest.raises(mcm.ArgumentError) as ei:
+                mcm.cholesky_lower(B)
+            assert "51" in str(ei.value)
+    finally:
+        lib.mcm_dense_use_v2(2)
