@@ -157,8 +157,16 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
   const size_t total = nkb * nrg * 16;
   const size_t stride = (size_t)gridDim.x * 256;
   for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < total; w += stride) {
-    const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;     // blk = kb * nrg + rg
-    const size_t rg = blk % nrg, kb = blk / nrg;
+    // work order: within a group of OZ_KBT k-blocks the k-block index runs fastest, then the row group — a CTA's 16 blocks
+    // are 16 consecutive k-blocks of the same 8 rows, i.e. 4 KiB CONTIGUOUS per row (the rows are separate arrays, ~1 MB
+    // apart: with the row group running fastest every row contributed 256 bytes per CTA and the reads hopped DRAM pages)
+    const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;
+    constexpr size_t OZ_KBT = 16;
+    const size_t per_group = nrg * OZ_KBT;
+    const size_t kbt = blk / per_group, rem = blk % per_group;
+    size_t rg, kb;
+    if ((kbt + 1) * OZ_KBT <= nkb) { rg = rem / OZ_KBT; kb = kbt * OZ_KBT + rem % OZ_KBT; }
+    else { const size_t left = nkb - kbt * OZ_KBT; rg = rem / left; kb = kbt * OZ_KBT + rem % left; }   // ragged last group
     const size_t row = rg * 8 + r8;
     alignas(16) int8_t dg[OZ_S][16];
     if (row < (size_t)M) {
@@ -201,7 +209,7 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
 #pragma unroll
       for (int s = 0; s < OZ_S; ++s) *reinterpret_cast<int4*>(dg[s]) = make_int4(0, 0, 0, 0);
     }
-    const size_t off = w * 16;   // ((kb*nrg + rg)*2 + c)*128 + r8*16
+    const size_t off = (((kb * nrg + rg) * 2 + c) * 8 + r8) * 16;
 #pragma unroll
     for (int s = 0; s < OZ_S; ++s)
       *reinterpret_cast<int4*>(slices + (size_t)s * (mpad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
