@@ -58,8 +58,14 @@ k_pslice(const T* const* __restrict__ xs, const double* __restrict__ shift, cons
          size_t n, size_t npad, size_t kpad, int8_t* __restrict__ planes) {
   const size_t nrg = npad / 8;
   const size_t total = (kpad / PZ_KB) * nrg * 16;
-  const size_t stride = (size_t)gridDim.x * 256;
-  for (size_t w = (size_t)blockIdx.x * 256 + threadIdx.x; w < total; w += stride) {
+  // a CTA takes PS_RUN consecutive chunks of 256 work items: 512 consecutive particles of the same 32 variables, i.e.
+  // 4 KiB contiguous per variable array (one chunk alone is a 1 KiB run per array: the reads hopped DRAM pages)
+  constexpr size_t PS_RUN = 4;
+  const size_t nchunks = (total + 255) / 256;
+  for (size_t ch = (size_t)blockIdx.x * PS_RUN; ch < nchunks; ch += (size_t)gridDim.x * PS_RUN)
+  for (size_t ci = 0; ci < PS_RUN; ++ci) {
+    const size_t w = (ch + ci) * 256 + threadIdx.x;
+    if (w >= total) break;
     const size_t r8 = w & 7, c = (w >> 3) & 1, blk = w >> 4;
     const size_t rg = blk % nrg, kb = blk / nrg;
     const size_t row = rg * 8 + r8;
