@@ -5,10 +5,12 @@
 // (src/particles.jl:316-323); sort is also what wasserstein (src/distances.jl:7-13)
 // needs.  Order is Julia's `isless` on floats: -0.0 < +0.0, NaN last.
 //
-// Per pass: k_hist (per-CTA digit histogram, warp-aggregated shared atomics),
-// an exclusive scan over the [digit][CTA] table, and k_scatter, which ranks keys
-// stably with __match_any_sync inside each warp segment and places warp segments
-// by a per-digit prefix over the 8 warps of the CTA.
+// Per pass: k_hist (per-CTA digit histogram: every thread owns a byte column of a [256 digits][256 threads] table,
+// thread d sums row d with dp4a — no atomics), an exclusive scan over the [digit][CTA] table, and k_scatter, which
+// ranks keys stably without warp votes or atomics (own-column byte counters per warp, masked dp4a prefix over the
+// lower lanes), stages the tile in digit order in shared memory and writes runs of equal digits to consecutive
+// addresses.  (Earlier versions ranked with __match_any_sync / ballots and shared atomics: see the history notes at
+// the kernels.)
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -25,12 +27,28 @@ constexpr int IPT = 16;          // keys per thread
 constexpr int TILE = ST * IPT;   // keys per CTA
 constexpr int SEG = 32 * IPT;    // keys per warp segment
 
+// keys + the bitwise OR and AND of all of them (orand[0] |= key, orand[1] &= key): a digit whose bits are the same in
+// every key (OR == AND there) needs no pass — typical particle data shares sign and most of the exponent
 template <typename T, typename K>
-__global__ void __launch_bounds__(256) k_to_keys(const T* __restrict__ in, K* __restrict__ keys, size_t n, uint32_t* flags) {
+__global__ void __launch_bounds__(256) k_to_keys(const T* __restrict__ in, K* __restrict__ keys, size_t n, uint32_t* flags,
+                                                 unsigned long long* __restrict__ orand) {
   const size_t stride = (size_t)gridDim.x * 256;
   bool nan = false;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) keys[i] = to_key(in[i], nan);
+  unsigned long long o = 0ull, a = ~0ull;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    const K k = to_key(in[i], nan);
+    keys[i] = k;
+    o |= (unsigned long long)k; a &= (unsigned long long)k;
+  }
   if (nan) atomicOr(flags, (uint32_t)MCM_FLAG_NAN_QUANTILE);
+  if (orand) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      o |= __shfl_xor_sync(0xffffffffu, o, d);
+      a &= __shfl_xor_sync(0xffffffffu, a, d);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicOr(&orand[0], o); atomicAnd(&orand[1], a); }
+  }
 }
 template <typename T, typename K>
 __global__ void __launch_bounds__(256) k_from_keys(const K* __restrict__ keys, T* __restrict__ out, size_t n) {
@@ -340,10 +358,11 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
   }
 }
 
-// Sort n keys held in bufA (ping-pong with bufB); after an even number of passes the
-// result is back in bufA.  vals likewise.
+// Sort n keys held in bufA (ping-pong with bufB); the result is back in bufA (vals likewise).  `varying`: bits that
+// differ between some two keys (OR ^ AND from k_to_keys; all ones if unknown) — passes over digits that are the same in
+// every key are skipped (a stable pass on a constant digit is the identity).
 template <typename K, bool HAS_VAL>
-int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) {
+int radix_sort_keys_masked(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n, K varying) {
   Ctx& c = ctx();
   if (n >= 0xFFFF0000ull) return fail(MCM_ERR_UNSUPPORTED, "sort: n must be < 2^32");
   const uint32_t nblocks = (uint32_t)((n + TILE - 1) / TILE);
@@ -361,6 +380,7 @@ int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) 
   }
   for (int p = 0; p < passes; ++p) {
     const int shift = p * RB;
+    if (((varying >> shift) & (K)(NBINS - 1)) == 0) continue;
     k_hist<K><<<nblocks, ST, NBINS * HROW, c.stream>>>(src, (uint32_t)n, shift, hist, nblocks);
     MCM_CHECK_LAUNCH();
     int rc = device_scan<uint32_t, false>(hist, hlen, nullptr);
@@ -370,8 +390,16 @@ int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) 
     K* t = src; src = dst; dst = t;
     uint32_t* tv = vs; vs = vd; vd = tv;
   }
+  if (src != bufA) {          // an odd number of passes ran: bring the result home
+    MCM_CUDA(cudaMemcpyAsync(bufA, src, n * sizeof(K), cudaMemcpyDeviceToDevice, c.stream));
+    if (HAS_VAL) MCM_CUDA(cudaMemcpyAsync(valA, vs, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c.stream));
+  }
   MCM_CUDA(cudaFreeAsync(hist, c.stream));
   return MCM_OK;
+}
+template <typename K, bool HAS_VAL>
+int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) {
+  return radix_sort_keys_masked<K, HAS_VAL>(bufA, bufB, valA, valB, n, (K)~(K)0);
 }
 template int radix_sort_keys<uint64_t, true>(uint64_t*, uint64_t*, uint32_t*, uint32_t*, size_t);
 
@@ -386,22 +414,31 @@ static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
   else A = reinterpret_cast<K*>(out);
   MCM_CUDA(cudaMallocAsync((void**)&B, n * sizeof(K), c.stream));
   const int grid = stream_grid(n, 4, 8);
-  k_to_keys<T, K><<<grid, 256, 0, c.stream>>>(in, A, n, c.d_flags);
+  unsigned long long* d_orand = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&d_orand, 2 * sizeof(unsigned long long), c.stream));
+  const unsigned long long init[2] = {0ull, ~0ull};
+  MCM_CUDA(cudaMemcpyAsync(d_orand, init, sizeof(init), cudaMemcpyHostToDevice, c.stream));
+  k_to_keys<T, K><<<grid, 256, 0, c.stream>>>(in, A, n, c.d_flags, d_orand);
   MCM_CHECK_LAUNCH();
+  unsigned long long h_orand[2] = {~0ull, 0ull};
+  MCM_CUDA(cudaMemcpyAsync(h_orand, d_orand, sizeof(h_orand), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));      // one 16-byte read-back per sort decides which passes run
+  MCM_CUDA(cudaFreeAsync(d_orand, c.stream));
+  const K varying = (K)(h_orand[0] ^ h_orand[1]);
   int rc;
   if (perm_out) {
     MCM_CUDA(cudaMallocAsync((void**)&vA, n * sizeof(uint32_t), c.stream));
     MCM_CUDA(cudaMallocAsync((void**)&vB, n * sizeof(uint32_t), c.stream));
     k_iota<<<grid, 256, 0, c.stream>>>(vA, n);
     MCM_CHECK_LAUNCH();
-    rc = radix_sort_keys<K, true>(A, B, vA, vB, n);
+    rc = radix_sort_keys_masked<K, true>(A, B, vA, vB, n, varying);
     if (rc) return rc;
     k_u32_to_i64<<<grid, 256, 0, c.stream>>>(vA, perm_out, n);
     MCM_CHECK_LAUNCH();
     MCM_CUDA(cudaFreeAsync(vA, c.stream));
     MCM_CUDA(cudaFreeAsync(vB, c.stream));
   } else {
-    rc = radix_sort_keys<K, false>(A, B, nullptr, nullptr, n);
+    rc = radix_sort_keys_masked<K, false>(A, B, nullptr, nullptr, n, varying);
     if (rc) return rc;
   }
   if (!own_A) {
