@@ -225,13 +225,18 @@ template int device_scan<unsigned long long, true>(unsigned long long*, size_t, 
 //      consecutive addresses.
 // History at 1e8 64-bit keys per pass: __match_any ranking + 32 scattered stores per warp instruction 1.74 ms ->
 // ballot ranking + digit-ordered staging 1.19 ms (113 instructions per key, vote-bound) -> this version.
-constexpr int CROW = 32 + 4;   // bytes per (warp, digit) row: 32 lane counters + padding against bank conflicts
+// Count table: one 32-byte row of lane counters per (warp, digit), NO padding (round 2: 84 -> 71 KiB of shared memory per
+// CTA = 3 resident CTAs instead of 2; ncu showed the kernel latency-bound at 16 warps per SM).  Bank conflicts are avoided
+// by rotating the eight words of row d by d / 4: thread d reading logical word q of its row (the row sums) touches bank
+// 8 (d % 4) + (q + d / 4) % 8 — a bijection over d = 0..31 — and the per-key accesses (random d per lane) spread likewise.
+constexpr int CROW = 32;
+__device__ __forceinline__ int crow_word(uint32_t d, int q) { return (q + (int)(d >> 2)) & 7; }
 template <typename K, bool HAS_VAL> struct ScatterSmem {
   static constexpr size_t KEYS = (size_t)TILE * sizeof(K);
   static constexpr size_t VALS = HAS_VAL ? (size_t)TILE * sizeof(uint32_t) : 0;
   static constexpr size_t CNT = (size_t)(ST / 32) * NBINS * CROW;
   static constexpr size_t UNION = (KEYS + VALS) > CNT ? (KEYS + VALS) : CNT;    // the staged tile reuses the count table
-  static constexpr size_t WOFF = (size_t)(ST / 32) * NBINS * sizeof(uint32_t);
+  static constexpr size_t WOFF = (size_t)(ST / 32) * NBINS * sizeof(uint16_t);     // offsets inside a tile: < 4096
   static constexpr size_t BYTES = UNION + WOFF + 2 * NBINS * sizeof(uint32_t);
 };
 template <typename K, bool HAS_VAL>
@@ -244,7 +249,7 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
   unsigned char* cnt = sraw;                                             // [warp][digit][CROW]
   K* skeys = reinterpret_cast<K*>(sraw);                                 // (after the counting phase)
   uint32_t* svals = reinterpret_cast<uint32_t*>(sraw + SM::KEYS);
-  uint32_t (*woff)[NBINS] = reinterpret_cast<uint32_t (*)[NBINS]>(sraw + SM::UNION);
+  uint16_t (*woff)[NBINS] = reinterpret_cast<uint16_t (*)[NBINS]>(sraw + SM::UNION);
   uint32_t* tpre = reinterpret_cast<uint32_t*>(sraw + SM::UNION + SM::WOFF);   // first tile-sorted slot of digit d
   uint32_t* gdel = tpre + NBINS;                                                // global position minus tile slot
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -290,8 +295,9 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
   for (int j = 0; j < IPT; ++j) {
     if (mine + j < n) {
       const uint32_t d = (uint32_t)((key[j] >> shift) & (NBINS - 1));
-      const unsigned char c = wcnt[d * CROW + lane];
-      wcnt[d * CROW + lane] = (unsigned char)(c + 1);
+      unsigned char* cell = wcnt + d * CROW + crow_word(d, lane >> 2) * 4 + (lane & 3);
+      const unsigned char c = *cell;
+      *cell = (unsigned char)(c + 1);
       own64 |= (unsigned long long)c << (4 * j);
     }
   }
@@ -302,11 +308,11 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
     uint32_t run = 0;
 #pragma unroll
     for (int ww = 0; ww < ST / 32; ++ww) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(cnt + ((size_t)ww * NBINS + d) * CROW);   // CROW = 36: 4-byte aligned
+      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(cnt + ((size_t)ww * NBINS + d) * CROW);
       uint32_t c = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) c = __dp4a(r32[q], 0x01010101u, c);
-      woff[ww][d] = run;
+      for (int q = 0; q < 8; ++q) c = __dp4a(r32[crow_word((uint32_t)d, q)], 0x01010101u, c);
+      woff[ww][d] = (uint16_t)run;
       run += c;
     }
     uint32_t tot;
@@ -332,7 +338,7 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
       const uint32_t* r32 = reinterpret_cast<const uint32_t*>(wcnt + d * CROW);
       uint32_t before = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) before = __dp4a(r32[q], lmask[q], before);
+      for (int q = 0; q < 8; ++q) before = __dp4a(r32[crow_word(d, q)], lmask[q], before);
       slot[j] = tpre[d] + woff[w][d] + before + (uint32_t)((own64 >> (4 * j)) & 15ull);
     }
   }
