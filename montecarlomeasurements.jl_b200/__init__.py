@@ -18,7 +18,7 @@ from .particles import (
     asin, acos, atan, asind, acosd, atand, asinh, acosh, atanh,
     zero, sign, sqrt, rad2deg, deg2rad, floor, ceil, trunc, inv, abs2, float_, round_,
     maximum, minimum, mod, mod1, rem, div, hypot, add_sum, clamp, muladd, minmax, sincos, ratdiv,
-    moments, pmean, psum, pvar, pstd, pminimum, pmaximum, pextrema, pmiddle, meanstd, meanvar,
+    moments, pmean, psum, pvar, pstd, pminimum, pmaximum, pextrema, pmiddle, piterate, meanstd, meanvar,
     pquantile, pmedian, psort, psortperm, pcov, pcor, to_matrix,
     pgemm, pgemv, mul_, pdot, paxpy_,
     unsafe_comparisons, set_comparison_function, approx, lesssim, gtrsim,
@@ -30,7 +30,7 @@ from .sampling import (Exponential, LogNormal, Cauchy, Laplace, Logistic, Raylei
                        Frechet, Kumaraswamy, Gamma, Erlang, Chisq, InverseGamma, Beta, TDist, FDist, GenericDistribution,
                        UnivariateDistribution, boxtimes, boxplus, outer_product, otimes, rand_particles_dist, quantile_dist)
 from .sampling import (Normal, Uniform, MvNormal, systematic_sample, pm, mp, dotdot, transform_moments,
-                       mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower)
+                       mvnormal_particles, systematic_batch, index_bijection, cholesky_lower, solve_right_lower, sigmapoints)
 from .resampling import bootstrap, resample, resample_indices, rand_indices
 from .optimize import optimize, perturb, wasserstein, ess, rand_particles
 from .decision import union, intersect, with_nominal, nominal

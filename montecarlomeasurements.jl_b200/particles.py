@@ -47,6 +47,7 @@ class Particles:
       Particles(v)                  from a 1-D array (types.jl:55)
       Particles(N, dist)            systematic sample of a univariate distribution (types.jl:67-82)
       Particles(N) / Particles()    Normal(0,1), N = 2000 by default
+      Particles(T, N, dist)         element type first (types.jl:85-88): ArgumentError unless eltype(dist) == T
       Particles(m) with m 2-D       -> list of Particles, one per column; dim 1 is the particle dim (types.jl:35-52)
     """
 
@@ -60,6 +61,8 @@ class Particles:
         if cls is Particles and len(args) >= 1 and isinstance(args[0], np.ndarray) and args[0].ndim >= 2:
             m = args[0]
             return _from_matrix(m)
+        if cls is Particles and len(args) >= 1 and isinstance(args[0], type) and args[0] in (float, np.float32, np.float64):
+            return _s.particles_of_type(*args, **kw)                 # PT(::Type{T}, N, d) (types.jl:85-88)
         if cls is Particles and (len(args) == 0 or isinstance(args[0], numbers.Integral) or _s.is_distribution(args[0])):
             return _s.particles_from_distribution(*args, **kw)
         return object.__new__(cls)
@@ -651,6 +654,19 @@ def pmiddle(p):
     """middle(extrema) = (min+max)/2 (Statistics.middle of the particle vector)."""
     lo, hi = pextrema(p)
     return lo / 2 + hi / 2
+
+
+def piterate(p, state: int | None = None):
+    """piterate(p[, state]) = Base.iterate(p.particles[, state]) (particles.jl:316-323): (particle, next state) with a
+    1-based state like Julia's, or None past the end; one 8-byte read from the device per step.  A Number iterates once."""
+    if not isinstance(p, Particles):
+        return (p, None) if state is None else None
+    i = 1 if state is None else int(state)
+    if i < 1 or i > p.N:
+        return None
+    out = np.empty(1, dtype=p.np_dtype)
+    L.check(L.lib().mcm_download(out.ctypes.data_as(C.c_void_p), C.c_void_p(p.ptr + (i - 1) * out.itemsize), out.itemsize))
+    return out[0].item(), i + 1
 
 
 def meanstd(p): return pstd(p) / math.sqrt(p.N)    # particles.jl:485

@@ -19,8 +19,13 @@ from . import particles as P
 
 # ---- minimal Distributions.jl stand-ins (only what the hot path constructs) -----------------
 class Normal:
-    def __init__(self, mu=0.0, sigma=1.0):
+    def __init__(self, mu=0.0, sigma=None):
+        if sigma is None:                      # Normal(μ) = Normal(μ, one(μ)): Normal(0.1f0) stays Float32
+            sigma = np.float32(1.0) if isinstance(mu, np.float32) else 1.0
         self.mu, self.sigma = mu, sigma
+
+    def __repr__(self):
+        return f"Normal({self.mu!r}, {self.sigma!r})"
 
     @property
     def eltype(self):
@@ -258,6 +263,22 @@ def particles_from_distribution(N=None, d=None, *, permute=True, systematic=None
     return systematic_sample(N, d, permute=permute, seed=seed, perm=perm, as_particles=True)
 
 
+def particles_of_type(T, N=None, d=None, **kw):
+    """PT(::Type{T}, N = 2000, d = Normal(T(0), T(1)); kwargs...) (types.jl:85-88): the distribution's element type must be
+    T — `Particles(Float32, 250, Gamma(0.1))` throws ArgumentError in the reference (runtests.jl:241) because Gamma(0.1)
+    samples Float64."""
+    T = np.float64 if T is float else T
+    N = P.DEFAULT_NUM_PARTICLES if N is None else int(N)
+    if d is None:
+        d = Normal(T(0), T(1))
+    dd = _as_distribution(d)
+    et = np.dtype(getattr(dd, "eltype", np.float64))
+    if et != np.dtype(T):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, f"Element type of the provided distribution {d!r} does not match {np.dtype(T).name}. "
+                              "The element type of a distribution is the element type of a value sampled from it.")
+    return particles_from_distribution(N, d, **kw)
+
+
 def P_is_dist(x):
     return is_distribution(x)
 
@@ -329,6 +350,25 @@ def transform_moments(X, m, S, preserve_latin: bool = False):
     L.check(L.lib().mcm_transform_moments(X[0].dtype, pin, M, X[0].N, m.ctypes.data_as(L._dp), S.ctypes.data_as(L._dp),
                                           1 if preserve_latin else 0, pout))
     return outs
+
+
+def sigmapoints(m, S=None) -> np.ndarray:
+    """sigmapoints(m, Σ) / sigmapoints(d::Normal) / sigmapoints(d::MvNormal) (sigmapoints.jl:35-45): the (2n+1) x n matrix
+    [X; -X; 0] .+ m' with X = cholesky(n Σ).U (factorised on device, mcm_potrf).  `Particles(sigmapoints(m, Σ))` gives the
+    n uncertain values (dim 1 = particles); a scalar Σ is a VARIANCE, like in the reference."""
+    if isinstance(m, Normal) and S is None:
+        m, S = float(m.mu), float(m.sigma) ** 2
+    elif isinstance(m, MvNormal) and S is None:
+        m, S = m.mu, m.S
+    mv = np.atleast_1d(np.asarray(m, dtype=np.float64))
+    n = mv.size
+    Sm = np.asarray(S, dtype=np.float64)
+    if Sm.ndim == 0:
+        Sm = np.diag(np.full(n, float(Sm)))
+    if Sm.shape != (n, n):
+        raise L.ArgumentError(L.MCM_ERR_INVALID, f"DimensionMismatch: Σ must be {n} x {n}")
+    X = cholesky_lower(n * (Sm + Sm.T) / 2.0).T             # cholesky(Symmetric(nΣ)).U
+    return np.vstack([X, -X, np.zeros((1, n))]) + mv[None, :]
 
 
 def cholesky_lower(A) -> np.ndarray:

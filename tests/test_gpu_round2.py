@@ -520,3 +520,47 @@ def test_elementwise_fast_forms_equal_the_exact_functions(mcm):
         mcm.check_domain()
     mcm.sin(mcm.Particles(np.full(8192, 1e300)))           # huge but finite: library path, no DomainError
     mcm.check_domain()
+
+
+def test_element_type_first_constructors(mcm):
+    """runtests.jl:236-241: PT(Float32), PT(Float64), PT(Float32, 250), PT(Float32, 250, Normal(0.1f0)) and the
+    ArgumentError for PT(Float32, 250, Gamma(0.1)) (types.jl:85-88: eltype(d) must equal T)."""
+    a = mcm.Particles(np.float32)
+    assert a.np_dtype == np.float32 and a.N == 2000
+    assert mcm.Particles(np.float64).np_dtype == np.float64 and mcm.Particles(float).N == 2000
+    b = mcm.Particles(np.float32, 250)
+    assert b.np_dtype == np.float32 and b.N == 250
+    c = mcm.Particles(np.float32, 250, mcm.Normal(np.float32(0.1)))
+    assert c.np_dtype == np.float32 and c.N == 250 and abs(mcm.pmean(c) - 0.1) < 1e-6
+    with pytest.raises(mcm.ArgumentError):
+        mcm.Particles(np.float32, 250, mcm.Gamma(0.1))
+    with pytest.raises(mcm.ArgumentError):
+        mcm.Particles(np.float64, 250, mcm.Normal(np.float32(0.1)))
+    g = mcm.Particles(np.float64, 300, mcm.Gamma(0.5), seed=2)
+    assert g.N == 300 and g.np_dtype == np.float64 and g.to_numpy().min() > 0
+
+
+def test_piterate_walks_the_particle_vector(mcm):
+    """piterate(p) = iterate(p.particles) (particles.jl:316-323): Julia's (value, state) protocol."""
+    x = np.array([3.0, -1.5, 8.25])
+    p = mcm.Particles(x)
+    got, st = [], None
+    while True:
+        r = mcm.piterate(p) if st is None else mcm.piterate(p, st)
+        if r is None:
+            break
+        got.append(r[0]); st = r[1]
+    assert got == list(x) and mcm.piterate(2.5) == (2.5, None) and mcm.piterate(2.5, 1) is None
+
+
+def test_sigmapoints_like_the_reference(mcm):
+    """runtests.jl:324-339: 2n+1 sigma points reproduce mean and covariance exactly (to rounding)."""
+    s = mcm.sigmapoints(1, 3)
+    assert s.shape == (3, 1) and abs(s.var(ddof=1) - 3) < 1e-14 and s.mean() == 1
+    assert np.array_equal(mcm.sigmapoints(mcm.Normal(1, np.sqrt(3.0))), mcm.sigmapoints(1, np.sqrt(3.0) ** 2))
+    m, S = [1, 2], np.array([[3.0, 1.0], [1.0, 4.0]])
+    s = mcm.sigmapoints(m, S)
+    assert s.shape == (5, 2) and np.allclose(np.cov(s.T), S, rtol=1e-13) and np.allclose(s.mean(axis=0), m, atol=1e-15)
+    assert np.array_equal(mcm.sigmapoints(mcm.MvNormal(m, S)), s)
+    p = mcm.Particles(s)                                      # StaticParticles(sigmapoints(m, Σ)) (sigmapoints.jl docstring)
+    assert len(p) == 2 and p[0].N == 5 and np.allclose(mcm.pcov(p), S, rtol=1e-13) and np.allclose(mcm.pmean(p), m, atol=1e-15)
