@@ -654,6 +654,8 @@ def hbm_family(mcm, L, lib, stream, N, peak):
         "exp": (16, lambda: lib.mcm_unary(L.ENUMS["MCM_U_EXP"], L.F64, C.c_void_p(a.ptr), C.c_void_p(y.ptr), N)),
         "sin": (16, lambda: lib.mcm_unary(L.ENUMS["MCM_U_SIN"], L.F64, C.c_void_p(a.ptr), C.c_void_p(y.ptr), N)),
         "pmean+pstd (one pass)": (8, lambda: lib.mcm_moments(L.F64, C.c_void_p(a.ptr), N, mom.ctypes.data_as(L._dp))),
+        "pmean+pstd kernel only (mcm_moments_enqueue: result left on device, no host round trip per call)":
+            (8, lambda: lib.mcm_moments_enqueue(L.F64, C.c_void_p(a.ptr), N)),
     }
     with torch.cuda.stream(stream):
         for name, (bpp, fn) in cases.items():

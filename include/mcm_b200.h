@@ -285,6 +285,10 @@ int mcm_chain_jit_source(int dtype, const mcm_tape_ins* tape, int ntape, int loo
 /* ======================= statistics ======================================== */
 /* one pass: out_host[0..5] = {n, mean, M2 = sum (x-mean)^2, min, max, sum} */
 int mcm_moments(int dtype, const void* in, size_t n, double* out_host);
+/* the same kernel without the host round trip: enqueue (asynchronous; the result stays in a device slot) and collect the
+ * result of the LAST enqueue later */
+int mcm_moments_enqueue(int dtype, const void* in, size_t n);
+int mcm_moments_collect(double* out_host);
 /* A/B switch for the moments kernel on large inputs: 1 (default) = bulk-async (TMA) shared-memory
  * pipeline, 0 = direct 128-bit global loads.  Results are identical up to merge order. */
 int mcm_moments_use_bulk(int on);

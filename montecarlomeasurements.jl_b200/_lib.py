@@ -115,6 +115,8 @@ SIGNATURES = {
     "mcm_chain_jit_option": (_i, [_i, _i]),
     "mcm_chain_jit_source": (_i, [_i, C.POINTER(TapeIns), _i, _i, _i, _dp, _i, _i, _i, C.c_char_p, _sz, C.POINTER(_sz), C.c_char_p]),
     "mcm_moments": (_i, [_i, _vp, _sz, _dp]),
+    "mcm_moments_enqueue": (_i, [_i, _vp, _sz]),
+    "mcm_moments_collect": (_i, [_dp]),
     "mcm_moments_use_bulk": (_i, [_i]),
     "mcm_reduce": (_i, [_i, _i, _vp, _sz, _dp]),
     "mcm_count": (_i, [_i, _i, _vp, _sz, _d, C.POINTER(C.c_uint64)]),

@@ -316,6 +316,20 @@ extern "C" int mcm_moments(int dtype, const void* in, size_t n, double* out_host
   return read_back(out_host, slot, 6);
 }
 
+// Asynchronous form: the kernel is enqueued and its six moments stay in a device slot until mcm_moments_collect reads the
+// slot of the LAST enqueue (one read-back for a burst of reductions whose results are consumed later, and the way to time
+// the kernel without the host round trip every synchronous call pays).
+extern "C" int mcm_moments_enqueue(int dtype, const void* in, size_t n) {
+  MCM_NEED_INIT();
+  if (!in || n == 0) return fail(MCM_ERR_INVALID, "mcm_moments_enqueue: null pointer or no particles");
+  return moments_device(dtype, in, n, moments_result_slot());
+}
+extern "C" int mcm_moments_collect(double* out_host) {
+  MCM_NEED_INIT();
+  if (!out_host) return fail(MCM_ERR_INVALID, "mcm_moments_collect: null pointer");
+  return read_back(out_host, moments_result_slot(), 6);
+}
+
 extern "C" int mcm_moments_merge(const double* a, const double* b, double* out) {
   if (!a || !b || !out) return fail(MCM_ERR_INVALID, "mcm_moments_merge: null pointer");
   Mom ma{a[0], a[1], 0.0, a[2], a[3], a[4], a[5]}, mb{b[0], b[1], 0.0, b[2], b[3], b[4], b[5]};

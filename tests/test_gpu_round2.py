@@ -564,3 +564,18 @@ def test_sigmapoints_like_the_reference(mcm):
     assert np.array_equal(mcm.sigmapoints(mcm.MvNormal(m, S)), s)
     p = mcm.Particles(s)                                      # StaticParticles(sigmapoints(m, Σ)) (sigmapoints.jl docstring)
     assert len(p) == 2 and p[0].N == 5 and np.allclose(mcm.pcov(p), S, rtol=1e-13) and np.allclose(mcm.pmean(p), m, atol=1e-15)
+
+
+def test_moments_enqueue_collect_equals_the_synchronous_call(mcm):
+    L = mcm._lib
+    lib = L.lib()
+    rng = np.random.default_rng(2)
+    for n in (1, 1000, 3_000_001):
+        x = mcm.Particles(rng.normal(5.0, 2.0, n))
+        y = mcm.Particles(rng.normal(-1.0, 0.5, n))
+        ref = np.zeros(6); got = np.zeros(6)
+        L.check(lib.mcm_moments(L.F64, C.c_void_p(y.ptr), n, ref.ctypes.data_as(L._dp)))
+        L.check(lib.mcm_moments_enqueue(L.F64, C.c_void_p(x.ptr), n))
+        L.check(lib.mcm_moments_enqueue(L.F64, C.c_void_p(y.ptr), n))          # the last enqueue is the one collected
+        L.check(lib.mcm_moments_collect(got.ctypes.data_as(L._dp)))
+        assert np.array_equal(got, ref)
