@@ -91,6 +91,23 @@ struct FPoly {
   }
 };
 
+// degree known at compile time (2..16 coefficients): the Horner recurrences of the values a thread holds unroll and
+// interleave, and the coefficients are constant-bank operands — with the run-time trip count above every step is a
+// dependent FMA behind an indexed constant load (poly8: 0.84-0.90 of the HBM rate)
+template <typename T, bool FUSED, int NC>
+struct FPolyN {
+  T c[NC];
+  __device__ __forceinline__ T operator()(T x) const {
+    T acc = c[NC - 1];
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) {
+      if constexpr (FUSED) acc = math::m_fma(acc, x, c[k]);
+      else acc = acc * x + c[k];
+    }
+    return acc;
+  }
+};
+
 template <typename T>
 struct FAffine {
   T alpha, beta;
@@ -175,11 +192,26 @@ static int dispatch_lincomb(int nt, const void* const* xs, const double* coeffs,
   }
 }
 
+template <typename T, bool FUSED, int NC>
+static int run_poly_n(const Operands<T, 1>& ops, const double* coeffs, void* out, size_t n) {
+  FPolyN<T, FUSED, NC> f;
+  for (int k = 0; k < NC; ++k) f.c[k] = (T)coeffs[k];
+  return launch_map<T, 1, 4, false>(ops, static_cast<T*>(out), n, f);
+}
 template <typename T>
 static int run_poly(const void* in, const double* coeffs, int nc, int fused, void* out, size_t n) {
   Operands<T, 1> ops;
   ops.p[0] = static_cast<const T*>(in);
   ops.s[0] = 0;
+  switch (nc) {
+#define MCM_POLY_CASE(NC) \
+  case NC: return fused ? run_poly_n<T, true, NC>(ops, coeffs, out, n) : run_poly_n<T, false, NC>(ops, coeffs, out, n);
+    MCM_POLY_CASE(2) MCM_POLY_CASE(3) MCM_POLY_CASE(4) MCM_POLY_CASE(5) MCM_POLY_CASE(6) MCM_POLY_CASE(7) MCM_POLY_CASE(8)
+    MCM_POLY_CASE(9) MCM_POLY_CASE(10) MCM_POLY_CASE(11) MCM_POLY_CASE(12) MCM_POLY_CASE(13) MCM_POLY_CASE(14)
+    MCM_POLY_CASE(15) MCM_POLY_CASE(16)
+#undef MCM_POLY_CASE
+    default: break;
+  }
   if (fused) {
     FPoly<T, true> f;
     for (int k = 0; k < kMaxPoly; ++k) f.c[k] = k < nc ? (T)coeffs[k] : T(0);
