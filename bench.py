@@ -429,7 +429,8 @@ def e2e_bench(mcm, L, lib, run, N, n_total, world, barrier, torch, dist):
     per-rank moments are merged through the library's communicator."""
     t10 = run.t10
     hp = C.c_void_p()
-    L.check(lib.mcm_host_alloc(C.byref(hp), N * 8))
+    wc = os.environ.get("MCM_E2E_WC", "0") == "1"         # A/B: write-combined pinned input (no snoop on the DMA reads)
+    L.check((lib.mcm_host_alloc_wc if wc else lib.mcm_host_alloc)(C.byref(hp), N * 8))
     L.check(lib.mcm_download(hp, C.c_void_p(run.a.ptr), N * 8))
     hin = (C.c_void_p * 1)(hp.value)
     e2e_steps = 5
@@ -456,6 +457,7 @@ def e2e_bench(mcm, L, lib, run, N, n_total, world, barrier, torch, dist):
            "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
            "aggregate_h2d_GBps": 8 * n_total / (float(te.item()) / e2e_steps) / 1e9,
            "how": "mcm_chain_host: pinned host input -> chunked H2D overlapped with the fused kernel -> 6 moments D2H; y not returned",
+           "host_buffer": "write-combined pinned" if wc else "pinned",
            "check": {"pmean": me.mean, "pstd": me.std()}}
     L.check(lib.mcm_host_free(hp))
     return out

@@ -156,6 +156,7 @@ int mcm_free(void* dptr);                   /* stream-ordered; safe from a GC fi
 /* M vectors of bytes_each bytes in one call (the result of an operation on a vector of M uncertain variables) */
 int mcm_alloc_many(void** dptrs, int M, size_t bytes_each);
 int mcm_host_alloc(void** hptr, size_t bytes); /* pinned host staging */
+int mcm_host_alloc_wc(void** hptr, size_t bytes); /* pinned, write-combined: host writes, device reads (no snoop on the DMA) */
 int mcm_host_free(void* hptr);
 /* Particles(v::Vector) (types.jl:55)  /  Array(p), Vector(p) (particles.jl:458-459) */
 int mcm_upload(void* dst_dev, const void* src_host, size_t bytes);

@@ -88,6 +88,7 @@ SIGNATURES = {
     "mcm_alloc_many": (_i, [_vpp, _i, _sz]),
     "mcm_free": (_i, [_vp]),
     "mcm_host_alloc": (_i, [_vpp, _sz]),
+    "mcm_host_alloc_wc": (_i, [_vpp, _sz]),
     "mcm_host_free": (_i, [_vp]),
     "mcm_upload": (_i, [_vp, _vp, _sz]),
     "mcm_download": (_i, [_vp, _vp, _sz]),

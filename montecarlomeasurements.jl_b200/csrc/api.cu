@@ -213,6 +213,15 @@ extern "C" int mcm_host_alloc(void** hptr, size_t bytes) {
   return MCM_OK;
 }
 
+// write-combined pinned memory: for buffers the host only WRITES and the device reads (inputs of mcm_chain_host):
+// the DMA reads need no cache snoop.  Host reads of such memory are very slow.
+extern "C" int mcm_host_alloc_wc(void** hptr, size_t bytes) {
+  MCM_NEED_INIT();
+  if (!hptr) return fail(MCM_ERR_INVALID, "mcm_host_alloc_wc: null pointer");
+  MCM_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocWriteCombined));
+  return MCM_OK;
+}
+
 extern "C" int mcm_host_free(void* hptr) {
   if (!hptr) return MCM_OK;
   MCM_CUDA(cudaFreeHost(hptr));
