@@ -12,26 +12,40 @@
 
 namespace mcm {
 
-constexpr int LA_MAXN = 8;
+// Two table sizes: up to 8 x 8 the pointer tables fit the classic 4 KiB of kernel parameters; 9..16 use the large
+// parameter space of sm_70+ (6.3 KiB here).  Above 8 the loops of mcm_small_linalg.cuh stay rolled and the matrices
+// live in local memory (interleaved per thread by the hardware, so still coalesced).
+constexpr int LA_MAXN = 16;
 constexpr int LA_MAXPTR = LA_MAXN * LA_MAXN;
-struct LaArgs {
-  const void* A[LA_MAXPTR];
-  const void* B[LA_MAXPTR];
-  void* out[LA_MAXPTR];
-  void* out_im[LA_MAXN];
+template <int P>
+struct LaArgsT {
+  const void* A[P * P];
+  const void* B[P * P];
+  void* out[P * P];
+  void* out_im[P];
 };
+using LaArgs = LaArgsT<LA_MAXN>;
+template <int N> using LaArgsFor = LaArgsT<(N <= 8 ? 8 : LA_MAXN)>;
+template <int P>
+static LaArgsT<P> la_narrow(const LaArgs& g) {
+  LaArgsT<P> r{};
+  for (int e = 0; e < P * P; ++e) { r.A[e] = g.A[e]; r.B[e] = g.B[e]; r.out[e] = g.out[e]; }
+  for (int e = 0; e < P; ++e) r.out_im[e] = g.out_im[e];
+  return r;
+}
+#define MCM_LA_UNROLL _Pragma("unroll (N <= 8 ? 64 : 1)")
 
 template <typename T> __device__ __forceinline__ double la_ld(const void* p, size_t i) { return (double)static_cast<const T*>(p)[i]; }
 template <typename T> __device__ __forceinline__ void la_st(void* p, size_t i, double v) { static_cast<T*>(p)[i] = (T)v; }
 
 template <int OP, int N, typename T>
 __global__ void __launch_bounds__(128)
-k_batched_la(const __grid_constant__ LaArgs g, int m, size_t n_particles, uint32_t* flags) {
+k_batched_la(const __grid_constant__ LaArgsFor<N> g, int m, size_t n_particles, uint32_t* flags) {
   using namespace sla;
   const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (i >= n_particles) return;
   Mat<N> a;
-#pragma unroll
+MCM_LA_UNROLL
   for (int e = 0; e < N * N; ++e) a.a[e] = la_ld<T>(g.A[e], i);
   bool bad = false;
   if constexpr (OP == MCM_LA_SOLVE) {
@@ -39,10 +53,10 @@ k_batched_la(const __grid_constant__ LaArgs g, int m, size_t n_particles, uint32
     bad = lu_factor(a, piv) == 0;
     for (int j = 0; j < m; ++j) {
       double col[N];
-#pragma unroll
+MCM_LA_UNROLL
       for (int r = 0; r < N; ++r) col[r] = la_ld<T>(g.B[r * m + j], i);
       lu_solve(a, piv, col, 1);
-#pragma unroll
+MCM_LA_UNROLL
       for (int r = 0; r < N; ++r) la_st<T>(g.out[r * m + j], i, col[r]);
     }
   } else if constexpr (OP == MCM_LA_INV) {
@@ -51,7 +65,7 @@ k_batched_la(const __grid_constant__ LaArgs g, int m, size_t n_particles, uint32
     Mat<N> x;
     set_identity(x, 1.0);
     for (int j = 0; j < N; ++j) lu_solve(a, piv, &x.a[j], N);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N * N; ++e) la_st<T>(g.out[e], i, x.a[e]);
   } else if constexpr (OP == MCM_LA_DET) {
     int piv[N];
@@ -59,29 +73,29 @@ k_batched_la(const __grid_constant__ LaArgs g, int m, size_t n_particles, uint32
     la_st<T>(g.out[0], i, s == 0 ? 0.0 : det_from_lu(a, s));
   } else if constexpr (OP == MCM_LA_EXP) {
     bad = !expm(a);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N * N; ++e) la_st<T>(g.out[e], i, a.a[e]);
   } else if constexpr (OP == MCM_LA_EIGVALS) {
     double wr[N], wi[N];
     bad = !eig_general(a, wr, wi);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N; ++e) { la_st<T>(g.out[e], i, wr[e]); la_st<T>(g.out_im[e], i, wi[e]); }
   } else if constexpr (OP == MCM_LA_EIGVALS_SYM) {
     double w[N];
     eig_sym(a, w);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N; ++e) la_st<T>(g.out[e], i, w[e]);
   } else if constexpr (OP == MCM_LA_LYAP) {
     Mat<N> c, x;
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N * N; ++e) c.a[e] = la_ld<T>(g.B[e], i);
     bad = !lyap(a, c, x);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N * N; ++e) la_st<T>(g.out[e], i, x.a[e]);
   } else if constexpr (OP == MCM_LA_SVDVALS) {
     double sv[N];
     svdvals(a, sv);
-#pragma unroll
+MCM_LA_UNROLL
     for (int e = 0; e < N; ++e) la_st<T>(g.out[e], i, sv[e]);
   }
   if (bad) atomicOr(flags, (uint32_t)MCM_FLAG_DOMAIN);
@@ -92,7 +106,7 @@ static int la_launch(const LaArgs& g, int m, size_t n) {
   Ctx& c = ctx();
   const size_t grid = (n + 127) / 128;
   if (grid > 0x7fffffffull) return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg: too many particles");
-  k_batched_la<OP, N, T><<<(unsigned)grid, 128, 0, c.stream>>>(g, m, n, c.d_flags);
+  k_batched_la<OP, N, T><<<(unsigned)grid, 128, 0, c.stream>>>(la_narrow<(N <= 8 ? 8 : LA_MAXN)>(g), m, n, c.d_flags);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
@@ -111,6 +125,14 @@ static int la_by_n(int nmat, const LaArgs& g, int m, size_t n) {
       case 6: return la_launch<OP, 6, T>(g, m, n);
       case 7: return la_launch<OP, 7, T>(g, m, n);
       case 8: return la_launch<OP, 8, T>(g, m, n);
+      case 9: return la_launch<OP, 9, T>(g, m, n);
+      case 10: return la_launch<OP, 10, T>(g, m, n);
+      case 11: return la_launch<OP, 11, T>(g, m, n);
+      case 12: return la_launch<OP, 12, T>(g, m, n);
+      case 13: return la_launch<OP, 13, T>(g, m, n);
+      case 14: return la_launch<OP, 14, T>(g, m, n);
+      case 15: return la_launch<OP, 15, T>(g, m, n);
+      case 16: return la_launch<OP, 16, T>(g, m, n);
       default: break;
     }
   }
@@ -135,15 +157,23 @@ static int la_by_op(int op, int nmat, const LaArgs& g, int m, size_t n) {
 // ---- matrices with Complex{Particles} entries, and log of a real uncertain matrix ---------------------------------
 // complex.jl:104-181 (ℂⁿ2ℂⁿ_function: exp, exp!, log; ℂⁿ2ℂ_function: det; eigvals; svdvals) and particles.jl:603
 // (Base.log(::Matrix{<:AbstractParticles}) = ℝⁿ2ℂⁿ_function(log, p)): entry (r, c) is a pair of length-N vectors.
-struct LacArgs {
-  const void* Are[LA_MAXPTR];
-  const void* Aim[LA_MAXPTR];     // all null: a real matrix
-  void* ore[LA_MAXPTR];
-  void* oim[LA_MAXPTR];
+template <int P>
+struct LacArgsT {
+  const void* Are[P * P];
+  const void* Aim[P * P];     // all null: a real matrix
+  void* ore[P * P];
+  void* oim[P * P];
 };
+using LacArgs = LacArgsT<LA_MAXN>;
+template <int P>
+static LacArgsT<P> lac_narrow(const LacArgs& g) {
+  LacArgsT<P> r{};
+  for (int e = 0; e < P * P; ++e) { r.Are[e] = g.Are[e]; r.Aim[e] = g.Aim[e]; r.ore[e] = g.ore[e]; r.oim[e] = g.oim[e]; }
+  return r;
+}
 template <int OP, int N, typename T>
 __global__ void __launch_bounds__(128)
-k_batched_lac(const __grid_constant__ LacArgs g, int real_input, size_t n_particles, uint32_t* flags) {
+k_batched_lac(const __grid_constant__ LacArgsT<(N <= 8 ? 8 : LA_MAXN)> g, int real_input, size_t n_particles, uint32_t* flags) {
   using namespace sla;
   const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;
   if (i >= n_particles) return;
@@ -174,7 +204,7 @@ static int lac_launch(const LacArgs& g, int real_input, size_t n) {
   Ctx& c = ctx();
   const size_t grid = (n + 127) / 128;
   if (grid > 0x7fffffffull) return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg_complex: too many particles");
-  k_batched_lac<OP, N, T><<<(unsigned)grid, 128, 0, c.stream>>>(g, real_input, n, c.d_flags);
+  k_batched_lac<OP, N, T><<<(unsigned)grid, 128, 0, c.stream>>>(lac_narrow<(N <= 8 ? 8 : LA_MAXN)>(g), real_input, n, c.d_flags);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
@@ -189,6 +219,14 @@ static int lac_by_n(int nmat, const LacArgs& g, int real_input, size_t n) {
     case 6: return lac_launch<OP, 6, T>(g, real_input, n);
     case 7: return lac_launch<OP, 7, T>(g, real_input, n);
     case 8: return lac_launch<OP, 8, T>(g, real_input, n);
+    case 9: return lac_launch<OP, 9, T>(g, real_input, n);
+    case 10: return lac_launch<OP, 10, T>(g, real_input, n);
+    case 11: return lac_launch<OP, 11, T>(g, real_input, n);
+    case 12: return lac_launch<OP, 12, T>(g, real_input, n);
+    case 13: return lac_launch<OP, 13, T>(g, real_input, n);
+    case 14: return lac_launch<OP, 14, T>(g, real_input, n);
+    case 15: return lac_launch<OP, 15, T>(g, real_input, n);
+    case 16: return lac_launch<OP, 16, T>(g, real_input, n);
     default: return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg_complex: matrix size %d not supported", nmat);
   }
 }

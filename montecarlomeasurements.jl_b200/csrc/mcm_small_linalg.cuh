@@ -16,7 +16,9 @@
 
 #ifdef __CUDACC__
 #define MCM_SLA __device__ __forceinline__
-#define MCM_SLA_UNROLL _Pragma("unroll")
+// loops over N are fully unrolled up to N = 8 (everything in registers); above, the matrix lives in local memory and
+// the loops stay rolled (same operations in the same order: the bits do not depend on it)
+#define MCM_SLA_UNROLL _Pragma("unroll (N <= 8 ? 64 : 1)")
 #else
 #define MCM_SLA inline
 #define MCM_SLA_UNROLL

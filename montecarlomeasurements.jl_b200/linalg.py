@@ -19,7 +19,7 @@ from . import _lib as L
 from . import particles as P
 
 E = L.ENUMS
-MAX_N = 8
+MAX_N = 16
 
 
 def _as_table(M, what: str):

@@ -1,5 +1,5 @@
 """Time mcm_batched_linalg: N particles of n x n matrices, every operation; HBM bytes = 8 (inputs + outputs) per particle.
-    python scripts/probe_linalg.py [N]"""
+    python scripts/probe_linalg.py [N] [sizes, e.g. 12,16]"""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +16,8 @@ def best(fn, reps=3):
     return min(ts)
 
 
-for n in (2, 3, 4, 6, 8):
+SIZES = tuple(int(v) for v in sys.argv[2].split(',')) if len(sys.argv) > 2 else (2, 3, 4, 6, 8)
+for n in SIZES:
     A = [[mcm.systematic_sample(N, mcm.Normal(1.0 if i == j else 0.2, 0.05), seed=10 * i + j, as_particles=True)
           for j in range(n)] for i in range(n)]
     b = [A[i][0] for i in range(n)]

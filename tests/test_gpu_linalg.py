@@ -24,11 +24,11 @@ def gather(grid):
     return np.stack([np.stack([p.to_numpy() for p in row], axis=1) for row in grid], axis=1)
 
 
-@pytest.mark.parametrize("n", range(1, 9))
+@pytest.mark.parametrize("n", list(range(1, 9)) + [9, 12, 16])
 def test_device_equals_twin(mcm, twin, n):
     la = mcm.linalg
     rng = np.random.default_rng(100 + n)
-    N = 3000
+    N = 3000 if n <= 8 else 1500
     A = rng.normal(size=(N, n, n))
     B = rng.normal(size=(N, n, 2))
     At, Bt = table(mcm, A), table(mcm, B)
@@ -93,7 +93,7 @@ def test_errors_and_flags(mcm):
     with pytest.raises(mcm.MethodError):
         la.det([[1.0, 2.0], [3.0, 4.0]])                     # no particles
     with pytest.raises(mcm.MethodError):
-        la.det([[p] * 9 for _ in range(9)])                  # n > 8
+        la.det([[p] * 17 for _ in range(17)])                # n > 16
     with pytest.raises(mcm.MethodError):
         la.lyap([[p] * 5 for _ in range(5)], [[p] * 5 for _ in range(5)])    # lyap handles n <= 4
     mcm.check_domain()
@@ -150,7 +150,7 @@ def cgather(grid):
     return np.stack([np.stack([z.re.to_numpy() + 1j * z.im.to_numpy() for z in row], axis=1) for row in grid], axis=1)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 8, 9, 12, 16])
 def test_complex_matrix_functions_equal_the_twin(mcm, n):
     """Device == host twin bit for bit (tests/test_small_linalg_c_twin.py pins the twin against LAPACK / scipy)."""
     import test_small_linalg_c_twin as tw

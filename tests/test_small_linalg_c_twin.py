@@ -50,7 +50,7 @@ def twin():
     return build_twin()
 
 
-@pytest.mark.parametrize("n", range(1, 9))
+@pytest.mark.parametrize("n", list(range(1, 9)) + [9, 12, 16])
 def test_complex_twin_against_lapack(twin, n):
     rng = np.random.default_rng(100 + n)
     nb = 200

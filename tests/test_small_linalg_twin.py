@@ -43,7 +43,7 @@ def twin():
     return build_twin()
 
 
-@pytest.mark.parametrize("n", range(1, 9))
+@pytest.mark.parametrize("n", list(range(1, 9)) + [9, 12, 16])
 def test_twin_against_lapack(twin, n):
     rng = np.random.default_rng(n)
     nb = 500

@@ -30,6 +30,14 @@ extern "C" int slac_twin(int op, int n, const double* Ar, const double* Ai, doub
     case 6: return run<6>(op, Ar, Ai, outr, outi, nb);
     case 7: return run<7>(op, Ar, Ai, outr, outi, nb);
     case 8: return run<8>(op, Ar, Ai, outr, outi, nb);
+    case 9: return run<9>(op, Ar, Ai, outr, outi, nb);
+    case 10: return run<10>(op, Ar, Ai, outr, outi, nb);
+    case 11: return run<11>(op, Ar, Ai, outr, outi, nb);
+    case 12: return run<12>(op, Ar, Ai, outr, outi, nb);
+    case 13: return run<13>(op, Ar, Ai, outr, outi, nb);
+    case 14: return run<14>(op, Ar, Ai, outr, outi, nb);
+    case 15: return run<15>(op, Ar, Ai, outr, outi, nb);
+    case 16: return run<16>(op, Ar, Ai, outr, outi, nb);
     default: return 3;
   }
 }

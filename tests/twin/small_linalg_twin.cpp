@@ -86,6 +86,14 @@ extern "C" int sla_twin(int op, int n, const double* A, const double* B, int m, 
     case 6: return run<6>(op, A, B, m, out, out_im, nb);
     case 7: return run<7>(op, A, B, m, out, out_im, nb);
     case 8: return run<8>(op, A, B, m, out, out_im, nb);
+    case 9: return run<9>(op, A, B, m, out, out_im, nb);
+    case 10: return run<10>(op, A, B, m, out, out_im, nb);
+    case 11: return run<11>(op, A, B, m, out, out_im, nb);
+    case 12: return run<12>(op, A, B, m, out, out_im, nb);
+    case 13: return run<13>(op, A, B, m, out, out_im, nb);
+    case 14: return run<14>(op, A, B, m, out, out_im, nb);
+    case 15: return run<15>(op, A, B, m, out, out_im, nb);
+    case 16: return run<16>(op, A, B, m, out, out_im, nb);
   }
   return 3;
 }
