@@ -7,8 +7,8 @@
 //
 // Per pass: k_hist (per-CTA digit histogram: every thread owns a byte column of a [256 digits][256 threads] table,
 // thread d sums row d with dp4a — no atomics), an exclusive scan over the [digit][CTA] table, and k_scatter, which
-// ranks keys stably without warp votes or atomics (own-column byte counters per warp, masked dp4a prefix over the
-// lower lanes), stages the tile in digit order in shared memory and writes runs of equal digits to consecutive
+// ranks keys stably without warp votes or atomics (own-column byte counters per warp, turned in place into lane
+// prefixes so that a key finds its rank inside the warp with one 32-bit load), stages the tile in digit order in shared memory and writes runs of equal digits to consecutive
 // addresses.  (Earlier versions ranked with __match_any_sync / ballots and shared atomics: see the history notes at
 // the kernels.)
 #include <math.h>
@@ -96,17 +96,27 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
   __syncthreads();
   const uint32_t base = blockIdx.x * TILE;
   K k[IPT];
+  if (n - base >= (uint32_t)TILE) {          // full tile: no per-key bounds test
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t idx = base + i * ST + threadIdx.x;
-    k[i] = idx < n ? keys[idx] : (K)0;
-  }
+    for (int i = 0; i < IPT; ++i) k[i] = keys[base + i * ST + threadIdx.x];
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) {
-    const uint32_t idx = base + i * ST + threadIdx.x;
-    if (idx < n) {
+    for (int i = 0; i < IPT; ++i) {
       const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
       hcnt[d * HROW + threadIdx.x] += 1;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t idx = base + i * ST + threadIdx.x;
+      k[i] = idx < n ? keys[idx] : (K)0;
+    }
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) {
+      const uint32_t idx = base + i * ST + threadIdx.x;
+      if (idx < n) {
+        const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
+        hcnt[d * HROW + threadIdx.x] += 1;
+      }
     }
   }
   __syncthreads();
@@ -217,41 +227,41 @@ template int device_scan<unsigned long long, true>(unsigned long long*, size_t, 
 // No warp votes, no atomics.  Thread t owns the 16 CONSECUTIVE keys [16t, 16t+16) of the tile.
 //   1. every thread counts its keys in its own byte column of a per-warp table cnt[warp][digit][lane]; the value
 //      read before each increment is the key's rank among the thread's own earlier keys of that digit;
-//   2. the number of equal-digit keys held by lower lanes of the warp is a masked dp4a sum over the 32 bytes of row
-//      (warp, digit); thread d turns the per-warp row totals of digit d into offsets over the warps and the tile
+//   2. thread d turns every row (warp, d) in place into lane prefixes (one 32-bit load per key then gives the number
+//      of equal-digit keys held by lower lanes of the warp), the row totals into offsets over the warps and the tile
 //      totals into an exclusive scan over the digits;
 //   3. keys (and values) are placed into a shared-memory copy of the tile IN DIGIT ORDER (the copy reuses the
 //      memory of the count table) and written out from there, so consecutive threads store runs of equal digits to
 //      consecutive addresses.
 // History at 1e8 64-bit keys per pass: __match_any ranking + 32 scattered stores per warp instruction 1.74 ms ->
 // ballot ranking + digit-ordered staging 1.19 ms (113 instructions per key, vote-bound) -> this version.
-// Count table: one 32-byte row of lane counters per (warp, digit), NO padding (round 2: 84 -> 71 KiB of shared memory per
-// CTA = 3 resident CTAs instead of 2; ncu showed the kernel latency-bound at 16 warps per SM).  Bank conflicts are avoided
-// by rotating the eight words of row d by d / 4: thread d reading logical word q of its row (the row sums) touches bank
-// 8 (d % 4) + (q + d / 4) % 8 — a bijection over d = 0..31 — and the per-key accesses (random d per lane) spread likewise.
+// Count table: one 32-byte row of lane counters per (warp, digit), no padding (71 KiB of shared memory per CTA).  The
+// per-key accesses (random digit per lane) spread over the banks by themselves; the per-digit pass over whole rows
+// uses conflict-free 128-bit accesses (see 2a).  ncu (round 2): the kernel is latency-bound, not wavefront-bound
+// (shared pipe 47 %, issue 38 %), so it runs 2 CTAs per SM with ~120 registers: the 16 keys of a thread in flight at once.
 constexpr int CROW = 32;
-__device__ __forceinline__ int crow_word(uint32_t d, int q) { return (q + (int)(d >> 2)) & 7; }
+
 template <typename K, bool HAS_VAL> struct ScatterSmem {
   static constexpr size_t KEYS = (size_t)TILE * sizeof(K);
   static constexpr size_t VALS = HAS_VAL ? (size_t)TILE * sizeof(uint32_t) : 0;
   static constexpr size_t CNT = (size_t)(ST / 32) * NBINS * CROW;
   static constexpr size_t UNION = (KEYS + VALS) > CNT ? (KEYS + VALS) : CNT;    // the staged tile reuses the count table
   static constexpr size_t WOFF = (size_t)(ST / 32) * NBINS * sizeof(uint16_t);     // offsets inside a tile: < 4096
-  static constexpr size_t BYTES = UNION + WOFF + 2 * NBINS * sizeof(uint32_t);
+  static constexpr size_t BYTES = UNION + WOFF + NBINS * sizeof(uint32_t);
 };
-template <typename K, bool HAS_VAL>
-__global__ void __launch_bounds__(ST)
-k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin,
-          uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ hist_scanned,
-          uint32_t nblocks) {
+// FULL: the tile holds TILE keys — no per-key bounds test, so the 16 keys of a thread are independent straight-line
+// code (with the tests every key sat in its own BSSY/BSYNC region and its shared-memory loads could not be batched:
+// ncu showed 52 % of the stall samples on short_scoreboard).  Only the last tile of a pass runs FULL = false.
+template <typename K, bool HAS_VAL, bool FULL>
+__device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __restrict__ kin, K* __restrict__ kout,
+                                             const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout, uint32_t n,
+                                             int shift, const uint32_t* __restrict__ hist_scanned, uint32_t nblocks) {
   using SM = ScatterSmem<K, HAS_VAL>;
-  extern __shared__ __align__(16) unsigned char sraw[];
   unsigned char* cnt = sraw;                                             // [warp][digit][CROW]
   K* skeys = reinterpret_cast<K*>(sraw);                                 // (after the counting phase)
   uint32_t* svals = reinterpret_cast<uint32_t*>(sraw + SM::KEYS);
   uint16_t (*woff)[NBINS] = reinterpret_cast<uint16_t (*)[NBINS]>(sraw + SM::UNION);
-  uint32_t* tpre = reinterpret_cast<uint32_t*>(sraw + SM::UNION + SM::WOFF);   // first tile-sorted slot of digit d
-  uint32_t* gdel = tpre + NBINS;                                                // global position minus tile slot
+  uint32_t* gdel = reinterpret_cast<uint32_t*>(sraw + SM::UNION + SM::WOFF);   // global position minus tile slot
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   {
     uint4* z = reinterpret_cast<uint4*>(cnt);
@@ -262,7 +272,7 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
   const uint32_t ntile = min((uint32_t)TILE, n - tile0);
   K key[IPT];
   uint32_t val[IPT];
-  if (mine + IPT <= n) {                                                // 128 contiguous bytes per thread
+  if (FULL || mine + IPT <= n) {                                        // 128 contiguous bytes per thread
     constexpr int KV = 16 / (int)sizeof(K);
     const uint4* p = reinterpret_cast<const uint4*>(kin + mine);
 #pragma unroll
@@ -293,59 +303,73 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
   unsigned long long own64 = 0;   // 16 x 4-bit ranks packed (a thread has at most 16 keys per digit: rank <= 15)
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
-    if (mine + j < n) {
+    if (FULL || mine + j < n) {
       const uint32_t d = (uint32_t)((key[j] >> shift) & (NBINS - 1));
-      unsigned char* cell = wcnt + d * CROW + crow_word(d, lane >> 2) * 4 + (lane & 3);
+      unsigned char* cell = wcnt + d * CROW + lane;
       const unsigned char c = *cell;
       *cell = (unsigned char)(c + 1);
       own64 |= (unsigned long long)c << (4 * j);
     }
   }
   __syncthreads();
-  // 2a. per digit: totals per warp -> offsets over the warps; tile totals -> exclusive scan over the digits
+  // 2a. per digit d (thread d), per warp: the 32 lane counters of row (warp, d) become, IN PLACE, what a key needs to
+  //     find the equal-digit keys held by lower lanes with ONE 32-bit load: byte k >= 1 of word q = counters of lanes
+  //     4q .. 4q+k-1 (<= 48: 6 bits); byte 0 (always 0 as an in-word prefix) and bit 15 = the 9-bit total of the words
+  //     before q (<= 448).  (Until round 2 every key summed the eight words of its row with masked dp4a: 8 random-row
+  //     loads per key were 28 of the kernel's ~58 shared-memory wavefronts per warp instruction.)
+  //     Row totals -> offsets over the warps; tile totals -> exclusive scan over the digits, folded into woff.
   {
     const int d = threadIdx.x;
     uint32_t run = 0;
+    uint32_t wrun[ST / 32];
+    // a row is two 128-bit words; threads 4..7 of every eight take the halves in the other order, so the eight
+    // threads of a quarter-warp (rows 32 bytes apart) cover eight different 16-byte slots: no bank conflicts
+    const bool swp = (d >> 2) & 1;
 #pragma unroll
     for (int ww = 0; ww < ST / 32; ++ww) {
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(cnt + ((size_t)ww * NBINS + d) * CROW);
-      uint32_t c = 0;
+      uint4* row = reinterpret_cast<uint4*>(cnt + ((size_t)ww * NBINS + d) * CROW);
+      const uint4 f = row[swp ? 1 : 0], g = row[swp ? 0 : 1];
+      uint32_t wv[8];
+      wv[0] = swp ? g.x : f.x; wv[1] = swp ? g.y : f.y; wv[2] = swp ? g.z : f.z; wv[3] = swp ? g.w : f.w;
+      wv[4] = swp ? f.x : g.x; wv[5] = swp ? f.y : g.y; wv[6] = swp ? f.z : g.z; wv[7] = swp ? f.w : g.w;
+      uint32_t wp = 0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) c = __dp4a(r32[crow_word((uint32_t)d, q)], 0x01010101u, c);
-      woff[ww][d] = (uint16_t)run;
-      run += c;
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t c = wv[q];
+        wv[q] = ((c * 0x01010100u) & 0x3f3f3f00u) | (wp & 0xffu) | ((wp & 0x100u) << 7);
+        wp = __dp4a(c, 0x01010101u, wp);
+      }
+      const uint4 lo = make_uint4(wv[0], wv[1], wv[2], wv[3]), hi = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+      row[swp ? 1 : 0] = swp ? hi : lo;
+      row[swp ? 0 : 1] = swp ? lo : hi;
+      wrun[ww] = run;
+      run += wp;
     }
     uint32_t tot;
     const uint32_t ex = block_exclusive_scan<uint32_t>(run, &tot);
-    tpre[d] = ex;
+#pragma unroll
+    for (int ww = 0; ww < ST / 32; ++ww) woff[ww][d] = (uint16_t)(ex + wrun[ww]);   // first tile slot of (warp, digit)
     gdel[d] = hist_scanned[(size_t)d * nblocks + blockIdx.x] - ex;
   }
   __syncthreads();
-  // 2b. rank inside the warp = equal-digit keys of lower lanes + own rank; tile slot of every key
+  // 2b. tile slot = first slot of (warp, digit) + equal-digit keys of lower lanes + rank among the thread's own keys
   uint32_t slot[IPT];
-  // byte masks selecting the lanes below this one in word q (lanes 4q .. 4q+3) of a row: fixed per thread
-  uint32_t lmask[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int rem = lane - 4 * q;
-    lmask[q] = rem >= 4 ? 0x01010101u : (rem <= 0 ? 0u : (0x01010101u >> (8 * (4 - rem))));
-  }
+  const int lq = lane >> 2;
+  const uint32_t ish = 8u * (uint32_t)(lane & 3), imask = (lane & 3) ? 0x3fu : 0u;
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
     slot[j] = 0;
-    if (mine + j < n) {
+    if (FULL || mine + j < n) {
       const uint32_t d = (uint32_t)((key[j] >> shift) & (NBINS - 1));
-      const uint32_t* r32 = reinterpret_cast<const uint32_t*>(wcnt + d * CROW);
-      uint32_t before = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) before = __dp4a(r32[crow_word(d, q)], lmask[q], before);
-      slot[j] = tpre[d] + woff[w][d] + before + (uint32_t)((own64 >> (4 * j)) & 15ull);
+      const uint32_t wv = reinterpret_cast<const uint32_t*>(wcnt + d * CROW)[lq];
+      const uint32_t before = (wv & 0xffu) + ((wv >> 7) & 0x100u) + ((wv >> ish) & imask);
+      slot[j] = (uint32_t)woff[w][d] + before + (uint32_t)((own64 >> (4 * j)) & 15ull);
     }
   }
   __syncthreads();   // the count table is dead: its memory becomes the staged tile
 #pragma unroll
   for (int j = 0; j < IPT; ++j) {
-    if (mine + j < n) {
+    if (FULL || mine + j < n) {
       skeys[slot[j]] = key[j];
       if constexpr (HAS_VAL) svals[slot[j]] = val[j];
     }
@@ -354,7 +378,7 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
 #pragma unroll
   for (int r = 0; r < IPT; ++r) {
     const uint32_t sl = r * ST + threadIdx.x;
-    if (sl < ntile) {
+    if (FULL || sl < ntile) {
       const K k = skeys[sl];
       const uint32_t d = (uint32_t)((k >> shift) & (NBINS - 1));
       const uint32_t pos = gdel[d] + sl;
@@ -362,6 +386,18 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
       if constexpr (HAS_VAL) vout[pos] = svals[sl];
     }
   }
+}
+#ifndef MCM_SCATTER_MIN_CTAS
+#define MCM_SCATTER_MIN_CTAS 2
+#endif
+template <typename K, bool HAS_VAL>
+__global__ void __launch_bounds__(ST, MCM_SCATTER_MIN_CTAS)
+k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin,
+          uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ hist_scanned,
+          uint32_t nblocks) {
+  extern __shared__ __align__(16) unsigned char sraw[];
+  if (n - blockIdx.x * TILE >= (uint32_t)TILE) scatter_tile<K, HAS_VAL, true>(sraw, kin, kout, vin, vout, n, shift, hist_scanned, nblocks);
+  else scatter_tile<K, HAS_VAL, false>(sraw, kin, kout, vin, vout, n, shift, hist_scanned, nblocks);
 }
 
 // Sort n keys held in bufA (ping-pong with bufB); the result is back in bufA (vals likewise).  `varying`: bits that
