@@ -35,8 +35,26 @@ namespace mcm {
 
 constexpr int PZ_S = 7;                               // digits per value
 constexpr int PZ_TM = 128, PZ_TN = 64, PZ_KB = 32;    // particles per tile, outputs per tile, variables per k-block
+// MCM_PZ_BULK_STORE (experiment): the epilogue stages the tile's results in shared memory and hands them to the bulk-copy
+// engine (cp.async.bulk shared -> global, 1 KiB per output column) instead of 32 global stores per thread; the staging
+// tile (128 x 64 results) takes the place of the fourth operand stage.
+// Measured at C5 (1024 x 1024 triangular / dense, 1e6 particles): 13.09 / 19.5 ms against 12.59 / 19.0 ms for direct
+// stores with a 4-stage ring — the stores are not what limits the kernel (the per-tile overhead is ~9 k cycles whether
+// the k loop is short or long: accumulator drain + read-back, serial with the MMAs), so it is compiled out.
+#ifndef MCM_PZ_BULK_STORE
+#define MCM_PZ_BULK_STORE 0
+#endif
+// MCM_PZ_BATCH_LD (experiment): the three tcgen05.ld of a diagonal group issued together, one wait per group instead of
+// one per load.  Measured equal (12.63 / 19.2 ms against 12.65 / 19.2 ms): the read-back is not latency-bound on the waits.
+// What the measurements leave as the bound of the MMA phase is the SM's shared-memory bandwidth: per k-block the MMAs
+// read 10 x 4 KiB of particle planes + 56 KiB of coefficient planes and the bulk copies write 42 KiB — ~140 KiB against
+// 128 B/clk = ~1.1 k cycles, above the 896 cycles the tensor pipe needs (traced: ~970 per k-block).  Halving the
+// coefficient-side traffic needs cta_group::2 (each CTA of a pair holds half of the N operand).
+#ifndef MCM_PZ_BATCH_LD
+#define MCM_PZ_BATCH_LD 0
+#endif
 #ifndef MCM_PZ_STAGES
-#define MCM_PZ_STAGES 4
+#define MCM_PZ_STAGES (MCM_PZ_BULK_STORE ? 3 : 4)
 #endif
 constexpr int PZ_STAGES = MCM_PZ_STAGES;
 constexpr int PZ_THREADS = 320;     // producer warp, MMA warp, 8 epilogue warps
@@ -190,7 +208,7 @@ template <typename T>
 __global__ void __launch_bounds__(PZ_THREADS, 1)
 k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplanes, const int* __restrict__ kend,
            const double* __restrict__ rowscale, const double* __restrict__ bias, T* const* __restrict__ outs, int Mo,
-           size_t n, size_t npad, size_t kpad, size_t mopad, PzSchedule sch) {
+           size_t n, size_t npad, size_t kpad, size_t mopad, PzSchedule sch, int bulk_ok) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_full[PZ_STAGES];
   __shared__ __align__(8) unsigned long long bar_free[PZ_STAGES];
@@ -198,7 +216,7 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
   __shared__ __align__(8) unsigned long long bar_drained; // accumulators read back: TMEM reusable
   __shared__ uint32_t tmem_base_sh;
   __shared__ T* s_out[2][PZ_TN];          // per-tile output pointers / row scales / biases (double-buffered by tile parity)
-  __shared__ double s_rs[2][PZ_TN], s_bi[2][PZ_TN];
+  __shared__ __align__(16) double s_rs[2][PZ_TN], s_bi[2][PZ_TN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const size_t xplane = npad * kpad, aplane = mopad * kpad;
@@ -336,6 +354,20 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
         for (int g = 0; g < 3; ++g) {
           long long comb[32];
           const int dn = g < 2 ? 3 : 1;
+#if MCM_PZ_BATCH_LD
+          // the group's loads are issued together and waited for once (7 serial load + wait pairs per tile before)
+          uint32_t v[3][32];
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < dn) tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)((g * 3 + q) * PZ_TN + h * 32), v[q]);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 3; ++q)
+            if (q < dn) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) comb[j] = (q == 0) ? (long long)(int)v[q][j] : comb[j] * 256 + (long long)(int)v[q][j];
+            }
+#else
 #pragma unroll
           for (int q = 0; q < 3; ++q) {
             if (q < dn) {
@@ -347,6 +379,7 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
               for (int j = 0; j < 32; ++j) comb[j] = (q == 0) ? (long long)(int)v[j] : comb[j] * 256 + (long long)(int)v[j];
             }
           }
+#endif
           const double w = scalbn(1.0, -8 * (g * 3 + dn - 1 + 2));   // weight of the group's last diagonal
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fma((double)comb[j], w, f[j]);
@@ -356,8 +389,44 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&bar_drained)) : "memory");
       const size_t i = (size_t)ptile * PZ_TM + lg * 32 + lane;
+      const int buf = tile & 1;
+#if MCM_PZ_BULK_STORE
+      // Results -> staging tile [column][particle] in shared memory (a warp writes 256 contiguous bytes per column) ->
+      // one bulk copy of the column's 128 results per output (issued by lane 0 of each warp for its 8 columns).  The
+      // copies drain on the bulk-copy engine while these warps wait for the next tile's accumulators; the staging tile is
+      // reused once the previous tile's copies have READ it (wait_group.read).  A ragged last particle tile stores directly.
+      T* stage_t = reinterpret_cast<T*>(smem + (size_t)PZ_STAGES * PZ_STAGE_BYTES);
+      const bool full_tile = bulk_ok && (size_t)ptile * PZ_TM + PZ_TM <= n;
+      if (full_tile) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const double2* rs2 = reinterpret_cast<const double2*>(&s_rs[buf][h * 32]);
+        const double2* bi2 = reinterpret_cast<const double2*>(&s_bi[buf][h * 32]);
+        T* dst = stage_t + (size_t)(h * 32) * PZ_TM + lg * 32 + lane;
+#pragma unroll
+        for (int j2 = 0; j2 < 16; ++j2) {
+          const double2 r = rs2[j2], b = bi2[j2];
+          dst[(size_t)(2 * j2) * PZ_TM] = (T)fma(f[2 * j2], r.x, b.x);
+          dst[(size_t)(2 * j2 + 1) * PZ_TM] = (T)fma(f[2 * j2 + 1], r.y, b.y);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane == 0) {
+          const int ew = warp - 2;                       // 0..7: columns 8 ew .. 8 ew + 7
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int col = ew * 8 + q;
+            T* o = s_out[buf][col];
+            if (o)
+              asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                           ::"l"(o + (size_t)ptile * PZ_TM), "r"(smem_addr(stage_t + (size_t)col * PZ_TM)), "r"((unsigned)(PZ_TM * sizeof(T)))
+                           : "memory");
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else
+#endif
       if (i < n) {
-        const int buf = tile & 1;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           T* o = s_out[buf][h * 32 + j];
@@ -366,6 +435,9 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
       }
       ++tile;
     }
+#if MCM_PZ_BULK_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the staging tile must outlive its copies
+#endif
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -475,20 +547,24 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
     while (want > 1 && (njt < want || c.sm_count % want != 0)) want >>= 1;
     sch.share = want;
   }
+  int bulk_ok = 1;      // bulk copies need 16-byte aligned destinations
+  for (int j = 0; j < Mo; ++j) bulk_ok &= (reinterpret_cast<uintptr_t>(outs_host[j]) % 16 == 0) ? 1 : 0;
   int ncta = c.sm_count;
   if ((size_t)ncta > nptiles * sch.share) ncta = (int)(nptiles * sch.share);
   ncta = std::max(sch.share, ncta / sch.share * sch.share);
   sch.slots = ncta / sch.share;
-  constexpr size_t kSmem = (size_t)PZ_STAGES * PZ_STAGE_BYTES;
+  constexpr size_t kSmem = (size_t)PZ_STAGES * PZ_STAGE_BYTES + (MCM_PZ_BULK_STORE ? (size_t)PZ_TM * PZ_TN * sizeof(T) : 0);
   static bool attr = false;
   if (!attr) {
-    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
-    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
+    constexpr int kSmemMax = PZ_STAGES * PZ_STAGE_BYTES + (MCM_PZ_BULK_STORE ? PZ_TM * PZ_TN * 8 : 0);
+    static_assert(kSmemMax <= 227 * 1024, "operand ring + staging tile exceed the shared memory of an SM");
+    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    MCM_CUDA(cudaFuncSetAttribute(k_pgemm_i8<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     attr = true;
   }
   k_pgemm_i8<T><<<ncta, PZ_THREADS, kSmem, c.stream>>>(
       d_xplanes, d_aplanes, d_kend, d_rows, bias_host ? reinterpret_cast<const double*>(d_up + o_bias) : nullptr,
-      reinterpret_cast<T* const*>(d_up + o_outs), Mo, n, npad, kpad, mopad, sch);
+      reinterpret_cast<T* const*>(d_up + o_outs), Mo, n, npad, kpad, mopad, sch, bulk_ok);
   MCM_CHECK_LAUNCH();
   uint32_t flag = 0;
   MCM_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(flag), cudaMemcpyDeviceToHost, c.stream));
