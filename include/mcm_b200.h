@@ -335,6 +335,9 @@ int mcm_sortperm(int dtype, const void* in, int64_t* perm_out, void* sorted_out_
 /* pquantile(p, q) = Statistics.quantile(p.particles, q) type-7 (particles.jl:321);
  * q_host: nq probabilities in [0,1]; out_host: nq values.  pmedian == q=0.5. */
 int mcm_quantile(int dtype, const void* in, size_t n, const double* q_host, int nq, double* out_host);
+/* A/B switch: 1 (default) = mcm_sort / mcm_sortperm read the particles in their first pass and write floating-point
+ * values / Int64 indices in their last (no separate key-transform, iota and widening passes); 0 = separate passes. */
+int mcm_sort_use_fused(int on);
 /* A/B switch: 1 (default) = sampled brackets + one streaming read for n >= 131072 and <= 8 probabilities
  * (select_batch.cu), MSD radix select otherwise; 2 = MSD radix select always (select.cu, one 8 B/key read
  * per pass); 0 = full sort + index.  All return the exact order statistics. */

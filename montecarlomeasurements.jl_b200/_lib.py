@@ -133,6 +133,7 @@ SIGNATURES = {
     "mcm_sortperm": (_i, [_i, _vp, _vp, _vp, _sz]),
     "mcm_quantile": (_i, [_i, _vp, _sz, _dp, _i, _dp]),
     "mcm_quantile_use_select": (_i, [_i]),
+    "mcm_sort_use_fused": (_i, [_i]),
     "mcm_norminvcdf": (_i, [_i, _vp, _vp, _sz]),
     "mcm_systematic_normal": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),
     "mcm_systematic_uniform": (_i, [_i, _vp, _sz, _d, _d, _vp, C.c_uint64, C.c_uint64]),

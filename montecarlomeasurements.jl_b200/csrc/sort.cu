@@ -83,11 +83,45 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, bool valid) {
 // its own leader, so the atomic unit alone needs 64 cycles per 32 keys (0.675 ms per 1e8 keys, measured).  Here every
 // thread owns one byte column of a [256 digits][256 threads] table (a thread sees at most IPT = 16 keys, so a byte
 // is enough), increments it with plain loads/stores, and thread d then sums row d with dp4a.  Rows are padded to
-// 65 words so that both the column updates and the row sums are bank-conflict free.
-constexpr int HROW = ST + 4;   // bytes per digit row
-template <typename K>
+// 17 x 16 bytes: the row sums are 128-bit loads (rows 17 slots apart: the eight threads of a quarter-warp hit eight
+// different 16-byte slots), the column updates of a warp spread over all banks (bank = 4 d + lane / 4 mod 32).
+constexpr int HROW = ST + 16;   // bytes per digit row
+__device__ __forceinline__ void hist_fold_orand(unsigned long long o, unsigned long long a, bool nan, uint32_t* flags,
+                                                unsigned long long* orand) {
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    o |= __shfl_xor_sync(0xffffffffu, o, d);
+    a &= __shfl_xor_sync(0xffffffffu, a, d);
+  }
+  if (__any_sync(0xffffffffu, nan) && (threadIdx.x & 31) == 0) atomicOr(flags, (uint32_t)MCM_FLAG_NAN_QUANTILE);
+  if ((threadIdx.x & 31) == 0) {
+    const unsigned long long co = *reinterpret_cast<volatile unsigned long long*>(&orand[0]);
+    const unsigned long long ca = *reinterpret_cast<volatile unsigned long long*>(&orand[1]);
+    if (o & ~co) atomicOr(&orand[0], o);
+    if (~a & ca) atomicAnd(&orand[1], a);
+  }
+}
+// XIN: `keys` holds the raw bits of the floating-point input; the order-preserving key is formed in registers (the
+// first pass of mcm_sort reads the particles directly: no separate key-transform pass), NaNs raise the sticky flag,
+// and the OR / AND of all keys are folded into orand[0] / orand[1] (atomics only while a warp still changes them).
+template <typename K> struct FloatOf;
+template <> struct FloatOf<uint64_t> { using type = double; };
+template <> struct FloatOf<uint32_t> { using type = float; };
+template <typename K> __device__ __forceinline__ K key_of_bits(K raw, bool& nan) {
+  typename FloatOf<K>::type x;
+  memcpy(&x, &raw, sizeof(K));
+  return to_key(x, nan);
+}
+template <typename K> __device__ __forceinline__ K bits_of_key(K k) {
+  const typename FloatOf<K>::type x = from_key(k);
+  K raw;
+  memcpy(&raw, &x, sizeof(K));
+  return raw;
+}
+template <typename K, bool XIN>
 __global__ void __launch_bounds__(ST)
-k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks) {
+k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks,
+       uint32_t* __restrict__ flags, unsigned long long* __restrict__ orand) {
   extern __shared__ __align__(16) unsigned char hcnt[];   // [NBINS][HROW]
   {
     uint4* z = reinterpret_cast<uint4*>(hcnt);
@@ -99,6 +133,13 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
   if (n - base >= (uint32_t)TILE) {          // full tile: no per-key bounds test
 #pragma unroll
     for (int i = 0; i < IPT; ++i) k[i] = keys[base + i * ST + threadIdx.x];
+    if constexpr (XIN) {
+      bool nan = false;
+      unsigned long long o = 0ull, a = ~0ull;
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
+      hist_fold_orand(o, a, nan, flags, orand);
+    }
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
@@ -110,6 +151,16 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
       const uint32_t idx = base + i * ST + threadIdx.x;
       k[i] = idx < n ? keys[idx] : (K)0;
     }
+    if constexpr (XIN) {
+      bool nan = false;
+      unsigned long long o = 0ull, a = ~0ull;
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = base + i * ST + threadIdx.x;
+        if (idx < n) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
+      }
+      hist_fold_orand(o, a, nan, flags, orand);
+    }
 #pragma unroll
     for (int i = 0; i < IPT; ++i) {
       const uint32_t idx = base + i * ST + threadIdx.x;
@@ -120,10 +171,15 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
     }
   }
   __syncthreads();
-  const uint32_t* row = reinterpret_cast<const uint32_t*>(hcnt + threadIdx.x * HROW);
-  uint32_t tot = 0;
+  const uint4* row = reinterpret_cast<const uint4*>(hcnt + threadIdx.x * HROW);
+  uint32_t tot = 0, tot2 = 0;
 #pragma unroll 8
-  for (int w = 0; w < ST / 4; ++w) tot = __dp4a(row[w], 0x01010101u, tot);
+  for (int w = 0; w < ST / 16; ++w) {
+    const uint4 r = row[w];
+    tot = __dp4a(r.x, 0x01010101u, tot); tot2 = __dp4a(r.y, 0x01010101u, tot2);
+    tot = __dp4a(r.z, 0x01010101u, tot); tot2 = __dp4a(r.w, 0x01010101u, tot2);
+  }
+  tot += tot2;
   hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = tot;
 }
 
@@ -252,9 +308,12 @@ template <typename K, bool HAS_VAL> struct ScatterSmem {
 // FULL: the tile holds TILE keys — no per-key bounds test, so the 16 keys of a thread are independent straight-line
 // code (with the tests every key sat in its own BSSY/BSYNC region and its shared-memory loads could not be batched:
 // ncu showed 52 % of the stall samples on short_scoreboard).  Only the last tile of a pass runs FULL = false.
-template <typename K, bool HAS_VAL, bool FULL>
+// XIN: kin holds raw floating-point bits (keys formed in registers) and the values are the global indices themselves;
+// XOUT: the keys leave as floating-point bits and the values as Int64 (the last pass of mcm_sort / mcm_sortperm).
+template <typename K, bool HAS_VAL, bool FULL, bool XIN, bool XOUT>
 __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __restrict__ kin, K* __restrict__ kout,
-                                             const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout, uint32_t n,
+                                             const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
+                                             int64_t* __restrict__ vout64, uint32_t n,
                                              int shift, const uint32_t* __restrict__ hist_scanned, uint32_t nblocks) {
   using SM = ScatterSmem<K, HAS_VAL>;
   unsigned char* cnt = sraw;                                             // [warp][digit][CROW]
@@ -282,7 +341,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
 #pragma unroll
       for (int e = 0; e < KV; ++e) key[q * KV + e] = tk[e];
     }
-    if constexpr (HAS_VAL) {
+    if constexpr (HAS_VAL && !XIN) {
       const uint4* pv = reinterpret_cast<const uint4*>(vin + mine);
 #pragma unroll
       for (int q = 0; q < IPT / 4; ++q) {
@@ -294,7 +353,15 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
 #pragma unroll
     for (int j = 0; j < IPT; ++j) {
       key[j] = mine + j < n ? kin[mine + j] : (K)0;
-      if constexpr (HAS_VAL) val[j] = mine + j < n ? vin[mine + j] : 0u;
+      if constexpr (HAS_VAL && !XIN) val[j] = mine + j < n ? vin[mine + j] : 0u;
+    }
+  }
+  if constexpr (XIN) {
+    bool nan_unused = false;
+#pragma unroll
+    for (int j = 0; j < IPT; ++j) {
+      key[j] = key_of_bits<K>(key[j], nan_unused);
+      if constexpr (HAS_VAL) val[j] = mine + j;
     }
   }
   __syncthreads();
@@ -382,22 +449,50 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
       const K k = skeys[sl];
       const uint32_t d = (uint32_t)((k >> shift) & (NBINS - 1));
       const uint32_t pos = gdel[d] + sl;
-      kout[pos] = k;
-      if constexpr (HAS_VAL) vout[pos] = svals[sl];
+      kout[pos] = XOUT ? bits_of_key<K>(k) : k;
+      if constexpr (HAS_VAL) {
+        if constexpr (XOUT) vout64[pos] = (int64_t)svals[sl];
+        else vout[pos] = svals[sl];
+      }
     }
   }
 }
 #ifndef MCM_SCATTER_MIN_CTAS
 #define MCM_SCATTER_MIN_CTAS 2
 #endif
-template <typename K, bool HAS_VAL>
+template <typename K, bool HAS_VAL, bool XIN, bool XOUT>
 __global__ void __launch_bounds__(ST, MCM_SCATTER_MIN_CTAS)
 k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __restrict__ vin,
-          uint32_t* __restrict__ vout, uint32_t n, int shift, const uint32_t* __restrict__ hist_scanned,
-          uint32_t nblocks) {
+          uint32_t* __restrict__ vout, int64_t* __restrict__ vout64, uint32_t n, int shift,
+          const uint32_t* __restrict__ hist_scanned, uint32_t nblocks) {
   extern __shared__ __align__(16) unsigned char sraw[];
-  if (n - blockIdx.x * TILE >= (uint32_t)TILE) scatter_tile<K, HAS_VAL, true>(sraw, kin, kout, vin, vout, n, shift, hist_scanned, nblocks);
-  else scatter_tile<K, HAS_VAL, false>(sraw, kin, kout, vin, vout, n, shift, hist_scanned, nblocks);
+  if (n - blockIdx.x * TILE >= (uint32_t)TILE)
+    scatter_tile<K, HAS_VAL, true, XIN, XOUT>(sraw, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+  else
+    scatter_tile<K, HAS_VAL, false, XIN, XOUT>(sraw, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+}
+template <typename K, bool HAS_VAL, bool XIN, bool XOUT>
+static int scatter_launch(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, int64_t* vout64, uint32_t n, int shift,
+                          const uint32_t* hist_scanned, uint32_t nblocks) {
+  static bool attr = false;
+  if (!attr) {
+    MCM_CUDA(cudaFuncSetAttribute(k_scatter<K, HAS_VAL, XIN, XOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, HAS_VAL>::BYTES));
+    attr = true;
+  }
+  k_scatter<K, HAS_VAL, XIN, XOUT><<<nblocks, ST, ScatterSmem<K, HAS_VAL>::BYTES, ctx().stream>>>(kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
+}
+template <typename K, bool XIN>
+static int hist_launch(const K* keys, uint32_t n, int shift, uint32_t* hist, uint32_t nblocks, unsigned long long* orand) {
+  static bool attr = false;
+  if (!attr) {
+    MCM_CUDA(cudaFuncSetAttribute(k_hist<K, XIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, NBINS * HROW));
+    attr = true;
+  }
+  k_hist<K, XIN><<<nblocks, ST, NBINS * HROW, ctx().stream>>>(keys, n, shift, hist, nblocks, ctx().d_flags, orand);
+  MCM_CHECK_LAUNCH();
+  return MCM_OK;
 }
 
 // Sort n keys held in bufA (ping-pong with bufB); the result is back in bufA (vals likewise).  `varying`: bits that
@@ -414,21 +509,15 @@ int radix_sort_keys_masked(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, siz
   K* src = bufA; K* dst = bufB;
   uint32_t* vs = valA; uint32_t* vd = valB;
   constexpr int passes = (int)sizeof(K);
-  static bool attr = false;
-  if (!attr) {
-    MCM_CUDA(cudaFuncSetAttribute(k_hist<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, NBINS * HROW));
-    MCM_CUDA(cudaFuncSetAttribute(k_scatter<K, HAS_VAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, HAS_VAL>::BYTES));
-    attr = true;
-  }
   for (int p = 0; p < passes; ++p) {
     const int shift = p * RB;
     if (((varying >> shift) & (K)(NBINS - 1)) == 0) continue;
-    k_hist<K><<<nblocks, ST, NBINS * HROW, c.stream>>>(src, (uint32_t)n, shift, hist, nblocks);
-    MCM_CHECK_LAUNCH();
-    int rc = device_scan<uint32_t, false>(hist, hlen, nullptr);
+    int rc = hist_launch<K, false>(src, (uint32_t)n, shift, hist, nblocks, nullptr);
     if (rc) return rc;
-    k_scatter<K, HAS_VAL><<<nblocks, ST, ScatterSmem<K, HAS_VAL>::BYTES, c.stream>>>(src, dst, vs, vd, (uint32_t)n, shift, hist, nblocks);
-    MCM_CHECK_LAUNCH();
+    rc = device_scan<uint32_t, false>(hist, hlen, nullptr);
+    if (rc) return rc;
+    rc = scatter_launch<K, HAS_VAL, false, false>(src, dst, vs, vd, nullptr, (uint32_t)n, shift, hist, nblocks);
+    if (rc) return rc;
     K* t = src; src = dst; dst = t;
     uint32_t* tv = vs; vs = vd; vd = tv;
   }
@@ -446,7 +535,7 @@ int radix_sort_keys(K* bufA, K* bufB, uint32_t* valA, uint32_t* valB, size_t n) 
 template int radix_sort_keys<uint64_t, true>(uint64_t*, uint64_t*, uint32_t*, uint32_t*, size_t);
 
 template <typename T, typename K>
-static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
+static int sort_impl_unfused(const T* in, T* out, int64_t* perm_out, size_t n) {
   Ctx& c = ctx();
   if (n == 0) return MCM_OK;
   K* A = nullptr; K* B = nullptr;
@@ -491,6 +580,90 @@ static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
   }
   MCM_CUDA(cudaFreeAsync(B, c.stream));
   return MCM_OK;
+}
+
+// mcm_sort / mcm_sortperm without separate transform passes: the first pass reads the particles themselves (its
+// histogram kernel also returns the OR / AND of all keys, which decide the remaining passes), the last pass writes
+// floating-point values and Int64 indices.  Against sort_impl_unfused this saves the key-transform round trip
+// (k_to_keys + k_from_keys, 0.57 ms per 1e8 Float64) and, for sortperm, k_iota + k_u32_to_i64.
+template <typename T, typename K, bool HAS_VAL>
+static int sort_fused_passes(const K* in_bits, K* A, K* B, uint32_t* vA, uint32_t* vB, int64_t* perm_out, size_t n, K varying,
+                             uint32_t* hist, uint32_t nblocks) {
+  int plist[sizeof(K)], m = 0;
+  for (int p = 0; p < (int)sizeof(K); ++p)
+    if (((varying >> (p * RB)) & (K)(NBINS - 1)) != 0) plist[m++] = p;
+  const size_t hlen = (size_t)NBINS * nblocks;
+  const K* src = in_bits;
+  const uint32_t* vsrc = nullptr;
+  for (int i = 1; i <= m; ++i) {
+    const int shift = plist[i - 1] * RB;
+    K* dst = ((m - i) % 2 == 0) ? A : B;
+    uint32_t* vdst = HAS_VAL ? (((m - i) % 2 == 0) ? vA : vB) : nullptr;
+    int rc = MCM_OK;
+    if (i > 1) rc = hist_launch<K, false>(src, (uint32_t)n, shift, hist, nblocks, nullptr);   // pass 1: done by the caller
+    if (rc) return rc;
+    rc = device_scan<uint32_t, false>(hist, hlen, nullptr);
+    if (rc) return rc;
+    const bool first = i == 1, last = i == m;
+    if (first && last) rc = scatter_launch<K, HAS_VAL, true, true>(src, dst, vsrc, vdst, perm_out, (uint32_t)n, shift, hist, nblocks);
+    else if (first) rc = scatter_launch<K, HAS_VAL, true, false>(src, dst, vsrc, vdst, perm_out, (uint32_t)n, shift, hist, nblocks);
+    else if (last) rc = scatter_launch<K, HAS_VAL, false, true>(src, dst, vsrc, vdst, perm_out, (uint32_t)n, shift, hist, nblocks);
+    else rc = scatter_launch<K, HAS_VAL, false, false>(src, dst, vsrc, vdst, perm_out, (uint32_t)n, shift, hist, nblocks);
+    if (rc) return rc;
+    src = dst; vsrc = vdst;
+  }
+  return MCM_OK;
+}
+
+static int g_sort_fused = 1;
+extern "C" int mcm_sort_use_fused(int on) { g_sort_fused = on; return MCM_OK; }
+
+template <typename T, typename K>
+static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
+  Ctx& c = ctx();
+  if (n == 0) return MCM_OK;
+  // the fused form reads `in` while it writes `out` (no in-place calls), and needs 16-byte aligned rows for its vector loads
+  if (!g_sort_fused || (const void*)in == (const void*)out || n >= 0xFFFF0000ull ||
+      (reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) % 16 != 0)
+    return sort_impl_unfused<T, K>(in, out, perm_out, n);
+  const uint32_t nblocks = (uint32_t)((n + TILE - 1) / TILE);
+  uint32_t* hist = nullptr;
+  unsigned long long* d_orand = nullptr;
+  MCM_CUDA(cudaMallocAsync((void**)&hist, (size_t)NBINS * nblocks * sizeof(uint32_t), c.stream));
+  MCM_CUDA(cudaMallocAsync((void**)&d_orand, 2 * sizeof(unsigned long long), c.stream));
+  const unsigned long long init[2] = {0ull, ~0ull};
+  MCM_CUDA(cudaMemcpyAsync(d_orand, init, sizeof(init), cudaMemcpyHostToDevice, c.stream));
+  const K* in_bits = reinterpret_cast<const K*>(in);
+  int rc = hist_launch<K, true>(in_bits, (uint32_t)n, 0, hist, nblocks, d_orand);   // digit 0 + OR / AND + NaN flag
+  if (rc) return rc;
+  unsigned long long h_orand[2] = {~0ull, 0ull};
+  MCM_CUDA(cudaMemcpyAsync(h_orand, d_orand, sizeof(h_orand), cudaMemcpyDeviceToHost, c.stream));
+  MCM_CUDA(cudaStreamSynchronize(c.stream));      // one 16-byte read-back per sort decides which passes run
+  MCM_CUDA(cudaFreeAsync(d_orand, c.stream));
+  const K varying = (K)(h_orand[0] ^ h_orand[1]);
+  if ((varying & (K)(NBINS - 1)) == 0) {          // the lowest digit is the same in every key: its histogram was for nothing
+    MCM_CUDA(cudaFreeAsync(hist, c.stream));
+    return sort_impl_unfused<T, K>(in, out, perm_out, n);
+  }
+  K* A = nullptr; K* B = nullptr;
+  uint32_t* vA = nullptr; uint32_t* vB = nullptr;
+  const bool own_A = (out == nullptr);
+  if (own_A) MCM_CUDA(cudaMallocAsync((void**)&A, n * sizeof(K), c.stream));
+  else A = reinterpret_cast<K*>(out);
+  MCM_CUDA(cudaMallocAsync((void**)&B, n * sizeof(K), c.stream));
+  if (perm_out) {
+    MCM_CUDA(cudaMallocAsync((void**)&vA, n * sizeof(uint32_t), c.stream));
+    MCM_CUDA(cudaMallocAsync((void**)&vB, n * sizeof(uint32_t), c.stream));
+    rc = sort_fused_passes<T, K, true>(in_bits, A, B, vA, vB, perm_out, n, varying, hist, nblocks);
+    MCM_CUDA(cudaFreeAsync(vA, c.stream));
+    MCM_CUDA(cudaFreeAsync(vB, c.stream));
+  } else {
+    rc = sort_fused_passes<T, K, false>(in_bits, A, B, nullptr, nullptr, nullptr, n, varying, hist, nblocks);
+  }
+  if (own_A) MCM_CUDA(cudaFreeAsync(A, c.stream));
+  MCM_CUDA(cudaFreeAsync(B, c.stream));
+  MCM_CUDA(cudaFreeAsync(hist, c.stream));
+  return rc;
 }
 
 template <typename T>

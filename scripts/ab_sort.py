@@ -14,14 +14,15 @@ data = {"N(0,1) iid": mcm.rand_particles(n, seed=1), "N(pi,0.1) systematic, perm
 out = P._empty(n, L.F64)
 perm = P.DeviceIndex(n)
 for name, x in data.items():
-    for what in ("sort", "sortperm"):
+    for what in ("sort", "sortperm") + (("sort-unfused", "sortperm-unfused") if hasattr(lib, "mcm_sort_use_fused") else ()):
         ts = []
         with torch.cuda.stream(stream):
             for _ in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize(); t = time.perf_counter()
                 e0.record(stream)
-                if what == "sort":
+                lib.mcm_sort_use_fused(0 if what.endswith("unfused") else 1)
+                if what.startswith("sort") and not what.startswith("sortperm"):
                     L.check(lib.mcm_sort(L.F64, C.c_void_p(x.ptr), C.c_void_p(out.ptr), n))
                 else:
                     L.check(lib.mcm_sortperm(L.F64, C.c_void_p(x.ptr), C.c_void_p(perm.ptr), C.c_void_p(out.ptr), n))
