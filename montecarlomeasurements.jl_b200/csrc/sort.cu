@@ -13,6 +13,7 @@
 // the kernels.)
 #include <math.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "mcm_common.cuh"
 #include "mcm_keys.cuh"
@@ -63,6 +64,16 @@ __global__ void __launch_bounds__(256) k_u32_to_i64(const uint32_t* __restrict__
   const size_t stride = (size_t)gridDim.x * 256;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) o[i] = (int64_t)v[i];
 }
+
+// 16-byte asynchronous copies global -> shared (LDGSTS): both kernels of a pass are persistent and fetch the NEXT tile's
+// keys while they work on the current one.  Before round 2's last session every CTA loaded its tile, waited out the HBM
+// latency and only then started: ncu showed 22-26 % of the stall samples on the first use of the keys and half of the
+// HBM rate (k_hist read at 3.4 TB/s).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Lanes of the warp that hold the same 8-bit digit, by 8 ballots (VOTE + LOP3 each).  __match_any_sync gives the same
 // mask in one instruction but is far slower here: the histogram kernel built on it ran at 0.53 keys/clk/SM
@@ -118,69 +129,86 @@ template <typename K> __device__ __forceinline__ K bits_of_key(K k) {
   memcpy(&raw, &x, sizeof(K));
   return raw;
 }
+constexpr int HIST_TABLE = NBINS * HROW;
+template <typename K> constexpr int hist_smem() { return HIST_TABLE + TILE * (int)sizeof(K); }
+template <typename K>
+__device__ __forceinline__ void hist_prefetch(unsigned char* kbuf, const K* __restrict__ keys, uint32_t tile) {
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(keys + (size_t)tile * TILE);
+#pragma unroll
+  for (int q = 0; q < TILE * (int)sizeof(K) / 16 / ST; ++q) cp_async16(kbuf + (q * ST + threadIdx.x) * 16, src + (size_t)(q * ST + threadIdx.x) * 16);
+  cp_async_commit();
+}
 template <typename K, bool XIN>
-__global__ void __launch_bounds__(ST)
+__global__ void __launch_bounds__(ST, 2)
 k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblocks,
        uint32_t* __restrict__ flags, unsigned long long* __restrict__ orand) {
-  extern __shared__ __align__(16) unsigned char hcnt[];   // [NBINS][HROW]
-  {
-    uint4* z = reinterpret_cast<uint4*>(hcnt);
-    for (int i = threadIdx.x; i < NBINS * HROW / 16; i += ST) z[i] = make_uint4(0, 0, 0, 0);
-  }
-  __syncthreads();
-  const uint32_t base = blockIdx.x * TILE;
-  K k[IPT];
-  if (n - base >= (uint32_t)TILE) {          // full tile: no per-key bounds test
+  extern __shared__ __align__(16) unsigned char hraw[];
+  unsigned char* hcnt = hraw;                       // [NBINS][HROW]
+  unsigned char* kbuf = hraw + HIST_TABLE;          // the tile's keys, fetched one tile ahead
+  const K* kb = reinterpret_cast<const K*>(kbuf);
+  const uint32_t nfull = n / TILE;                  // tiles below nfull are full
+  uint32_t tile = blockIdx.x;
+  if (tile < nfull) hist_prefetch<K>(kbuf, keys, tile);
+  for (; tile < nblocks; tile += gridDim.x) {
+    {
+      uint4* z = reinterpret_cast<uint4*>(hcnt);
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) k[i] = keys[base + i * ST + threadIdx.x];
-    if constexpr (XIN) {
-      bool nan = false;
-      unsigned long long o = 0ull, a = ~0ull;
-#pragma unroll
-      for (int i = 0; i < IPT; ++i) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
-      hist_fold_orand(o, a, nan, flags, orand);
+      for (int i = 0; i < HIST_TABLE / 16 / ST; ++i) z[i * ST + threadIdx.x] = make_uint4(0, 0, 0, 0);
+      static_assert(HIST_TABLE % (16 * ST) == 0, "table zeroed in whole rounds");
     }
+    const uint32_t base = tile * TILE;
+    const bool full = tile < nfull;
+    K k[IPT];
+    if (full) {
+      cp_async_wait_all();
+      __syncthreads();                               // every thread's copies have landed; the table is zeroed
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
-      hcnt[d * HROW + threadIdx.x] += 1;
-    }
-  } else {
+      for (int i = 0; i < IPT; ++i) k[i] = kb[i * ST + threadIdx.x];
+    } else {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t idx = base + i * ST + threadIdx.x;
-      k[i] = idx < n ? keys[idx] : (K)0;
+      for (int i = 0; i < IPT; ++i) {
+        const uint32_t idx = base + i * ST + threadIdx.x;
+        k[i] = idx < n ? keys[idx] : (K)0;
+      }
     }
+    __syncthreads();                                 // the key buffer has been read: the next tile may overwrite it
+    if (tile + gridDim.x < nfull) hist_prefetch<K>(kbuf, keys, tile + gridDim.x);
     if constexpr (XIN) {
       bool nan = false;
       unsigned long long o = 0ull, a = ~0ull;
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
-        const uint32_t idx = base + i * ST + threadIdx.x;
-        if (idx < n) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
+        if (full || base + i * ST + threadIdx.x < n) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
       }
       hist_fold_orand(o, a, nan, flags, orand);
     }
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i) {
-      const uint32_t idx = base + i * ST + threadIdx.x;
-      if (idx < n) {
+      for (int i = 0; i < IPT; ++i) {
         const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
         hcnt[d * HROW + threadIdx.x] += 1;
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IPT; ++i) {
+        if (base + i * ST + threadIdx.x < n) {
+          const uint32_t d = (uint32_t)((k[i] >> shift) & (NBINS - 1));
+          hcnt[d * HROW + threadIdx.x] += 1;
+        }
+      }
     }
-  }
-  __syncthreads();
-  const uint4* row = reinterpret_cast<const uint4*>(hcnt + threadIdx.x * HROW);
-  uint32_t tot = 0, tot2 = 0;
+    __syncthreads();
+    const uint4* row = reinterpret_cast<const uint4*>(hcnt + threadIdx.x * HROW);
+    uint32_t tot = 0, tot2 = 0;
 #pragma unroll 8
-  for (int w = 0; w < ST / 16; ++w) {
-    const uint4 r = row[w];
-    tot = __dp4a(r.x, 0x01010101u, tot); tot2 = __dp4a(r.y, 0x01010101u, tot2);
-    tot = __dp4a(r.z, 0x01010101u, tot); tot2 = __dp4a(r.w, 0x01010101u, tot2);
+    for (int w = 0; w < ST / 16; ++w) {
+      const uint4 r = row[w];
+      tot = __dp4a(r.x, 0x01010101u, tot); tot2 = __dp4a(r.y, 0x01010101u, tot2);
+      tot = __dp4a(r.z, 0x01010101u, tot); tot2 = __dp4a(r.w, 0x01010101u, tot2);
+    }
+    hist[(size_t)threadIdx.x * nblocks + tile] = tot + tot2;
+    __syncthreads();                                 // the row sums are done before the table is zeroed again
   }
-  tot += tot2;
-  hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = tot;
 }
 
 // ---- exclusive scan (3 kernels; chunk = 2048 per CTA) ---------------------------
@@ -303,15 +331,33 @@ template <typename K, bool HAS_VAL> struct ScatterSmem {
   static constexpr size_t CNT = (size_t)(ST / 32) * NBINS * CROW;
   static constexpr size_t UNION = (KEYS + VALS) > CNT ? (KEYS + VALS) : CNT;    // the staged tile reuses the count table
   static constexpr size_t WOFF = (size_t)(ST / 32) * NBINS * sizeof(uint16_t);     // offsets inside a tile: < 4096
-  static constexpr size_t BYTES = UNION + WOFF + NBINS * sizeof(uint32_t);
+  static constexpr size_t TABLES = UNION + WOFF + NBINS * sizeof(uint32_t);
+  // the next tile's keys, fetched while this one is processed: one row of IPT keys per thread, padded by 16 bytes so
+  // that the threads' 128-bit reads of their own rows are conflict-free (row stride = an odd number of 16-byte slots)
+  static constexpr size_t KROW = IPT * sizeof(K) + 16;
+  static constexpr size_t BYTES = TABLES + (size_t)ST * KROW;
 };
 // FULL: the tile holds TILE keys — no per-key bounds test, so the 16 keys of a thread are independent straight-line
 // code (with the tests every key sat in its own BSSY/BSYNC region and its shared-memory loads could not be batched:
 // ncu showed 52 % of the stall samples on short_scoreboard).  Only the last tile of a pass runs FULL = false.
 // XIN: kin holds raw floating-point bits (keys formed in registers) and the values are the global indices themselves;
 // XOUT: the keys leave as floating-point bits and the values as Int64 (the last pass of mcm_sort / mcm_sortperm).
+// chunk g (16 bytes) of the tile goes to row g / CPR, slot g % CPR: coalesced global reads, conflict-free shared writes
+template <typename K, bool HAS_VAL>
+__device__ __forceinline__ void scatter_prefetch(unsigned char* kbuf, const K* __restrict__ kin, uint32_t tile) {
+  constexpr int CPR = IPT * (int)sizeof(K) / 16;      // chunks per row
+  constexpr int KROW = (int)ScatterSmem<K, HAS_VAL>::KROW;
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(kin + (size_t)tile * TILE);
+#pragma unroll
+  for (int q = 0; q < CPR; ++q) {
+    const int g = q * ST + threadIdx.x;
+    cp_async16(kbuf + (g / CPR) * KROW + (g % CPR) * 16, src + (size_t)g * 16);
+  }
+  cp_async_commit();
+}
 template <typename K, bool HAS_VAL, bool FULL, bool XIN, bool XOUT>
-__device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __restrict__ kin, K* __restrict__ kout,
+__device__ __forceinline__ void scatter_tile(unsigned char* sraw, uint32_t tile, bool prefetch_next, uint32_t next_tile,
+                                             const K* __restrict__ kin, K* __restrict__ kout,
                                              const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                              int64_t* __restrict__ vout64, uint32_t n,
                                              int shift, const uint32_t* __restrict__ hist_scanned, uint32_t nblocks) {
@@ -326,14 +372,20 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
     uint4* z = reinterpret_cast<uint4*>(cnt);
     for (int i = threadIdx.x; i < (int)(SM::CNT / 16); i += ST) z[i] = make_uint4(0, 0, 0, 0);
   }
-  const uint32_t tile0 = blockIdx.x * TILE;
+  unsigned char* kbuf = sraw + SM::TABLES;
+  const uint32_t tile0 = tile * TILE;
   const uint32_t mine = tile0 + threadIdx.x * IPT;                      // first key of this thread
   const uint32_t ntile = min((uint32_t)TILE, n - tile0);
   K key[IPT];
   uint32_t val[IPT];
+  if constexpr (FULL) {
+    cp_async_wait_all();
+    __syncthreads();                                                    // every thread's copies of this tile have landed
+  }
   if (FULL || mine + IPT <= n) {                                        // 128 contiguous bytes per thread
     constexpr int KV = 16 / (int)sizeof(K);
-    const uint4* p = reinterpret_cast<const uint4*>(kin + mine);
+    const uint4* p = FULL ? reinterpret_cast<const uint4*>(kbuf + (size_t)threadIdx.x * SM::KROW)
+                          : reinterpret_cast<const uint4*>(kin + mine);
 #pragma unroll
     for (int q = 0; q < IPT / KV; ++q) {
       const uint4 t = p[q];
@@ -364,7 +416,8 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
       if constexpr (HAS_VAL) val[j] = mine + j;
     }
   }
-  __syncthreads();
+  __syncthreads();                                                      // table zeroed; the key buffer has been read
+  if (prefetch_next) scatter_prefetch<K, HAS_VAL>(kbuf, kin, next_tile);
   // 1. own-column counting; own[j] = rank among this thread's earlier keys with the same digit
   unsigned char* wcnt = cnt + (size_t)w * NBINS * CROW;
   unsigned long long own64 = 0;   // 16 x 4-bit ranks packed (a thread has at most 16 keys per digit: rank <= 15)
@@ -416,7 +469,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
     const uint32_t ex = block_exclusive_scan<uint32_t>(run, &tot);
 #pragma unroll
     for (int ww = 0; ww < ST / 32; ++ww) woff[ww][d] = (uint16_t)(ex + wrun[ww]);   // first tile slot of (warp, digit)
-    gdel[d] = hist_scanned[(size_t)d * nblocks + blockIdx.x] - ex;
+    gdel[d] = hist_scanned[(size_t)d * nblocks + tile] - ex;
   }
   __syncthreads();
   // 2b. tile slot = first slot of (warp, digit) + equal-digit keys of lower lanes + rank among the thread's own keys
@@ -456,6 +509,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* sraw, const K* __res
       }
     }
   }
+  __syncthreads();                                                      // the staged tile and gdel are dead: next tile
 }
 #ifndef MCM_SCATTER_MIN_CTAS
 #define MCM_SCATTER_MIN_CTAS 2
@@ -466,10 +520,16 @@ k_scatter(const K* __restrict__ kin, K* __restrict__ kout, const uint32_t* __res
           uint32_t* __restrict__ vout, int64_t* __restrict__ vout64, uint32_t n, int shift,
           const uint32_t* __restrict__ hist_scanned, uint32_t nblocks) {
   extern __shared__ __align__(16) unsigned char sraw[];
-  if (n - blockIdx.x * TILE >= (uint32_t)TILE)
-    scatter_tile<K, HAS_VAL, true, XIN, XOUT>(sraw, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
-  else
-    scatter_tile<K, HAS_VAL, false, XIN, XOUT>(sraw, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+  const uint32_t nfull = n / TILE;                  // tiles below nfull are full; only they are fetched ahead
+  uint32_t tile = blockIdx.x;
+  if (tile < nfull) scatter_prefetch<K, HAS_VAL>(sraw + ScatterSmem<K, HAS_VAL>::TABLES, kin, tile);
+  for (; tile < nblocks; tile += gridDim.x) {
+    const uint32_t next = tile + gridDim.x;
+    if (tile < nfull)
+      scatter_tile<K, HAS_VAL, true, XIN, XOUT>(sraw, tile, next < nfull, next, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+    else
+      scatter_tile<K, HAS_VAL, false, XIN, XOUT>(sraw, tile, false, next, kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+  }
 }
 template <typename K, bool HAS_VAL, bool XIN, bool XOUT>
 static int scatter_launch(const K* kin, K* kout, const uint32_t* vin, uint32_t* vout, int64_t* vout64, uint32_t n, int shift,
@@ -479,7 +539,8 @@ static int scatter_launch(const K* kin, K* kout, const uint32_t* vin, uint32_t* 
     MCM_CUDA(cudaFuncSetAttribute(k_scatter<K, HAS_VAL, XIN, XOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ScatterSmem<K, HAS_VAL>::BYTES));
     attr = true;
   }
-  k_scatter<K, HAS_VAL, XIN, XOUT><<<nblocks, ST, ScatterSmem<K, HAS_VAL>::BYTES, ctx().stream>>>(kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
+  const uint32_t grid = std::min<uint32_t>(nblocks, (uint32_t)(MCM_SCATTER_MIN_CTAS * ctx().sm_count));   // persistent: tiles strided over the CTAs
+  k_scatter<K, HAS_VAL, XIN, XOUT><<<grid, ST, ScatterSmem<K, HAS_VAL>::BYTES, ctx().stream>>>(kin, kout, vin, vout, vout64, n, shift, hist_scanned, nblocks);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
@@ -487,10 +548,11 @@ template <typename K, bool XIN>
 static int hist_launch(const K* keys, uint32_t n, int shift, uint32_t* hist, uint32_t nblocks, unsigned long long* orand) {
   static bool attr = false;
   if (!attr) {
-    MCM_CUDA(cudaFuncSetAttribute(k_hist<K, XIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, NBINS * HROW));
+    MCM_CUDA(cudaFuncSetAttribute(k_hist<K, XIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, hist_smem<K>()));
     attr = true;
   }
-  k_hist<K, XIN><<<nblocks, ST, NBINS * HROW, ctx().stream>>>(keys, n, shift, hist, nblocks, ctx().d_flags, orand);
+  const uint32_t grid = std::min<uint32_t>(nblocks, (uint32_t)(2 * ctx().sm_count));
+  k_hist<K, XIN><<<grid, ST, hist_smem<K>(), ctx().stream>>>(keys, n, shift, hist, nblocks, ctx().d_flags, orand);
   MCM_CHECK_LAUNCH();
   return MCM_OK;
 }
