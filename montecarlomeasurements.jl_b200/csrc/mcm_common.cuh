@@ -14,7 +14,11 @@
 #endif
 
 namespace mcm {
+#ifdef MCM_JIT_THREADS
+static constexpr int kThreads = MCM_JIT_THREADS;   // generated chain kernels may choose their CTA size (chain_jit.cu)
+#else
 static constexpr int kThreads = 256;          // CTA size for streaming kernels
+#endif
 }
 
 #ifndef __CUDACC_RTC__
