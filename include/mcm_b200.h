@@ -425,7 +425,7 @@ int mcm_quantile_dist(int dtype, int kind, double a, double b, double c, const v
 /* randperm(rng, N) stand-in: device permutation from a counter-based generator
  * (Philox-4x32-10 keys + stable radix sort).  Stream differs from Julia's RNG (H5). */
 int mcm_randperm(int64_t* perm_out, size_t n, uint64_t seed);
-/* Keyed pseudo-random permutation of [0, n_total) evaluated per index (6-round Feistel network +
+/* Keyed pseudo-random permutation of [0, n_total) evaluated per index (4-round Feistel network +
  * cycle walking; no sort, no storage): out[j] = pi_{seed,column}(i0 + j).  The communication-free
  * replacement for randperm at sampling.jl:11 when the sample is large or sharded. */
 int mcm_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t column, uint64_t i0, uint64_t n_total);

@@ -668,7 +668,7 @@ ORC_API void orc_index_bijection(int64_t* out, size_t n, uint64_t seed, uint64_t
     uint64_t x = i0 + j;
     do {
       uint32_t L = (uint32_t)(x >> rbits) & lmask, R = (uint32_t)x & rmask;
-      for (int r = 0; r < 6; r += 2) {   /* kFeistelRounds */
+      for (int r = 0; r < 4; r += 2) {   /* kFeistelRounds */
         L ^= orc_feistel_mix(R, key[r]) & lmask;
         R ^= orc_feistel_mix(L, key[r + 1]) & rmask;
       }

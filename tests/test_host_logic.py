@@ -191,3 +191,32 @@ def test_chain_kernel_generation_and_nvrtc_compile_without_a_gpu(m, tmp_path):
     bad = (L.TapeIns * 1)()
     bad[0].op = 0x7f
     assert lib.mcm_chain_jit_source(L.F64, bad, 1, 1, 1, None, 0, -1, 0, None, 0, None, None) != 0
+
+
+@pytest.mark.parametrize("n", [100000, 1 << 18, 300007])
+def test_index_bijection_statistics(orc, n):
+    """The keyed bijection that stands in for randperm (sampling.jl:11): columns are permutations, pairwise rank
+    correlations / correlation with the identity / between neighbours stay inside 4.5 / sqrt(n), and the 32 x 32 joint
+    position tables (column vs column, column vs identity) are uniform (chi-square within 6 sigma)."""
+    cols = [orc.index_bijection(n, 5, c) for c in range(5)]
+    ident = np.arange(n)
+    for p in cols:
+        assert np.array_equal(np.sort(p), ident)
+    lim = 4.5 / np.sqrt(n)
+    for a in range(5):
+        assert abs(np.corrcoef(cols[a], ident)[0, 1]) < lim
+        assert abs(np.corrcoef(cols[a][:-1], cols[a][1:])[0, 1]) < lim
+        for b in range(a):
+            assert abs(np.corrcoef(cols[a], cols[b])[0, 1]) < lim
+    B = 32
+    dof = (B - 1) * (B - 1)
+
+    def chi2(p, q):
+        t = np.bincount((p * B // n) * B + (q * B // n), minlength=B * B).astype(float)
+        rp = np.bincount(p * B // n, minlength=B).astype(float)
+        e = np.outer(rp, rp) / n
+        return ((t.reshape(B, B) - e) ** 2 / e).sum()
+    for a in range(3):
+        assert abs(chi2(cols[a], ident) - dof) < 6 * np.sqrt(2 * dof)
+        for b in range(a):
+            assert abs(chi2(cols[a], cols[b]) - dof) < 6 * np.sqrt(2 * dof)
