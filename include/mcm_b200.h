@@ -487,7 +487,7 @@ int mcm_filter_range(int dtype, const void* in, size_t n, double lo, double hi, 
  * Device replacement for the host loops of R^n2R^n_function / R^n2C^n_function (particles.jl:241-282), eigvals
  * (:395-406), exp / exp! / lyap (:603-607) and `\` on particle matrices: entry (r,c) of the uncertain nmat x nmat
  * matrix is the length-n device vector A[r*nmat + c]; particle i of every entry forms matrix i.  One thread per
- * particle.  nmat <= 16 (lyap: <= 4); up to 8 the matrix is held in registers, above in per-thread local memory.  Results agree with LAPACK to rounding (tolerance tier), not bit for bit.
+ * particle.  nmat <= 16 (lyap: <= 8); up to 8 the matrix is held in registers, above in per-thread local memory.  Results agree with LAPACK to rounding (tolerance tier), not bit for bit.
  *   SOLVE        out[r*m + c] = (A \ B)[r,c], B = nmat x m table (LU, partial pivoting)
  *   INV, EXP     out[r*nmat + c]; EXP is Higham's scaling and squaring as LinearAlgebra.exp!, without balancing
  *   DET          out[0]

@@ -114,7 +114,7 @@ static int la_launch(const LaArgs& g, int m, size_t n) {
 // sizes LO..HI of one operation (each translation unit instantiates one range: see batched*.cu)
 template <int OP, typename T, int N, int HI>
 static int la_by_n(int nmat, const LaArgs& g, int m, size_t n) {
-  if constexpr (N > HI || (OP == MCM_LA_LYAP && N > 4)) {
+  if constexpr (N > HI || (OP == MCM_LA_LYAP && N > 8)) {      // lyap: Kronecker system of order n^2 <= 64 per thread
     return fail(MCM_ERR_UNSUPPORTED, "mcm_batched_linalg: matrix size %d not supported for this operation", nmat);
   } else {
     if (nmat == N) return la_launch<OP, N, T>(g, m, n);

@@ -9,7 +9,7 @@
 //   eig_sym                cyclic Jacobi, ascending
 //   eig_general            elimination to Hessenberg form + Francis double-shift QR (EISPACK hqr); returned sorted by
 //                          (real, imaginary) — LAPACK's deflation order is not reproducible
-//   lyap                   A X + X A' + C = 0 through the Kronecker system (n <= 4)
+//   lyap                   A X + X A' + C = 0 through the Kronecker system (n <= 8: order n^2 <= 64)
 //   svdvals                one-sided Jacobi (Hestenes), descending
 #pragma once
 #include <math.h>

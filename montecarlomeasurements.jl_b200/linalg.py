@@ -117,7 +117,7 @@ def eigvals_sym(A):
 
 
 def lyap(A, Cm):
-    """`lyap(A, C)` (particles.jl:607): X with A X + X A' + C = 0, per particle (n <= 4)."""
+    """`lyap(A, C)` (particles.jl:607): X with A X + X A' + C = 0, per particle (n <= 8: the Kronecker system of order n^2 is factored per thread)."""
     r, _, outs, _ = _call("LYAP", A, Cm, lambda n, m: n * n, who="lyap")
     return _grid(outs, r, r)
 

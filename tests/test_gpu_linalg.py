@@ -46,8 +46,8 @@ def test_device_equals_twin(mcm, twin, n):
     assert np.array_equal(ws, twin_run(twin, "eigvals_sym", S, nout=N * n).reshape(N, n))
     sv = np.stack([p.to_numpy() for p in la.svdvals(At)], 1)
     assert np.array_equal(sv, twin_run(twin, "svdvals", A, nout=N * n).reshape(N, n))
-    if n <= 4:
-        Ast = A - 3 * np.eye(n)
+    if n <= 8:
+        Ast = A - max(3.0, 1.5 * np.sqrt(n) + 1.5) * np.eye(n)
         Cm = rng.normal(size=(N, n, n))
         X = gather(la.lyap(table(mcm, Ast), table(mcm, Cm)))
         assert np.array_equal(X, twin_run(twin, "lyap", Ast, Cm, n, N * n * n).reshape(N, n, n))
@@ -95,7 +95,7 @@ def test_errors_and_flags(mcm):
     with pytest.raises(mcm.MethodError):
         la.det([[p] * 17 for _ in range(17)])                # n > 16
     with pytest.raises(mcm.MethodError):
-        la.lyap([[p] * 5 for _ in range(5)], [[p] * 5 for _ in range(5)])    # lyap handles n <= 4
+        la.lyap([[p] * 9 for _ in range(9)], [[p] * 9 for _ in range(9)])    # lyap handles n <= 8
     mcm.check_domain()
     la.inv([[p, p], [p, p]])                                 # exactly singular (zero pivot) for most particles
     with pytest.raises(mcm.DomainError):

@@ -54,7 +54,7 @@ static int run(int op, const double* A, const double* B, int m, double* out, dou
         break;
       }
       case 6: {
-        if constexpr (N <= 4) {
+        if constexpr (N <= 8) {
           Mat<N> c, x;
           for (int i = 0; i < N * N; ++i) c.a[i] = B[b * N * N + i];
           lyap(a, c, x);
