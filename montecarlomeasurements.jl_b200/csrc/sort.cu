@@ -149,6 +149,8 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
   const uint32_t nfull = n / TILE;                  // tiles below nfull are full
   uint32_t tile = blockIdx.x;
   if (tile < nfull) hist_prefetch<K>(kbuf, keys, tile);
+  bool nan = false;                                 // XIN: folded over all tiles of this CTA, reduced once at the end
+  unsigned long long o = 0ull, a = ~0ull;
   for (; tile < nblocks; tile += gridDim.x) {
     {
       uint4* z = reinterpret_cast<uint4*>(hcnt);
@@ -174,13 +176,10 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
     __syncthreads();                                 // the key buffer has been read: the next tile may overwrite it
     if (tile + gridDim.x < nfull) hist_prefetch<K>(kbuf, keys, tile + gridDim.x);
     if constexpr (XIN) {
-      bool nan = false;
-      unsigned long long o = 0ull, a = ~0ull;
 #pragma unroll
       for (int i = 0; i < IPT; ++i) {
         if (full || base + i * ST + threadIdx.x < n) { k[i] = key_of_bits<K>(k[i], nan); o |= (unsigned long long)k[i]; a &= (unsigned long long)k[i]; }
       }
-      hist_fold_orand(o, a, nan, flags, orand);
     }
     if (full) {
 #pragma unroll
@@ -209,6 +208,7 @@ k_hist(const K* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__
     hist[(size_t)threadIdx.x * nblocks + tile] = tot + tot2;
     __syncthreads();                                 // the row sums are done before the table is zeroed again
   }
+  if constexpr (XIN) hist_fold_orand(o, a, nan, flags, orand);
 }
 
 // ---- exclusive scan (3 kernels; chunk = 2048 per CTA) ---------------------------
