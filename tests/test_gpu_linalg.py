@@ -216,3 +216,24 @@ def test_complex_matrix_reference_style_assertions(mcm):
         mcm.check_domain()
     with pytest.raises(mcm.MethodError):
         la.logm(np.zeros((2, 2)))
+
+
+@pytest.mark.parametrize("n", [3, 8, 12])
+def test_float32_particles_round_the_float64_result(mcm, twin, n):
+    """Float32 entries: the per-thread algorithm runs in Float64 on the widened inputs and the result is rounded once
+    (the reference's host loop would run LAPACK in Float32; documented deviation, tighter)."""
+    la = mcm.linalg
+    rng = np.random.default_rng(700 + n)
+    N = 1000
+    A = (rng.normal(size=(N, n, n)) + 3.0 * np.eye(n)).astype(np.float32)
+    B = rng.normal(size=(N, n, 1)).astype(np.float32)
+    At, Bt = table(mcm, A), table(mcm, B)
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    got = gather(la.solve(At, Bt))
+    assert got.dtype == np.float32
+    assert np.array_equal(got, twin_run(twin, "solve", A64, B64, 1, N * n).reshape(N, n, 1).astype(np.float32))
+    assert np.array_equal(la.det(At).to_numpy(), twin_run(twin, "det", A64, nout=N).astype(np.float32))
+    assert np.array_equal(gather(la.expm(table(mcm, 0.2 * A))), twin_run(twin, "exp", (np.float32(0.2) * A).astype(np.float64), nout=N * n * n).reshape(N, n, n).astype(np.float32))
+    sv = np.stack([p.to_numpy() for p in la.svdvals(At)], 1)
+    assert np.array_equal(sv, twin_run(twin, "svdvals", A64, nout=N * n).reshape(N, n).astype(np.float32))
+    mcm.check_domain()
