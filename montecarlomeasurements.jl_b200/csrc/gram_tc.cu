@@ -168,7 +168,7 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
     if ((kbt + 1) * OZ_KBT <= nkb) { rg = rem / OZ_KBT; kb = kbt * OZ_KBT + rem % OZ_KBT; }
     else { const size_t left = nkb - kbt * OZ_KBT; rg = rem / left; kb = kbt * OZ_KBT + rem % left; }   // ragged last group
     const size_t row = rg * 8 + r8;
-    alignas(16) int8_t dg[OZ_S][16];
+    int4 pl[OZ_S];
     if (row < (size_t)M) {
       const T* x = vars[row];
       const double mu = means[row];
@@ -193,26 +193,22 @@ k_slice(const T* const* __restrict__ vars, const double* __restrict__ means, con
 #pragma unroll
         for (int j = 0; j < 16; ++j) xv[j] = (k0 + j < n) ? x[k0 + j] : (T)mu;
       }
+      unsigned long long Kd[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const size_t k = k0 + j;
-        long long I = (k < n) ? __double2ll_rn(((double)xv[j] - mu) * sc) : 0ll;
-#pragma unroll
-        for (int s = OZ_S - 1; s >= 1; --s) {
-          const long long d = ((I + 128) & 255) - 128;
-          dg[s][j] = (int8_t)d;
-          I = (I - d) >> 8;
-        }
-        dg[0][j] = (int8_t)I;
+        const long long I = (k < n) ? __double2ll_rn(((double)xv[j] - mu) * sc) : 0ll;
+        Kd[j] = balanced_digit_bytes<OZ_S>(I);          // all digits in one addition (mcm_tcgen05.cuh)
       }
+      pack_digit_planes<OZ_S>(Kd, pl);
     } else {
 #pragma unroll
-      for (int s = 0; s < OZ_S; ++s) *reinterpret_cast<int4*>(dg[s]) = make_int4(0, 0, 0, 0);
+      for (int s = 0; s < OZ_S; ++s) pl[s] = make_int4(0, 0, 0, 0);
     }
     const size_t off = (((kb * nrg + rg) * 2 + c) * 8 + r8) * 16;
 #pragma unroll
     for (int s = 0; s < OZ_S; ++s)
-      *reinterpret_cast<int4*>(slices + (size_t)s * (mpad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
+      *reinterpret_cast<int4*>(slices + (size_t)s * (mpad * kpad) + off) = pl[s];
   }
 }
 

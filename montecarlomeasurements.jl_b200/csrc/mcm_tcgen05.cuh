@@ -210,4 +210,38 @@ k_rowstats(const T* const* __restrict__ vars, const double* __restrict__ means, 
 }
 
 
+
+// ---- balanced base-256 digits of a 64-bit integer in one addition ------------------------------------------------
+// The Ozaki slicers need the S signed digits d_b in [-128, 127] with I = sum_b d_b 256^b.  Peeling them off one at a
+// time (d = ((I + 128) & 255) - 128; I = (I - d) >> 8) costs ~10 integer instructions per digit in 64-bit arithmetic:
+// ncu showed k_pslice at 59 instructions per value, ALU pipe 56 %, half the HBM rate.  Since
+//     I + sum_b 128 * 256^b = sum_b (d_b + 128) 256^b     with every (d_b + 128) in [0, 255],
+// the UNSIGNED bytes of I + C (C = S bytes of 0x80) are d_b + 128, and flipping bit 7 of each byte turns them into the
+// int8 digits: two 64-bit operations for all digits.  The top byte wraps exactly like the (int8_t) cast of the loop's
+// remainder did, so the planes are bit-identical to the loop's for every I.
+template <int S>
+__device__ __forceinline__ unsigned long long balanced_digit_bytes(long long I) {
+  static_assert(S >= 1 && S <= 8, "at most eight digits per 64-bit value");
+  constexpr unsigned long long C = 0x8080808080808080ull >> (8 * (8 - S));
+  return ((unsigned long long)I + C) ^ C;               // byte b (b < S) = digit of weight 256^b, as int8
+}
+// plane s (s = 0 most significant) of 16 values -> 16 bytes: byte S-1-s of every K[j], gathered with byte permutes
+template <int S>
+__device__ __forceinline__ void pack_digit_planes(const unsigned long long (&K)[16], int4 (&out)[S]) {
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    const int b = S - 1 - s;
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = b < 4 ? (uint32_t)K[4 * q + i] : (uint32_t)(K[4 * q + i] >> 32);
+      const uint32_t sel = (uint32_t)(b & 3) | ((4u + (uint32_t)(b & 3)) << 4);
+      w[q] = __byte_perm(__byte_perm(v[0], v[1], sel), __byte_perm(v[2], v[3], sel), 0x5410);
+    }
+    out[s] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+}
+
 }  // namespace mcm

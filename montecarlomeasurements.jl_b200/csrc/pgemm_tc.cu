@@ -88,28 +88,20 @@ k_pslice(const T* const* __restrict__ xs, const double* __restrict__ shift, cons
     const size_t rg = blk % nrg, kb = blk / nrg;
     const size_t row = rg * 8 + r8;
     const int k0 = (int)(kb * PZ_KB + c * 16);
-    alignas(16) int8_t dg[PZ_S][16];
     double xv[16];                   // all 16 loads issued before the first digit is extracted
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int k = k0 + j;
       xv[j] = (k < K && row < n) ? ((double)__ldcs(xs[k] + row) - shift[k]) * scale56[k] : 0.0;
     }
+    unsigned long long Kd[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      long long I = __double2ll_rn(xv[j]);
-#pragma unroll
-      for (int s = PZ_S - 1; s >= 1; --s) {
-        const long long d = ((I + 128) & 255) - 128;
-        dg[s][j] = (int8_t)d;
-        I = (I - d) >> 8;
-      }
-      dg[0][j] = (int8_t)I;
-    }
+    for (int j = 0; j < 16; ++j) Kd[j] = balanced_digit_bytes<PZ_S>(__double2ll_rn(xv[j]));
+    int4 pl[PZ_S];
+    pack_digit_planes<PZ_S>(Kd, pl);
     const size_t off = w * 16;
 #pragma unroll
-    for (int s = 0; s < PZ_S; ++s)
-      *reinterpret_cast<int4*>(planes + (size_t)s * (npad * kpad) + off) = *reinterpret_cast<const int4*>(dg[s]);
+    for (int s = 0; s < PZ_S; ++s) *reinterpret_cast<int4*>(planes + (size_t)s * (npad * kpad) + off) = pl[s];
   }
 }
 
@@ -172,24 +164,19 @@ k_pz_coef(const double* __restrict__ A, int Mo, int Mi, const double* __restrict
   const size_t jg = blk % njg, kb = blk / njg;
   const size_t j = jg * 8 + r8;
   const int k0 = (int)(kb * PZ_KB + c * 16);
-  alignas(16) int8_t dg[PZ_S][16];
   const double cs = j < (size_t)Mo ? cscale[j] : 0.0;
+  unsigned long long Kd[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const int k = k0 + q;
     long long I = 0;
     if (k < Mi && cs != 0.0) I = __double2ll_rn(A[j * (size_t)Mi + k] * apow[k] * cs);
-#pragma unroll
-    for (int s = PZ_S - 1; s >= 1; --s) {
-      const long long d = ((I + 128) & 255) - 128;
-      dg[s][q] = (int8_t)d;
-      I = (I - d) >> 8;
-    }
-    dg[0][q] = (int8_t)I;
+    Kd[q] = balanced_digit_bytes<PZ_S>(I);
   }
+  int4 pl[PZ_S];
+  pack_digit_planes<PZ_S>(Kd, pl);
 #pragma unroll
-  for (int s = 0; s < PZ_S; ++s)
-    *reinterpret_cast<int4*>(planes + (size_t)s * (mopad * kpad) + w * 16) = *reinterpret_cast<const int4*>(dg[s]);
+  for (int s = 0; s < PZ_S; ++s) *reinterpret_cast<int4*>(planes + (size_t)s * (mopad * kpad) + w * 16) = pl[s];
 }
 
 struct PzSchedule {
