@@ -697,7 +697,7 @@ static int sort_impl(const T* in, T* out, int64_t* perm_out, size_t n) {
   MCM_CUDA(cudaMemcpyAsync(d_orand, init, sizeof(init), cudaMemcpyHostToDevice, c.stream));
   const K* in_bits = reinterpret_cast<const K*>(in);
   int rc = hist_launch<K, true>(in_bits, (uint32_t)n, 0, hist, nblocks, d_orand);   // digit 0 + OR / AND + NaN flag
-  if (rc) return rc;
+  if (rc) { cudaFreeAsync(hist, c.stream); cudaFreeAsync(d_orand, c.stream); return rc; }
   unsigned long long h_orand[2] = {~0ull, 0ull};
   MCM_CUDA(cudaMemcpyAsync(h_orand, d_orand, sizeof(h_orand), cudaMemcpyDeviceToHost, c.stream));
   MCM_CUDA(cudaStreamSynchronize(c.stream));      // one 16-byte read-back per sort decides which passes run
