@@ -37,6 +37,7 @@ from .decision import union, intersect, with_nominal, nominal
 from . import linalg, complexp
 from .complexp import ComplexParticles, complex_particles
 from .bymap import bymap, bypmap, prob, register_primitive, register_primitive_multi, register_primitive_single
+from .deconstruct import has_particles, mean_object, replace_particles
 from . import sharded, tape
 
 StaticParticles = Particles  # storage is identical on device; N defaults differ (types.jl:26-30)

@@ -579,3 +579,25 @@ def test_moments_enqueue_collect_equals_the_synchronous_call(mcm):
         L.check(lib.mcm_moments_enqueue(L.F64, C.c_void_p(y.ptr), n))          # the last enqueue is the one collected
         L.check(lib.mcm_moments_collect(got.ctypes.data_as(L._dp)))
         assert np.array_equal(got, ref)
+
+
+def test_has_particles_and_mean_object(mcm):
+    """deconstruct.jl:5-20, 93-95 (runtests.jl uses them on ControlSystems-style structs): traversal on the host,
+    means on the device."""
+    import dataclasses
+
+    @dataclasses.dataclass
+    class Sys:
+        A: list
+        gain: object
+        name: str
+
+    p, q = mcm.pm(2.0, 0.1), mcm.pm(-1.0, 0.2)
+    s = Sys(A=[[p, 1.0], [0.0, q]], gain=q, name="plant")
+    assert mcm.has_particles(s) and mcm.has_particles([1.0, (2.0, p)]) and mcm.has_particles({"k": p})
+    assert not mcm.has_particles(Sys(A=[[1.0]], gain=3.0, name="x")) and not mcm.has_particles(np.ones(3))
+    m = mcm.mean_object(s)
+    assert isinstance(m, Sys) and m.name == "plant" and not mcm.has_particles(m)
+    assert m.A[0][0] == mcm.pmean(p) and m.A[1][1] == mcm.pmean(q) and m.gain == mcm.pmean(q) and m.A[0][1] == 1.0
+    first = mcm.replace_particles({"a": p, "b": 4})
+    assert first["a"] == p.to_numpy()[0] and first["b"] == 4
