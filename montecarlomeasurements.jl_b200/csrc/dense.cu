@@ -15,6 +15,9 @@
 
 namespace mcm {
 
+int pgemm_tensor_device_A(int dtype, const double* A_dev, int Mo, int Mi, const void* const* xs, const double* shift_host,
+                          const double* bias_host, void* const* outs, size_t n);   // pgemm.cu
+
 constexpr int DN_NB = 64;   // panel width
 static int g_dense_v2 = 2;   // mcm_dense_use_v2: 2 = as 1 with the panelled diagonal block (k_potrf_diag_v3); 1 = register-tiled diagonal block, right-looking solve, chol(S) on a side stream; 0 = first versions
 constexpr int DN_T = 256;
@@ -506,6 +509,20 @@ extern "C" int mcm_transform_moments(int dtype, const void* const* xs, int M, si
   }
   rc = trsm_right_lower_device(dC, dLS, M, M);   // dLS <- chol(S).L / xl
   if (rc) { drop_stats(); release(); return rc; }
+  // Both factors are lower triangular, so is A; its upper part is cleared explicitly (it is exactly zero already; this
+  // keeps the early exit of the application kernels independent of that).  The tensor application takes A where it
+  // is: only the M means visit the host.  (Until the last session of round 2 A was downloaded, cleared and scanned on
+  // the host, copied to pinned staging and uploaded again: ~3 ms of an idle GPU at C5.)
+  k_zero_upper<<<(unsigned)((mm + 255) / 256), 256, 0, c.stream>>>(dLS, M, M);
+  MCM_CHECK_LAUNCH();
+  {
+    std::vector<double> mu_dev(M);
+    MCM_CUDA(cudaMemcpyAsync(mu_dev.data(), dmu, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    MCM_CUDA(cudaStreamSynchronize(c.stream));
+    rc = pgemm_tensor_device_A(dtype, dLS, M, M, xs, mu_dev.data(), m_host, outs, n);
+    if (rc != -1) { release(); drop_stats(); return rc; }
+  }
+  // not taken by the tensor path (small problem, heavy-tailed variable, switched off): the host form of mcm_pgemm.
   // A and the means go back through PINNED staging (a pageable 8 MB copy each way cost ~2 ms here)
   std::vector<double> A_fallback, mu(M);
   double* A = static_cast<double*>(pinned_scratch(0, mm * sizeof(double)));

@@ -184,7 +184,7 @@ k_pgemm(const double* __restrict__ A, int lda, const int* __restrict__ kend, con
 
 template <typename T>
 int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_host, const double* shift_host,
-                      const double* bias_host, T* const* outs_host, size_t n);
+                      const double* bias_host, T* const* outs_host, size_t n, const double* A_dev);
 static int g_pgemm_use_tensor = 1;
 static int g_pgemm_last_engine = 0;   // 0 = FP64 DMMA, 1 = tcgen05 int8 (Ozaki)
 
@@ -193,6 +193,29 @@ static int g_pgemm_last_engine = 0;   // 0 = FP64 DMMA, 1 = tcgen05 int8 (Ozaki)
 using namespace mcm;
 
 extern "C" int mcm_pgemm_use_tensor(int on) { g_pgemm_use_tensor = on; return MCM_OK; }
+
+namespace mcm {
+// The tensor path of mcm_pgemm for a coefficient matrix that already lives on the device (mcm_transform_moments: the
+// factor product never visits the host: no 8 MB download, host triangle pass, finiteness scan, staging copy and upload
+// at C5).  Returns MCM_OK (done), -1 (not taken: the caller downloads A and calls mcm_pgemm) or an error.
+int pgemm_tensor_device_A(int dtype, const double* A_dev, int Mo, int Mi, const void* const* xs, const double* shift_host,
+                          const double* bias_host, void* const* outs, size_t n) {
+  if (!g_pgemm_use_tensor || Mo < 64 || Mi < 128 || n < 8192) return -1;
+  const size_t esz = dtype == MCM_F64 ? 8 : 4;
+  for (int k = 0; k < Mi; ++k)
+    if (!xs[k] || reinterpret_cast<uintptr_t>(xs[k]) % esz) return -1;
+  for (int j = 0; j < Mo; ++j) {
+    if (!outs[j] || reinterpret_cast<uintptr_t>(outs[j]) % esz) return -1;
+    for (int k = 0; k < Mi; ++k)
+      if (outs[j] == xs[k]) return -1;
+  }
+  const int rc = dtype == MCM_F64
+                     ? pgemm_tensor_impl<double>(nullptr, Mo, Mi, (const double* const*)xs, shift_host, bias_host, (double* const*)outs, n, A_dev)
+                     : pgemm_tensor_impl<float>(nullptr, Mo, Mi, (const float* const*)xs, shift_host, bias_host, (float* const*)outs, n, A_dev);
+  if (rc == MCM_OK) g_pgemm_last_engine = 1;
+  return rc;
+}
+}  // namespace mcm
 extern "C" int mcm_pgemm_last_engine(void) { return g_pgemm_last_engine; }
 
 extern "C" int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const void* const* xs, const double* shift_host,
@@ -219,8 +242,8 @@ extern "C" int mcm_pgemm(int dtype, const double* A_host, int Mo, int Mi, const 
   g_pgemm_last_engine = 0;
   if (g_pgemm_use_tensor && Mo >= 64 && Mi >= 128 && n >= 8192) {
     const int rc = dtype == MCM_F64
-                       ? pgemm_tensor_impl<double>(A_host, Mo, Mi, (const double* const*)xs, shift_host, bias_host, (double* const*)outs, n)
-                       : pgemm_tensor_impl<float>(A_host, Mo, Mi, (const float* const*)xs, shift_host, bias_host, (float* const*)outs, n);
+                       ? pgemm_tensor_impl<double>(A_host, Mo, Mi, (const double* const*)xs, shift_host, bias_host, (double* const*)outs, n, nullptr)
+                       : pgemm_tensor_impl<float>(A_host, Mo, Mi, (const float* const*)xs, shift_host, bias_host, (float* const*)outs, n, nullptr);
     if (rc == MCM_OK) { g_pgemm_last_engine = 1; return MCM_OK; }
     if (rc != -1) return rc;
   }

@@ -431,10 +431,12 @@ k_pgemm_i8(const int8_t* __restrict__ xplanes, const int8_t* __restrict__ aplane
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(PZ_TMEM_COLS));
 }
 
-// returns MCM_OK, an error, or -1 = declined (caller runs the DMMA kernel)
+// returns MCM_OK, an error, or -1 = declined (caller runs the DMMA kernel).
+// A_dev != nullptr: the coefficient matrix is already on the device (row-major Mo x Mi, e.g. the factor product of
+// mcm_transform_moments) — no host copy of it is read, checked or uploaded; a non-finite entry is caught by k_pz_rows.
 template <typename T>
 int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_host, const double* shift_host,
-                      const double* bias_host, T* const* outs_host, size_t n) {
+                      const double* bias_host, T* const* outs_host, size_t n, const double* A_dev) {
   Ctx& c = ctx();
   const size_t kpad = ((size_t)Mi + PZ_KB - 1) / PZ_KB * PZ_KB;
   const size_t npad = (n + PZ_TM - 1) / PZ_TM * PZ_TM;
@@ -443,14 +445,15 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   const int njt = (int)(mopad / PZ_TN);
   const size_t nptiles = npad / PZ_TM;
   if (nptiles > 0x7fffffffull) return -1;
-  for (size_t q = 0; q < (size_t)Mo * Mi; ++q)
-    if (!std::isfinite(A_host[q])) return -1;
+  if (!A_dev)
+    for (size_t q = 0; q < (size_t)Mo * Mi; ++q)
+      if (!std::isfinite(A_host[q])) return -1;
 
   // ---- one upload: input/output pointer tables, shift, bias, A
   auto al = [](size_t b) { return (b + 15) / 16 * 16; };
   const size_t o_xs = 0, o_outs = al((size_t)Mi * sizeof(void*)), o_shift = o_outs + al((size_t)Mo * sizeof(void*));
   const size_t o_bias = o_shift + kpad * sizeof(double), o_A = o_bias + mopad * sizeof(double);
-  const size_t up_bytes = o_A + (size_t)Mo * Mi * sizeof(double);
+  const size_t up_bytes = o_A + (A_dev ? 0 : (size_t)Mo * Mi * sizeof(double));
   // staged in pinned memory (slot 2; a pageable upload of the 8 MB of A at C5 cost ~2 ms and synchronised)
   std::vector<unsigned char> up_fallback;
   unsigned char* up = static_cast<unsigned char*>(pinned_scratch(2, up_bytes));
@@ -460,7 +463,7 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   memcpy(up + o_outs, outs_host, (size_t)Mo * sizeof(void*));
   if (shift_host) memcpy(up + o_shift, shift_host, (size_t)Mi * sizeof(double));
   if (bias_host) memcpy(up + o_bias, bias_host, (size_t)Mo * sizeof(double));
-  memcpy(up + o_A, A_host, (size_t)Mo * Mi * sizeof(double));
+  if (!A_dev) memcpy(up + o_A, A_host, (size_t)Mo * Mi * sizeof(double));
   // ---- device workspace: ex, ratio, sc56, apow, rowscale, cscale, kend, flag, coefficient planes
   const size_t w_ex = 0, w_ratio = al((size_t)Mi * sizeof(int)), w_sc = w_ratio + al((size_t)Mi * sizeof(double));
   const size_t w_apow = w_sc + kpad * sizeof(double), w_rows = w_apow + kpad * sizeof(double);
@@ -474,7 +477,7 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   MCM_CUDA(cudaMemsetAsync(d_ws + w_rows, 0, w_planes - w_rows, c.stream));   // rowscale, cscale, kend, flag
   const T* const* d_xs = reinterpret_cast<const T* const*>(d_up + o_xs);
   const double* d_shift = reinterpret_cast<const double*>(d_up + o_shift);
-  const double* d_A = reinterpret_cast<const double*>(d_up + o_A);
+  const double* d_A = A_dev ? A_dev : reinterpret_cast<const double*>(d_up + o_A);
   int* d_ex = reinterpret_cast<int*>(d_ws + w_ex);
   double* d_ratio = reinterpret_cast<double*>(d_ws + w_ratio);
   double* d_sc = reinterpret_cast<double*>(d_ws + w_sc);
@@ -561,7 +564,7 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   return flag ? -1 : MCM_OK;   // out-of-range coefficient scale: the caller recomputes on the DMMA kernel
 }
 
-template int pgemm_tensor_impl<double>(const double*, int, int, const double* const*, const double*, const double*, double* const*, size_t);
-template int pgemm_tensor_impl<float>(const double*, int, int, const float* const*, const double*, const double*, float* const*, size_t);
+template int pgemm_tensor_impl<double>(const double*, int, int, const double* const*, const double*, const double*, double* const*, size_t, const double*);
+template int pgemm_tensor_impl<float>(const double*, int, int, const float* const*, const double*, const double*, float* const*, size_t, const double*);
 
 }  // namespace mcm
