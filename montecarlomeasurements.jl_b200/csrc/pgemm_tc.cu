@@ -15,8 +15,8 @@
 // on the DMMA kernel.
 //
 // Tile: 128 particles (TMEM lanes, so the epilogue writes 256 contiguous bytes of one output per warp store) x
-// 64 outputs; k-blocks of 32 variables.  PERSISTENT kernel, one CTA per SM: two CTAs share a particle tile and
-// split its output tiles, so the 148 CTAs keep 74 digit tiles (7 planes x 128 x K bytes) hot in L2 while they
+// 64 outputs; k-blocks of 32 variables.  PERSISTENT kernel, one CTA per SM: four CTAs share a particle tile (rotating parts) and
+// split its output tiles, so the 148 CTAs keep 37 digit tiles (7 planes x 128 x K bytes) hot in L2 while they
 // sweep all output tiles; the TMA producer runs ahead across tile boundaries.
 //   warp 0 lane 0 : producer, 14 cp.async.bulk per k-block (digit planes are stored tile-ready) -> 4-stage ring
 //   warp 1 lane 0 : 28 tcgen05.mma (M128 N64 K32) per k-block, tcgen05.commit -> mbarriers
@@ -183,10 +183,12 @@ struct PzSchedule {
   int nptiles, njt, share, slots;   // share = CTAs per particle tile, slots = particle tiles in flight
 };
 
-// tile sequence of CTA c: particle tiles slot, slot + slots, ...; for each, output tiles njt-1-part, -share, ...
+// tile sequence of CTA c: particle tiles slot, slot + slots, ...; for each, output tiles njt-1-part, -share, ... where the
+// part rotates with the particle tile: for a triangular A the k loops shrink with jt, so a fixed part gave one CTA of every
+// pair 144 k-blocks per particle tile and the other 128 (share = 2, njt = 16) — 11 % more work on half of the CTAs
 #define PZ_TILE_LOOP(sch)                                                                      \
   for (int ptile = (int)blockIdx.x / (sch).share; ptile < (sch).nptiles; ptile += (sch).slots) \
-    for (int jt = (sch).njt - 1 - ((int)blockIdx.x % (sch).share); jt >= 0; jt -= (sch).share)
+    for (int jt = (sch).njt - 1 - (((int)blockIdx.x % (sch).share + ptile / (sch).slots) % (sch).share); jt >= 0; jt -= (sch).share)
 
 // warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane group = warp % 4)
 constexpr int PZ_EPI_WARPS = 8;     // two per TMEM lane group: 32 of the 64 output columns each
@@ -530,10 +532,13 @@ int pgemm_tensor_impl(const double* A_host, int Mo, int Mi, const T* const* xs_h
   sch.nptiles = (int)nptiles;
   sch.njt = njt;
   {
-    // CTAs per particle tile: more sharing = fewer digit tiles alive in L2 (74 x 917 KB at share 2 straddles the two L2
-    // partitions: ncu showed a 40 % hit rate); MCM_PGEMM_SHARE overrides for experiments
+    // CTAs per particle tile.  With the rotating part (PZ_TILE_LOOP) the CTAs of a group stay on the same particle tile,
+    // so its digit planes are read from DRAM once and served from L2 to the others.  Measured at C5 (ncu, triangular /
+    // dense A): share 1: 12.1 / 22.8 ms with 39.7 / 107 GB of DRAM reads; share 2: 10.7 / 18.7 ms, 10.1 / 19.2 GB;
+    // share 4: 10.6 / 18.1 ms, 7.4 / 7.9 GB = the 7.2 GB of digit planes.  (With a fixed part share 2 read 37 GB: the
+    // unevenly loaded CTAs of a pair drifted apart.)  MCM_PGEMM_SHARE overrides for experiments.
     const char* e = getenv("MCM_PGEMM_SHARE");
-    int want = e ? atoi(e) : 2;
+    int want = e ? atoi(e) : 4;
     while (want > 1 && (njt < want || c.sm_count % want != 0)) want >>= 1;
     sch.share = want;
   }
