@@ -4,6 +4,7 @@
 #pragma once
 #include <math.h>
 #include "mcm_common.cuh"
+#include "mcm_digits.cuh"
 
 namespace mcm {
 
@@ -219,12 +220,7 @@ k_rowstats(const T* const* __restrict__ vars, const double* __restrict__ means, 
 // the UNSIGNED bytes of I + C (C = S bytes of 0x80) are d_b + 128, and flipping bit 7 of each byte turns them into the
 // int8 digits: two 64-bit operations for all digits.  The top byte wraps exactly like the (int8_t) cast of the loop's
 // remainder did, so the planes are bit-identical to the loop's for every I.
-template <int S>
-__device__ __forceinline__ unsigned long long balanced_digit_bytes(long long I) {
-  static_assert(S >= 1 && S <= 8, "at most eight digits per 64-bit value");
-  constexpr unsigned long long C = 0x8080808080808080ull >> (8 * (8 - S));
-  return ((unsigned long long)I + C) ^ C;               // byte b (b < S) = digit of weight 256^b, as int8
-}
+// (balanced_digit_bytes lives in mcm_digits.cuh: plain C++, also compiled by tests/test_digit_split.py)
 // plane s (s = 0 most significant) of 16 values -> 16 bytes: byte S-1-s of every K[j], gathered with byte permutes
 template <int S>
 __device__ __forceinline__ void pack_digit_planes(const unsigned long long (&K)[16], int4 (&out)[S]) {
